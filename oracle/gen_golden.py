@@ -1,0 +1,173 @@
+"""TEST INFRASTRUCTURE -- regenerates tests/golden/*.npz from the UNMODIFIED
+reference (run in the build container only):
+
+    python oracle/gen_golden.py
+
+Each fixture holds the inputs needed to rebuild the case (or the seeds that
+regenerate them) and per-step vectors recorded from the reference's own
+objects by oracle/ref_harness.py.
+"""
+import copy
+import os
+import sys
+
+import numpy
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import ref_harness as rh  # noqa: E402
+from pauxy_b200.hamiltonians import (generate_hamiltonian,  # noqa: E402
+                                     synthetic_cholesky_hamiltonian)
+
+GOLD = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                    'tests', 'golden')
+
+
+def options(nwalkers, dt, steps, blocks, seed, stab=10, popc=1, walkers=None):
+    o = {'verbosity': 0, 'get_sha1': False,
+         'qmc': {'timestep': dt, 'steps': steps, 'blocks': blocks, 'rng_seed': seed,
+                 'num_walkers': nwalkers, 'stabilise_freq': stab,
+                 'pop_control_freq': popc},
+         'estimates': {'mixed': {'energy_eval_freq': 1, 'verbose': False}},
+         'trial': {'name': 'MultiSlater'}}
+    if walkers:
+        o['walkers'] = walkers
+    return o
+
+
+def save(name, meta, tr, setup=None, keep_xi=True, keep_phi=True, extra=None):
+    out = dict(meta)
+    for k in ('weight_prop', 'weight', 'unscaled_weight', 'ot', 'hybrid_energy', 'eloc',
+              'parent_ix', 'comb_r', 'eshift', 'estimates', 'detR', 'total_weight',
+              'init_ot', 'init_estimates', 'nfb_trig', 'nhe_trig', 'rows', 'active'):
+        out[k] = tr[k]
+    if keep_xi:
+        out['xi'] = tr['xi']
+    if keep_phi:
+        out['phi_final'] = tr['phi_final']
+    else:
+        out['phi_final_head'] = tr['phi_final'][:2]
+    if setup is not None:
+        for k, v in setup.items():
+            out['setup_' + k] = v
+    if extra:
+        out.update(extra)
+    path = os.path.join(GOLD, name + '.npz')
+    numpy.savez_compressed(path, **out)
+    print(name, '%.1f KB' % (os.path.getsize(path) / 1024.),
+          'nfb', int(tr['nfb_trig']), 'nhe', int(tr['nhe_trig']),
+          'comb events', int((tr['parent_ix'] != 1).sum()),
+          'min/max w_prop %.3g %.3g' % (tr['weight_prop'].min(), tr['weight_prop'].max()))
+
+
+def case_test_generic():
+    """pauxy/qmc/tests/test_afqmc.py:190-229 verbatim inputs."""
+    numpy.random.seed(7)
+    h1e, chol, enuc, _ = generate_hamiltonian(11, (3, 3), cplx=False)
+    hs = chol.reshape((-1, 121)).T.copy()
+    opts = {'verbosity': 0, 'get_sha1': False,
+            'qmc': {'timestep': 0.005, 'steps': 10, 'blocks': 10, 'rng_seed': 8},
+            'estimates': {'mixed': {'energy_eval_freq': 1, 'verbose': False}},
+            'trial': {'name': 'MultiSlater'}}
+    a = rh.run_reference_untraced(h1e, hs, enuc, (3, 3), copy.deepcopy(opts))
+    m = a.estimators.estimators['mixed']
+    m.update(a.system, a.qmc, a.trial, a.psi, 0)
+    numer = m.estimates[m.names.enumer]
+    rows = rh.estimator_rows()
+    a2, tr = rh.run_reference_traced(h1e, hs, enuc, (3, 3), copy.deepcopy(opts))
+    assert numpy.array_equal(rows[:, :10], tr['rows'][:, :10])
+    meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array((3, 3)), dt=0.005,
+                nwalkers=10, steps=10, blocks=10, seed=8, stab=10, popc=1,
+                ref_numer_after_run=numer, ref_test_golden_numer=3.8763193646854273,
+                ref_test_golden_etotal=1.5485077038208)
+    save('test_generic', meta, tr, setup=rh.reference_setup_arrays(a2))
+
+
+def case_c1():
+    numpy.random.seed(7)
+    h1e, chol, enuc, _ = generate_hamiltonian(12, (4, 4), cplx=False)
+    hs = chol.reshape((-1, 144)).T.copy()
+    opts = options(32, 0.005, 10, 4, 8, stab=5, popc=1)
+    a, tr = rh.run_reference_traced(h1e, hs, enuc, (4, 4), opts)
+    meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array((4, 4)), dt=0.005,
+                nwalkers=32, steps=10, blocks=4, seed=8, stab=5, popc=1)
+    save('c1', meta, tr, setup=rh.reference_setup_arrays(a))
+
+
+def case_stress(name, pop, walkers=None, scale_chol=6.0, dt=0.02):
+    """Small case scaled so that the force-bias clip, the hybrid-energy bound,
+    the weight cap and comb/pair-branch events all fire."""
+    numpy.random.seed(11)
+    h1e, chol, enuc, _ = generate_hamiltonian(8, (3, 3), cplx=False)
+    hs = scale_chol * chol.reshape((-1, 64)).T.copy()
+    opts = options(16, dt, 5, 6, 21, stab=3, popc=1, walkers=walkers)
+    a, tr = rh.run_reference_traced(h1e, hs, enuc, (3, 3), opts)
+    meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array((3, 3)), dt=dt,
+                nwalkers=16, steps=5, blocks=6, seed=21, stab=3, popc=1,
+                pop_control=pop, min_weight=(walkers or {}).get('min_weight', 0.1),
+                max_weight=(walkers or {}).get('max_weight', 4.0))
+    save(name, meta, tr, setup=rh.reference_setup_arrays(a))
+
+
+def case_shape(name, M, na, N, W, steps, seed_h, stab):
+    """BASELINE c2/c3/c4 shapes at reduced walker count; inputs regenerate
+    from seeds, fields from the global legacy stream."""
+    h1e, hs, ecore = synthetic_cholesky_hamiltonian(M, N, seed_h)
+    opts = options(W, 0.005, steps, 1, 8, stab=stab, popc=1)
+    a, tr = rh.run_reference_traced(h1e, hs, ecore, (na, na), opts)
+    meta = dict(nbasis=M, nelec=numpy.array((na, na)), nchol=N, dt=0.005, nwalkers=W,
+                steps=steps, blocks=1, seed=8, stab=stab, popc=1, seed_h=seed_h,
+                h1e_checksum=h1e.sum(), hs_checksum=hs.sum())
+    save(name, meta, tr, keep_xi=False, keep_phi=False)
+
+
+def case_local_energy():
+    """pauxy/estimators/tests/test_generic.py:33-64 inputs and golden."""
+    rh._install_paths()
+    from pauxy.systems.generic import Generic
+    from pauxy.trial_wavefunction.multi_slater import MultiSlater
+    from pauxy.estimators.greens_function import gab_spin
+    from pauxy.estimators.generic import local_energy_generic_cholesky_opt
+    from pauxy.utils.testing import get_random_nomsd
+    numpy.random.seed(7)
+    nmo = 24
+    nelec = (4, 2)
+    h1e, chol, enuc, eri = generate_hamiltonian(nmo, nelec, cplx=False)
+    system = Generic(nelec=nelec, h1e=numpy.array([h1e, h1e]),
+                     chol=chol.reshape((-1, nmo * nmo)).T.copy(), ecore=enuc)
+    wfn = get_random_nomsd(system, ndet=1, cplx=False)
+    trial = MultiSlater(system, wfn)
+    trial.half_rotate(system)
+    e = local_energy_generic_cholesky_opt(system, trial.G, Ghalf=trial.GH,
+                                          rchol=trial._rchol)
+    path = os.path.join(GOLD, 'local_energy.npz')
+    numpy.savez_compressed(path, h1e=h1e, hs_pot=system.hs_pot, ecore=enuc,
+                           nelec=numpy.array(nelec), psi=trial.psi[0],
+                           energy=numpy.array(e),
+                           ref_test_golden=numpy.array([20.6826247016273,
+                                                        23.0173528796140,
+                                                        -2.3347281779866]))
+    print('local_energy', e)
+
+
+if __name__ == '__main__':
+    os.makedirs(GOLD, exist_ok=True)
+    which = sys.argv[1:] or ['tg', 'c1', 'stress', 'pb', 'le', 'c2s', 'c3s', 'c4s']
+    if 'tg' in which:
+        case_test_generic()
+    if 'c1' in which:
+        case_c1()
+    if 'stress' in which:
+        case_stress('stress_comb', 'comb')
+    if 'pb' in which:
+        case_stress('stress_pair_branch', 'pair_branch',
+                    walkers={'population_control': 'pair_branch',
+                             'min_weight': 0.9, 'max_weight': 1.1},
+                    scale_chol=3.0, dt=0.01)
+    if 'le' in which:
+        case_local_energy()
+    if 'c2s' in which:
+        case_shape('c2_shape', 24, 5, 120, 32, 12, 1002, 5)
+    if 'c3s' in which:
+        case_shape('c3_shape', 60, 7, 300, 16, 6, 1003, 5)
+    if 'c4s' in which:
+        case_shape('c4_shape', 108, 21, 500, 16, 6, 1004, 5)

@@ -1,0 +1,27 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, 'tests', 'golden')
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def golden_path(name):
+    return os.path.join(GOLDEN, name + '.npz')
+
+
+@pytest.fixture(scope='session')
+def golden():
+    import numpy
+
+    def load(name):
+        return dict(numpy.load(golden_path(name), allow_pickle=False))
+    return load
