@@ -1,0 +1,194 @@
+/*
+ * pauxy_b200 -- C-ABI of the B200 phaseless-AFQMC walker-propagation hot path.
+ *
+ * The reference (pauxy-qmc/pauxy) is pure Python and has no FFI: its plugin
+ * surface for this path is the duck-typed propagator / walker / estimator
+ * classes called from AFQMC.run (pauxy/qmc/afqmc.py:223-255).  This header is
+ * the boundary a ctypes binding in those classes would call; each entry point
+ * names the reference code it replaces.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative PXB_ERR_* otherwise;
+ *     pxb_last_error() returns a message.  Nothing calls exit().
+ *   - "dev" pointers are CUDA device pointers (e.g. torch.Tensor.data_ptr()).
+ *   - complex128 arrays are interleaved (re, im) doubles, C order, in the
+ *     reference's own layouts.
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*);
+ *     calls are asynchronous unless stated otherwise.
+ */
+#ifndef PAUXY_B200_H
+#define PAUXY_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PXB_OK 0
+#define PXB_ERR_ARG -1          /* bad argument / shape */
+#define PXB_ERR_CUDA -2         /* CUDA runtime error (see pxb_last_error) */
+#define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
+#define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
+
+#define PXB_ABI_VERSION 1
+
+typedef struct pxb_context* pxb_handle;
+
+/* Problem description.  Mirrors system.nbasis/nup/ndown/nfields
+ * (pauxy/systems/generic.py:74-166), qmc.dt (pauxy/qmc/options.py:88), and the
+ * propagator option expansion_order (pauxy/propagation/continuous.py:37). */
+typedef struct {
+  int32_t nbasis;     /* M */
+  int32_t nup;        /* na */
+  int32_t ndown;      /* nb */
+  int32_t nchol;      /* N = nfields */
+  int32_t nwalkers;   /* walkers on THIS device */
+  int32_t exp_order;  /* Taylor order of exp(VHS), reference default 6 */
+  int32_t device;     /* CUDA device ordinal */
+  int32_t total_walkers; /* walkers over ALL devices (0: == nwalkers) */
+  double dt;
+} pxb_config;
+
+/* Walker-state fields living in the arena; pxb_field() gives their location
+ * so the host can view them (e.g. as torch tensors over the arena).  They are
+ * the per-walker scalars of pauxy/walkers/walker.py:24-61. */
+enum pxb_field_id {
+  PXB_F_WEIGHT = 0,          /* f64  [W]    walker.weight              */
+  PXB_F_UNSCALED_WEIGHT = 1, /* f64  [W]    walker.unscaled_weight     */
+  PXB_F_OT = 2,              /* c128 [W]    walker.ot == walker.ovlp   */
+  PXB_F_HYBRID_ENERGY = 3,   /* c128 [W]    walker.hybrid_energy       */
+  PXB_F_ELOC = 4,            /* c128 [W,3]  (E, E1, E2) last evaluated */
+  PXB_F_DETR = 5,            /* f64  [W]    walker.detR                */
+  PXB_F_LOG_DETR = 6,        /* f64  [W]    walker.log_detR            */
+  PXB_F_ESTIMATES = 7,       /* c128 [10]   Mixed.estimates accumulators (mixed.py:460-469) */
+  PXB_F_COUNTERS = 8,        /* i64  [8]    nfb_trig, nhe_trig, n_inactive, n_comb_moves (-1: total weight < 1e-8) */
+  PXB_F_PARENT_IX = 9,       /* i32  [Wtot] comb parent_ix of the last pop-control */
+  PXB_F_XBAR = 10,           /* c128 [W,N]  force bias after clipping (debug/parity) */
+  PXB_F_XSHIFTED = 11,       /* c128 [W,N]  x = xi - xbar (natural layout copy, debug/parity) */
+  PXB_F_CMF_CFB = 12,        /* c128 [W,2]  (cmf, cfb) of the last propagate */
+  PXB_F_OVLP_NEW = 13,       /* c128 [W]    overlap after the last propagate */
+  PXB_F_TOTAL_WEIGHT = 14,   /* f64  [1]    walker.total_weight (same for all walkers) */
+  PXB_F_PAIRS = 15,          /* i32  [1+2*Wtot] n_pairs then (clone, kill) global indices */
+  PXB_F_COUNT = 16
+};
+
+int pxb_abi_version(void);
+/* number of CUDA kernels launched through this handle so far (bench.py gpu_launches) */
+long long pxb_launch_count(pxb_handle h);
+
+/* ---- lifecycle -------------------------------------------------------- */
+int pxb_create(pxb_handle* out, const pxb_config* cfg);
+int pxb_destroy(pxb_handle h);
+const char* pxb_last_error(pxb_handle h);
+
+/* Device memory is owned by the caller: one arena of pxb_arena_bytes() bytes
+ * (256-byte aligned).  pxb_bind_arena zero-fills it on `stream`. */
+int pxb_arena_bytes(pxb_handle h, size_t* bytes);
+int pxb_bind_arena(pxb_handle h, void* dev_arena, size_t bytes, void* stream);
+int pxb_field(pxb_handle h, int field_id, size_t* offset_bytes, size_t* size_bytes);
+
+/* ---- Hamiltonian / trial (setup, once) ----------------------------------
+ * Device pointers to the reference's arrays, read during the call only:
+ *   hs_pot   f64  [M*M, N]      system.hs_pot            (systems/generic.py:154)
+ *   rchol    c128 [(na+nb)*M,N] trial._rchol             (trial_wavefunction/multi_slater.py:370-418)
+ *   bh1      c128 [2, M, M]     propagator.BH1           (propagation/generic.py:106-107)
+ *   h1rot    c128 [(na+nb), M]  psi_s^dagger H1[s] (rows: up orbitals, then down);
+ *                               e1b = sum h1rot * Theta == sum H1*G (estimators/generic.py:178)
+ *   psi      c128 [M, na+nb]    trial.psi                (walkers/handler.py:57-61)
+ *   mf_shift c128 [N]           propagator.mf_shift      (propagation/generic.py:66-80)
+ * rchol, bh1 and psi must be real-valued (imag == 0) in this version:
+ * PXB_ERR_UNSUPPORTED otherwise (checked on the device, synchronous call). */
+int pxb_set_hamiltonian(pxb_handle h, const double* dev_hs_pot, const void* dev_rchol,
+                        const void* dev_bh1, const void* dev_h1rot, const void* dev_psi,
+                        const void* dev_mf_shift, double ecore, void* stream);
+
+/* ---- walker state --------------------------------------------------------
+ * phi: c128 [W, M, na+nb] device, the reference layout of walker.phi stacked
+ * over walkers (walkers/walker.py:29). */
+int pxb_set_phi(pxb_handle h, const void* dev_phi, void* stream);
+int pxb_get_phi(pxb_handle h, void* dev_phi, void* stream);
+/* Walkers.__init__ + SingleDetWalker.__init__ (walkers/handler.py:36-164,
+ * walkers/single_det.py:31-94): phi = trial.init for every walker, weight = 1,
+ * ot = calc_overlap, hybrid_energy = 0, total_weight = total_walkers. */
+int pxb_init_walkers(pxb_handle h, const void* dev_init_phi /* c128 [M,ne] */,
+                     double total_walkers, void* stream);
+
+/* ---- the hot path -------------------------------------------------------- */
+/* Continuous.propagate_walker_phaseless for every walker with |weight| > 1e-8,
+ * followed by the 10 % weight cap (propagation/continuous.py:232-292,
+ * qmc/afqmc.py:231-236).
+ *   dev_xi : f64 [W, N] auxiliary fields xi for this step (row w is read only
+ *            if walker w is active), or NULL to draw them on the device with
+ *            Philox4x32-10 keyed by (rng_seed, step, global walker index).
+ *   walker_offset : global index of local walker 0 (rank * W), Philox only. */
+int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed,
+                  int64_t walker_offset, double eshift, int64_t step, void* stream);
+
+/* Walkers.orthogonalise -> SingleDetWalker.reortho (walkers/handler.py:166-181,
+ * walkers/single_det.py:215-255), phaseless branch. */
+int pxb_orthogonalise(pxb_handle h, void* stream);
+
+/* greens_function + local_energy_generic_cholesky_opt for every walker
+ * (walkers/single_det.py:295-321, estimators/generic.py:156-221) -> ELOC. */
+int pxb_local_energy(pxb_handle h, void* stream);
+
+/* Mixed.update accumulation (estimators/mixed.py:211-225) into ESTIMATES;
+ * with_energy != 0 adds the enumer/e1b/e2b/edenom terms from ELOC. */
+int pxb_accumulate(pxb_handle h, int with_energy, void* stream);
+int pxb_zero_estimates(pxb_handle h, void* stream);
+
+/* ---- population control (walkers/handler.py:225-412) -------------------- */
+/* Single-device pop_control with the comb: total weight (sequential sum),
+ * rescale, comb selection with the caller's uniform r (numpy.random.random()
+ * in the reference, handler.py:276), walker copies, weights reset to 1.
+ * Entirely on the device, no host synchronisation. */
+int pxb_pop_control_comb(pxb_handle h, double r, void* stream);
+
+/* Multi-device pieces.  dev_global_abs_weights: f64 [Wtot] = |weight| of all
+ * walkers in global order (all-gathered by the caller).
+ *  pxb_pop_rescale : total = sequential sum; unscaled_weight = weight;
+ *                    weight /= total/Wtot; TOTAL_WEIGHT = total
+ *                    (handler.py:233-249).
+ *  pxb_comb_plan   : parent_ix (PARENT_IX) and the (clone, kill) pair list
+ *                    (PAIRS) from the rescaled global weights (handler.py:271-301).
+ *  pxb_pair_branch_plan_host : host-side pair_branch selection (handler.py:
+ *                    340-386) -- sorting + uniform draws happen on the host. */
+int pxb_pop_rescale(pxb_handle h, const double* dev_global_abs_weights, int64_t wtot,
+                    void* stream);
+int pxb_comb_plan(pxb_handle h, const double* dev_global_abs_weights, int64_t wtot, double r,
+                  void* stream);
+/* Walker payload movement (Walker.get_buffer/set_buffer, walkers/walker.py:
+ * 63-131): the fields that matter downstream -- phi, weight, unscaled_weight,
+ * ot, hybrid_energy, eloc, detR, log_detR.
+ *  pxb_copy_walkers : local slot src[i] -> local slot dst[i], i < n (int32 dev lists)
+ *  pxb_pack_walkers / pxb_unpack_walkers : to / from a contiguous buffer of
+ *      n * pxb_payload_doubles() doubles, for send/recv between devices. */
+int pxb_payload_doubles(pxb_handle h, size_t* ndoubles);
+int pxb_copy_walkers(pxb_handle h, const int32_t* dev_src, const int32_t* dev_dst, int n,
+                     void* stream);
+int pxb_pack_walkers(pxb_handle h, const int32_t* dev_slots, int n, double* dev_buffer,
+                     void* stream);
+int pxb_unpack_walkers(pxb_handle h, const int32_t* dev_slots, int n, const double* dev_buffer,
+                       void* stream);
+int pxb_set_weights(pxb_handle h, double value, void* stream); /* handler.py:337-338 */
+
+/* Host helpers (pure C, no device): bit-exact restatements used by the host
+ * mirror when the selection has to happen on the host. */
+int pxb_comb_plan_host(const double* weights, int64_t n, double r, int32_t* parent_ix);
+
+/* ---- stage-level entry points (tests, profiling) -------------------------
+ * Each runs one stage of the pipeline on the current state. */
+int pxb_stage_greens(pxb_handle h, int with_e1b, void* stream);      /* A1: Theta, ovlp */
+int pxb_stage_force_bias_gemm(pxb_handle h, void* stream);           /* A3/C1: X_s = R_s^T Theta_s */
+int pxb_stage_exchange(pxb_handle h, void* stream);                  /* C1: exx_s from the current Theta */
+int pxb_get_theta(pxb_handle h, void* dev_theta /* c128 [W, ne, M] */, void* stream);
+int pxb_get_x(pxb_handle h, void* dev_x /* c128 [2, W, N] */, void* stream);
+int pxb_get_vhs(pxb_handle h, void* dev_vhs /* c128 [W, M, M] */, void* stream);
+int pxb_get_exx(pxb_handle h, void* dev_exx /* c128 [2, W] */, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PAUXY_B200_H */

@@ -1,0 +1,97 @@
+"""ctypes binding of libpauxy_b200.so (include/pauxy_b200.h).
+
+The product path has no CPU fallback: if the CUDA library is missing this
+module raises at import of the engine, loudly.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'csrc', 'libpauxy_b200.so')
+
+PXB_OK = 0
+ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_ERR_UNSUPPORTED'}
+
+# enum pxb_field_id
+F_WEIGHT, F_UNSCALED_WEIGHT, F_OT, F_HYBRID_ENERGY, F_ELOC, F_DETR, F_LOG_DETR, \
+    F_ESTIMATES, F_COUNTERS, F_PARENT_IX, F_XBAR, F_XSHIFTED, F_CMF_CFB, F_OVLP_NEW, \
+    F_TOTAL_WEIGHT, F_PAIRS, F_COUNT = range(17)
+
+
+class PxbConfig(ctypes.Structure):
+    _fields_ = [('nbasis', ctypes.c_int32), ('nup', ctypes.c_int32), ('ndown', ctypes.c_int32),
+                ('nchol', ctypes.c_int32), ('nwalkers', ctypes.c_int32),
+                ('exp_order', ctypes.c_int32), ('device', ctypes.c_int32),
+                ('total_walkers', ctypes.c_int32), ('dt', ctypes.c_double)]
+
+
+class PxbError(RuntimeError):
+    def __init__(self, code, msg):
+        RuntimeError.__init__(self, "%s (%d): %s" % (ERRORS.get(code, 'PXB_ERR'), code, msg))
+        self.code = code
+
+
+_vp = ctypes.c_void_p
+_PROTOS = {
+    'pxb_abi_version': (ctypes.c_int, []),
+    'pxb_launch_count': (ctypes.c_longlong, [_vp]),
+    'pxb_stage_exchange': (ctypes.c_int, [_vp, _vp]),
+    'pxb_create': (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(PxbConfig)]),
+    'pxb_destroy': (ctypes.c_int, [_vp]),
+    'pxb_last_error': (ctypes.c_char_p, [_vp]),
+    'pxb_arena_bytes': (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
+    'pxb_bind_arena': (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, _vp]),
+    'pxb_field': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t),
+                                 ctypes.POINTER(ctypes.c_size_t)]),
+    'pxb_set_hamiltonian': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _vp]),
+    'pxb_set_phi': (ctypes.c_int, [_vp, _vp, _vp]),
+    'pxb_get_phi': (ctypes.c_int, [_vp, _vp, _vp]),
+    'pxb_init_walkers': (ctypes.c_int, [_vp, _vp, ctypes.c_double, _vp]),
+    'pxb_propagate': (ctypes.c_int, [_vp, _vp, ctypes.c_uint64, ctypes.c_int64, ctypes.c_double,
+                                     ctypes.c_int64, _vp]),
+    'pxb_orthogonalise': (ctypes.c_int, [_vp, _vp]),
+    'pxb_local_energy': (ctypes.c_int, [_vp, _vp]),
+    'pxb_accumulate': (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    'pxb_zero_estimates': (ctypes.c_int, [_vp, _vp]),
+    'pxb_pop_control_comb': (ctypes.c_int, [_vp, ctypes.c_double, _vp]),
+    'pxb_pop_rescale': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
+    'pxb_comb_plan': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_double, _vp]),
+    'pxb_payload_doubles': (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_size_t)]),
+    'pxb_copy_walkers': (ctypes.c_int, [_vp, _vp, _vp, ctypes.c_int, _vp]),
+    'pxb_pack_walkers': (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
+    'pxb_unpack_walkers': (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
+    'pxb_set_weights': (ctypes.c_int, [_vp, ctypes.c_double, _vp]),
+    'pxb_comb_plan_host': (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_double, _vp]),
+    'pxb_stage_greens': (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    'pxb_stage_force_bias_gemm': (ctypes.c_int, [_vp, _vp]),
+    'pxb_get_theta': (ctypes.c_int, [_vp, _vp, _vp]),
+    'pxb_get_x': (ctypes.c_int, [_vp, _vp, _vp]),
+    'pxb_get_vhs': (ctypes.c_int, [_vp, _vp, _vp]),
+    'pxb_get_exx': (ctypes.c_int, [_vp, _vp, _vp]),
+}
+
+_lib = None
+
+
+def declared_symbols():
+    return sorted(_PROTOS.keys())
+
+
+def load():
+    """Load the shared library and set prototypes (idempotent)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise ImportError(
+            "pauxy_b200: CUDA library %s not built (run `python -m pauxy_b200.build`); "
+            "there is no CPU fallback" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _PROTOS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.pxb_abi_version() != 1:
+        raise ImportError("pauxy_b200: ABI version mismatch")
+    _lib = lib
+    return lib

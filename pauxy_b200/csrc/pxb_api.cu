@@ -1,0 +1,783 @@
+// C-ABI of the B200 AFQMC hot path (see include/pauxy_b200.h).
+#include "../../include/pauxy_b200.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "pxb_common.cuh"
+#include "pxb_exchange.cuh"
+#include "pxb_gemm.cuh"
+#include "pxb_small.cuh"
+#include "pxb_taylor.cuh"
+
+using namespace pxb;
+
+namespace {
+
+struct Region {
+  size_t off = 0, bytes = 0;
+};
+
+enum ArenaId {
+  A_LF, A_RF, A_BF, A_PSIT, A_H1ROT, A_VBAR,
+  A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
+  A_EXX, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG,
+  A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
+  A_COUNT = A_FIELD0 + PXB_F_COUNT
+};
+
+}  // namespace
+
+struct pxb_context {
+  pxb_config cfg;
+  Dims d;
+  Region reg[A_COUNT];
+  size_t arena_bytes = 0;
+  unsigned char* arena = nullptr;
+  bool ham_set = false;
+  int phi_cur = 0;  // which of PHI_A / PHI_B holds the walkers
+  int sm_count = 148;
+  int max_smem_optin = 0;
+  long long launches = 0;  // kernels launched through this handle
+  std::string err;
+
+  template <class T>
+  T* ptr(int id) const {
+    return reinterpret_cast<T*>(arena + reg[id].off);
+  }
+  template <class T>
+  T* field(int fid) const {
+    return ptr<T>(A_FIELD0 + fid);
+  }
+  double* phi() const { return ptr<double>(phi_cur ? A_PHI_B : A_PHI_A); }
+  double* phi_other() const { return ptr<double>(phi_cur ? A_PHI_A : A_PHI_B); }
+};
+
+namespace {
+
+int fail(pxb_handle h, int code, const std::string& msg) {
+  if (h) h->err = msg;
+  return code;
+}
+
+#define PXB_CUDA(h, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return fail(h, PXB_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define PXB_REQUIRE_READY(h)                                                     \
+  do {                                                                           \
+    if (!(h)) return PXB_ERR_ARG;                                                \
+    if (!(h)->arena) return fail(h, PXB_ERR_STATE, "arena not bound");           \
+    if (!(h)->ham_set) return fail(h, PXB_ERR_STATE, "hamiltonian not set");     \
+  } while (0)
+
+inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
+  size_t g = (n + block - 1) / block;
+  if (g > (size_t)cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+CopyArgs copy_args(pxb_handle h) {
+  CopyArgs c;
+  c.phi = h->phi();
+  c.weight = h->field<double>(PXB_F_WEIGHT);
+  c.unscaled = h->field<double>(PXB_F_UNSCALED_WEIGHT);
+  c.ot = h->field<double2>(PXB_F_OT);
+  c.ehyb = h->field<double2>(PXB_F_HYBRID_ENERGY);
+  c.eloc = h->field<double2>(PXB_F_ELOC);
+  c.detR = h->field<double>(PXB_F_DETR);
+  c.log_detR = h->field<double>(PXB_F_LOG_DETR);
+  c.d = h->d;
+  return c;
+}
+
+// ---- stage launchers ---------------------------------------------------------
+int run_greens(pxb_handle h, const double* phi, bool want_theta, double2* ovlp_out, bool with_e1b,
+               cudaStream_t st) {
+  const Dims& d = h->d;
+  GreensArgs a;
+  a.phi = phi;
+  a.theta = h->ptr<double>(A_THETA);
+  a.psiT = h->ptr<double>(A_PSIT);
+  a.h1rot = h->ptr<double2>(A_H1ROT);
+  a.ovlp_out = ovlp_out;
+  a.e1b_out = with_e1b ? h->ptr<double2>(A_E1B) : nullptr;
+  a.d = d;
+  a.want_theta = want_theta ? 1 : 0;
+  const int nth = 256;
+  const size_t smem = greens_smem_bytes(d, nth);
+  if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "greens: problem too large for shared memory");
+  PXB_CUDA(h, cudaFuncSetAttribute(greens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ++h->launches;
+  greens_kernel<<<d.Wp, nth, smem, st>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+// X_s[w][n] = sum_{i,p} R_s[(i,p), n] Theta_s[w][i][p]
+int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
+  const Dims& d = h->d;
+  for (int s = 0; s < 2; ++s) {
+    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
+    EpiX epi{h->ptr<double>(A_X) + (size_t)s * d.Wp * d.Np * 2, d.Wp, d.Np};
+    if (ns == 0) {
+      PXB_CUDA(h, cudaMemsetAsync(epi.X, 0, (size_t)d.Wp * d.Np * 16, st));
+      continue;
+    }
+    GemmArgs g;
+    g.A = h->ptr<double>(A_RF) + rf_spin_base(d, s);
+    g.B = h->ptr<double>(A_THETA) + (size_t)ioff * d.KC * 32;
+    g.strideAz = g.strideBz = 0;
+    g.strideBO = (size_t)d.ne * d.KC * 32;
+    g.strideBI = 0;
+    g.ntInner = 1;
+    g.MTiles = d.XG;
+    g.NTiles = d.WG;
+    g.KS = ns * d.KC;
+    ++h->launches;
+    PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
+  }
+  return PXB_OK;
+}
+
+int run_vhs_gemm(pxb_handle h, cudaStream_t st) {
+  const Dims& d = h->d;
+  GemmArgs g;
+  g.A = h->ptr<double>(A_LF);
+  g.B = h->ptr<double>(A_XF);
+  g.strideAz = g.strideBz = 0;
+  g.strideBO = (size_t)d.NKC * 32;
+  g.strideBI = 0;
+  g.ntInner = 1;
+  g.MTiles = d.RT;
+  g.NTiles = d.WG;
+  g.KS = d.NKC;
+  EpiVHS epi{h->ptr<double>(A_VF), d.KC, d.MT, d.sqrt_dt, vf_walker(d)};
+  ++h->launches;
+  PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
+  return PXB_OK;
+}
+
+int run_one_body(pxb_handle h, const double* in, double* out, const int* active, cudaStream_t st) {
+  const Dims& d = h->d;
+  for (int s = 0; s < 2; ++s) {
+    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
+    if (ns == 0) continue;
+    GemmArgs g;
+    g.A = h->ptr<double>(A_BF) + (size_t)s * d.MT * d.KC * 32;
+    g.B = in + (size_t)ioff * d.KC * 32;
+    g.strideAz = g.strideBz = 0;
+    g.strideBO = (size_t)d.ne * d.KC * 32;
+    g.strideBI = (size_t)d.KC * 32;
+    g.ntInner = ns;
+    g.MTiles = d.MT;
+    g.NTiles = d.WG * ns;
+    g.KS = d.KC;
+    EpiOF epi{out, active, d.ne, d.KC, ioff, ns};
+    if (d.MT % 7 == 0) {
+      ++h->launches;
+      PXB_CUDA(h, (launch_gemm<7, 4, 2, 4>(g, epi, 1, st)));
+    } else {
+      ++h->launches;
+      PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
+    }
+  }
+  return PXB_OK;
+}
+
+template <int WMT, int NTMAX>
+int launch_taylor(pxb_handle h, TaylorArgs& a, int NT, int nwarps, cudaStream_t st) {
+  const Dims& d = h->d;
+  const size_t smem = (size_t)d.KC * NT * 32 * sizeof(double);
+  if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "taylor: tile too large for shared memory");
+  PXB_CUDA(h, cudaFuncSetAttribute(taylor_kernel<WMT, NTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)smem));
+  ++h->launches;
+  taylor_kernel<WMT, NTMAX><<<d.W * a.nchunks, nwarps * 32, smem, st>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
+  const Dims& d = h->d;
+  TaylorArgs a;
+  a.VF = h->ptr<double>(A_VF);
+  a.phi = phi;
+  a.active = active;
+  a.d = d;
+  // orbitals per CTA: at most 48 (12 n-tiles), balanced over chunks, multiple of 4
+  int nchunks = (d.ne + 47) / 48;
+  int ochunk = round_up((d.ne + nchunks - 1) / nchunks, 4);
+  nchunks = (d.ne + ochunk - 1) / ochunk;
+  a.ochunk = ochunk;
+  a.nchunks = nchunks;
+  const int NT = ochunk / 4;
+  // m-tiles per warp: 2 when that fits in 8 warps, else as many as needed
+  int wmt = (d.MT + 7) / 8;
+  if (wmt < 2 && d.MT >= 2) wmt = 2;
+  if (wmt > 4) return fail(h, PXB_ERR_ARG, "taylor: nbasis > 256 not supported in this version");
+  const int nwarps = (d.MT + wmt - 1) / wmt;
+#define PXB_TAYLOR_CASE(W_, N_)                                   \
+  if (wmt == W_ && NT <= N_) return launch_taylor<W_, N_>(h, a, NT, nwarps, st);
+  PXB_TAYLOR_CASE(1, 4)
+  PXB_TAYLOR_CASE(1, 12)
+  PXB_TAYLOR_CASE(2, 4)
+  PXB_TAYLOR_CASE(2, 8)
+  PXB_TAYLOR_CASE(2, 12)
+  PXB_TAYLOR_CASE(3, 12)
+  PXB_TAYLOR_CASE(4, 12)
+#undef PXB_TAYLOR_CASE
+  return fail(h, PXB_ERR_ARG, "taylor: no kernel instance for this shape");
+}
+
+int run_exchange(pxb_handle h, cudaStream_t st) {
+  const Dims& d = h->d;
+  ExArgs a;
+  a.RF = h->ptr<double>(A_RF);
+  a.theta = h->ptr<double>(A_THETA);
+  a.exx = h->ptr<double>(A_EXX);
+  a.d = d;
+  const int nmax = d.na > d.nb ? d.na : d.nb;
+  if ((nmax + 3) / 4 > EX_MAX_BLOCKS) return fail(h, PXB_ERR_ARG, "exchange: more than 64 occupied orbitals per spin");
+  const size_t bbytes = (size_t)nmax * d.KC * 32 * 8;
+  const size_t tail = exchange_tail_bytes();
+  const int grid = std::min(2 * d.WG, h->sm_count);
+  if (bbytes + tail <= (size_t)h->max_smem_optin) {
+    a.smem_b_doubles = (int)(bbytes / 8);
+    PXB_CUDA(h, cudaFuncSetAttribute(exchange_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(bbytes + tail)));
+    ++h->launches;
+    exchange_kernel<4, true><<<grid, EX_WARPS * 32, bbytes + tail, st>>>(a);
+  } else {
+    a.smem_b_doubles = 0;
+    ++h->launches;
+    exchange_kernel<4, false><<<grid, EX_WARPS * 32, tail, st>>>(a);
+  }
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+}  // namespace
+
+// =============================================================================
+extern "C" {
+
+int pxb_abi_version(void) { return PXB_ABI_VERSION; }
+
+long long pxb_launch_count(pxb_handle h) { return h ? h->launches : -1; }
+
+const char* pxb_last_error(pxb_handle h) { return h ? h->err.c_str() : "null handle"; }
+
+int pxb_create(pxb_handle* out, const pxb_config* cfg) {
+  if (!out || !cfg) return PXB_ERR_ARG;
+  *out = nullptr;
+  if (cfg->nbasis < 1 || cfg->nup < 1 || cfg->ndown < 0 || cfg->nchol < 1 || cfg->nwalkers < 1 ||
+      cfg->nup > cfg->nbasis || cfg->ndown > cfg->nbasis || cfg->dt <= 0.0 || cfg->exp_order < 1)
+    return PXB_ERR_ARG;
+  pxb_context* h = new (std::nothrow) pxb_context();
+  if (!h) return PXB_ERR_ARG;
+  h->cfg = *cfg;
+  Dims& d = h->d;
+  d.M = cfg->nbasis;
+  d.na = cfg->nup;
+  d.nb = cfg->ndown;
+  d.ne = d.na + d.nb;
+  d.N = cfg->nchol;
+  d.W = cfg->nwalkers;
+  d.Wtot = cfg->total_walkers > 0 ? cfg->total_walkers : cfg->nwalkers;
+  d.Mp = round_up(d.M, 4);
+  d.KC = d.Mp / 4;
+  d.M8 = round_up(d.M, 8);
+  d.MT = d.M8 / 8;
+  d.Wp = round_up(d.W, 4);
+  d.WG = d.Wp / 4;
+  d.Np = round_up(d.N, 8);
+  d.XG = d.Np / 8;
+  d.NKC = d.Np / 4;
+  d.RT = ((d.M + 1) / 2) * d.KC;
+  d.exp_order = cfg->exp_order;
+  d.dt = cfg->dt;
+  d.sqrt_dt = sqrt(cfg->dt);
+  d.ebound = sqrt(2.0 / cfg->dt);
+  d.ecore = 0.0;
+
+  cudaError_t e = cudaSetDevice(cfg->device);
+  if (e == cudaSuccess) {
+    cudaDeviceGetAttribute(&h->sm_count, cudaDevAttrMultiProcessorCount, cfg->device);
+    cudaDeviceGetAttribute(&h->max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, cfg->device);
+  } else {
+    // no device (e.g. symbol-load check on a CPU box): keep defaults, compute calls will fail loudly
+    cudaGetLastError();
+    h->max_smem_optin = 227 * 1024;
+  }
+
+  size_t off = 0;
+  auto add = [&](int id, size_t bytes) {
+    h->reg[id].off = off;
+    h->reg[id].bytes = bytes;
+    off += (bytes + 255) / 256 * 256;
+  };
+  const size_t W = d.Wp, Wt = (size_t)d.Wtot;
+  add(A_LF, lf_size(d) * 8);
+  add(A_RF, rf_size(d) * 8);
+  add(A_BF, bf_size(d) * 8);
+  add(A_PSIT, (size_t)d.ne * d.Mp * 8);
+  add(A_H1ROT, (size_t)d.ne * d.Mp * 16);
+  add(A_VBAR, (size_t)d.Np * 16);
+  add(A_PHI_A, of_size(d) * 8);
+  add(A_PHI_B, of_size(d) * 8);
+  add(A_THETA, of_size(d) * 8);
+  add(A_X, (size_t)2 * W * d.Np * 16);
+  add(A_XF, xf_size(d) * 8);
+  add(A_VF, (size_t)W * vf_walker(d) * 8);
+  add(A_EXX, 2 * W * 16);
+  add(A_E1B, W * 16);
+  add(A_OVLP_OLD, W * 16);
+  add(A_ACTIVE, W * 4);
+  add(A_GW, Wt * 8);
+  add(A_GWS, Wt * 8);
+  add(A_CPROBS, Wt * 8);
+  add(A_FLAG, 256);
+  add(A_FIELD0 + PXB_F_WEIGHT, W * 8);
+  add(A_FIELD0 + PXB_F_UNSCALED_WEIGHT, W * 8);
+  add(A_FIELD0 + PXB_F_OT, W * 16);
+  add(A_FIELD0 + PXB_F_HYBRID_ENERGY, W * 16);
+  add(A_FIELD0 + PXB_F_ELOC, W * 3 * 16);
+  add(A_FIELD0 + PXB_F_DETR, W * 8);
+  add(A_FIELD0 + PXB_F_LOG_DETR, W * 8);
+  add(A_FIELD0 + PXB_F_ESTIMATES, 10 * 16);
+  add(A_FIELD0 + PXB_F_COUNTERS, 8 * 8);
+  add(A_FIELD0 + PXB_F_PARENT_IX, Wt * 4);
+  add(A_FIELD0 + PXB_F_XBAR, W * d.Np * 16);
+  add(A_FIELD0 + PXB_F_XSHIFTED, W * d.Np * 16);
+  add(A_FIELD0 + PXB_F_CMF_CFB, W * 2 * 16);
+  add(A_FIELD0 + PXB_F_OVLP_NEW, W * 16);
+  add(A_FIELD0 + PXB_F_TOTAL_WEIGHT, 8);
+  add(A_FIELD0 + PXB_F_PAIRS, (1 + 2 * Wt) * 4);
+  h->arena_bytes = off;
+  *out = h;
+  return PXB_OK;
+}
+
+int pxb_destroy(pxb_handle h) {
+  delete h;
+  return PXB_OK;
+}
+
+int pxb_arena_bytes(pxb_handle h, size_t* bytes) {
+  if (!h || !bytes) return PXB_ERR_ARG;
+  *bytes = h->arena_bytes;
+  return PXB_OK;
+}
+
+int pxb_bind_arena(pxb_handle h, void* dev_arena, size_t bytes, void* stream) {
+  if (!h || !dev_arena) return PXB_ERR_ARG;
+  if (bytes < h->arena_bytes) return fail(h, PXB_ERR_ARG, "arena too small");
+  if ((reinterpret_cast<uintptr_t>(dev_arena) & 255) != 0) return fail(h, PXB_ERR_ARG, "arena must be 256-byte aligned");
+  PXB_CUDA(h, cudaSetDevice(h->cfg.device));
+  PXB_CUDA(h, cudaMemsetAsync(dev_arena, 0, h->arena_bytes, S(stream)));
+  h->arena = static_cast<unsigned char*>(dev_arena);
+  h->ham_set = false;
+  h->phi_cur = 0;
+  return PXB_OK;
+}
+
+int pxb_field(pxb_handle h, int field_id, size_t* offset_bytes, size_t* size_bytes) {
+  if (!h || field_id < 0 || field_id >= PXB_F_COUNT) return PXB_ERR_ARG;
+  if (offset_bytes) *offset_bytes = h->reg[A_FIELD0 + field_id].off;
+  if (size_bytes) *size_bytes = h->reg[A_FIELD0 + field_id].bytes;
+  return PXB_OK;
+}
+
+int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, const void* bh1,
+                        const void* h1rot, const void* psi, const void* mf_shift, double ecore,
+                        void* stream) {
+  if (!h) return PXB_ERR_ARG;
+  if (!h->arena) return fail(h, PXB_ERR_STATE, "arena not bound");
+  if (!hs_pot || !rchol || !bh1 || !h1rot || !psi || !mf_shift) return fail(h, PXB_ERR_ARG, "null pointer");
+  const Dims& d = h->d;
+  cudaStream_t st = S(stream);
+  int* flag = h->ptr<int>(A_FLAG);
+  PXB_CUDA(h, cudaMemsetAsync(flag, 0, 4, st));
+  ++h->launches;
+  pack_lf_kernel<<<grid_for(lf_size(d)), 256, 0, st>>>(hs_pot, h->ptr<double>(A_LF), d);
+  ++h->launches;
+  pack_rf_kernel<<<grid_for(rf_size(d)), 256, 0, st>>>(static_cast<const double2*>(rchol),
+                                                       h->ptr<double>(A_RF), d, flag);
+  ++h->launches;
+  pack_bf_kernel<<<grid_for(bf_size(d)), 256, 0, st>>>(static_cast<const double2*>(bh1), h->ptr<double>(A_BF),
+                                                       d, flag);
+  ++h->launches;
+  pack_small_kernel<<<grid_for((size_t)d.ne * d.Mp), 256, 0, st>>>(
+      static_cast<const double2*>(psi), static_cast<const double2*>(h1rot),
+      static_cast<const double2*>(mf_shift), h->ptr<double>(A_PSIT), h->ptr<double2>(A_H1ROT),
+      h->ptr<double2>(A_VBAR), d, flag);
+  PXB_CUDA(h, cudaGetLastError());
+  int hflag = 0;
+  PXB_CUDA(h, cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
+  PXB_CUDA(h, cudaStreamSynchronize(st));
+  if (hflag != 0) {
+    char buf[160];
+    snprintf(buf, sizeof buf,
+             "complex-valued input not supported in this version (rchol:%d bh1:%d psi:%d)", hflag & 1,
+             (hflag >> 1) & 1, (hflag >> 2) & 1);
+    return fail(h, PXB_ERR_UNSUPPORTED, buf);
+  }
+  h->d.ecore = ecore;
+  h->ham_set = true;
+  return PXB_OK;
+}
+
+int pxb_set_phi(pxb_handle h, const void* dev_phi, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  ++h->launches;
+  phi_to_of_kernel<<<grid_for((size_t)d.Wp * d.ne * d.Mp), 256, 0, S(stream)>>>(
+      static_cast<const double2*>(dev_phi), h->phi(), d, 0);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_get_phi(pxb_handle h, void* dev_phi, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  ++h->launches;
+  of_to_natural_kernel<<<grid_for((size_t)d.W * d.ne * d.M), 256, 0, S(stream)>>>(
+      h->phi(), static_cast<double2*>(dev_phi), d, 1);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_init_walkers(pxb_handle h, const void* dev_init_phi, double total_walkers, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  cudaStream_t st = S(stream);
+  ++h->launches;
+  phi_to_of_kernel<<<grid_for((size_t)d.Wp * d.ne * d.Mp), 256, 0, st>>>(
+      static_cast<const double2*>(dev_init_phi), h->phi(), d, 1);
+  PXB_CUDA(h, cudaGetLastError());
+  int rc = run_greens(h, h->phi(), false, h->ptr<double2>(A_OVLP_OLD), false, st);
+  if (rc) return rc;
+  ++h->launches;
+  init_scalars_kernel<<<(d.Wp + 255) / 256, 256, 0, st>>>(
+      h->field<double>(PXB_F_WEIGHT), h->field<double>(PXB_F_UNSCALED_WEIGHT), h->field<double2>(PXB_F_OT),
+      h->ptr<double2>(A_OVLP_OLD), h->field<double2>(PXB_F_HYBRID_ENERGY), h->field<double>(PXB_F_DETR),
+      h->field<double>(PXB_F_LOG_DETR), h->field<double>(PXB_F_TOTAL_WEIGHT), total_walkers, d);
+  PXB_CUDA(h, cudaGetLastError());
+  PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ESTIMATES), 0, 160, st));
+  PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_COUNTERS), 0, 64, st));
+  PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ELOC), 0, (size_t)d.Wp * 48, st));
+  return PXB_OK;
+}
+
+int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t walker_offset,
+                  double eshift, int64_t step, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  cudaStream_t st = S(stream);
+  int* active = h->ptr<int>(A_ACTIVE);
+  long long* counters = h->field<long long>(PXB_F_COUNTERS);
+  int rc;
+  ++h->launches;
+  active_kernel<<<(d.Wp + 255) / 256, 256, 0, st>>>(h->field<double>(PXB_F_WEIGHT), active, counters, d);
+  PXB_CUDA(h, cudaGetLastError());
+  // (a) Green's function of the current walkers -> Theta, ovlp_old
+  if ((rc = run_greens(h, h->phi(), true, h->ptr<double2>(A_OVLP_OLD), false, st))) return rc;
+  // (c1) force bias GEMM can start from Theta; (b) one-body half step phi -> other
+  if ((rc = run_force_bias_gemm(h, st))) return rc;
+  FieldArgs f;
+  f.X = h->ptr<double2>(A_X);
+  f.xi = dev_xi;
+  f.vbar = h->ptr<double2>(A_VBAR);
+  f.active = active;
+  f.XF = h->ptr<double>(A_XF);
+  f.xbar_out = h->field<double2>(PXB_F_XBAR);
+  f.xs_out = h->field<double2>(PXB_F_XSHIFTED);
+  f.cmfcfb = h->field<double2>(PXB_F_CMF_CFB);
+  f.counters = counters;
+  f.d = d;
+  f.seed = rng_seed;
+  f.step = (uint64_t)step;
+  f.walker_offset = walker_offset;
+  ++h->launches;
+  field_kernel<<<(d.Wp + 7) / 8, 256, 0, st>>>(f);
+  PXB_CUDA(h, cudaGetLastError());
+  if ((rc = run_vhs_gemm(h, st))) return rc;
+  double* work = h->phi_other();
+  if ((rc = run_one_body(h, h->phi(), work, nullptr, st))) return rc;
+  if ((rc = run_taylor(h, work, active, st))) return rc;
+  // (d) second half step writes back into the walker buffer, active walkers only
+  if ((rc = run_one_body(h, work, h->phi(), active, st))) return rc;
+  // (e) new overlap, (f) weights
+  if ((rc = run_greens(h, h->phi(), false, h->field<double2>(PXB_F_OVLP_NEW), false, st))) return rc;
+  WeightArgs wa;
+  wa.weight = h->field<double>(PXB_F_WEIGHT);
+  wa.ot = h->field<double2>(PXB_F_OT);
+  wa.ehyb = h->field<double2>(PXB_F_HYBRID_ENERGY);
+  wa.ovlp_old = h->ptr<double2>(A_OVLP_OLD);
+  wa.ovlp_new = h->field<double2>(PXB_F_OVLP_NEW);
+  wa.cmfcfb = h->field<double2>(PXB_F_CMF_CFB);
+  wa.active = active;
+  wa.total_weight = h->field<double>(PXB_F_TOTAL_WEIGHT);
+  wa.counters = counters;
+  wa.d = d;
+  wa.eshift = eshift;
+  wa.step = step;
+  ++h->launches;
+  weight_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(wa);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_orthogonalise(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  QrArgs a;
+  a.phi = h->phi();
+  a.ot = h->field<double2>(PXB_F_OT);
+  a.detR = h->field<double>(PXB_F_DETR);
+  a.log_detR = h->field<double>(PXB_F_LOG_DETR);
+  a.d = d;
+  const int nth = 256;
+  const size_t smem = qr_smem_bytes(d, nth);
+  if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "qr: problem too large for shared memory");
+  PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ++h->launches;
+  qr_kernel<<<d.Wp, nth, smem, S(stream)>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_local_energy(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  cudaStream_t st = S(stream);
+  int rc;
+  if ((rc = run_greens(h, h->phi(), true, h->ptr<double2>(A_OVLP_OLD), true, st))) return rc;
+  if ((rc = run_force_bias_gemm(h, st))) return rc;
+  if ((rc = run_exchange(h, st))) return rc;
+  EnergyArgs e;
+  e.X = h->ptr<double2>(A_X);
+  e.exx = h->ptr<double2>(A_EXX);
+  e.e1b = h->ptr<double2>(A_E1B);
+  e.eloc = h->field<double2>(PXB_F_ELOC);
+  e.d = d;
+  ++h->launches;
+  energy_kernel<<<(d.W + 7) / 8, 256, 0, st>>>(e);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_accumulate(pxb_handle h, int with_energy, void* stream) {
+  PXB_REQUIRE_READY(h);
+  AccArgs a;
+  a.weight = h->field<double>(PXB_F_WEIGHT);
+  a.unscaled = h->field<double>(PXB_F_UNSCALED_WEIGHT);
+  a.ot = h->field<double2>(PXB_F_OT);
+  a.ehyb = h->field<double2>(PXB_F_HYBRID_ENERGY);
+  a.eloc = h->field<double2>(PXB_F_ELOC);
+  a.estimates = h->field<double2>(PXB_F_ESTIMATES);
+  a.d = h->d;
+  a.with_energy = with_energy;
+  ++h->launches;
+  accumulate_kernel<<<1, 1024, 0, S(stream)>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_zero_estimates(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ESTIMATES), 0, 160, S(stream)));
+  return PXB_OK;
+}
+
+int pxb_pop_rescale(pxb_handle h, const double* gw, int64_t wtot, void* stream) {
+  PXB_REQUIRE_READY(h);
+  if (wtot != h->d.Wtot) return fail(h, PXB_ERR_ARG, "wtot != total_walkers given at create");
+  RescaleArgs a;
+  a.gw = gw;
+  a.gws = h->ptr<double>(A_GWS);
+  a.weight = h->field<double>(PXB_F_WEIGHT);
+  a.unscaled = h->field<double>(PXB_F_UNSCALED_WEIGHT);
+  a.total_weight = h->field<double>(PXB_F_TOTAL_WEIGHT);
+  a.counters = h->field<long long>(PXB_F_COUNTERS);
+  a.W = h->d.W;
+  a.Wtot = (int)wtot;
+  ++h->launches;
+  pop_rescale_kernel<<<1, 1024, 0, S(stream)>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_comb_plan(pxb_handle h, const double* gw, int64_t wtot, double r, void* stream) {
+  PXB_REQUIRE_READY(h);
+  (void)gw;  // the rescaled copy written by pxb_pop_rescale is what the comb runs on
+  if (wtot != h->d.Wtot) return fail(h, PXB_ERR_ARG, "wtot != total_walkers given at create");
+  CombArgs a;
+  a.gws = h->ptr<double>(A_GWS);
+  a.cprobs = h->ptr<double>(A_CPROBS);
+  a.parent_ix = h->field<int>(PXB_F_PARENT_IX);
+  a.pairs = h->field<int>(PXB_F_PAIRS);
+  a.counters = h->field<long long>(PXB_F_COUNTERS);
+  a.Wtot = (int)wtot;
+  a.r = r;
+  ++h->launches;
+  comb_plan_kernel<<<1, 1024, 0, S(stream)>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_set_weights(pxb_handle h, double value, void* stream) {
+  PXB_REQUIRE_READY(h);
+  ++h->launches;
+  fill_kernel<<<(h->d.W + 255) / 256, 256, 0, S(stream)>>>(h->field<double>(PXB_F_WEIGHT), value, h->d.W);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_pop_control_comb(pxb_handle h, double r, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  if (d.Wtot != d.W) return fail(h, PXB_ERR_ARG, "pxb_pop_control_comb is the single-device path");
+  if (d.W == 1) return PXB_OK;  // handler.py:226-227
+  cudaStream_t st = S(stream);
+  double* gw = h->ptr<double>(A_GW);
+  ++h->launches;
+  abs_weight_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(h->field<double>(PXB_F_WEIGHT), gw, d.W);
+  PXB_CUDA(h, cudaGetLastError());
+  int rc;
+  if ((rc = pxb_pop_rescale(h, gw, d.W, stream))) return rc;
+  if ((rc = pxb_comb_plan(h, gw, d.W, r, stream))) return rc;
+  ++h->launches;
+  copy_pairs_kernel<<<std::min(d.W, 4 * h->sm_count), 256, 0, st>>>(copy_args(h), h->field<int>(PXB_F_PAIRS), 0);
+  PXB_CUDA(h, cudaGetLastError());
+  return pxb_set_weights(h, 1.0, stream);
+}
+
+int pxb_payload_doubles(pxb_handle h, size_t* n) {
+  if (!h || !n) return PXB_ERR_ARG;
+  *n = (size_t)h->d.ne * h->d.KC * 8 + 16;
+  return PXB_OK;
+}
+
+int pxb_copy_walkers(pxb_handle h, const int32_t* src, const int32_t* dst, int n, void* stream) {
+  PXB_REQUIRE_READY(h);
+  if (n <= 0) return PXB_OK;
+  ++h->launches;
+  copy_list_kernel<<<std::min(n, 4 * h->sm_count), 256, 0, S(stream)>>>(copy_args(h), src, dst, n);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_pack_walkers(pxb_handle h, const int32_t* slots, int n, double* buf, void* stream) {
+  PXB_REQUIRE_READY(h);
+  if (n <= 0) return PXB_OK;
+  ++h->launches;
+  pack_kernel<<<std::min(n, 4 * h->sm_count), 256, 0, S(stream)>>>(copy_args(h), slots, n, buf, 0);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_unpack_walkers(pxb_handle h, const int32_t* slots, int n, const double* buf, void* stream) {
+  PXB_REQUIRE_READY(h);
+  if (n <= 0) return PXB_OK;
+  ++h->launches;
+  pack_kernel<<<std::min(n, 4 * h->sm_count), 256, 0, S(stream)>>>(copy_args(h), slots, n,
+                                                                  const_cast<double*>(buf), 1);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+// handler.py:271-286 on the host, bit-exact (sequential sum and cumsum, two-pointer sweep)
+int pxb_comb_plan_host(const double* weights, int64_t n, double r, int32_t* parent_ix) {
+  if (!weights || !parent_ix || n < 1) return PXB_ERR_ARG;
+  std::vector<double> cprobs((size_t)n);
+  volatile double total = 0.0;
+  for (int64_t i = 0; i < n; ++i) {
+    total = total + weights[i];
+    cprobs[(size_t)i] = total;
+    parent_ix[i] = 0;
+  }
+  volatile double spacing = total / (double)n;
+  int64_t iw = 0, ic = 0;
+  while (ic < n) {
+    volatile double s = (double)ic + r;
+    volatile double tooth = s * spacing;
+    if (tooth < cprobs[(size_t)iw]) {
+      parent_ix[iw] += 1;
+      ++ic;
+    } else {
+      ++iw;
+      if (iw >= n) return PXB_ERR_ARG;  // the reference raises IndexError here
+    }
+  }
+  return PXB_OK;
+}
+
+// ---- stage-level entry points -------------------------------------------------
+int pxb_stage_exchange(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  return run_exchange(h, S(stream));
+}
+
+int pxb_stage_greens(pxb_handle h, int with_e1b, void* stream) {
+  PXB_REQUIRE_READY(h);
+  return run_greens(h, h->phi(), true, h->ptr<double2>(A_OVLP_OLD), with_e1b != 0, S(stream));
+}
+
+int pxb_stage_force_bias_gemm(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  return run_force_bias_gemm(h, S(stream));
+}
+
+int pxb_get_theta(pxb_handle h, void* dev_theta, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  ++h->launches;
+  of_to_natural_kernel<<<grid_for((size_t)d.W * d.ne * d.M), 256, 0, S(stream)>>>(
+      h->ptr<double>(A_THETA), static_cast<double2*>(dev_theta), d, 0);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_get_x(pxb_handle h, void* dev_x, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  // X is stored [2][Wp][Np]; compact to [2][W][N]
+  for (int s = 0; s < 2; ++s)
+    PXB_CUDA(h, cudaMemcpy2DAsync(static_cast<char*>(dev_x) + (size_t)s * d.W * d.N * 16, (size_t)d.N * 16,
+                                  h->ptr<char>(A_X) + (size_t)s * d.Wp * d.Np * 16, (size_t)d.Np * 16,
+                                  (size_t)d.N * 16, d.W, cudaMemcpyDeviceToDevice, S(stream)));
+  return PXB_OK;
+}
+
+int pxb_get_vhs(pxb_handle h, void* dev_vhs, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  ++h->launches;
+  vf_to_natural_kernel<<<grid_for((size_t)d.W * d.M * d.M), 256, 0, S(stream)>>>(
+      h->ptr<double>(A_VF), static_cast<double2*>(dev_vhs), d);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_get_exx(pxb_handle h, void* dev_exx, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  for (int s = 0; s < 2; ++s)
+    PXB_CUDA(h, cudaMemcpyAsync(static_cast<char*>(dev_exx) + (size_t)s * d.W * 16,
+                                h->ptr<char>(A_EXX) + (size_t)s * d.Wp * 16, (size_t)d.W * 16,
+                                cudaMemcpyDeviceToDevice, S(stream)));
+  return PXB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,1051 @@
+// Memory/latency-bound stages: layout packing, overlap + LU inverse +
+// rotated Green's function, modified Gram-Schmidt re-orthogonalisation, field
+// shift, weight update, energy assembly, estimator accumulation, comb.
+#pragma once
+#include "pxb_common.cuh"
+
+namespace pxb {
+
+// ============================================================================
+// packing of the constant operands (setup)
+// ============================================================================
+// flag[0] |= 1 if a supposedly real input has a non-zero imaginary part
+__global__ void pack_lf_kernel(const double* __restrict__ hs_pot, double* __restrict__ LF, Dims d) {
+  const size_t total = lf_size(d);
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int tt = idx & 3, gp = (idx >> 2) & 7;
+    const size_t r = idx >> 5;
+    const int kcn = r % d.NKC;
+    const int rt = r / d.NKC;
+    const int kc = rt % d.KC, ms = rt / d.KC, s = ms & 3, mtv = ms >> 2;
+    const int p = 8 * mtv + 2 * s + (gp >> 2), q = 4 * kc + (gp & 3), n = 4 * kcn + tt;
+    double v = 0.0;
+    if (p < d.M && q < d.M && n < d.N) v = hs_pot[((size_t)p * d.M + q) * d.N + n];
+    LF[idx] = v;
+  }
+}
+
+__global__ void pack_rf_kernel(const double2* __restrict__ rchol, double* __restrict__ RF, Dims d,
+                               int* flag) {
+  const size_t total = rf_size(d);
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    int s = 0;
+    size_t rel = idx;
+    const size_t b1 = rf_spin_base(d, 1);
+    if (idx >= b1) {
+      s = 1;
+      rel = idx - b1;
+    }
+    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
+    const int tt = rel & 3, g = (rel >> 2) & 7;
+    size_t r = rel >> 5;
+    const int pc = r % d.KC;
+    r /= d.KC;
+    const int il = r % ns, xg = r / ns;
+    const int p = 4 * pc + tt, n = 8 * xg + g;
+    double v = 0.0;
+    if (p < d.M && n < d.N) {
+      double2 z = rchol[((size_t)(ioff + il) * d.M + p) * d.N + n];
+      v = z.x;
+      if (z.y != 0.0) atomicOr(flag, 1);
+    }
+    RF[idx] = v;
+  }
+}
+
+__global__ void pack_bf_kernel(const double2* __restrict__ bh1, double* __restrict__ BF, Dims d,
+                               int* flag) {
+  const size_t total = bf_size(d);
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int tt = idx & 3, g = (idx >> 2) & 7;
+    size_t r = idx >> 5;
+    const int kc = r % d.KC;
+    r /= d.KC;
+    const int mt = r % d.MT, s = r / d.MT;
+    const int p = 8 * mt + g, q = 4 * kc + tt;
+    double v = 0.0;
+    if (p < d.M && q < d.M) {
+      double2 z = bh1[((size_t)s * d.M + p) * d.M + q];
+      v = z.x;
+      if (z.y != 0.0) atomicOr(flag, 2);
+    }
+    BF[idx] = v;
+  }
+}
+
+// psiT[j][p] (real, ld Mp), h1rot [ne][Mp] complex, vbar [Np] complex
+__global__ void pack_small_kernel(const double2* __restrict__ psi, const double2* __restrict__ h1rot,
+                                  const double2* __restrict__ mf, double* __restrict__ psiT,
+                                  double2* __restrict__ h1r, double2* __restrict__ vbar, Dims d,
+                                  int* flag) {
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+  for (int idx = tid; idx < d.ne * d.Mp; idx += nth) {
+    const int j = idx / d.Mp, p = idx % d.Mp;
+    double v = 0.0;
+    double2 h = make_double2(0.0, 0.0);
+    if (p < d.M) {
+      double2 z = psi[(size_t)p * d.ne + j];
+      v = z.x;
+      if (z.y != 0.0) atomicOr(flag, 4);
+      h = h1rot[(size_t)j * d.M + p];
+    }
+    psiT[idx] = v;
+    h1r[idx] = h;
+  }
+  for (int n = tid; n < d.Np; n += nth) vbar[n] = n < d.N ? mf[n] : make_double2(0.0, 0.0);
+}
+
+// ============================================================================
+// walker matrix packing: reference layout [W][M][ne] complex <-> OF
+// ============================================================================
+__global__ void phi_to_of_kernel(const double2* __restrict__ phi, double* __restrict__ of, Dims d,
+                                 int bcast_single) {
+  // one thread per (w, i, p) complex element of the padded OF array
+  const size_t total = (size_t)d.Wp * d.ne * d.Mp;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int p = idx % d.Mp;
+    size_t r = idx / d.Mp;
+    const int i = r % d.ne, w = r / d.ne;
+    double2 v = make_double2(0.0, 0.0);
+    if (p < d.M) {
+      if (bcast_single)
+        v = phi[(size_t)p * d.ne + i];
+      else if (w < d.W)
+        v = phi[((size_t)w * d.M + p) * d.ne + i];
+      else
+        v = phi[((size_t)0 * d.M + p) * d.ne + i];  // padding walkers mirror walker 0
+    }
+    *reinterpret_cast<double2*>(of + of_index(d, w, i, p, 0)) = v;
+  }
+}
+
+// generic unpack of an OF-layout array to [W][rows=ne][M] (transpose=0, Theta) or
+// [W][M][ne] (transpose=1, phi)
+__global__ void of_to_natural_kernel(const double* __restrict__ of, double2* __restrict__ out, Dims d,
+                                     int as_phi) {
+  const size_t total = (size_t)d.W * d.ne * d.M;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int p = idx % d.M;
+    size_t r = idx / d.M;
+    const int i = r % d.ne, w = r / d.ne;
+    double2 v = *reinterpret_cast<const double2*>(of + of_index(d, w, i, p, 0));
+    if (as_phi)
+      out[((size_t)w * d.M + p) * d.ne + i] = v;
+    else
+      out[((size_t)w * d.ne + i) * d.M + p] = v;
+  }
+}
+
+__global__ void vf_to_natural_kernel(const double* __restrict__ VF, double2* __restrict__ out, Dims d) {
+  const size_t total = (size_t)d.W * d.M * d.M;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int q = idx % d.M;
+    size_t r = idx / d.M;
+    const int p = r % d.M, w = r / d.M;
+    const double* b = VF + (size_t)w * vf_walker(d) + ((size_t)(p >> 3) * d.KC + (q >> 2)) * 64 +
+                      (p & 7) * 4 + (q & 3);
+    out[idx] = make_double2(b[0], b[32]);
+  }
+}
+
+// ============================================================================
+// K1: overlap matrix, LU (partial pivoting), slogdet, Theta = O^-1 phi^T, e1b
+//   walkers/single_det.py:295-321 (greens_function) and :170-199 (calc_overlap)
+// One CTA per walker, both spins.
+// ============================================================================
+struct GreensArgs {
+  const double* phi;    // OF
+  double* theta;        // OF (may be null when mode == overlap only)
+  const double* psiT;   // [ne][Mp] real
+  const double2* h1rot; // [ne][Mp]
+  double2* ovlp_out;    // [Wp]
+  double2* e1b_out;     // [Wp] or null
+  Dims d;
+  int want_theta;
+};
+
+__device__ __forceinline__ double cabs1(cplx z) { return fabs(z.re) + fabs(z.im); }
+
+__global__ void __launch_bounds__(256) greens_kernel(GreensArgs a) {
+  extern __shared__ __align__(16) unsigned char gs_raw[];
+  const Dims& d = a.d;
+  const int w = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int LD = d.Mp + 1;
+  const int nmax = max(d.na, d.nb);
+  cplx* ph = reinterpret_cast<cplx*>(gs_raw);          // [ne][LD]
+  cplx* lu = ph + (size_t)d.ne * LD;                   // [2][nmax*nmax]
+  cplx* rdiag = lu + 2 * nmax * nmax;                  // [2][nmax] reciprocal of U diagonal
+  double* red = reinterpret_cast<double*>(rdiag + 2 * nmax);  // [2*nth] reduction scratch
+  int* piv = reinterpret_cast<int*>(red + 2 * nth);    // [2] pivot rows, [2] permutation sign
+  const int wg = w >> 2, wl = w & 3;
+
+  // 1. phi -> shared, orbital-major
+  for (int idx = tid; idx < d.ne * d.Mp; idx += nth) {
+    const int p = idx % d.Mp, i = idx / d.Mp;
+    double2 v = *reinterpret_cast<const double2*>(a.phi + (((size_t)wg * d.ne + i) * d.KC + (p >> 2)) * 32 +
+                                                  wl * 8 + (p & 3) * 2);
+    ph[i * LD + p] = {v.x, v.y};
+  }
+  if (tid < 2) piv[2 + tid] = 1;
+  __syncthreads();
+
+  // 2. O_s[i][j] = sum_p phi[p, i] psi[p, j]     (psi real)
+  const int npair = d.na * d.na + d.nb * d.nb;
+  for (int idx = tid; idx < npair; idx += nth) {
+    int s = 0, r = idx;
+    if (idx >= d.na * d.na) {
+      s = 1;
+      r = idx - d.na * d.na;
+    }
+    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
+    const int i = r / ns, j = r % ns;
+    const cplx* pr = ph + (size_t)(ioff + i) * LD;
+    const double* ps = a.psiT + (size_t)(ioff + j) * d.Mp;
+    double sr = 0.0, si = 0.0;
+    for (int p = 0; p < d.M; ++p) {
+      const double c = ps[p];
+      sr += pr[p].re * c;
+      si += pr[p].im * c;
+    }
+    lu[s * nmax * nmax + i * ns + j] = {sr, si};
+  }
+  __syncthreads();
+
+  // 3. LU with partial pivoting, both spins in lock step; row swaps are applied
+  //    to the right-hand side rows (phi^T) as they happen
+  for (int k = 0; k < nmax; ++k) {
+    if (tid < 2) {
+      const int s = tid, ns = s ? d.nb : d.na;
+      if (k < ns) {
+        cplx* L = lu + s * nmax * nmax;
+        int best = k;
+        double bv = cabs1(L[k * ns + k]);
+        for (int i = k + 1; i < ns; ++i) {
+          const double v = cabs1(L[i * ns + k]);
+          if (v > bv) {
+            bv = v;
+            best = i;
+          }
+        }
+        piv[s] = best;
+        if (best != k) piv[2 + s] = -piv[2 + s];
+      }
+    }
+    __syncthreads();
+    // swap rows k <-> piv in LU and in the RHS
+    for (int s = 0; s < 2; ++s) {
+      const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
+      if (k >= ns) continue;
+      const int pr = piv[s];
+      if (pr == k) continue;
+      cplx* L = lu + s * nmax * nmax;
+      for (int j = tid; j < ns; j += nth) {
+        cplx tmp = L[k * ns + j];
+        L[k * ns + j] = L[pr * ns + j];
+        L[pr * ns + j] = tmp;
+      }
+      if (a.want_theta)
+        for (int p = tid; p < d.Mp; p += nth) {
+          cplx tmp = ph[(ioff + k) * LD + p];
+          ph[(ioff + k) * LD + p] = ph[(ioff + pr) * LD + p];
+          ph[(ioff + pr) * LD + p] = tmp;
+        }
+    }
+    __syncthreads();
+    // multipliers
+    for (int s = 0; s < 2; ++s) {
+      const int ns = s ? d.nb : d.na;
+      if (k >= ns) continue;
+      cplx* L = lu + s * nmax * nmax;
+      const cplx ukk = L[k * ns + k];
+      for (int i = k + 1 + tid; i < ns; i += nth) L[i * ns + k] = cdiv(L[i * ns + k], ukk);
+    }
+    __syncthreads();
+    // trailing update
+    for (int s = 0; s < 2; ++s) {
+      const int ns = s ? d.nb : d.na;
+      if (k >= ns) continue;
+      cplx* L = lu + s * nmax * nmax;
+      const int m = ns - k - 1;
+      for (int idx = tid; idx < m * m; idx += nth) {
+        const int i = k + 1 + idx / m, j = k + 1 + idx % m;
+        L[i * ns + j] = csub(L[i * ns + j], cmul(L[i * ns + k], L[k * ns + j]));
+      }
+    }
+    __syncthreads();
+  }
+
+  // 4. sign * exp(logdet)  (numpy.linalg.slogdet semantics), reciprocal diagonal
+  if (tid == 0) {
+    cplx sign = {1.0, 0.0};
+    double logdet = 0.0;
+    for (int s = 0; s < 2; ++s) {
+      const int ns = s ? d.nb : d.na;
+      const cplx* L = lu + s * nmax * nmax;
+      if (piv[2 + s] < 0) sign = {-sign.re, -sign.im};
+      for (int k = 0; k < ns; ++k) {
+        const cplx u = L[k * ns + k];
+        const double au = hypot(u.re, u.im);
+        sign = cmul(sign, {u.re / au, u.im / au});
+        logdet += log(au);
+      }
+    }
+    const double e = exp(logdet);
+    a.ovlp_out[w] = make_double2(sign.re * e, sign.im * e);
+  }
+  if (!a.want_theta) return;
+  for (int idx = tid; idx < 2 * nmax; idx += nth) {
+    const int s = idx / nmax, k = idx % nmax, ns = s ? d.nb : d.na;
+    if (k < ns) rdiag[idx] = cdiv({1.0, 0.0}, lu[s * nmax * nmax + k * ns + k]);
+  }
+  __syncthreads();
+
+  // 5. solve L U Theta = P phi^T, one right-hand-side column p per thread
+  for (int idx = tid; idx < 2 * d.Mp; idx += nth) {
+    const int s = idx / d.Mp, p = idx % d.Mp;
+    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
+    const cplx* L = lu + s * nmax * nmax;
+    cplx* col = ph + (size_t)ioff * LD + p;
+    for (int i = 1; i < ns; ++i) {
+      cplx acc = col[i * LD];
+      for (int j = 0; j < i; ++j) acc = csub(acc, cmul(L[i * ns + j], col[j * LD]));
+      col[i * LD] = acc;
+    }
+    for (int i = ns - 1; i >= 0; --i) {
+      cplx acc = col[i * LD];
+      for (int j = i + 1; j < ns; ++j) acc = csub(acc, cmul(L[i * ns + j], col[j * LD]));
+      col[i * LD] = cmul(acc, rdiag[s * nmax + i]);
+    }
+  }
+  __syncthreads();
+
+  // 6. Theta -> OF, e1b = sum h1rot * Theta
+  double er = 0.0, ei = 0.0;
+  for (int idx = tid; idx < d.ne * d.Mp; idx += nth) {
+    const int p = idx % d.Mp, i = idx / d.Mp;
+    cplx v = ph[i * LD + p];
+    if (p >= d.M) v = {0.0, 0.0};
+    *reinterpret_cast<double2*>(a.theta + (((size_t)wg * d.ne + i) * d.KC + (p >> 2)) * 32 + wl * 8 +
+                                (p & 3) * 2) = make_double2(v.re, v.im);
+    if (a.e1b_out != nullptr) {
+      const double2 h = a.h1rot[idx];
+      er += h.x * v.re - h.y * v.im;
+      ei += h.x * v.im + h.y * v.re;
+    }
+  }
+  if (a.e1b_out != nullptr) {
+    red[tid] = er;
+    red[nth + tid] = ei;
+    __syncthreads();
+    for (int s = nth >> 1; s > 0; s >>= 1) {
+      if (tid < s) {
+        red[tid] += red[tid + s];
+        red[nth + tid] += red[nth + tid + s];
+      }
+      __syncthreads();
+    }
+    if (tid == 0) a.e1b_out[w] = make_double2(red[0], red[nth]);
+  }
+}
+
+inline size_t greens_smem_bytes(const Dims& d, int nth) {
+  const int nmax = d.na > d.nb ? d.na : d.nb;
+  return sizeof(cplx) * ((size_t)d.ne * (d.Mp + 1) + 2 * nmax * nmax + 2 * nmax) +
+         sizeof(double) * 2 * nth + 4 * sizeof(int) + 16;
+}
+
+// ============================================================================
+// K8: re-orthogonalisation (walkers/single_det.py:215-255).  QR with R_ii > 0
+// by modified Gram-Schmidt, one CTA per walker (both spins).
+// ============================================================================
+struct QrArgs {
+  double* phi;  // OF, in place
+  double2* ot;
+  double* detR;
+  double* log_detR;
+  Dims d;
+};
+
+__global__ void __launch_bounds__(256) qr_kernel(QrArgs a) {
+  extern __shared__ __align__(16) unsigned char qs_raw[];
+  const Dims& d = a.d;
+  const int w = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarp = nth >> 5;
+  const int LD = d.Mp + 1;
+  cplx* ph = reinterpret_cast<cplx*>(qs_raw);           // [ne][LD]
+  double* red = reinterpret_cast<double*>(ph + (size_t)d.ne * LD);  // [nwarp]
+  __shared__ double s_norm;
+  const int wg = w >> 2, wl = w & 3;
+  for (int idx = tid; idx < d.ne * d.Mp; idx += nth) {
+    const int p = idx % d.Mp, i = idx / d.Mp;
+    double2 v = *reinterpret_cast<const double2*>(a.phi + (((size_t)wg * d.ne + i) * d.KC + (p >> 2)) * 32 +
+                                                  wl * 8 + (p & 3) * 2);
+    ph[i * LD + p] = {v.x, v.y};
+  }
+  __syncthreads();
+  double logdet = 0.0;
+  for (int s = 0; s < 2; ++s) {
+    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
+    for (int k = 0; k < ns; ++k) {
+      cplx* vk = ph + (size_t)(ioff + k) * LD;
+      // norm of column k
+      double part = 0.0;
+      for (int p = tid; p < d.M; p += nth) part += vk[p].re * vk[p].re + vk[p].im * vk[p].im;
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
+      if (lane == 0) red[warp] = part;
+      __syncthreads();
+      if (tid == 0) {
+        double tot = 0.0;
+        for (int i = 0; i < nwarp; ++i) tot += red[i];
+        s_norm = sqrt(tot);
+      }
+      __syncthreads();
+      const double nrm = s_norm;
+      logdet += log(nrm);
+      for (int p = tid; p < d.M; p += nth) {
+        vk[p].re /= nrm;
+        vk[p].im /= nrm;
+      }
+      __syncthreads();
+      // orthogonalise the later columns against v_k: one warp per column
+      for (int j = k + 1 + warp; j < ns; j += nwarp) {
+        cplx* vj = ph + (size_t)(ioff + j) * LD;
+        double rr = 0.0, ri = 0.0;  // r = v_k^H v_j
+        for (int p = lane; p < d.M; p += 32) {
+          rr += vk[p].re * vj[p].re + vk[p].im * vj[p].im;
+          ri += vk[p].re * vj[p].im - vk[p].im * vj[p].re;
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) {
+          rr += __shfl_xor_sync(0xffffffffu, rr, m);
+          ri += __shfl_xor_sync(0xffffffffu, ri, m);
+        }
+        for (int p = lane; p < d.M; p += 32) {
+          vj[p].re -= rr * vk[p].re - ri * vk[p].im;
+          vj[p].im -= rr * vk[p].im + ri * vk[p].re;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  for (int idx = tid; idx < d.ne * d.Mp; idx += nth) {
+    const int p = idx % d.Mp, i = idx / d.Mp;
+    const cplx v = ph[i * LD + p];
+    *reinterpret_cast<double2*>(a.phi + (((size_t)wg * d.ne + i) * d.KC + (p >> 2)) * 32 + wl * 8 +
+                                (p & 3) * 2) = make_double2(v.re, v.im);
+  }
+  if (tid == 0 && w < d.W) {
+    // detR = exp(log_det - detR_shift[=0]); log_detR += log(detR); ot = ot / detR
+    const double detR = exp(logdet);
+    a.detR[w] = detR;
+    a.log_detR[w] += log(detR);
+    double2 o = a.ot[w];
+    a.ot[w] = make_double2(o.x / detR, o.y / detR);
+  }
+}
+
+inline size_t qr_smem_bytes(const Dims& d, int nth) {
+  return sizeof(cplx) * (size_t)d.ne * (d.Mp + 1) + sizeof(double) * (nth / 32) + 16;
+}
+
+// ============================================================================
+// Philox4x32-10 + Box-Muller (throughput mode fields)
+// ============================================================================
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+    c[0] = n0;
+    c[1] = lo1;
+    c[2] = n2;
+    c[3] = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+}
+// two independent N(0,1) from one counter (walker, field pair, step)
+__device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t step, uint64_t gw, uint32_t pair,
+                                               double& z0, double& z1) {
+  uint32_t c[4] = {(uint32_t)gw, (uint32_t)(gw >> 32) ^ (pair * 0x85ebca6bu), pair, (uint32_t)step};
+  philox4x32_10(c, (uint32_t)seed ^ (uint32_t)(step >> 32), (uint32_t)(seed >> 32));
+  const double u0 = ((double)c[0] * 4294967296.0 + (double)c[1] + 0.5) * (1.0 / 18446744073709551616.0);
+  const double u1 = ((double)c[2] * 4294967296.0 + (double)c[3] + 0.5) * (1.0 / 18446744073709551616.0);
+  const double r = sqrt(-2.0 * log(u0));
+  double sn, cs;
+  sincospi(2.0 * u1, &sn, &cs);
+  z0 = r * cs;
+  z1 = r * sn;
+}
+
+// ============================================================================
+// K2b: field shift (propagation/continuous.py:133-158, generic.py:152)
+//   xbar = -sqrt(dt) (i V - vbar), clip |xbar| > 1, x = xi - xbar,
+//   cmf = -sqrt(dt) x.vbar, cfb = xi.xbar - xbar.xbar/2.   One warp per walker.
+// ============================================================================
+struct FieldArgs {
+  const double2* X;      // [2][Wp][Np]
+  const double* xi;      // [W][N] or null (Philox)
+  const double2* vbar;   // [Np]
+  const int* active;
+  double* XF;            // field fragment layout out
+  double2* xbar_out;     // [Wp][Np]
+  double2* xs_out;       // [Wp][Np] natural-layout copy of x
+  double2* cmfcfb;       // [Wp][2]
+  long long* counters;
+  Dims d;
+  uint64_t seed, step;
+  long long walker_offset;
+};
+
+__global__ void __launch_bounds__(256) field_kernel(FieldArgs a) {
+  const Dims& d = a.d;
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= d.Wp) return;
+  const bool live = (w < d.W) && (a.active == nullptr || a.active[w] != 0);
+  const double2* Xa = a.X + (size_t)w * d.Np;
+  const double2* Xb = a.X + ((size_t)d.Wp + w) * d.Np;
+  double cmf_r = 0, cmf_i = 0, s1_r = 0, s1_i = 0, s2_r = 0, s2_i = 0;
+  int ntrig = 0;
+  // lanes walk pairs of fields so that a Philox call yields both normals of a pair
+  for (int n0 = 2 * lane; n0 < d.Np; n0 += 64) {
+    double z[2] = {0.0, 0.0};
+    if (live) {
+      if (a.xi != nullptr) {
+        if (n0 < d.N) z[0] = a.xi[(size_t)w * d.N + n0];
+        if (n0 + 1 < d.N) z[1] = a.xi[(size_t)w * d.N + n0 + 1];
+      } else {
+        philox_normal2(a.seed, a.step, (uint64_t)(a.walker_offset + w), (uint32_t)(n0 >> 1), z[0], z[1]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int n = n0 + u;
+      double xr = 0.0, xi_ = 0.0, br = 0.0, bi = 0.0;
+      if (live && n < d.N) {
+        const double2 va = Xa[n], vb = Xb[n], mf = a.vbar[n];
+        const double vr = va.x + vb.x, vi = va.y + vb.y;
+        // xbar = -sqrt_dt * (1j*V - vbar)
+        br = -d.sqrt_dt * (-vi - mf.x);
+        bi = -d.sqrt_dt * (vr - mf.y);
+        const double ab = hypot(br, bi);
+        if (ab > 1.0) {
+          br /= ab;
+          bi /= ab;
+          ++ntrig;
+        }
+        xr = z[u] - br;
+        xi_ = -bi;
+        // cmf: x * vbar ; cfb: xi*xbar, xbar*xbar
+        cmf_r += xr * mf.x - xi_ * mf.y;
+        cmf_i += xr * mf.y + xi_ * mf.x;
+        s1_r += z[u] * br;
+        s1_i += z[u] * bi;
+        s2_r += br * br - bi * bi;
+        s2_i += 2.0 * br * bi;
+      }
+      *reinterpret_cast<double2*>(a.XF + xf_index(d, w, n, 0)) = make_double2(xr, xi_);
+      if (a.xbar_out != nullptr) a.xbar_out[(size_t)w * d.Np + n] = make_double2(br, bi);
+      if (a.xs_out != nullptr) a.xs_out[(size_t)w * d.Np + n] = make_double2(xr, xi_);
+    }
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    cmf_r += __shfl_xor_sync(0xffffffffu, cmf_r, m);
+    cmf_i += __shfl_xor_sync(0xffffffffu, cmf_i, m);
+    s1_r += __shfl_xor_sync(0xffffffffu, s1_r, m);
+    s1_i += __shfl_xor_sync(0xffffffffu, s1_i, m);
+    s2_r += __shfl_xor_sync(0xffffffffu, s2_r, m);
+    s2_i += __shfl_xor_sync(0xffffffffu, s2_i, m);
+    ntrig += __shfl_xor_sync(0xffffffffu, ntrig, m);
+  }
+  if (lane == 0) {
+    a.cmfcfb[2 * w] = make_double2(-d.sqrt_dt * cmf_r, -d.sqrt_dt * cmf_i);
+    a.cmfcfb[2 * w + 1] = make_double2(s1_r - 0.5 * s2_r, s1_i - 0.5 * s2_i);
+    if (ntrig) atomicAdd(reinterpret_cast<unsigned long long*>(a.counters), (unsigned long long)ntrig);
+  }
+}
+
+// ============================================================================
+// active mask (qmc/afqmc.py:232)
+// ============================================================================
+__global__ void active_kernel(const double* __restrict__ weight, int* __restrict__ active,
+                              long long* counters, Dims d) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= d.Wp) return;
+  int act = 0;
+  if (w < d.W) {
+    act = fabs(weight[w]) > 1e-8 ? 1 : 0;
+    if (!act) atomicAdd(reinterpret_cast<unsigned long long*>(counters + 2), 1ull);
+  }
+  active[w] = act;
+}
+
+// ============================================================================
+// K6: hybrid weight update + cap (propagation/continuous.py:202-214,264-292,
+//     qmc/afqmc.py:235-236)
+// ============================================================================
+struct WeightArgs {
+  double* weight;
+  double2* ot;
+  double2* ehyb;
+  const double2* ovlp_old;
+  const double2* ovlp_new;
+  const double2* cmfcfb;
+  const int* active;
+  const double* total_weight;
+  long long* counters;
+  Dims d;
+  double eshift;
+  long long step;
+};
+
+__global__ void weight_kernel(WeightArgs a) {
+  const Dims& d = a.d;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= d.W) return;
+  double wt = a.weight[w];
+  if (a.active[w]) {
+    const double2 oo = a.ovlp_old[w], on = a.ovlp_new[w];
+    const cplx ratio = cdiv({on.x, on.y}, {oo.x, oo.y});
+    const double2 cmf = a.cmfcfb[2 * w], cfb = a.cmfcfb[2 * w + 1];
+    // cmath.log: principal branch
+    const double lr = log(hypot(ratio.re, ratio.im)), li = atan2(ratio.im, ratio.re);
+    double eh_r = -(lr + cfb.x + cmf.x) / d.dt;
+    const double eh_i = -(li + cfb.y + cmf.y) / d.dt;
+    if (fabs(a.eshift) >= 1e-10) {
+      if (eh_r > a.eshift + d.ebound) {
+        eh_r = a.eshift + d.ebound;
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 1), 1ull);
+      } else if (eh_r < a.eshift - d.ebound) {
+        eh_r = a.eshift - d.ebound;
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 1), 1ull);
+      }
+    }
+    const double2 eo = a.ehyb[w];
+    // importance function exp(-dt (0.5 (Eh + Eh_old) - eshift))
+    const double ar = -d.dt * (0.5 * (eh_r + eo.x) - a.eshift);
+    const double ai = -d.dt * (0.5 * (eh_i + eo.y));
+    const double er = exp(ar);
+    double sn, cs;
+    sincos(ai, &sn, &cs);
+    const double magn = hypot(er * cs, er * sn);
+    a.ehyb[w] = make_double2(eh_r, eh_i);
+    if (!isinf(magn)) {
+      const double dtheta = -d.dt * eh_i - cfb.y;
+      const double cf = fmax(0.0, cos(dtheta));
+      wt = wt * (magn * cf);
+      a.ot[w] = on;
+    } else {
+      wt = 0.0;
+      a.ot[w] = on;
+    }
+  }
+  if (a.step > 1) {
+    const double cap = a.total_weight[0] * 0.10;
+    if (fabs(wt) > cap) wt = cap;
+  }
+  a.weight[w] = wt;
+}
+
+// ============================================================================
+// K7b: energy assembly (estimators/generic.py:187-189,216-221)
+// ============================================================================
+struct EnergyArgs {
+  const double2* X;    // [2][Wp][Np]
+  const double2* exx;  // [2][Wp]
+  const double2* e1b;  // [Wp]
+  double2* eloc;       // [W][3]
+  Dims d;
+};
+
+__global__ void __launch_bounds__(256) energy_kernel(EnergyArgs a) {
+  const Dims& d = a.d;
+  const int lane = threadIdx.x & 31;
+  const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= d.W) return;
+  const double2* Xa = a.X + (size_t)w * d.Np;
+  const double2* Xb = a.X + ((size_t)d.Wp + w) * d.Np;
+  double aa_r = 0, aa_i = 0, bb_r = 0, bb_i = 0, ab_r = 0, ab_i = 0;
+  for (int n = lane; n < d.N; n += 32) {
+    const double2 x = Xa[n], y = Xb[n];
+    aa_r += x.x * x.x - x.y * x.y;
+    aa_i += 2.0 * x.x * x.y;
+    bb_r += y.x * y.x - y.y * y.y;
+    bb_i += 2.0 * y.x * y.y;
+    ab_r += x.x * y.x - x.y * y.y;
+    ab_i += x.x * y.y + x.y * y.x;
+  }
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    aa_r += __shfl_xor_sync(0xffffffffu, aa_r, m);
+    aa_i += __shfl_xor_sync(0xffffffffu, aa_i, m);
+    bb_r += __shfl_xor_sync(0xffffffffu, bb_r, m);
+    bb_i += __shfl_xor_sync(0xffffffffu, bb_i, m);
+    ab_r += __shfl_xor_sync(0xffffffffu, ab_r, m);
+    ab_i += __shfl_xor_sync(0xffffffffu, ab_i, m);
+  }
+  if (lane == 0) {
+    const double ec_r = aa_r + bb_r + 2.0 * ab_r, ec_i = aa_i + bb_i + 2.0 * ab_i;
+    const double2 xa = a.exx[w], xb = a.exx[(size_t)d.Wp + w], e1 = a.e1b[w];
+    const double e2_r = 0.5 * (ec_r - (xa.x + xb.x)), e2_i = 0.5 * (ec_i - (xa.y + xb.y));
+    a.eloc[3 * (size_t)w + 0] = make_double2(e1.x + e2_r + d.ecore, e1.y + e2_i);
+    a.eloc[3 * (size_t)w + 1] = make_double2(e1.x + d.ecore, e1.y);
+    a.eloc[3 * (size_t)w + 2] = make_double2(e2_r, e2_i);
+  }
+}
+
+// ============================================================================
+// K9: Mixed.update accumulation (estimators/mixed.py:211-225).  One CTA, fixed
+// reduction tree (deterministic).  estimates: complex[10], enum order
+// uweight, weight, enumer, edenom, eproj, e1b, e2b, ehyb, ovlp, time.
+// ============================================================================
+struct AccArgs {
+  const double* weight;
+  const double* unscaled;
+  const double2* ot;
+  const double2* ehyb;
+  const double2* eloc;
+  double2* estimates;
+  Dims d;
+  int with_energy;
+};
+
+__global__ void __launch_bounds__(1024) accumulate_kernel(AccArgs a) {
+  __shared__ double red[9][32];
+  const Dims& d = a.d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double v[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int w = tid; w < d.W; w += 1024) {
+    const double wt = a.weight[w];
+    if (a.with_energy) {
+      v[0] += wt * a.eloc[3 * (size_t)w].x;      // enumer
+      v[1] += wt * a.eloc[3 * (size_t)w + 1].x;  // e1b
+      v[2] += wt * a.eloc[3 * (size_t)w + 2].x;  // e2b
+      v[3] += wt;                                // edenom
+    }
+    v[4] += a.unscaled[w];
+    v[5] += wt;
+    const double2 o = a.ot[w], e = a.ehyb[w];
+    v[6] += wt * hypot(o.x, o.y);
+    v[7] += wt * e.x;
+    v[8] += wt * e.y;
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], m);
+    if (lane == 0) red[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) {
+      double x = red[k][lane];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
+      v[k] = x;
+    }
+    if (lane == 0) {
+      a.estimates[2].x += v[0];
+      a.estimates[5].x += v[1];
+      a.estimates[6].x += v[2];
+      a.estimates[3].x += v[3];
+      a.estimates[0].x += v[4];
+      a.estimates[1].x += v[5];
+      a.estimates[8].x += v[6];
+      a.estimates[7].x += v[7];
+      a.estimates[7].y += v[8];
+    }
+  }
+}
+
+// ============================================================================
+// K10: population control (walkers/handler.py:225-338)
+// ============================================================================
+__global__ void abs_weight_kernel(const double* __restrict__ weight, double* __restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = fabs(weight[i]);
+}
+
+// total = python-style sequential sum of the global |weights| (handler.py:233);
+// gws = gw / scale (handler.py:251); local weights rescaled (handler.py:247-249).
+// One CTA; the sum itself is done by thread 0 in index order.
+struct RescaleArgs {
+  const double* gw;     // [Wtot]
+  double* gws;          // [Wtot] scratch: rescaled global weights
+  double* weight;       // local [W]
+  double* unscaled;     // local [W]
+  double* total_weight; // [1]
+  long long* counters;
+  int W, Wtot;
+};
+
+__global__ void __launch_bounds__(1024) pop_rescale_kernel(RescaleArgs a) {
+  __shared__ double chunk[1024];
+  __shared__ double s_total;
+  const int tid = threadIdx.x;
+  double total = 0.0;  // only meaningful in thread 0
+  for (int base = 0; base < a.Wtot; base += 1024) {
+    if (base + tid < a.Wtot) chunk[tid] = a.gw[base + tid];
+    __syncthreads();
+    if (tid == 0) {
+      const int m = min(1024, a.Wtot - base);
+      for (int i = 0; i < m; ++i) total = __dadd_rn(total, chunk[i]);
+    }
+    __syncthreads();
+  }
+  if (tid == 0) s_total = total;
+  __syncthreads();
+  total = s_total;
+  if (total < 1e-8) {
+    // the reference exits here (handler.py:236-241); we flag and leave weights untouched
+    if (tid == 0) a.counters[3] = -1;
+    return;
+  }
+  const double scale = __ddiv_rn(total, (double)a.Wtot);
+  if (tid == 0) a.total_weight[0] = total;
+  for (int i = tid; i < a.Wtot; i += 1024) a.gws[i] = __ddiv_rn(a.gw[i], scale);
+  for (int i = tid; i < a.W; i += 1024) {
+    const double wt = a.weight[i];
+    a.unscaled[i] = wt;
+    a.weight[i] = __ddiv_rn(wt, scale);
+  }
+}
+
+// comb selection (handler.py:271-301).  cprobs = sequential cumsum; every tooth
+// finds the first walker with tooth < cprobs[iw] (identical to the reference's
+// two-pointer sweep because both sequences are non-decreasing).
+struct CombArgs {
+  const double* gws;  // [Wtot] rescaled weights
+  double* cprobs;     // [Wtot] scratch
+  int* parent_ix;     // [Wtot]
+  int* pairs;         // [1 + 2*Wtot]
+  long long* counters;
+  int Wtot;
+  double r;
+};
+
+__global__ void __launch_bounds__(1024) comb_plan_kernel(CombArgs a) {
+  __shared__ double chunk[1024];
+  __shared__ double s_total;
+  __shared__ int s_cnt[2][1024];
+  __shared__ int s_base[2];
+  const int tid = threadIdx.x, n = a.Wtot;
+  double run = 0.0;
+  for (int base = 0; base < n; base += 1024) {
+    if (base + tid < n) chunk[tid] = a.gws[base + tid];
+    __syncthreads();
+    if (tid == 0) {
+      const int m = min(1024, n - base);
+      for (int i = 0; i < m; ++i) {
+        run = __dadd_rn(run, chunk[i]);
+        chunk[i] = run;
+      }
+    }
+    __syncthreads();
+    if (base + tid < n) a.cprobs[base + tid] = chunk[tid];
+    __syncthreads();
+  }
+  if (tid == 0) s_total = run;
+  for (int i = tid; i < n; i += 1024) a.parent_ix[i] = 0;
+  __syncthreads();
+  __threadfence_block();
+  const double spacing = __ddiv_rn(s_total, (double)n);
+  for (int ic = tid; ic < n; ic += 1024) {
+    const double tooth = __dmul_rn(__dadd_rn((double)ic, a.r), spacing);
+    int lo = 0, hi = n;  // first iw with tooth < cprobs[iw]
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      if (tooth < a.cprobs[mid])
+        hi = mid;
+      else
+        lo = mid + 1;
+    }
+    if (lo >= n) lo = n - 1;  // the reference would raise IndexError here
+    atomicAdd(&a.parent_ix[lo], 1);
+  }
+  __syncthreads();
+  // ascending kill (parent == 0) and clone (parent > 1) lists, zipped position-wise
+  if (tid < 2) s_base[tid] = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + tid;
+    const int p = (i < n) ? a.parent_ix[i] : 1;
+    const int isk = (p == 0), isc = (p > 1);
+    s_cnt[0][tid] = isk;
+    s_cnt[1][tid] = isc;
+    __syncthreads();
+    // inclusive scan (Hillis-Steele) on both flags
+    for (int off = 1; off < 1024; off <<= 1) {
+      int vk = 0, vc = 0;
+      if (tid >= off) {
+        vk = s_cnt[0][tid - off];
+        vc = s_cnt[1][tid - off];
+      }
+      __syncthreads();
+      s_cnt[0][tid] += vk;
+      s_cnt[1][tid] += vc;
+      __syncthreads();
+    }
+    if (isk) a.pairs[1 + 2 * (s_base[0] + s_cnt[0][tid] - 1) + 1] = i;
+    if (isc) a.pairs[1 + 2 * (s_base[1] + s_cnt[1][tid] - 1)] = i;
+    __syncthreads();
+    if (tid == 0) {
+      s_base[0] += s_cnt[0][1023];
+      s_base[1] += s_cnt[1][1023];
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const int np = min(s_base[0], s_base[1]);
+    a.pairs[0] = np;
+    a.counters[3] += np;
+  }
+}
+
+// payload copy: phi (OF layout) + per-walker scalars
+struct CopyArgs {
+  double* phi;
+  double* weight;
+  double* unscaled;
+  double2* ot;
+  double2* ehyb;
+  double2* eloc;
+  double* detR;
+  double* log_detR;
+  Dims d;
+};
+
+__device__ __forceinline__ size_t payload_doubles(const Dims& d) {
+  return (size_t)d.ne * d.KC * 8 + 16;
+}
+
+// pairs: device list [1 + 2*n] of GLOBAL indices; only pairs with both ends on
+// this device (offset <= idx < offset + W) are copied here
+__global__ void __launch_bounds__(256) copy_pairs_kernel(CopyArgs a, const int* pairs, int offset) {
+  const Dims& d = a.d;
+  const int np = pairs[0];
+  for (int pi = blockIdx.x; pi < np; pi += gridDim.x) {
+    const int src = pairs[1 + 2 * pi] - offset, dst = pairs[2 + 2 * pi] - offset;
+    if (src < 0 || src >= d.W || dst < 0 || dst >= d.W) continue;
+    const int n8 = d.ne * d.KC;
+    for (int idx = threadIdx.x; idx < n8 * 4; idx += blockDim.x) {
+      const int r = idx >> 2, q = idx & 3;
+      const size_t so = ((size_t)(src >> 2) * n8 + r) * 32 + (src & 3) * 8 + q * 2;
+      const size_t dn = ((size_t)(dst >> 2) * n8 + r) * 32 + (dst & 3) * 8 + q * 2;
+      *reinterpret_cast<double2*>(a.phi + dn) = *reinterpret_cast<const double2*>(a.phi + so);
+    }
+    if (threadIdx.x == 0) {
+      a.weight[dst] = a.weight[src];
+      a.unscaled[dst] = a.unscaled[src];
+      a.ot[dst] = a.ot[src];
+      a.ehyb[dst] = a.ehyb[src];
+      a.detR[dst] = a.detR[src];
+      a.log_detR[dst] = a.log_detR[src];
+      for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)dst + k] = a.eloc[3 * (size_t)src + k];
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) copy_list_kernel(CopyArgs a, const int* src_l, const int* dst_l,
+                                                        int n) {
+  const Dims& d = a.d;
+  for (int pi = blockIdx.x; pi < n; pi += gridDim.x) {
+    const int src = src_l[pi], dst = dst_l[pi];
+    const int n8 = d.ne * d.KC;
+    for (int idx = threadIdx.x; idx < n8 * 4; idx += blockDim.x) {
+      const int r = idx >> 2, q = idx & 3;
+      const size_t so = ((size_t)(src >> 2) * n8 + r) * 32 + (src & 3) * 8 + q * 2;
+      const size_t dn = ((size_t)(dst >> 2) * n8 + r) * 32 + (dst & 3) * 8 + q * 2;
+      *reinterpret_cast<double2*>(a.phi + dn) = *reinterpret_cast<const double2*>(a.phi + so);
+    }
+    if (threadIdx.x == 0) {
+      a.weight[dst] = a.weight[src];
+      a.unscaled[dst] = a.unscaled[src];
+      a.ot[dst] = a.ot[src];
+      a.ehyb[dst] = a.ehyb[src];
+      a.detR[dst] = a.detR[src];
+      a.log_detR[dst] = a.log_detR[src];
+      for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)dst + k] = a.eloc[3 * (size_t)src + k];
+    }
+  }
+}
+
+// pack / unpack for transfers between devices: buffer[n][payload_doubles]
+__global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots, int n, double* buf,
+                                                   int unpack) {
+  const Dims& d = a.d;
+  const size_t pd = payload_doubles(d);
+  for (int pi = blockIdx.x; pi < n; pi += gridDim.x) {
+    const int w = slots[pi];
+    double* b = buf + (size_t)pi * pd;
+    const int n8 = d.ne * d.KC;
+    for (int idx = threadIdx.x; idx < n8 * 4; idx += blockDim.x) {
+      const int r = idx >> 2, q = idx & 3;
+      double2* g = reinterpret_cast<double2*>(a.phi + ((size_t)(w >> 2) * n8 + r) * 32 + (w & 3) * 8 + q * 2);
+      double2* l = reinterpret_cast<double2*>(b + (size_t)r * 8 + q * 2);
+      if (unpack)
+        *g = *l;
+      else
+        *l = *g;
+    }
+    if (threadIdx.x == 0) {
+      double* s = b + (size_t)n8 * 8;
+      if (unpack) {
+        a.weight[w] = s[0];
+        a.unscaled[w] = s[1];
+        a.ot[w] = make_double2(s[2], s[3]);
+        a.ehyb[w] = make_double2(s[4], s[5]);
+        a.detR[w] = s[6];
+        a.log_detR[w] = s[7];
+        for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)w + k] = make_double2(s[8 + 2 * k], s[9 + 2 * k]);
+      } else {
+        s[0] = a.weight[w];
+        s[1] = a.unscaled[w];
+        s[2] = a.ot[w].x;
+        s[3] = a.ot[w].y;
+        s[4] = a.ehyb[w].x;
+        s[5] = a.ehyb[w].y;
+        s[6] = a.detR[w];
+        s[7] = a.log_detR[w];
+        for (int k = 0; k < 3; ++k) {
+          s[8 + 2 * k] = a.eloc[3 * (size_t)w + k].x;
+          s[9 + 2 * k] = a.eloc[3 * (size_t)w + k].y;
+        }
+        s[14] = s[15] = 0.0;
+      }
+    }
+  }
+}
+
+__global__ void fill_kernel(double* p, double v, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+__global__ void init_scalars_kernel(double* weight, double* unscaled, double2* ot, const double2* ovlp,
+                                    double2* ehyb, double* detR, double* log_detR, double* total_weight,
+                                    double total, Dims d) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w == 0) total_weight[0] = total;
+  if (w >= d.Wp) return;
+  const bool real = w < d.W;
+  weight[w] = real ? 1.0 : 0.0;
+  unscaled[w] = real ? 1.0 : 0.0;
+  ot[w] = ovlp[w];
+  ehyb[w] = make_double2(0.0, 0.0);
+  detR[w] = 1.0;
+  log_detR[w] = 0.0;
+}
+
+}  // namespace pxb

@@ -1,0 +1,286 @@
+"""Device-side walker batch: thin Python owner of one pxb handle.
+
+PyTorch is used for device memory (one arena tensor), streams and copies
+only; every computation is a call into libpauxy_b200.so.  Walker state is a
+structure of arrays in the arena, exposed here as torch views.
+"""
+import ctypes
+
+import numpy
+import torch
+
+from . import _lib as L
+
+
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class Engine(object):
+    """One device's share of the walker population.
+
+    Parameters mirror system.nbasis / nup / ndown / nfields, qmc.dt and
+    propagator.exp_nmax of the reference (pauxy/propagation/continuous.py:37-40).
+    """
+
+    def __init__(self, nbasis, nup, ndown, nchol, nwalkers, dt, exp_order=6, device=None,
+                 total_walkers=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("pauxy_b200.Engine needs a CUDA device (no CPU fallback)")
+        self.lib = L.load()
+        if device is None:
+            device = torch.device('cuda', torch.cuda.current_device())
+        self.device = torch.device(device)
+        self.M, self.na, self.nb, self.N, self.W = nbasis, nup, ndown, nchol, nwalkers
+        self.ne = nup + ndown
+        self.Wtot = total_walkers if total_walkers else nwalkers
+        self.dt = dt
+        self.Wp = _round_up(nwalkers, 4)
+        self.Np = _round_up(nchol, 8)
+        cfg = L.PxbConfig(nbasis, nup, ndown, nchol, nwalkers, exp_order,
+                          self.device.index or 0, self.Wtot, dt)
+        self._h = ctypes.c_void_p()
+        rc = self.lib.pxb_create(ctypes.byref(self._h), ctypes.byref(cfg))
+        if rc != 0:
+            raise L.PxbError(rc, "pxb_create: bad configuration")
+        nbytes = ctypes.c_size_t()
+        self._check(self.lib.pxb_arena_bytes(self._h, ctypes.byref(nbytes)))
+        self.arena_bytes = nbytes.value
+        with torch.cuda.device(self.device):
+            self.arena = torch.empty(self.arena_bytes + 256, dtype=torch.uint8, device=self.device)
+            base = self.arena.data_ptr()
+            self._shift = (-base) % 256
+            self._check(self.lib.pxb_bind_arena(self._h, base + self._shift, self.arena_bytes,
+                                                self._stream()))
+        self._make_views()
+        self._xi_pinned = None
+        self._xi_dev = None
+
+    # ------------------------------------------------------------------ utils
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.lib.pxb_last_error(self._h)
+            raise L.PxbError(rc, msg.decode() if msg else '')
+
+    def _view(self, fid, dtype, shape=None):
+        off, size = ctypes.c_size_t(), ctypes.c_size_t()
+        self._check(self.lib.pxb_field(self._h, fid, ctypes.byref(off), ctypes.byref(size)))
+        a = self._shift + off.value
+        t = self.arena[a:a + size.value].view(dtype)
+        return t if shape is None else t.view(shape)
+
+    def _make_views(self):
+        W, Wp, Np = self.W, self.Wp, self.Np
+        f64, c128 = torch.float64, torch.complex128
+        self.weight = self._view(L.F_WEIGHT, f64)[:W]
+        self.unscaled_weight = self._view(L.F_UNSCALED_WEIGHT, f64)[:W]
+        self.ot = self._view(L.F_OT, c128)[:W]
+        self.hybrid_energy = self._view(L.F_HYBRID_ENERGY, c128)[:W]
+        self.eloc = self._view(L.F_ELOC, c128, (Wp, 3))[:W]
+        self.detR = self._view(L.F_DETR, f64)[:W]
+        self.log_detR = self._view(L.F_LOG_DETR, f64)[:W]
+        self.estimates = self._view(L.F_ESTIMATES, c128)
+        self.counters = self._view(L.F_COUNTERS, torch.int64)
+        self.parent_ix = self._view(L.F_PARENT_IX, torch.int32)
+        self.xbar = self._view(L.F_XBAR, c128, (Wp, Np))[:W, :self.N]
+        self.xshifted = self._view(L.F_XSHIFTED, c128, (Wp, Np))[:W, :self.N]
+        self.cmf_cfb = self._view(L.F_CMF_CFB, c128, (Wp, 2))[:W]
+        self.ovlp_new = self._view(L.F_OVLP_NEW, c128)[:W]
+        self.total_weight = self._view(L.F_TOTAL_WEIGHT, f64)
+        self.pairs = self._view(L.F_PAIRS, torch.int32)
+
+    def _dev(self, a, dtype):
+        t = torch.as_tensor(numpy.ascontiguousarray(a, dtype=dtype))
+        return t.to(self.device)
+
+    def close(self):
+        if self._h:
+            self.lib.pxb_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ setup
+    def set_hamiltonian(self, hs_pot, rchol, bh1, h1rot, psi, mf_shift, ecore):
+        """Upload the reference's arrays (numpy, reference layouts/dtypes)."""
+        M, ne, N = self.M, self.ne, self.N
+        assert hs_pot.shape == (M * M, N) and rchol.shape == (ne * M, N)
+        assert bh1.shape == (2, M, M) and h1rot.shape == (ne, M) and psi.shape == (M, ne)
+        if numpy.iscomplexobj(hs_pot):
+            if numpy.abs(hs_pot.imag).max() != 0.0:
+                raise L.PxbError(-4, "complex Cholesky vectors are not supported in this version")
+            hs_pot = hs_pot.real
+        with torch.cuda.device(self.device):
+            t = [self._dev(hs_pot, numpy.float64), self._dev(rchol, numpy.complex128),
+                 self._dev(bh1, numpy.complex128), self._dev(h1rot, numpy.complex128),
+                 self._dev(psi, numpy.complex128), self._dev(mf_shift, numpy.complex128)]
+            self._check(self.lib.pxb_set_hamiltonian(self._h, *[x.data_ptr() for x in t],
+                                                     float(numpy.real(ecore)), self._stream()))
+        del t
+
+    def init_walkers(self, init_phi, total_walkers=None):
+        tw = float(self.Wtot if total_walkers is None else total_walkers)
+        with torch.cuda.device(self.device):
+            t = self._dev(init_phi, numpy.complex128)
+            self._check(self.lib.pxb_init_walkers(self._h, t.data_ptr(), tw, self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    # ------------------------------------------------------------------ state
+    def set_phi(self, phi):
+        """phi: [W, M, ne] complex128 (numpy or cuda tensor)."""
+        t = phi if torch.is_tensor(phi) else self._dev(phi, numpy.complex128)
+        assert tuple(t.shape) == (self.W, self.M, self.ne) and t.is_contiguous()
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_set_phi(self._h, t.data_ptr(), self._stream()))
+            torch.cuda.current_stream(self.device).synchronize()
+
+    def get_phi(self):
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.W, self.M, self.ne), dtype=torch.complex128, device=self.device)
+            self._check(self.lib.pxb_get_phi(self._h, out.data_ptr(), self._stream()))
+        return out
+
+    # --------------------------------------------------------------- hot path
+    def stage_xi(self, xi_host):
+        """Copy host fields [W, N] float64 through pinned memory; returns the device tensor."""
+        if self._xi_pinned is None:
+            self._xi_pinned = torch.empty((self.W, self.N), dtype=torch.float64).pin_memory()
+            self._xi_dev = torch.empty((self.W, self.N), dtype=torch.float64, device=self.device)
+            self._xi_event = torch.cuda.Event()
+        else:
+            self._xi_event.synchronize()   # the previous H2D copy has drained the pinned buffer
+        self._xi_pinned.numpy()[...] = xi_host
+        self._xi_dev.copy_(self._xi_pinned, non_blocking=True)
+        self._xi_event.record(torch.cuda.current_stream(self.device))
+        return self._xi_dev
+
+    def propagate(self, xi=None, eshift=0.0, step=1, seed=0, walker_offset=0):
+        """xi: None (device Philox), numpy [W,N] or cuda float64 tensor [W,N]."""
+        with torch.cuda.device(self.device):
+            ptr = None
+            if xi is not None:
+                if not torch.is_tensor(xi):
+                    xi = self.stage_xi(xi)
+                assert xi.dtype == torch.float64 and tuple(xi.shape) == (self.W, self.N)
+                assert xi.is_contiguous()
+                ptr = xi.data_ptr()
+            self._check(self.lib.pxb_propagate(self._h, ptr, int(seed), int(walker_offset),
+                                               float(eshift), int(step), self._stream()))
+
+    def orthogonalise(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_orthogonalise(self._h, self._stream()))
+
+    def local_energy(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_local_energy(self._h, self._stream()))
+
+    def accumulate(self, with_energy=True):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_accumulate(self._h, 1 if with_energy else 0, self._stream()))
+
+    def zero_estimates(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_zero_estimates(self._h, self._stream()))
+
+    # ----------------------------------------------------- population control
+    def pop_control_comb(self, r):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_pop_control_comb(self._h, float(r), self._stream()))
+
+    def pop_rescale(self, global_abs_weights):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_pop_rescale(self._h, global_abs_weights.data_ptr(),
+                                                 int(global_abs_weights.numel()), self._stream()))
+
+    def comb_plan(self, global_abs_weights, r):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_comb_plan(self._h, global_abs_weights.data_ptr(),
+                                               int(global_abs_weights.numel()), float(r),
+                                               self._stream()))
+
+    def payload_doubles(self):
+        n = ctypes.c_size_t()
+        self._check(self.lib.pxb_payload_doubles(self._h, ctypes.byref(n)))
+        return n.value
+
+    def copy_walkers(self, src, dst):
+        """src, dst: int32 cuda tensors of local slots."""
+        if src.numel() == 0:
+            return
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_copy_walkers(self._h, src.data_ptr(), dst.data_ptr(),
+                                                  int(src.numel()), self._stream()))
+
+    def pack_walkers(self, slots, buf):
+        if slots.numel() == 0:
+            return
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_pack_walkers(self._h, slots.data_ptr(), int(slots.numel()),
+                                                  buf.data_ptr(), self._stream()))
+
+    def unpack_walkers(self, slots, buf):
+        if slots.numel() == 0:
+            return
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_unpack_walkers(self._h, slots.data_ptr(), int(slots.numel()),
+                                                    buf.data_ptr(), self._stream()))
+
+    def set_weights(self, value):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_set_weights(self._h, float(value), self._stream()))
+
+    # ------------------------------------------------------------ stage access
+    def stage_greens(self, with_e1b=False):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_stage_greens(self._h, 1 if with_e1b else 0, self._stream()))
+
+    def stage_force_bias_gemm(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_stage_force_bias_gemm(self._h, self._stream()))
+
+    def stage_exchange(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_stage_exchange(self._h, self._stream()))
+
+    def launch_count(self):
+        return int(self.lib.pxb_launch_count(self._h))
+
+    def _get(self, fn, shape):
+        with torch.cuda.device(self.device):
+            out = torch.empty(shape, dtype=torch.complex128, device=self.device)
+            self._check(fn(self._h, out.data_ptr(), self._stream()))
+        return out
+
+    def get_theta(self):
+        return self._get(self.lib.pxb_get_theta, (self.W, self.ne, self.M))
+
+    def get_x(self):
+        return self._get(self.lib.pxb_get_x, (2, self.W, self.N))
+
+    def get_vhs(self):
+        return self._get(self.lib.pxb_get_vhs, (self.W, self.M, self.M))
+
+    def get_exx(self):
+        return self._get(self.lib.pxb_get_exx, (2, self.W))
+
+    def synchronize(self):
+        torch.cuda.current_stream(self.device).synchronize()
+
+
+def comb_plan_host(weights, r):
+    """Bit-exact host comb (pauxy/walkers/handler.py:271-286) via the C library."""
+    lib = L.load()
+    w = numpy.ascontiguousarray(weights, dtype=numpy.float64)
+    out = numpy.zeros(len(w), dtype=numpy.int32)
+    rc = lib.pxb_comb_plan_host(w.ctypes.data, len(w), float(r), out.ctypes.data)
+    if rc != 0:
+        raise L.PxbError(rc, "comb sweep ran past the last walker")
+    return out

@@ -1,0 +1,119 @@
+"""Propagator plugin: continuous Hubbard-Stratonovich propagation for a generic
+Hamiltonian, batched over walkers on the device.
+
+Same class / factory names and option keys as the reference
+(pauxy/propagation/utils.py:8-13, continuous.py:10-80, generic.py:9-64); the
+per-walker `propagate_walker` of the reference becomes one `propagate_walkers`
+call over the whole device batch.
+"""
+import math
+
+import numpy
+import scipy.linalg
+
+
+class GenericContinuous(object):
+    """Setup-only members of pauxy.propagation.generic.GenericContinuous:
+    mean-field shift (generic.py:66-80), one-body propagator (generic.py:88-107),
+    mf_core (generic.py:49)."""
+
+    def __init__(self, system, trial, qmc, options=None, verbose=False):
+        options = options or {}
+        if not options.get('optimised', True):
+            raise NotImplementedError("pauxy_b200: only the optimised (half-rotated) force bias "
+                                      "and VHS construction exist on the device")
+        if trial.ndets != 1:
+            raise NotImplementedError("pauxy_b200: multi-determinant trials are not on the hot path")
+        self.dt = qmc.dt
+        self.sqrt_dt = qmc.dt ** 0.5
+        self.isqrt_dt = 1j * self.sqrt_dt
+        self.mf_shift = self.construct_mean_field_shift(system, trial)
+        self.construct_one_body_propagator(system, qmc.dt)
+        self.mf_core = system.ecore + 0.5 * numpy.dot(self.mf_shift, self.mf_shift)
+        self.nstblz = qmc.nstblz
+        self.ebound = (2.0 / self.dt) ** 0.5
+
+    def construct_mean_field_shift(self, system, trial):
+        return 1j * numpy.dot(system.hs_pot.T, (trial.G[0] + trial.G[1]).ravel())
+
+    def construct_one_body_propagator(self, system, dt):
+        nb = system.nbasis
+        shift = 1j * system.hs_pot.dot(self.mf_shift).reshape(nb, nb)
+        H1 = system.h1e_mod - numpy.array([shift, shift])
+        self.BH1 = numpy.array([scipy.linalg.expm(-0.5 * dt * H1[0]),
+                                scipy.linalg.expm(-0.5 * dt * H1[1])])
+
+
+class Continuous(object):
+    """pauxy.propagation.continuous.Continuous for the phaseless + hybrid mode."""
+
+    def __init__(self, system, trial, qmc, options=None, verbose=False):
+        options = options or {}
+        self.free_projection = options.get('free_projection', False)
+        self.hybrid = options.get('hybrid', True)
+        self.force_bias = options.get('force_bias', True)
+        if self.free_projection:
+            raise NotImplementedError("pauxy_b200: free projection is a 'next' row "
+                                      "(SURVEY.md section 8f.4)")
+        if not self.hybrid:
+            raise NotImplementedError(
+                "pauxy_b200: the local-energy weight update crashes in the reference for "
+                "SingleDet + Generic (SURVEY.md row A8'), there is no oracle for it")
+        if not self.force_bias:
+            raise NotImplementedError("pauxy_b200: force_bias=False is not built")
+        if options.get('stochastic_ri', False):
+            raise NotImplementedError("pauxy_b200: stochastic RI is out of scope")
+        self.exp_nmax = options.get('expansion_order', 6)
+        self.dt = qmc.dt
+        self.sqrt_dt = qmc.dt ** 0.5
+        self.isqrt_dt = 1j * self.sqrt_dt
+        if system.name != "Generic":
+            raise NotImplementedError("pauxy_b200: only system.name == 'Generic' is built")
+        self.propagator = GenericContinuous(system, trial, qmc, options=options, verbose=verbose)
+        mf_core = self.propagator.mf_core
+        self.mf_const_fac = math.exp(-self.dt * mf_core.real)
+        self.BT_BP = self.propagator.BH1
+        self.nstblz = qmc.nstblz
+        self.ebound = (2.0 / self.dt) ** 0.5
+        self.rng = options.get('rng', 'host')  # 'host': numpy legacy stream (parity); 'philox': device
+        self.rng_seed = 0
+        self.verbose = verbose
+        self._nfb_base = 0
+        self._nhe_base = 0
+        self.engine = None
+
+    def bind(self, engine):
+        self.engine = engine
+
+    @property
+    def nfb_trig(self):
+        return int(self.engine.counters[0].item())
+
+    @property
+    def nhe_trig(self):
+        return int(self.engine.counters[1].item())
+
+    def propagate_walkers(self, psi, system, trial, eshift, step, comm=None):
+        """Hot loop 1 of AFQMC.run (pauxy/qmc/afqmc.py:231-236) for the whole
+        device batch: propagate_walker_phaseless for every walker with
+        |weight| > 1e-8, then the 10 % weight cap."""
+        eng = self.engine
+        if self.rng == 'host':
+            xi = psi.draw_fields(system.nfields, comm)
+            eng.propagate(xi, eshift=eshift, step=step)
+        else:
+            eng.propagate(None, eshift=eshift, step=step, seed=self.rng_seed,
+                          walker_offset=psi.walker_offset)
+
+    def propagate_walker(self, walker, system, trial, eshift):
+        raise NotImplementedError("pauxy_b200 propagates the device batch at once: "
+                                  "use propagate_walkers(psi, ...)")
+
+
+def get_propagator_driver(system, trial, qmc, options=None, verbose=False):
+    """pauxy/propagation/utils.py:8-13: continuous HS is the only kind for Generic."""
+    options = options or {}
+    hs = options.get('hubbard_stratonovich', 'continuous')
+    if 'discrete' in hs:
+        raise NotImplementedError("pauxy_b200: discrete HS belongs to the Hubbard model")
+    return Continuous(system, trial, qmc, options=options, verbose=verbose)

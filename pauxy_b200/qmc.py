@@ -1,0 +1,191 @@
+"""AFQMC driver: the host loop of pauxy.qmc.afqmc.AFQMC with the per-walker
+Python loops replaced by one batched device call per phase.
+
+Same constructor / run / finalise interface, option sections and aliases as
+the reference (pauxy/qmc/afqmc.py:82-199 construction, :200-255 run,
+pauxy/qmc/options.py:84-122 QMCOpts, pauxy/qmc/utils.py:3-16 seeding).
+"""
+import time
+
+import numpy
+import torch
+
+from .comm import SingleComm
+from .engine import Engine
+from .estimators import Estimators
+from .propagation import get_propagator_driver
+from .trial import get_trial_wavefunction
+from .walkers import Walkers, get_input_value
+
+
+class QMCOpts(object):
+    """pauxy/qmc/options.py:84-122."""
+
+    def __init__(self, inputs, system, verbose=False):
+        self.nwalkers = get_input_value(inputs, 'num_walkers', default=10, alias=['nwalkers'])
+        self.dt = get_input_value(inputs, 'timestep', default=0.005, alias=['dt'])
+        self.nsteps = get_input_value(inputs, 'num_steps', default=10, alias=['nsteps', 'steps'])
+        self.nblocks = get_input_value(inputs, 'blocks', default=1000,
+                                       alias=['num_blocks', 'nblocks'])
+        self.total_steps = self.nsteps * self.nblocks
+        self.nstblz = get_input_value(inputs, 'stabilise_freq', default=10,
+                                      alias=['nstabilise', 'reortho'])
+        self.npop_control = get_input_value(inputs, 'pop_control_freq', default=1,
+                                            alias=['npop_control', 'pop_control'])
+        self.eqlb_time = get_input_value(inputs, 'equilibration_time', default=2.0,
+                                         alias=['tau_eqlb'])
+        self.neqlb = int(self.eqlb_time / self.dt)
+        self.beta = get_input_value(inputs, 'beta', default=None)
+        self.rng_seed = get_input_value(inputs, 'rng_seed', default=None,
+                                        alias=['random_seed', 'seed'])
+        if self.beta is not None:
+            raise NotImplementedError("pauxy_b200: finite-temperature AFQMC is out of scope")
+
+
+def set_rng_seed(seed, comm, per_rank_streams=False):
+    """pauxy/qmc/utils.py:3-16.  The reference seeds `seed + rank`; here every
+    rank keeps the SAME stream by default so that an N-device run reproduces
+    the one-rank run."""
+    if seed is None:
+        seed = int(numpy.random.randint(0, 1e8)) if comm.rank == 0 else None
+        seed = comm.bcast(seed, root=0)
+    if per_rank_streams:
+        seed = seed + comm.rank
+    numpy.random.seed(seed)
+    return seed
+
+
+class AFQMC(object):
+    """AFQMC driver (phaseless, generic Hamiltonian, single-determinant trial)."""
+
+    def __init__(self, comm=None, options=None, system=None, trial=None, parallel=False,
+                 verbose=False, device=None):
+        options = options or {}
+        comm = comm if comm is not None else SingleComm()
+        self.comm = comm
+        self.verbosity = int(verbose) if verbose is not None else options.get('verbosity', 0)
+        if comm.rank != 0:
+            self.verbosity = 0
+        verbose = self.verbosity > 0
+        self.root = comm.rank == 0
+        self.rank = comm.rank
+        self._init_time = time.time()
+        self.run_time = time.asctime()
+        if system is None:
+            raise NotImplementedError("pauxy_b200: pass system=Generic(...); integral files need "
+                                      "HDF5 (SURVEY.md section 8f.2)")
+        self.system = system
+        qmc_opt = get_input_value(options, 'qmc', default={}, alias=['qmc_options'])
+        self.qmc = QMCOpts(qmc_opt, self.system, verbose=self.verbosity > 1)
+        prop_opt = options.get('propagator', {})
+        self.qmc.rng_seed = set_rng_seed(self.qmc.rng_seed, comm,
+                                         per_rank_streams=prop_opt.get('per_rank_streams', False))
+        self.cplx = True
+        twf_opt = get_input_value(options, 'trial', default={}, alias=['trial_wavefunction'])
+        if trial is not None:
+            self.trial = trial
+            if self.trial._rchol is None:
+                self.trial.half_rotate(self.system)
+        else:
+            self.trial = get_trial_wavefunction(self.system, options=twf_opt, comm=comm,
+                                                verbose=verbose)
+        if comm.rank == 0:
+            self.trial.calculate_energy(self.system)
+        comm.barrier()
+        self.propagators = get_propagator_driver(self.system, self.trial, self.qmc,
+                                                 options=prop_opt, verbose=verbose)
+        self.propagators.rng_seed = int(self.qmc.rng_seed)
+        self.tsetup = time.time() - self._init_time
+        wlk_opts = get_input_value(options, 'walkers', default={}, alias=['walker', 'walker_opts'])
+        est_opts = get_input_value(options, 'estimators', default={},
+                                   alias=['estimates', 'estimator'])
+        # walkers per rank (afqmc.py:163-176)
+        self.qmc.nwalkers = int(self.qmc.nwalkers / comm.size)
+        if self.qmc.nwalkers == 0:
+            self.qmc.nwalkers = 1
+        self.qmc.ntot_walkers = self.qmc.nwalkers * comm.size
+        s = self.system
+        self.engine = Engine(s.nbasis, s.nup, s.ndown, s.nfields, self.qmc.nwalkers, self.qmc.dt,
+                             exp_order=self.propagators.exp_nmax, device=device,
+                             total_walkers=self.qmc.ntot_walkers)
+        p = self.propagators.propagator
+        self.engine.set_hamiltonian(s.hs_pot, self.trial._rchol, p.BH1,
+                                    self.trial.half_rotated_h1(s), self.trial.psi, p.mf_shift,
+                                    s.ecore)
+        self.propagators.bind(self.engine)
+        self.estimators = Estimators(est_opts, self.root, self.qmc, self.system, self.trial,
+                                     self.propagators.BT_BP, verbose, engine=self.engine)
+        self.psi = Walkers(self.system, self.trial, self.qmc, self.engine, walker_opts=wlk_opts,
+                           verbose=verbose, comm=comm)
+        self.setup_timers()
+        self.sync_timers = bool(options.get('sync_timers', False))
+        if verbose:
+            self.estimators.estimators['mixed'].print_header()
+
+    def _tick(self):
+        if self.sync_timers:
+            self.engine.synchronize()
+        return time.time()
+
+    def run(self, psi=None, comm=None, verbose=True, observer=None):
+        """Open-ended random walk: the loop of pauxy/qmc/afqmc.py:200-255."""
+        if psi is not None:
+            self.psi = psi
+        comm = comm if comm is not None else self.comm
+        self.setup_timers()
+        mixed = self.estimators.estimators['mixed']
+        eshift = 0
+        # estimates for the initial distribution of walkers
+        mixed.update(self.system, self.qmc, self.trial, self.psi, 0,
+                     self.propagators.free_projection)
+        if verbose:
+            mixed.print_step(comm, comm.size, 0, 1)
+        for step in range(1, self.qmc.total_steps + 1):
+            start_step = self._tick()
+            if step % self.qmc.nstblz == 0:
+                start = self._tick()
+                self.psi.orthogonalise(self.trial, self.propagators.free_projection)
+                self.tortho += self._tick() - start
+            start = self._tick()
+            self.propagators.propagate_walkers(self.psi, self.system, self.trial, eshift, step,
+                                               comm=comm)
+            self.tprop += self._tick() - start
+            if step % self.qmc.npop_control == 0:
+                start = self._tick()
+                self.psi.pop_control(comm)
+                self.tpopc += self._tick() - start
+            start = self._tick()
+            self.estimators.update(self.system, self.qmc, self.trial, self.psi, step,
+                                   self.propagators.free_projection)
+            self.testim += self._tick() - start
+            self.estimators.print_step(comm, comm.size, step)
+            if step < self.qmc.neqlb:
+                eshift = mixed.get_shift(self.propagators.hybrid)
+            else:
+                eshift += (mixed.get_shift() - eshift)
+            self.tstep += self._tick() - start_step
+            if observer is not None:
+                observer(step, self)
+        self.engine.synchronize()
+
+    def finalise(self, verbose=False):
+        if self.root and verbose:
+            print("# End Time: {:s}".format(time.asctime()))
+            print("# Running time : {:.6f} seconds".format(time.time() - self._init_time))
+            print("# Timing breakdown (per processor, per block/step):")
+            print("# - Setup: {:.6f} s".format(self.tsetup))
+            nsteps = max(self.qmc.nsteps, 1)
+            nstblz = max(nsteps // self.qmc.nstblz, 1)
+            npcon = max(nsteps // self.qmc.npop_control, 1)
+            print("# - Step: {:.6f} s".format(self.tstep / nsteps))
+            print("# - Orthogonalisation: {:.6f} s".format(self.tortho / nstblz))
+            print("# - Propagation: {:.6f} s".format(self.tprop / nsteps))
+            print("# - Estimators: {:.6f} s".format(self.testim / nsteps))
+            print("# - Population control: {:.6f} s".format(self.tpopc / npcon))
+
+    def setup_timers(self):
+        self.tortho = 0
+        self.tprop = 0
+        self.testim = 0
+        self.tpopc = 0
+        self.tstep = 0

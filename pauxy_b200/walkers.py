@@ -1,0 +1,309 @@
+"""Walker population on the device with the reference's handler interface.
+
+`Walkers` mirrors pauxy.walkers.handler.Walkers (handler.py:19-164:
+construction, :166-181 orthogonalise, :225-412 pop_control / comb /
+pair_branch); `SingleDetWalker` objects are thin views of one slot of the
+structure-of-arrays state owned by the Engine (pauxy/walkers/walker.py:24-61,
+single_det.py:31-94).  Device->host copies happen only on attribute access.
+"""
+import numpy
+import scipy.linalg
+import torch
+
+
+def get_input_value(inputs, key, default=0, alias=None, verbose=False):
+    """Option lookup with aliases (pauxy/utils/io.py:304-323)."""
+    val = inputs.get(key, None)
+    if val is None and alias is not None:
+        for a in alias:
+            val = inputs.get(a, None)
+            if val is not None:
+                break
+    return default if val is None else val
+
+
+class SingleDetWalker(object):
+    """View of walker `index` of the device batch."""
+
+    def __init__(self, handler, index):
+        self._h = handler
+        self._i = index
+        self.nup = handler.system.nup
+        self.ndown = handler.system.ndown
+        self.le_oratio = 1.0
+        self.phase = 1 + 0j
+        self.alive = 1
+        self.field_configs = None
+        self.stack = None
+
+    def _scalar(self, name):
+        return getattr(self._h.engine, name)[self._i].item()
+
+    weight = property(lambda s: s._scalar('weight'),
+                      lambda s, v: s._h.engine.weight.__setitem__(s._i, float(v)))
+    unscaled_weight = property(lambda s: s._scalar('unscaled_weight'),
+                               lambda s, v: s._h.engine.unscaled_weight.__setitem__(s._i, float(v)))
+    ot = property(lambda s: s._scalar('ot'),
+                  lambda s, v: s._h.engine.ot.__setitem__(s._i, complex(v)))
+    ovlp = ot
+    hybrid_energy = property(lambda s: s._scalar('hybrid_energy'),
+                             lambda s, v: s._h.engine.hybrid_energy.__setitem__(s._i, complex(v)))
+    detR = property(lambda s: s._scalar('detR'))
+    log_detR = property(lambda s: s._scalar('log_detR'))
+    total_weight = property(lambda s: s._h.engine.total_weight[0].item())
+
+    @property
+    def phi(self):
+        return self._h.phi_host()[self._i]
+
+    @phi.setter
+    def phi(self, value):
+        phi = self._h.engine.get_phi()
+        phi[self._i] = torch.as_tensor(numpy.asarray(value, dtype=numpy.complex128)).to(phi.device)
+        self._h.engine.set_phi(phi)
+        self._h._phi_cache = None
+
+    @property
+    def E_L(self):
+        return self._h.engine.eloc[self._i, 0].item().real
+
+    def local_energy(self, system, two_rdm=None, rchol=None, eri=None, UVT=None):
+        """(E, T, V) of this walker from the batched device evaluation
+        (walkers/single_det.py:340-364 -> estimators/generic.py:156-221)."""
+        self._h.engine.local_energy()
+        e = self._h.engine.eloc[self._i].cpu().numpy()
+        return (complex(e[0]), complex(e[1]), complex(e[2]))
+
+    def greens_function(self, trial):
+        """Host-side G / Gmod of this walker for inspection (single_det.py:295-321);
+        the device keeps its own Theta."""
+        phi = self.phi
+        nup = self.nup
+        self.Gmod, self.G, dets = [], [], []
+        for sl in (slice(0, nup), slice(nup, nup + self.ndown)):
+            ovlp = numpy.dot(phi[:, sl].T, trial.psi[:, sl].conj())
+            gmod = numpy.dot(scipy.linalg.inv(ovlp), phi[:, sl].T)
+            self.Gmod.append(gmod)
+            self.G.append(numpy.dot(trial.psi[:, sl].conj(), gmod))
+            dets.append(numpy.linalg.slogdet(ovlp))
+        self.G = numpy.array(self.G)
+        return dets[0][0] * dets[1][0] * numpy.exp(dets[0][1] + dets[1][1])
+
+    def get_buffer(self):
+        """Minimal communication payload of this walker (walkers/walker.py:63-131
+        packs every numeric attribute; only these matter downstream)."""
+        eng = self._h.engine
+        slot = torch.tensor([self._i], dtype=torch.int32, device=eng.device)
+        buf = torch.empty(eng.payload_doubles(), dtype=torch.float64, device=eng.device)
+        eng.pack_walkers(slot, buf)
+        return buf.cpu().numpy()
+
+    def set_buffer(self, buff):
+        eng = self._h.engine
+        slot = torch.tensor([self._i], dtype=torch.int32, device=eng.device)
+        buf = torch.as_tensor(numpy.ascontiguousarray(buff, dtype=numpy.float64)).to(eng.device)
+        eng.unpack_walkers(slot, buf)
+        self._h._phi_cache = None
+
+
+class Walkers(object):
+    """Container of the walkers owned by this rank (device batch)."""
+
+    def __init__(self, system, trial, qmc, engine, walker_opts=None, verbose=False, comm=None,
+                 nprop_tot=None, nbp=None):
+        walker_opts = walker_opts or {}
+        if nbp is not None:
+            raise NotImplementedError("pauxy_b200: back propagation is a 'next' row (SURVEY 8f.1)")
+        self.system = system
+        self.engine = engine
+        self.nwalkers = qmc.nwalkers
+        self.ntot_walkers = qmc.ntot_walkers
+        self.rank = 0 if comm is None else comm.rank
+        self.walker_offset = self.rank * self.nwalkers  # global index rank*nw + i (handler.py:303-321)
+        self.write_freq = walker_opts.get('write_freq', 0)
+        self.write_restart = False
+        if self.write_freq > 0:
+            raise NotImplementedError("pauxy_b200: walker restart files need HDF5 (SURVEY 8f.2)")
+        self.use_log_shift = walker_opts.get('use_log_shift', False)
+        if self.use_log_shift:
+            raise NotImplementedError("pauxy_b200: use_log_shift is not built")
+        self.walker_type = 'SD'
+        self.pcont_method = get_input_value(walker_opts, 'population_control', default='comb')
+        self.min_weight = walker_opts.get('min_weight', 0.1)
+        self.max_weight = walker_opts.get('max_weight', 4.0)
+        self.target_weight = qmc.ntot_walkers
+        self.nw = qmc.nwalkers
+        engine.init_walkers(trial.init, qmc.ntot_walkers)
+        self.walkers = [SingleDetWalker(self, i) for i in range(self.nwalkers)]
+        self.buff_size = engine.payload_doubles()
+        self._phi_cache = None
+        self.last_parent_ix = None
+
+    def phi_host(self):
+        return self.engine.get_phi().cpu().numpy()
+
+    # ----------------------------------------------------------------- fields
+    def draw_fields(self, nfields, comm=None):
+        """Auxiliary fields for this step from the GLOBAL legacy numpy stream in
+        global walker order, one normal(size=(n_active, N)) block -- identical
+        to the reference's per-walker draws (continuous.py:133).
+        With several ranks every rank draws the whole block and keeps its rows,
+        so results do not depend on the number of devices."""
+        eng = self.engine
+        w = eng.weight
+        if comm is not None and comm.size > 1:
+            gw = comm.allgather_tensor(w).cpu().numpy()
+        else:
+            gw = w.cpu().numpy()
+        active = numpy.abs(gw) > 1e-8
+        xi_active = numpy.random.normal(0.0, 1.0, (int(active.sum()), nfields))
+        lo, hi = self.walker_offset, self.walker_offset + self.nwalkers
+        xi = numpy.zeros((self.nwalkers, nfields))
+        rows = numpy.cumsum(active) - 1
+        mine = active[lo:hi]
+        xi[mine] = xi_active[rows[lo:hi][mine]]
+        return xi
+
+    # ------------------------------------------------------------ re-ortho
+    def orthogonalise(self, trial, free_projection):
+        if free_projection:
+            raise NotImplementedError("pauxy_b200: free projection is not built")
+        self.engine.orthogonalise()
+        self._phi_cache = None
+
+    # --------------------------------------------------- population control
+    def pop_control(self, comm):
+        if self.ntot_walkers == 1:
+            return
+        if self.pcont_method == "comb":
+            self.comb(comm)
+        elif self.pcont_method == "pair_branch":
+            self.pair_branch(comm)
+        else:
+            raise ValueError("Unknown population control method.")
+        self._phi_cache = None
+
+    def _check_total_weight(self):
+        if int(self.engine.counters[3].item()) < 0:
+            # the reference prints and sys.exit()s (handler.py:236-241)
+            raise RuntimeError("# Warning: total walker weight < 1e-8. Something is seriously wrong.")
+
+    def comb(self, comm):
+        """handler.py:225-338.  One uniform draw from the global stream per call."""
+        eng = self.engine
+        r = numpy.random.random()
+        if comm is None or comm.size == 1:
+            eng.pop_control_comb(r)
+            return
+        gw = comm.allgather_tensor(torch.abs(eng.weight))
+        eng.pop_rescale(gw)
+        eng.comb_plan(gw, r)
+        pairs = eng.pairs.cpu().numpy()
+        self._check_total_weight()
+        npairs = int(pairs[0])
+        pl = pairs[1:1 + 2 * npairs].reshape(npairs, 2)
+        self._move(comm, [(int(c), int(k)) for c, k in pl])
+        eng.set_weights(1.0)
+
+    def pair_branch(self, comm):
+        """handler.py:340-412; the selection (stable sort + uniform draws) runs on
+        the host over the gathered weights, walker data moves on the device."""
+        eng = self.engine
+        if comm is not None and comm.size > 1:
+            gw_t = comm.allgather_tensor(torch.abs(eng.weight))
+        else:
+            gw_t = torch.abs(eng.weight)
+        eng.pop_rescale(gw_t)
+        total = eng.total_weight[0].item()
+        self._check_total_weight()
+        scale = total / self.target_weight
+        gw = gw_t.cpu().numpy() / scale
+        new_w, pairs = pair_branch_plan(gw, numpy.random.rand, self.min_weight, self.max_weight)
+        lo, hi = self.walker_offset, self.walker_offset + self.nwalkers
+        # cloned walkers take the averaged weight before their buffer is sent
+        changed = [c for c, _ in pairs if lo <= c < hi]
+        if changed:
+            idx = torch.tensor([c - lo for c in changed], dtype=torch.long, device=eng.device)
+            eng.weight[idx] = torch.as_tensor(new_w[changed]).to(eng.device)
+        self._move(comm, pairs)
+
+    def _move(self, comm, pairs):
+        """Copy walker `clone` over walker `kill` for every (clone, kill) pair of
+        GLOBAL indices (handler.py:301-334): device copy when both live here,
+        packed send/recv between devices otherwise."""
+        eng = self.engine
+        local, out, inc = plan_moves(pairs, self.nw, self.rank)
+        if local:
+            src = torch.tensor([c for c, _ in local], dtype=torch.int32, device=eng.device)
+            dst = torch.tensor([k for _, k in local], dtype=torch.int32, device=eng.device)
+            eng.copy_walkers(src, dst)
+        if comm is None or comm.size == 1:
+            return
+        pd = eng.payload_doubles()
+        sends, recvs, unpack = [], [], []
+        for peer in sorted(out):
+            slots = torch.tensor(out[peer], dtype=torch.int32, device=eng.device)
+            buf = torch.empty(len(out[peer]) * pd, dtype=torch.float64, device=eng.device)
+            eng.pack_walkers(slots, buf)
+            sends.append((peer, buf))
+        for peer in sorted(inc):
+            slots = torch.tensor(inc[peer], dtype=torch.int32, device=eng.device)
+            buf = torch.empty(len(inc[peer]) * pd, dtype=torch.float64, device=eng.device)
+            recvs.append((peer, buf))
+            unpack.append((slots, buf))
+        comm.exchange(sends, recvs)
+        for slots, buf in unpack:
+            eng.unpack_walkers(slots, buf)
+
+    def set_total_weight(self, total_weight):
+        self.engine.total_weight[0] = float(total_weight)
+
+
+def plan_moves(pairs, nw, rank):
+    """Split (clone, kill) pairs of GLOBAL walker indices by where the two ends
+    live (rank = index // nw, slot = index % nw, handler.py:303-321).
+    Returns (local [(src_slot, dst_slot)], out {peer: [src_slot]}, inc {peer:
+    [dst_slot]}); per peer the two slot lists are in the same pair order on
+    both sides, so packed buffers line up."""
+    lo = rank * nw
+    local, out, inc = [], {}, {}
+    for c, k in pairs:
+        rc, rk = c // nw, k // nw
+        if rc == rank and rk == rank:
+            local.append((c - lo, k - lo))
+        elif rc == rank:
+            out.setdefault(rk, []).append(c - lo)
+        elif rk == rank:
+            inc.setdefault(rc, []).append(k - lo)
+    return local, out, inc
+
+
+def pair_branch_plan(abs_weights, rand, min_weight, max_weight):
+    """Pair-branch selection of handler.py:340-386 on the gathered (rescaled)
+    |weights|.  Returns (new_weights, [(clone, kill)]) with the reference's
+    effective pairing: all messages carry the same tag on one rank, so the k-th
+    cloned walker (ascending index) overwrites the k-th killed walker."""
+    w = numpy.array(abs_weights, dtype=numpy.float64)
+    order = numpy.argsort(w, kind='mergesort')
+    ws = w[order].copy()
+    s, e = 0, len(ws) - 1
+    clones, kills = [], []
+    while s < e:
+        if ws[s] < min_weight or ws[e] > max_weight:
+            wab = ws[s] + ws[e]
+            r = rand()
+            if r < ws[e] / wab:
+                ws[e], ws[s] = 0.5 * wab, 0.0
+                clones.append(int(order[e]))
+                kills.append(int(order[s]))
+            else:
+                ws[s], ws[e] = 0.5 * wab, 0.0
+                clones.append(int(order[s]))
+                kills.append(int(order[e]))
+            s += 1
+            e -= 1
+        else:
+            break
+    new_w = numpy.empty_like(ws)
+    new_w[order] = ws
+    return new_w, list(zip(sorted(clones), sorted(kills)))

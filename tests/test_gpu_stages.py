@@ -1,0 +1,181 @@
+"""Stage-level parity of the CUDA path against the oracle (GPU box).
+
+Tolerance: north_star asks <= 1e-10 relative for overlaps, weights and local
+energies; stages are held to 1e-11 or tighter (relative to the largest
+magnitude of the compared array)."""
+import numpy
+import pytest
+
+from oracle import afqmc_oracle as orc
+from helpers import host_setup, make_engine, oracle_ham, random_walkers, relerr
+from pauxy_b200.hamiltonians import generate_hamiltonian, synthetic_cholesky_hamiltonian
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-11
+
+
+def _case(name):
+    if name == 'c1':
+        numpy.random.seed(7)
+        h1e, chol, enuc, _ = generate_hamiltonian(12, (4, 4))
+        return h1e, chol.reshape((-1, 144)).T.copy(), enuc, (4, 4), 0.005, None
+    if name == 'odd':   # M not a multiple of 4/8, nup != ndown, random real trial, N odd
+        numpy.random.seed(3)
+        h1e, chol, enuc, _ = generate_hamiltonian(10, (4, 2))
+        hs = chol.reshape((-1, 100)).T.copy()
+        if hs.shape[1] % 2 == 0:
+            hs = hs[:, :-1].copy()
+        rs = numpy.random.RandomState(5)
+        psi = rs.normal(size=(10, 6)).astype(numpy.complex128)
+        return h1e, hs, enuc, (4, 2), 0.01, psi
+    if name == 'c2':
+        h1e, hs, ecore = synthetic_cholesky_hamiltonian(24, 120, 1002)
+        return h1e, hs, ecore, (5, 5), 0.005, None
+    if name == 'c3':
+        h1e, hs, ecore = synthetic_cholesky_hamiltonian(60, 300, 1003)
+        return h1e, hs, ecore, (7, 7), 0.005, None
+    if name == 'c4':
+        h1e, hs, ecore = synthetic_cholesky_hamiltonian(108, 500, 1004)
+        return h1e, hs, ecore, (21, 21), 0.005, None
+    raise KeyError(name)
+
+
+CASES = [('c1', 13), ('odd', 7), ('c2', 18), ('c3', 9), ('c4', 6)]
+
+
+@pytest.fixture(scope='module', params=CASES, ids=[c[0] for c in CASES])
+def setup(request):
+    name, W = request.param
+    h1e, hs, ecore, nelec, dt, psi = _case(name)
+    system, trial, prop = host_setup(h1e, hs, ecore, nelec, dt, psi)
+    ham = oracle_ham(h1e, hs, ecore, nelec, dt, psi)
+    eng = make_engine(system, trial, prop, W, dt)
+    phi = random_walkers(ham, W, seed=11)
+    return dict(name=name, W=W, ham=ham, eng=eng, phi=phi, system=system)
+
+
+def test_host_setup_matches_oracle(setup):
+    # the product's host setup against the (reference-pinned) oracle
+    ham, system = setup['ham'], setup['system']
+    assert relerr(system.h1e_mod, ham.h1e_mod) < 1e-14
+
+
+def test_phi_roundtrip(setup):
+    eng, phi = setup['eng'], setup['phi']
+    eng.set_phi(phi)
+    back = eng.get_phi().cpu().numpy()
+    assert numpy.array_equal(back, phi)
+
+
+def test_greens_function(setup):
+    eng, phi, ham = setup['eng'], setup['phi'], setup['ham']
+    eng.set_phi(phi)
+    eng.stage_greens(with_e1b=True)
+    theta = eng.get_theta().cpu().numpy()
+    tha, thb, det = orc.greens_function(ham, phi)
+    ref = numpy.concatenate([tha, thb], axis=1)
+    assert relerr(theta, ref) < TOL
+
+
+def test_force_bias_gemm(setup):
+    eng, phi, ham = setup['eng'], setup['phi'], setup['ham']
+    eng.set_phi(phi)
+    eng.stage_greens()
+    eng.stage_force_bias_gemm()
+    X = eng.get_x().cpu().numpy()
+    tha, thb, _ = orc.greens_function(ham, phi)
+    W, M, na = phi.shape[0], ham.nbasis, ham.nup
+    Xa = numpy.dot(tha.reshape(W, -1), ham.rchol[:na * M])
+    Xb = numpy.dot(thb.reshape(W, -1), ham.rchol[na * M:])
+    assert relerr(X[0], Xa) < TOL
+    assert relerr(X[1], Xb) < TOL
+
+
+def test_propagate_one_step(setup):
+    """A1..A9 for one step from random walkers with host fields."""
+    eng, phi, ham, W = setup['eng'], setup['phi'], setup['ham'], setup['W']
+    rs = numpy.random.RandomState(21)
+    xi = rs.normal(size=(W, ham.nchol))
+    eng.init_walkers(ham.psi)
+    eng.set_phi(phi)
+    w0 = 0.5 + rs.rand(W)
+    w0[1] = 0.0                        # an inactive walker: must be left untouched
+    import torch
+    eng.weight.copy_(torch.as_tensor(w0))
+    ot0 = orc.calc_overlap(ham, phi)
+    eng.ot.copy_(torch.as_tensor(ot0))
+    eh0 = rs.normal(size=W) + 1j * 0.01 * rs.normal(size=W)
+    eng.hybrid_energy.copy_(torch.as_tensor(eh0))
+    eshift = 0.37
+    eng.propagate(xi, eshift=eshift, step=2)
+    eng.synchronize()
+
+    # oracle
+    active = numpy.abs(w0) > 1e-8
+    tha, thb, ovlp_old = orc.greens_function(ham, phi)
+    p1 = orc.kinetic_real(ham, phi)
+    xbar, _ = orc.force_bias(ham, tha, thb)
+    x, cmf, cfb, ntrig = orc.shift_fields(ham, xi, xbar)
+    vhs = orc.construct_vhs(ham, x)
+    p2 = orc.apply_exponential(p1, vhs)
+    p3 = orc.kinetic_real(ham, p2)
+    ovlp_new = orc.calc_overlap(ham, p3)
+
+    assert relerr(eng.xshifted.cpu().numpy()[active], x[active]) < TOL
+    assert relerr(eng.get_vhs().cpu().numpy()[active], vhs[active]) < TOL
+    cc = eng.cmf_cfb.cpu().numpy()
+    assert relerr(cc[active, 0], cmf[active]) < TOL
+    assert relerr(cc[active, 1], cfb[active]) < TOL
+    out = eng.get_phi().cpu().numpy()
+    assert relerr(out[active], p3[active]) < TOL
+    assert numpy.array_equal(out[~active], phi[~active])
+    assert relerr(eng.ovlp_new.cpu().numpy()[active], ovlp_new[active]) < TOL
+    wt = eng.weight.cpu().numpy()
+    ot = eng.ot.cpu().numpy()
+    eh = eng.hybrid_energy.cpu().numpy()
+    cap = 0.1 * W
+    for i in range(W):
+        if not active[i]:
+            assert wt[i] == w0[i] and ot[i] == ot0[i] and eh[i] == eh0[i]
+            continue
+        wr, otr, ehr, _ = orc.update_weight_hybrid(ham, float(w0[i]), complex(ovlp_old[i]),
+                                                   complex(ovlp_new[i]), complex(eh0[i]),
+                                                   complex(cfb[i]), complex(cmf[i]), eshift)
+        if abs(wr) > cap:
+            wr = cap
+        assert abs(wt[i] - wr) <= 1e-10 * max(abs(wr), 1e-300)
+        assert abs(ot[i] - otr) <= 1e-10 * abs(otr)
+        assert abs(eh[i] - ehr) <= 1e-9 * max(abs(ehr), 1.0)
+
+
+def test_local_energy(setup):
+    eng, phi, ham = setup['eng'], setup['phi'], setup['ham']
+    eng.set_phi(phi)
+    eng.local_energy()
+    eloc = eng.eloc.cpu().numpy()
+    tha, thb, _ = orc.greens_function(ham, phi)
+    ref = orc.local_energy(ham, tha, thb)
+    assert relerr(eloc, ref) < TOL
+
+
+def test_reortho(setup):
+    eng, phi, ham, W = setup['eng'], setup['phi'], setup['ham'], setup['W']
+    import torch
+    eng.init_walkers(ham.psi)
+    eng.set_phi(phi)
+    ot0 = orc.calc_overlap(ham, phi)
+    eng.ot.copy_(torch.as_tensor(ot0))
+    eng.local_energy()
+    e_before = eng.eloc.cpu().numpy().copy()
+    eng.orthogonalise()
+    q = eng.get_phi().cpu().numpy()
+    ref, detR, logdet = orc.reortho(ham, phi)
+    assert relerr(q, ref) < 1e-10
+    assert relerr(eng.detR.cpu().numpy(), detR) < 1e-11
+    assert relerr(eng.ot.cpu().numpy(), ot0 / detR) < 1e-11
+    # reference property (walkers/tests/test_single_det.py): detR * ot_new == ot_old,
+    # and the local energy is unchanged by re-orthogonalisation
+    assert relerr(orc.calc_overlap(ham, q) * detR, ot0) < 1e-11
+    eng.local_energy()
+    assert relerr(eng.eloc.cpu().numpy(), e_before) < 1e-10

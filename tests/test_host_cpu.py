@@ -1,0 +1,182 @@
+"""Host logic, C-ABI surface and multi-rank plumbing (no GPU needed)."""
+import ctypes
+import os
+import re
+
+import numpy
+import pytest
+
+from oracle import afqmc_oracle as orc
+from helpers import host_setup
+from pauxy_b200 import _lib
+from pauxy_b200.walkers import pair_branch_plan, plan_moves
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from pauxy_b200 import build
+    build.build()
+    header = open(os.path.join(ROOT, 'include', 'pauxy_b200.h')).read()
+    declared = set(re.findall(r'\b(pxb_[a-z0-9_]+)\s*\(', header))
+    assert len(declared) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "missing export %s" % name
+    assert declared == set(_lib.declared_symbols())
+    assert _lib.load().pxb_abi_version() == 1
+
+
+def test_create_validates_arguments_without_gpu():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    bad = _lib.PxbConfig(10, 11, 3, 5, 4, 6, 0, 0, 0.005)   # nup > nbasis
+    assert lib.pxb_create(ctypes.byref(h), ctypes.byref(bad)) == -1
+    ok = _lib.PxbConfig(108, 21, 21, 500, 8192, 6, 0, 0, 0.005)
+    assert lib.pxb_create(ctypes.byref(h), ctypes.byref(ok)) == 0
+    n = ctypes.c_size_t()
+    assert lib.pxb_arena_bytes(h, ctypes.byref(n)) == 0
+    assert 2e9 < n.value < 8e9        # c4 working set: a few GB of the 180 GB
+    # compute entry points refuse to run before the arena / hamiltonian are set
+    assert lib.pxb_propagate(h, None, 0, 0, 0.0, 1, None) == -3
+    assert lib.pxb_local_energy(h, None) == -3
+    lib.pxb_destroy(h)
+
+
+def test_comb_host_bit_exact(golden):
+    from pauxy_b200.engine import comb_plan_host
+    rs = numpy.random.RandomState(5)
+    for n in (2, 7, 32, 1000):
+        for trial in range(5):
+            w = rs.rand(n) ** 3
+            w[rs.randint(n)] = 0.0
+            w = w / (w.sum() / n)
+            r = rs.rand()
+            assert numpy.array_equal(comb_plan_host(w, r), orc.comb_parents(w, r, n))
+    g = golden('stress_comb')
+    for s in range(g['weight_prop'].shape[0]):
+        wp = numpy.abs(g['weight_prop'][s])
+        gw = wp / (sum(wp) / len(wp))
+        assert numpy.array_equal(comb_plan_host(gw, float(g['comb_r'][s])), g['parent_ix'][s])
+
+
+def test_pair_branch_plan_matches_oracle():
+    rs = numpy.random.RandomState(9)
+    for trial in range(20):
+        w = numpy.abs(1.0 + 0.4 * rs.normal(size=24))
+        draws = list(rs.rand(24))
+        a = pair_branch_plan(w, iter(draws).__next__, 0.7, 1.3)
+        b = orc.pair_branch_plan(w, iter(draws).__next__, 0.7, 1.3)
+        assert numpy.array_equal(a[0], b[0]) and a[1] == b[1]
+
+
+@pytest.mark.parametrize('name', ['test_generic', 'c1', 'stress_comb'])
+def test_host_setup_matches_reference(golden, name):
+    g = golden(name)
+    system, trial, prop = host_setup(g['h1e'], g['hs_pot'], float(g['ecore']),
+                                     tuple(int(x) for x in g['nelec']), float(g['dt']))
+    numpy.testing.assert_allclose(prop.mf_shift, g['setup_mf_shift'], rtol=1e-12, atol=1e-14)
+    numpy.testing.assert_allclose(prop.BH1, g['setup_BH1'], rtol=1e-12, atol=1e-14)
+    numpy.testing.assert_allclose(trial._rchol, g['setup_rchol'], rtol=1e-12, atol=1e-14)
+    numpy.testing.assert_allclose(system.h1e_mod, g['setup_h1e_mod'], rtol=1e-12, atol=1e-14)
+    numpy.testing.assert_allclose(prop.mf_core, g['setup_mf_core'], rtol=1e-12)
+    # half-rotated one-body matrix reproduces sum(H1*G) for the trial's own G
+    h1rot = trial.half_rotated_h1(system)
+    gh = numpy.concatenate(trial.GH)
+    e1 = numpy.sum(system.H1[0] * trial.G[0]) + numpy.sum(system.H1[1] * trial.G[1])
+    assert abs(numpy.sum(h1rot * gh) - e1) < 1e-12 * abs(e1)
+
+
+def test_qmc_options_aliases():
+    from pauxy_b200.qmc import QMCOpts
+    q = QMCOpts({'dt': 0.01, 'nsteps': 5, 'blocks': 3, 'nwalkers': 7, 'reortho': 2,
+                 'pop_control': 4, 'seed': 3}, None)
+    assert (q.dt, q.nsteps, q.nblocks, q.nwalkers, q.nstblz, q.npop_control, q.rng_seed) == \
+        (0.01, 5, 3, 7, 2, 4, 3)
+    assert q.total_steps == 15 and q.neqlb == 200
+    d = QMCOpts({}, None)
+    assert (d.nwalkers, d.dt, d.nsteps, d.nblocks, d.nstblz, d.npop_control) == \
+        (10, 0.005, 10, 1000, 10, 1)
+
+
+def test_unsupported_modes_fail_loudly():
+    from pauxy_b200.propagation import Continuous
+    g_h1e = numpy.eye(4)
+    hs = numpy.zeros((16, 3))
+    system, trial, prop = host_setup(g_h1e, hs, 0.0, (1, 1), 0.01)
+
+    class Q(object):
+        dt = 0.01
+        nstblz = 10
+    for opts in ({'free_projection': True}, {'hybrid': False}, {'optimised': False}):
+        with pytest.raises(NotImplementedError):
+            Continuous(system, trial, Q(), options=opts)
+
+
+def test_plan_moves_partitions_pairs():
+    pairs = [(1, 6), (9, 2), (5, 4), (12, 13), (3, 15)]
+    nw = 4
+    seen = []
+    for rank in range(4):
+        local, out, inc = plan_moves(pairs, nw, rank)
+        for c, k in local:
+            seen.append((c + rank * nw, k + rank * nw))
+        for peer, slots in out.items():
+            peer_inc = plan_moves(pairs, nw, peer)[2][rank]
+            assert len(peer_inc) == len(slots)
+            for s, d in zip(slots, peer_inc):
+                seen.append((s + rank * nw, d + peer * nw))
+    assert sorted(seen) == sorted(pairs)
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from pauxy_b200.comm import TorchComm
+    comm = TorchComm()
+    nw = 4
+    w = torch.arange(nw, dtype=torch.float64) + 10 * rank
+    gw = comm.allgather_tensor(w)
+    est = torch.full((10,), complex(rank + 1, 0.5), dtype=torch.complex128)
+    comm.allreduce_sum_(est)
+    # walker moves: global (clone, kill) pairs crossing ranks in both directions
+    pairs = [(1, 6), (5, 2), (3, 0), (7, 4)]
+    local, out, inc = plan_moves(pairs, nw, rank)
+    payload = torch.arange(nw, dtype=torch.float64).reshape(nw, 1) * 100 + rank * 1000 + \
+        torch.arange(3, dtype=torch.float64)
+    state = payload.clone()
+    for s, d in local:
+        state[d] = payload[s]
+    sends = [(p, payload[torch.tensor(sl)].reshape(-1).clone()) for p, sl in sorted(out.items())]
+    recvs = [(p, torch.empty(len(sl) * 3, dtype=torch.float64)) for p, sl in sorted(inc.items())]
+    comm.exchange(sends, recvs)
+    for (p, buf), (_, sl) in zip(recvs, sorted(inc.items())):
+        state[torch.tensor(sl)] = buf.reshape(len(sl), 3)
+    q.put((rank, gw.tolist(), est[0].item(), state.tolist()))
+    dist.destroy_process_group()
+
+
+def test_two_rank_plumbing_gloo():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=120) for _ in procs)
+    for p in procs:
+        p.join(60)
+    for rank, gw, est, state in res:
+        assert gw == [0.0, 1.0, 2.0, 3.0, 10.0, 11.0, 12.0, 13.0]
+        assert est == complex(3.0, 1.0)
+    # global payload after the moves: walker k holds walker c's payload
+    allstate = res[0][3] + res[1][3]
+    orig = [[w * 100.0 + r * 1000 + j for j in range(3)] for r in range(2) for w in range(4)]
+    expect = [list(x) for x in orig]
+    for c, k in [(1, 6), (5, 2), (3, 0), (7, 4)]:
+        expect[k] = orig[c]
+    assert allstate == expect
