@@ -42,6 +42,8 @@ struct pxb_context {
   int sm_count = 148;
   int max_smem_optin = 0;
   long long launches = 0;  // kernels launched through this handle
+  // Theta / overlap / e1b (A_THETA, A_E1B) correspond to the current walkers; X to the current Theta
+  bool theta_valid = false, x_valid = false;
   std::string err;
 
   template <class T>
@@ -89,6 +91,8 @@ inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
 CopyArgs copy_args(pxb_handle h) {
   CopyArgs c;
   c.phi = h->phi();
+  c.theta = h->ptr<double>(A_THETA);
+  c.e1b = h->ptr<double2>(A_E1B);
   c.weight = h->field<double>(PXB_F_WEIGHT);
   c.unscaled = h->field<double>(PXB_F_UNSCALED_WEIGHT);
   c.ot = h->field<double2>(PXB_F_OT);
@@ -110,13 +114,15 @@ int run_greens(pxb_handle h, const double* phi, bool want_theta, double2* ovlp_o
   a.psiT = h->ptr<double>(A_PSIT);
   a.h1rot = h->ptr<double2>(A_H1ROT);
   a.ovlp_out = ovlp_out;
-  a.e1b_out = with_e1b ? h->ptr<double2>(A_E1B) : nullptr;
+  a.e1b_out = (with_e1b || want_theta) ? h->ptr<double2>(A_E1B) : nullptr;
   a.d = d;
   a.want_theta = want_theta ? 1 : 0;
   const int nth = 256;
   const size_t smem = greens_smem_bytes(d, nth);
   if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "greens: problem too large for shared memory");
   PXB_CUDA(h, cudaFuncSetAttribute(greens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PXB_CUDA(h, cudaFuncSetAttribute(greens_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)cudaSharedmemCarveoutMaxShared));
   ++h->launches;
   greens_kernel<<<d.Wp, nth, smem, st>>>(a);
   PXB_CUDA(h, cudaGetLastError());
@@ -194,15 +200,17 @@ int run_one_body(pxb_handle h, const double* in, double* out, const int* active,
   return PXB_OK;
 }
 
-template <int WMT, int NTMAX>
+template <int WMT, int NTMAX, int NWARPS, int MINB>
 int launch_taylor(pxb_handle h, TaylorArgs& a, int NT, int nwarps, cudaStream_t st) {
   const Dims& d = h->d;
   const size_t smem = (size_t)d.KC * NT * 32 * sizeof(double);
   if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "taylor: tile too large for shared memory");
-  PXB_CUDA(h, cudaFuncSetAttribute(taylor_kernel<WMT, NTMAX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)smem));
+  auto kern = taylor_kernel<WMT, NTMAX, NWARPS, MINB>;
+  PXB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PXB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)cudaSharedmemCarveoutMaxShared));
   ++h->launches;
-  taylor_kernel<WMT, NTMAX><<<d.W * a.nchunks, nwarps * 32, smem, st>>>(a);
+  kern<<<d.W * a.nchunks, nwarps * 32, smem, st>>>(a);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -226,15 +234,17 @@ int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   if (wmt < 2 && d.MT >= 2) wmt = 2;
   if (wmt > 4) return fail(h, PXB_ERR_ARG, "taylor: nbasis > 256 not supported in this version");
   const int nwarps = (d.MT + wmt - 1) / wmt;
-#define PXB_TAYLOR_CASE(W_, N_)                                   \
-  if (wmt == W_ && NT <= N_) return launch_taylor<W_, N_>(h, a, NT, nwarps, st);
-  PXB_TAYLOR_CASE(1, 4)
-  PXB_TAYLOR_CASE(1, 12)
-  PXB_TAYLOR_CASE(2, 4)
-  PXB_TAYLOR_CASE(2, 8)
-  PXB_TAYLOR_CASE(2, 12)
-  PXB_TAYLOR_CASE(3, 12)
-  PXB_TAYLOR_CASE(4, 12)
+#define PXB_TAYLOR_CASE(W_, N_, NW_, MB_) \
+  if (wmt == W_ && NT <= N_ && nwarps <= NW_) return launch_taylor<W_, N_, NW_, MB_>(h, a, NT, nwarps, st);
+  PXB_TAYLOR_CASE(1, 4, 8, 2)
+  PXB_TAYLOR_CASE(1, 12, 8, 2)
+  PXB_TAYLOR_CASE(2, 4, 8, 2)
+  PXB_TAYLOR_CASE(2, 8, 8, 2)
+  PXB_TAYLOR_CASE(2, 11, 7, 2)
+  PXB_TAYLOR_CASE(2, 12, 7, 2)
+  PXB_TAYLOR_CASE(2, 12, 8, 1)
+  PXB_TAYLOR_CASE(3, 12, 8, 1)
+  PXB_TAYLOR_CASE(4, 12, 8, 1)
 #undef PXB_TAYLOR_CASE
   return fail(h, PXB_ERR_ARG, "taylor: no kernel instance for this shape");
 }
@@ -263,6 +273,24 @@ int run_exchange(pxb_handle h, cudaStream_t st) {
     exchange_kernel<4, false><<<grid, EX_WARPS * 32, tail, st>>>(a);
   }
   PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+// Theta, overlap and e1b of the CURRENT walkers (recomputed only when stale)
+int ensure_theta(pxb_handle h, cudaStream_t st) {
+  if (h->theta_valid) return PXB_OK;
+  int rc = run_greens(h, h->phi(), true, h->ptr<double2>(A_OVLP_OLD), true, st);
+  if (rc) return rc;
+  h->theta_valid = true;
+  h->x_valid = false;
+  return PXB_OK;
+}
+
+int ensure_x(pxb_handle h, cudaStream_t st) {
+  if (h->x_valid) return PXB_OK;
+  int rc = run_force_bias_gemm(h, st);
+  if (rc) return rc;
+  h->x_valid = true;
   return PXB_OK;
 }
 
@@ -388,6 +416,7 @@ int pxb_bind_arena(pxb_handle h, void* dev_arena, size_t bytes, void* stream) {
   h->arena = static_cast<unsigned char*>(dev_arena);
   h->ham_set = false;
   h->phi_cur = 0;
+  h->theta_valid = h->x_valid = false;
   return PXB_OK;
 }
 
@@ -434,6 +463,7 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
   }
   h->d.ecore = ecore;
   h->ham_set = true;
+  h->theta_valid = h->x_valid = false;
   return PXB_OK;
 }
 
@@ -444,6 +474,7 @@ int pxb_set_phi(pxb_handle h, const void* dev_phi, void* stream) {
   phi_to_of_kernel<<<grid_for((size_t)d.Wp * d.ne * d.Mp), 256, 0, S(stream)>>>(
       static_cast<const double2*>(dev_phi), h->phi(), d, 0);
   PXB_CUDA(h, cudaGetLastError());
+  h->theta_valid = h->x_valid = false;
   return PXB_OK;
 }
 
@@ -465,7 +496,8 @@ int pxb_init_walkers(pxb_handle h, const void* dev_init_phi, double total_walker
   phi_to_of_kernel<<<grid_for((size_t)d.Wp * d.ne * d.Mp), 256, 0, st>>>(
       static_cast<const double2*>(dev_init_phi), h->phi(), d, 1);
   PXB_CUDA(h, cudaGetLastError());
-  int rc = run_greens(h, h->phi(), false, h->ptr<double2>(A_OVLP_OLD), false, st);
+  h->theta_valid = h->x_valid = false;
+  int rc = ensure_theta(h, st);
   if (rc) return rc;
   ++h->launches;
   init_scalars_kernel<<<(d.Wp + 255) / 256, 256, 0, st>>>(
@@ -490,10 +522,11 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   ++h->launches;
   active_kernel<<<(d.Wp + 255) / 256, 256, 0, st>>>(h->field<double>(PXB_F_WEIGHT), active, counters, d);
   PXB_CUDA(h, cudaGetLastError());
-  // (a) Green's function of the current walkers -> Theta, ovlp_old
-  if ((rc = run_greens(h, h->phi(), true, h->ptr<double2>(A_OVLP_OLD), false, st))) return rc;
-  // (c1) force bias GEMM can start from Theta; (b) one-body half step phi -> other
-  if ((rc = run_force_bias_gemm(h, st))) return rc;
+  // (a) Theta of the current walkers (normally still valid from the previous step's
+  //     closing Green's function / the estimator); ovlp_old is walker.ot
+  if ((rc = ensure_theta(h, st))) return rc;
+  // (c1) force bias GEMM X_s = R_s^T Theta_s (shared with the Coulomb term of the estimator)
+  if ((rc = ensure_x(h, st))) return rc;
   FieldArgs f;
   f.X = h->ptr<double2>(A_X);
   f.xi = dev_xi;
@@ -517,13 +550,16 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   if ((rc = run_taylor(h, work, active, st))) return rc;
   // (d) second half step writes back into the walker buffer, active walkers only
   if ((rc = run_one_body(h, work, h->phi(), active, st))) return rc;
-  // (e) new overlap, (f) weights
-  if ((rc = run_greens(h, h->phi(), false, h->field<double2>(PXB_F_OVLP_NEW), false, st))) return rc;
+  // (e) Green's function of the propagated walkers: its determinant is the new overlap
+  //     (single_det.py:170-199) and its Theta serves the estimator and the next step
+  h->theta_valid = h->x_valid = false;
+  if ((rc = run_greens(h, h->phi(), true, h->field<double2>(PXB_F_OVLP_NEW), true, st))) return rc;
+  h->theta_valid = true;
+  // (f) weights
   WeightArgs wa;
   wa.weight = h->field<double>(PXB_F_WEIGHT);
   wa.ot = h->field<double2>(PXB_F_OT);
   wa.ehyb = h->field<double2>(PXB_F_HYBRID_ENERGY);
-  wa.ovlp_old = h->ptr<double2>(A_OVLP_OLD);
   wa.ovlp_new = h->field<double2>(PXB_F_OVLP_NEW);
   wa.cmfcfb = h->field<double2>(PXB_F_CMF_CFB);
   wa.active = active;
@@ -551,6 +587,8 @@ int pxb_orthogonalise(pxb_handle h, void* stream) {
   const size_t smem = qr_smem_bytes(d, nth);
   if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "qr: problem too large for shared memory");
   PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)cudaSharedmemCarveoutMaxShared));
   ++h->launches;
   qr_kernel<<<d.Wp, nth, smem, S(stream)>>>(a);
   PXB_CUDA(h, cudaGetLastError());
@@ -562,8 +600,8 @@ int pxb_local_energy(pxb_handle h, void* stream) {
   const Dims& d = h->d;
   cudaStream_t st = S(stream);
   int rc;
-  if ((rc = run_greens(h, h->phi(), true, h->ptr<double2>(A_OVLP_OLD), true, st))) return rc;
-  if ((rc = run_force_bias_gemm(h, st))) return rc;
+  if ((rc = ensure_theta(h, st))) return rc;
+  if ((rc = ensure_x(h, st))) return rc;
   if ((rc = run_exchange(h, st))) return rc;
   EnergyArgs e;
   e.X = h->ptr<double2>(A_X);
@@ -660,12 +698,13 @@ int pxb_pop_control_comb(pxb_handle h, double r, void* stream) {
   ++h->launches;
   copy_pairs_kernel<<<std::min(d.W, 4 * h->sm_count), 256, 0, st>>>(copy_args(h), h->field<int>(PXB_F_PAIRS), 0);
   PXB_CUDA(h, cudaGetLastError());
+  h->x_valid = false;  // Theta and e1b travel with the walkers, X does not
   return pxb_set_weights(h, 1.0, stream);
 }
 
 int pxb_payload_doubles(pxb_handle h, size_t* n) {
   if (!h || !n) return PXB_ERR_ARG;
-  *n = (size_t)h->d.ne * h->d.KC * 8 + 16;
+  *n = (size_t)2 * h->d.ne * h->d.KC * 8 + 18;
   return PXB_OK;
 }
 
@@ -675,6 +714,7 @@ int pxb_copy_walkers(pxb_handle h, const int32_t* src, const int32_t* dst, int n
   ++h->launches;
   copy_list_kernel<<<std::min(n, 4 * h->sm_count), 256, 0, S(stream)>>>(copy_args(h), src, dst, n);
   PXB_CUDA(h, cudaGetLastError());
+  h->x_valid = false;
   return PXB_OK;
 }
 
@@ -694,6 +734,7 @@ int pxb_unpack_walkers(pxb_handle h, const int32_t* slots, int n, const double* 
   pack_kernel<<<std::min(n, 4 * h->sm_count), 256, 0, S(stream)>>>(copy_args(h), slots, n,
                                                                   const_cast<double*>(buf), 1);
   PXB_CUDA(h, cudaGetLastError());
+  h->x_valid = false;
   return PXB_OK;
 }
 
@@ -726,17 +767,24 @@ int pxb_comb_plan_host(const double* weights, int64_t n, double r, int32_t* pare
 // ---- stage-level entry points -------------------------------------------------
 int pxb_stage_exchange(pxb_handle h, void* stream) {
   PXB_REQUIRE_READY(h);
+  int rc = ensure_theta(h, S(stream));
+  if (rc) return rc;
   return run_exchange(h, S(stream));
 }
 
 int pxb_stage_greens(pxb_handle h, int with_e1b, void* stream) {
   PXB_REQUIRE_READY(h);
-  return run_greens(h, h->phi(), true, h->ptr<double2>(A_OVLP_OLD), with_e1b != 0, S(stream));
+  (void)with_e1b;
+  h->theta_valid = h->x_valid = false;
+  return ensure_theta(h, S(stream));
 }
 
 int pxb_stage_force_bias_gemm(pxb_handle h, void* stream) {
   PXB_REQUIRE_READY(h);
-  return run_force_bias_gemm(h, S(stream));
+  int rc = ensure_theta(h, S(stream));
+  if (rc) return rc;
+  h->x_valid = false;
+  return ensure_x(h, S(stream));
 }
 
 int pxb_get_theta(pxb_handle h, void* dev_theta, void* stream) {

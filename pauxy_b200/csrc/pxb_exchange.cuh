@@ -30,6 +30,96 @@ struct ExArgs {
 constexpr int EX_WARPS = 8;
 constexpr int EX_MAX_BLOCKS = 16;  // orbital blocks per spin (<= 64 occupied orbitals at BS = 4)
 
+// One work item with compile-time block sizes: NI x NJ tiles of T[.., I, J] and, off
+// the diagonal, NJ x NI tiles of T[.., J, I].  No predication inside the k-loop: a
+// predicated-off DMMA still occupies the FP64 pipe (measured: 72 % pipe-active at 55 %
+// useful rate with run-time block sizes).
+template <int NI, int NJ, bool DIAG, bool BSMEM>
+__device__ __forceinline__ void exchange_item(const double* __restrict__ aI,
+                                              const double* __restrict__ aJ,
+                                              const double* __restrict__ bI,
+                                              const double* __restrict__ bJ, int rowstride, int KC,
+                                              double& sum_re, double& sum_im) {
+  constexpr int NJ2 = DIAG ? 1 : NJ;  // J-side fragments are unused on the diagonal
+  double acc1[NI][NJ][2], acc2[NJ2][NI][2];
+#pragma unroll
+  for (int i = 0; i < NI; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) acc1[i][j][0] = acc1[i][j][1] = 0.0;
+#pragma unroll
+  for (int j = 0; j < NJ2; ++j)
+#pragma unroll
+    for (int i = 0; i < NI; ++i) acc2[j][i][0] = acc2[j][i][1] = 0.0;
+
+  double fa_i[NI], fb_i[NI], fa_j[NJ2], fb_j[NJ2];
+  double na_i[NI], nb_i[NI], na_j[NJ2], nb_j[NJ2];
+#pragma unroll
+  for (int i = 0; i < NI; ++i) {
+    fa_i[i] = ldg_nc(aI + i * rowstride);
+    fb_i[i] = BSMEM ? bI[i * rowstride] : ldg_nc(bI + i * rowstride);
+  }
+  if (!DIAG) {
+#pragma unroll
+    for (int j = 0; j < NJ2; ++j) {
+      fa_j[j] = ldg_nc(aJ + j * rowstride);
+      fb_j[j] = BSMEM ? bJ[j * rowstride] : ldg_nc(bJ + j * rowstride);
+    }
+  }
+  for (int pc = 0; pc < KC; ++pc) {
+    const int pn = (pc + 1 < KC ? pc + 1 : pc) * 32;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      na_i[i] = ldg_nc(aI + i * rowstride + pn);
+      nb_i[i] = BSMEM ? bI[i * rowstride + pn] : ldg_nc(bI + i * rowstride + pn);
+    }
+    if (!DIAG) {
+#pragma unroll
+      for (int j = 0; j < NJ2; ++j) {
+        na_j[j] = ldg_nc(aJ + j * rowstride + pn);
+        nb_j[j] = BSMEM ? bJ[j * rowstride + pn] : ldg_nc(bJ + j * rowstride + pn);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int j = 0; j < NJ; ++j)
+        dmma(acc1[i][j][0], acc1[i][j][1], fa_i[i], DIAG ? fb_i[j] : fb_j[j]);
+    if (!DIAG) {
+#pragma unroll
+      for (int j = 0; j < NJ2; ++j)
+#pragma unroll
+        for (int i = 0; i < NI; ++i) dmma(acc2[j][i][0], acc2[j][i][1], fa_j[j], fb_i[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+      fa_i[i] = na_i[i];
+      fb_i[i] = nb_i[i];
+    }
+    if (!DIAG) {
+#pragma unroll
+      for (int j = 0; j < NJ2; ++j) {
+        fa_j[j] = na_j[j];
+        fb_j[j] = nb_j[j];
+      }
+    }
+  }
+  // thread-local trace: lane (g,t) holds T[x0+g, i, j] of walker 4wg+t
+  double pr = 0.0, pi = 0.0;
+#pragma unroll
+  for (int i = 0; i < NI; ++i)
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+      const double ar = acc1[i][j][0], ai = acc1[i][j][1];
+      const double br = DIAG ? acc1[j][i][0] : acc2[j][i][0];
+      const double bi = DIAG ? acc1[j][i][1] : acc2[j][i][1];
+      pr += ar * br - ai * bi;
+      pi += ar * bi + ai * br;
+    }
+  const double f = DIAG ? 1.0 : 2.0;
+  sum_re += f * pr;
+  sum_im += f * pi;
+}
+
 template <int BS, bool BSMEM>
 __global__ void __launch_bounds__(EX_WARPS * 32, 1) exchange_kernel(ExArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -101,83 +191,34 @@ __global__ void __launch_bounds__(EX_WARPS * 32, 1) exchange_kernel(ExArgs a) {
 
     double sum_re = 0.0, sum_im = 0.0;
     const int nitems = d.XG * npb;
+    const int rowstride = d.KC * 32;
     for (int it = warp; it < nitems; it += EX_WARPS) {
       const int xg = it / npb, pb = it % npb;
       const int bI = pbI[pb], bJ = pbJ[pb];
-      const bool diag = (bI == bJ);
       const int I0 = bI * base + min(bI, rem), ni = base + (bI < rem ? 1 : 0);
       const int J0 = bJ * base + min(bJ, rem), nj = base + (bJ < rem ? 1 : 0);
-
       const double* aI = RFs + ((size_t)xg * ns + I0) * d.KC * 32 + lane;
       const double* aJ = RFs + ((size_t)xg * ns + J0) * d.KC * 32 + lane;
       const double* bIp = Bsrc + (size_t)I0 * d.KC * 32 + boff;
       const double* bJp = Bsrc + (size_t)J0 * d.KC * 32 + boff;
-      const int rowstride = d.KC * 32;
-
-      double acc1[BS][BS][2], acc2[BS][BS][2];
-#pragma unroll
-      for (int i = 0; i < BS; ++i)
-#pragma unroll
-        for (int j = 0; j < BS; ++j) {
-          acc1[i][j][0] = acc1[i][j][1] = 0.0;
-          acc2[i][j][0] = acc2[i][j][1] = 0.0;
-        }
-      double fa_i[BS], fa_j[BS], fb_i[BS], fb_j[BS];
-      double na_i[BS], na_j[BS], nb_i[BS], nb_j[BS];
-#pragma unroll
-      for (int i = 0; i < BS; ++i) {
-        const int ii = (i < ni) ? i : 0, jj = (i < nj) ? i : 0;
-        fa_i[i] = ldg_nc(aI + ii * rowstride);
-        fa_j[i] = ldg_nc(aJ + jj * rowstride);
-        fb_i[i] = BSMEM ? bIp[ii * rowstride] : ldg_nc(bIp + ii * rowstride);
-        fb_j[i] = BSMEM ? bJp[jj * rowstride] : ldg_nc(bJp + jj * rowstride);
+      const int code = (bI == bJ ? 16 : 0) + (ni - 1) * 4 + (nj - 1);
+#define PXB_EX_CASE(NI_, NJ_)                                                                       \
+  case (NI_ - 1) * 4 + (NJ_ - 1):                                                                   \
+    exchange_item<NI_, NJ_, false, BSMEM>(aI, aJ, bIp, bJp, rowstride, d.KC, sum_re, sum_im);      \
+    break;
+#define PXB_EX_DIAG(NI_)                                                                            \
+  case 16 + (NI_ - 1) * 4 + (NI_ - 1):                                                              \
+    exchange_item<NI_, NI_, true, BSMEM>(aI, aJ, bIp, bJp, rowstride, d.KC, sum_re, sum_im);       \
+    break;
+      switch (code) {
+        PXB_EX_CASE(1, 1) PXB_EX_CASE(1, 2) PXB_EX_CASE(2, 1) PXB_EX_CASE(2, 2)
+        PXB_EX_CASE(2, 3) PXB_EX_CASE(3, 2) PXB_EX_CASE(3, 3) PXB_EX_CASE(3, 4)
+        PXB_EX_CASE(4, 3) PXB_EX_CASE(4, 4)
+        PXB_EX_DIAG(1) PXB_EX_DIAG(2) PXB_EX_DIAG(3) PXB_EX_DIAG(4)
+        default: __trap();
       }
-      for (int pc = 0; pc < d.KC; ++pc) {
-        const int pn = (pc + 1 < d.KC ? pc + 1 : pc) * 32;
-#pragma unroll
-        for (int i = 0; i < BS; ++i) {
-          const int ii = (i < ni) ? i : 0, jj = (i < nj) ? i : 0;
-          na_i[i] = ldg_nc(aI + ii * rowstride + pn);
-          na_j[i] = ldg_nc(aJ + jj * rowstride + pn);
-          nb_i[i] = BSMEM ? bIp[ii * rowstride + pn] : ldg_nc(bIp + ii * rowstride + pn);
-          nb_j[i] = BSMEM ? bJp[jj * rowstride + pn] : ldg_nc(bJp + jj * rowstride + pn);
-        }
-#pragma unroll
-        for (int i = 0; i < BS; ++i)
-#pragma unroll
-          for (int j = 0; j < BS; ++j)
-            if (i < ni && j < nj) dmma(acc1[i][j][0], acc1[i][j][1], fa_i[i], fb_j[j]);
-        if (!diag) {
-#pragma unroll
-          for (int j = 0; j < BS; ++j)
-#pragma unroll
-            for (int i = 0; i < BS; ++i)
-              if (i < ni && j < nj) dmma(acc2[j][i][0], acc2[j][i][1], fa_j[j], fb_i[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < BS; ++i) {
-          fa_i[i] = na_i[i];
-          fa_j[i] = na_j[i];
-          fb_i[i] = nb_i[i];
-          fb_j[i] = nb_j[i];
-        }
-      }
-      // thread-local trace: lane (g,t) holds T[x0+g, i, j] of walker 4wg+t
-      double pr = 0.0, pi = 0.0;
-#pragma unroll
-      for (int i = 0; i < BS; ++i)
-#pragma unroll
-        for (int j = 0; j < BS; ++j)
-          if (i < ni && j < nj) {
-            const double ar = acc1[i][j][0], ai = acc1[i][j][1];
-            const double br = diag ? acc1[j][i][0] : acc2[j][i][0];
-            const double bi = diag ? acc1[j][i][1] : acc2[j][i][1];
-            pr += ar * br - ai * bi;
-            pi += ar * bi + ai * br;
-          }
-      const double f = diag ? 1.0 : 2.0;
-      sum_re += f * pr;
-      sum_im += f * pi;
+#undef PXB_EX_CASE
+#undef PXB_EX_DIAG
     }
     // reduce over the 8 x-lanes (g) of each walker column t, then over warps
 #pragma unroll

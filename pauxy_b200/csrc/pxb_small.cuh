@@ -76,7 +76,7 @@ __global__ void pack_bf_kernel(const double2* __restrict__ bh1, double* __restri
   }
 }
 
-// psiT[j][p] (real, ld Mp), h1rot [ne][Mp] complex, vbar [Np] complex
+// psiT[p][j] (real, [Mp][ne]), h1rot [ne][Mp] complex, vbar [Np] complex
 __global__ void pack_small_kernel(const double2* __restrict__ psi, const double2* __restrict__ h1rot,
                                   const double2* __restrict__ mf, double* __restrict__ psiT,
                                   double2* __restrict__ h1r, double2* __restrict__ vbar, Dims d,
@@ -92,7 +92,7 @@ __global__ void pack_small_kernel(const double2* __restrict__ psi, const double2
       if (z.y != 0.0) atomicOr(flag, 4);
       h = h1rot[(size_t)j * d.M + p];
     }
-    psiT[idx] = v;
+    psiT[(size_t)p * d.ne + j] = v;
     h1r[idx] = h;
   }
   for (int n = tid; n < d.Np; n += nth) vbar[n] = n < d.N ? mf[n] : make_double2(0.0, 0.0);
@@ -172,17 +172,32 @@ struct GreensArgs {
 
 __device__ __forceinline__ double cabs1(cplx z) { return fabs(z.re) + fabs(z.im); }
 
+// warp-level arg-max of (value, index): largest value, lowest index on ties (as LAPACK izamax)
+__device__ __forceinline__ void warp_argmax(double& v, int& idx) {
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    const double ov = __shfl_xor_sync(0xffffffffu, v, m);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, m);
+    if (ov > v || (ov == v && oi < idx)) {
+      v = ov;
+      idx = oi;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(256) greens_kernel(GreensArgs a) {
   extern __shared__ __align__(16) unsigned char gs_raw[];
   const Dims& d = a.d;
   const int w = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
   const int LD = d.Mp + 1;
   const int nmax = max(d.na, d.nb);
   cplx* ph = reinterpret_cast<cplx*>(gs_raw);          // [ne][LD]
   cplx* lu = ph + (size_t)d.ne * LD;                   // [2][nmax*nmax]
   cplx* rdiag = lu + 2 * nmax * nmax;                  // [2][nmax] reciprocal of U diagonal
   double* red = reinterpret_cast<double*>(rdiag + 2 * nmax);  // [2*nth] reduction scratch
-  int* piv = reinterpret_cast<int*>(red + 2 * nth);    // [2] pivot rows, [2] permutation sign
+  int* piv = reinterpret_cast<int*>(red + 2 * nth);    // [2][nmax] pivot rows, then [2] permutation sign
+  int* psign = piv + 2 * nmax;
   const int wg = w >> 2, wl = w & 3;
 
   // 1. phi -> shared, orbital-major
@@ -192,10 +207,9 @@ __global__ void __launch_bounds__(256) greens_kernel(GreensArgs a) {
                                                   wl * 8 + (p & 3) * 2);
     ph[i * LD + p] = {v.x, v.y};
   }
-  if (tid < 2) piv[2 + tid] = 1;
   __syncthreads();
 
-  // 2. O_s[i][j] = sum_p phi[p, i] psi[p, j]     (psi real)
+  // 2. O_s[i][j] = sum_p phi[p, i] psi[p, j]     (psi real, stored [p][j]: lanes read consecutive j)
   const int npair = d.na * d.na + d.nb * d.nb;
   for (int idx = tid; idx < npair; idx += nth) {
     int s = 0, r = idx;
@@ -206,10 +220,11 @@ __global__ void __launch_bounds__(256) greens_kernel(GreensArgs a) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     const int i = r / ns, j = r % ns;
     const cplx* pr = ph + (size_t)(ioff + i) * LD;
-    const double* ps = a.psiT + (size_t)(ioff + j) * d.Mp;
+    const double* ps = a.psiT + ioff + j;  // psiT is [Mp][ne] here
     double sr = 0.0, si = 0.0;
+#pragma unroll 4
     for (int p = 0; p < d.M; ++p) {
-      const double c = ps[p];
+      const double c = __ldg(ps + (size_t)p * d.ne);
       sr += pr[p].re * c;
       si += pr[p].im * c;
     }
@@ -217,78 +232,56 @@ __global__ void __launch_bounds__(256) greens_kernel(GreensArgs a) {
   }
   __syncthreads();
 
-  // 3. LU with partial pivoting, both spins in lock step; row swaps are applied
-  //    to the right-hand side rows (phi^T) as they happen
-  for (int k = 0; k < nmax; ++k) {
-    if (tid < 2) {
-      const int s = tid, ns = s ? d.nb : d.na;
-      if (k < ns) {
-        cplx* L = lu + s * nmax * nmax;
-        int best = k;
-        double bv = cabs1(L[k * ns + k]);
-        for (int i = k + 1; i < ns; ++i) {
-          const double v = cabs1(L[i * ns + k]);
-          if (v > bv) {
-            bv = v;
-            best = i;
-          }
+  // 3. LU with partial pivoting: one warp per spin, no block-level barriers
+  if (warp < 2) {
+    const int s = warp, ns = s ? d.nb : d.na;
+    cplx* L = lu + s * nmax * nmax;
+    int sign = 1;
+    for (int k = 0; k < ns; ++k) {
+      double bv = -1.0;
+      int bi = k;
+      for (int i = k + lane; i < ns; i += 32) {
+        const double v = cabs1(L[i * ns + k]);
+        if (v > bv) {
+          bv = v;
+          bi = i;
         }
-        piv[s] = best;
-        if (best != k) piv[2 + s] = -piv[2 + s];
       }
-    }
-    __syncthreads();
-    // swap rows k <-> piv in LU and in the RHS
-    for (int s = 0; s < 2; ++s) {
-      const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
-      if (k >= ns) continue;
-      const int pr = piv[s];
-      if (pr == k) continue;
-      cplx* L = lu + s * nmax * nmax;
-      for (int j = tid; j < ns; j += nth) {
-        cplx tmp = L[k * ns + j];
-        L[k * ns + j] = L[pr * ns + j];
-        L[pr * ns + j] = tmp;
-      }
-      if (a.want_theta)
-        for (int p = tid; p < d.Mp; p += nth) {
-          cplx tmp = ph[(ioff + k) * LD + p];
-          ph[(ioff + k) * LD + p] = ph[(ioff + pr) * LD + p];
-          ph[(ioff + pr) * LD + p] = tmp;
+      warp_argmax(bv, bi);
+      if (lane == 0) piv[s * nmax + k] = bi;
+      if (bi != k) {
+        sign = -sign;
+        for (int j = lane; j < ns; j += 32) {
+          const cplx tmp = L[k * ns + j];
+          L[k * ns + j] = L[bi * ns + j];
+          L[bi * ns + j] = tmp;
         }
-    }
-    __syncthreads();
-    // multipliers
-    for (int s = 0; s < 2; ++s) {
-      const int ns = s ? d.nb : d.na;
-      if (k >= ns) continue;
-      cplx* L = lu + s * nmax * nmax;
+      }
+      __syncwarp();
       const cplx ukk = L[k * ns + k];
-      for (int i = k + 1 + tid; i < ns; i += nth) L[i * ns + k] = cdiv(L[i * ns + k], ukk);
-    }
-    __syncthreads();
-    // trailing update
-    for (int s = 0; s < 2; ++s) {
-      const int ns = s ? d.nb : d.na;
-      if (k >= ns) continue;
-      cplx* L = lu + s * nmax * nmax;
+      const cplx rk = cdiv({1.0, 0.0}, ukk);
+      if (lane == 0) rdiag[s * nmax + k] = rk;
+      for (int i = k + 1 + lane; i < ns; i += 32) L[i * ns + k] = cdiv(L[i * ns + k], ukk);
+      __syncwarp();
       const int m = ns - k - 1;
-      for (int idx = tid; idx < m * m; idx += nth) {
+      for (int idx = lane; idx < m * m; idx += 32) {
         const int i = k + 1 + idx / m, j = k + 1 + idx % m;
         L[i * ns + j] = csub(L[i * ns + j], cmul(L[i * ns + k], L[k * ns + j]));
       }
+      __syncwarp();
     }
-    __syncthreads();
+    if (lane == 0) psign[s] = sign;
   }
+  __syncthreads();
 
-  // 4. sign * exp(logdet)  (numpy.linalg.slogdet semantics), reciprocal diagonal
+  // 4. sign * exp(logdet)  (numpy.linalg.slogdet semantics)
   if (tid == 0) {
     cplx sign = {1.0, 0.0};
     double logdet = 0.0;
     for (int s = 0; s < 2; ++s) {
       const int ns = s ? d.nb : d.na;
       const cplx* L = lu + s * nmax * nmax;
-      if (piv[2 + s] < 0) sign = {-sign.re, -sign.im};
+      if (ns > 0 && psign[s] < 0) sign = {-sign.re, -sign.im};
       for (int k = 0; k < ns; ++k) {
         const cplx u = L[k * ns + k];
         const double au = hypot(u.re, u.im);
@@ -300,18 +293,22 @@ __global__ void __launch_bounds__(256) greens_kernel(GreensArgs a) {
     a.ovlp_out[w] = make_double2(sign.re * e, sign.im * e);
   }
   if (!a.want_theta) return;
-  for (int idx = tid; idx < 2 * nmax; idx += nth) {
-    const int s = idx / nmax, k = idx % nmax, ns = s ? d.nb : d.na;
-    if (k < ns) rdiag[idx] = cdiv({1.0, 0.0}, lu[s * nmax * nmax + k * ns + k]);
-  }
-  __syncthreads();
 
-  // 5. solve L U Theta = P phi^T, one right-hand-side column p per thread
+  // 5. solve L U Theta = P phi^T, one right-hand-side column p per thread (the row
+  //    interchanges are applied to the thread's own column first)
   for (int idx = tid; idx < 2 * d.Mp; idx += nth) {
     const int s = idx / d.Mp, p = idx % d.Mp;
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     const cplx* L = lu + s * nmax * nmax;
     cplx* col = ph + (size_t)ioff * LD + p;
+    for (int k = 0; k < ns; ++k) {
+      const int pk = piv[s * nmax + k];
+      if (pk != k) {
+        const cplx tmp = col[k * LD];
+        col[k * LD] = col[pk * LD];
+        col[pk * LD] = tmp;
+      }
+    }
     for (int i = 1; i < ns; ++i) {
       cplx acc = col[i * LD];
       for (int j = 0; j < i; ++j) acc = csub(acc, cmul(L[i * ns + j], col[j * LD]));
@@ -340,24 +337,31 @@ __global__ void __launch_bounds__(256) greens_kernel(GreensArgs a) {
     }
   }
   if (a.e1b_out != nullptr) {
-    red[tid] = er;
-    red[nth + tid] = ei;
-    __syncthreads();
-    for (int s = nth >> 1; s > 0; s >>= 1) {
-      if (tid < s) {
-        red[tid] += red[tid + s];
-        red[nth + tid] += red[nth + tid + s];
-      }
-      __syncthreads();
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+      er += __shfl_xor_sync(0xffffffffu, er, m);
+      ei += __shfl_xor_sync(0xffffffffu, ei, m);
     }
-    if (tid == 0) a.e1b_out[w] = make_double2(red[0], red[nth]);
+    if (lane == 0) {
+      red[warp] = er;
+      red[32 + warp] = ei;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double sr = 0.0, si = 0.0;
+      for (int k = 0; k < (nth >> 5); ++k) {
+        sr += red[k];
+        si += red[32 + k];
+      }
+      a.e1b_out[w] = make_double2(sr, si);
+    }
   }
 }
 
 inline size_t greens_smem_bytes(const Dims& d, int nth) {
   const int nmax = d.na > d.nb ? d.na : d.nb;
   return sizeof(cplx) * ((size_t)d.ne * (d.Mp + 1) + 2 * nmax * nmax + 2 * nmax) +
-         sizeof(double) * 2 * nth + 4 * sizeof(int) + 16;
+         sizeof(double) * 2 * nth + (2 * nmax + 4) * sizeof(int) + 16;
 }
 
 // ============================================================================
@@ -598,7 +602,6 @@ struct WeightArgs {
   double* weight;
   double2* ot;
   double2* ehyb;
-  const double2* ovlp_old;
   const double2* ovlp_new;
   const double2* cmfcfb;
   const int* active;
@@ -615,7 +618,9 @@ __global__ void weight_kernel(WeightArgs a) {
   if (w >= d.W) return;
   double wt = a.weight[w];
   if (a.active[w]) {
-    const double2 oo = a.ovlp_old[w], on = a.ovlp_new[w];
+    // ovlp_old == walker.ot: the overlap of the walker before this step (single_det.py:321 equals
+    // the stored ot up to rounding; after a re-orthogonalisation ot was divided by detR)
+    const double2 oo = a.ot[w], on = a.ovlp_new[w];
     const cplx ratio = cdiv({on.x, on.y}, {oo.x, oo.y});
     const double2 cmf = a.cmfcfb[2 * w], cfb = a.cmfcfb[2 * w + 1];
     // cmath.log: principal branch
@@ -916,6 +921,8 @@ __global__ void __launch_bounds__(1024) comb_plan_kernel(CombArgs a) {
 // payload copy: phi (OF layout) + per-walker scalars
 struct CopyArgs {
   double* phi;
+  double* theta;   // rotated Green's function travels with the walker (stays valid)
+  double2* e1b;
   double* weight;
   double* unscaled;
   double2* ot;
@@ -927,7 +934,7 @@ struct CopyArgs {
 };
 
 __device__ __forceinline__ size_t payload_doubles(const Dims& d) {
-  return (size_t)d.ne * d.KC * 8 + 16;
+  return (size_t)2 * d.ne * d.KC * 8 + 18;
 }
 
 // pairs: device list [1 + 2*n] of GLOBAL indices; only pairs with both ends on
@@ -944,8 +951,10 @@ __global__ void __launch_bounds__(256) copy_pairs_kernel(CopyArgs a, const int* 
       const size_t so = ((size_t)(src >> 2) * n8 + r) * 32 + (src & 3) * 8 + q * 2;
       const size_t dn = ((size_t)(dst >> 2) * n8 + r) * 32 + (dst & 3) * 8 + q * 2;
       *reinterpret_cast<double2*>(a.phi + dn) = *reinterpret_cast<const double2*>(a.phi + so);
+      *reinterpret_cast<double2*>(a.theta + dn) = *reinterpret_cast<const double2*>(a.theta + so);
     }
     if (threadIdx.x == 0) {
+      a.e1b[dst] = a.e1b[src];
       a.weight[dst] = a.weight[src];
       a.unscaled[dst] = a.unscaled[src];
       a.ot[dst] = a.ot[src];
@@ -968,8 +977,10 @@ __global__ void __launch_bounds__(256) copy_list_kernel(CopyArgs a, const int* s
       const size_t so = ((size_t)(src >> 2) * n8 + r) * 32 + (src & 3) * 8 + q * 2;
       const size_t dn = ((size_t)(dst >> 2) * n8 + r) * 32 + (dst & 3) * 8 + q * 2;
       *reinterpret_cast<double2*>(a.phi + dn) = *reinterpret_cast<const double2*>(a.phi + so);
+      *reinterpret_cast<double2*>(a.theta + dn) = *reinterpret_cast<const double2*>(a.theta + so);
     }
     if (threadIdx.x == 0) {
+      a.e1b[dst] = a.e1b[src];
       a.weight[dst] = a.weight[src];
       a.unscaled[dst] = a.unscaled[src];
       a.ot[dst] = a.ot[src];
@@ -992,15 +1003,21 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
     const int n8 = d.ne * d.KC;
     for (int idx = threadIdx.x; idx < n8 * 4; idx += blockDim.x) {
       const int r = idx >> 2, q = idx & 3;
-      double2* g = reinterpret_cast<double2*>(a.phi + ((size_t)(w >> 2) * n8 + r) * 32 + (w & 3) * 8 + q * 2);
+      const size_t go = ((size_t)(w >> 2) * n8 + r) * 32 + (w & 3) * 8 + q * 2;
+      double2* g = reinterpret_cast<double2*>(a.phi + go);
+      double2* gt = reinterpret_cast<double2*>(a.theta + go);
       double2* l = reinterpret_cast<double2*>(b + (size_t)r * 8 + q * 2);
-      if (unpack)
+      double2* lt = reinterpret_cast<double2*>(b + (size_t)n8 * 8 + (size_t)r * 8 + q * 2);
+      if (unpack) {
         *g = *l;
-      else
+        *gt = *lt;
+      } else {
         *l = *g;
+        *lt = *gt;
+      }
     }
     if (threadIdx.x == 0) {
-      double* s = b + (size_t)n8 * 8;
+      double* s = b + (size_t)2 * n8 * 8;
       if (unpack) {
         a.weight[w] = s[0];
         a.unscaled[w] = s[1];
@@ -1009,6 +1026,7 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
         a.detR[w] = s[6];
         a.log_detR[w] = s[7];
         for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)w + k] = make_double2(s[8 + 2 * k], s[9 + 2 * k]);
+        a.e1b[w] = make_double2(s[14], s[15]);
       } else {
         s[0] = a.weight[w];
         s[1] = a.unscaled[w];
@@ -1022,7 +1040,9 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
           s[8 + 2 * k] = a.eloc[3 * (size_t)w + k].x;
           s[9 + 2 * k] = a.eloc[3 * (size_t)w + k].y;
         }
-        s[14] = s[15] = 0.0;
+        s[14] = a.e1b[w].x;
+        s[15] = a.e1b[w].y;
+        s[16] = s[17] = 0.0;
       }
     }
   }

@@ -1,11 +1,17 @@
 // Taylor expansion  phi <- sum_{n<=order} VHS^n / n! phi   per walker
 // (propagation/continuous.py:82-111; both spin blocks use the same VHS,
-// :169-171).  complex x complex as two real DMMA streams:
+// :169-171), evaluated in Horner form
+//     S_order = phi,   S_{n-1} = phi + (VHS S_n) / n,   result = S_0
+// which is the same polynomial as the reference's running sum (Temp = VHS Temp / n;
+// phi += Temp) with rounding differences at the 1e-16 level, and needs no
+// read-modify-write of phi between orders.
+//
+// complex x complex as two real DMMA streams:
 //     C = A_re * B^ + A_im * (i B)^        B^ = [.. (o,re) (o,im) ..] real columns
 // One CTA = one walker x one chunk of orbitals (columns are independent).
-// T_n lives in shared memory in B-fragment order, the accumulators of T_{n+1}
-// in registers; VHS (A-fragment order, written by the VHS GEMM epilogue)
-// streams from L2 once per order; phi accumulates in place in HBM/L2.
+// S_n lives in shared memory in B-fragment order, the accumulators of the next
+// iterate in registers; VHS (A-fragment order, written by the VHS GEMM
+// epilogue) streams from L2 once per order.
 #pragma once
 #include "pxb_common.cuh"
 
@@ -20,9 +26,13 @@ struct TaylorArgs {
   int nchunks;
 };
 
-// WMT m-tiles per warp, NTMAX >= n-tiles per CTA
-template <int WMT, int NTMAX>
-__global__ void __launch_bounds__(256) taylor_kernel(TaylorArgs a) {
+// position of B element (k = t, n = g) inside a 32-double block: the 16 lanes of a
+// half warp (g < 4 or g >= 4) read 16 consecutive doubles -> no bank conflicts
+__device__ __forceinline__ int tb_off(int k, int n) { return (n >> 2) * 16 + k * 4 + (n & 3); }
+
+// WMT m-tiles per warp, NTMAX >= n-tiles per CTA, NWARPS warps per CTA
+template <int WMT, int NTMAX, int NWARPS, int MINB>
+__global__ void __launch_bounds__(NWARPS * 32, MINB) taylor_kernel(TaylorArgs a) {
   extern __shared__ __align__(16) double Ts[];  // [KC][NT][32]
   const Dims& d = a.d;
   const int w = blockIdx.x / a.nchunks, chunk = blockIdx.x % a.nchunks;
@@ -34,9 +44,9 @@ __global__ void __launch_bounds__(256) taylor_kernel(TaylorArgs a) {
   const int g = lane >> 2, t = lane & 3;
   const int wg = w >> 2, wl = w & 3;
 
-  // T_0 = phi columns o0..o0+no (zero padded to 4*NT orbitals)
+  // S_order = phi columns o0..o0+no (zero padded to 4*NT orbitals)
   for (int idx = tid; idx < d.KC * NT * 16; idx += blockDim.x) {
-    // idx -> (kc, nt, tt, oo): element pair (re, im) of orbital o0 + 4nt + oo at p = 4kc + tt
+    // idx -> (kc, nt, tt, oo): (re, im) of orbital o0 + 4nt + oo at basis index p = 4kc + tt
     const int oo = idx & 3, tt = (idx >> 2) & 3, r = idx >> 4;
     const int nt = r % NT, kc = r / NT;
     const int ol = 4 * nt + oo;
@@ -44,15 +54,17 @@ __global__ void __launch_bounds__(256) taylor_kernel(TaylorArgs a) {
     if (ol < no)
       v = *reinterpret_cast<const double2*>(a.phi + (((size_t)wg * d.ne + o0 + ol) * d.KC + kc) * 32 +
                                             wl * 8 + tt * 2);
-    *reinterpret_cast<double2*>(Ts + ((size_t)kc * NT + nt) * 32 + tt * 8 + oo * 2) = v;
+    *reinterpret_cast<double2*>(Ts + ((size_t)kc * NT + nt) * 32 + tb_off(tt, 2 * oo)) = v;
   }
   __syncthreads();
 
   const int mt0 = warp * WMT;
   const double* Aw = a.VF + (size_t)w * vf_walker(d);
   const bool warp_active = mt0 < d.MT;
+  const int boff = tb_off(t, g), boffp = tb_off(t, g ^ 1);
+  const double sgn = (g & 1) ? 1.0 : -1.0;  // (i B)^: (re, im) -> (-im, re)
 
-  for (int n = 1; n <= d.exp_order; ++n) {
+  for (int n = d.exp_order; n >= 1; --n) {
     double acc[WMT][NTMAX][2];
 #pragma unroll
     for (int i = 0; i < WMT; ++i)
@@ -76,13 +88,12 @@ __global__ void __launch_bounds__(256) taylor_kernel(TaylorArgs a) {
           nr[i] = ldg_nc(Ap[i] + kn);
           ni[i] = ldg_nc(Ap[i] + kn + 32);
         }
-        const double* Tk = Ts + (size_t)kc * NT * 32 + t * 8;
+        const double* Tk = Ts + (size_t)kc * NT * 32;
 #pragma unroll
         for (int j = 0; j < NTMAX; ++j) {
           if (j < NT) {
-            const double b = Tk[j * 32 + g];
-            const double bp = Tk[j * 32 + (g ^ 1)];
-            const double bq = (g & 1) ? bp : -bp;  // (i B)^: (re,im) -> (-im, re)
+            const double b = Tk[j * 32 + boff];
+            const double bq = sgn * Tk[j * 32 + boffp];
 #pragma unroll
             for (int i = 0; i < WMT; ++i) {
               dmma(acc[i][j][0], acc[i][j][1], ar[i], b);
@@ -97,7 +108,7 @@ __global__ void __launch_bounds__(256) taylor_kernel(TaylorArgs a) {
         }
       }
     }
-    __syncthreads();  // every warp has finished reading T_{n-1}
+    __syncthreads();  // every warp has finished reading S_n
     if (warp_active) {
 #pragma unroll
       for (int i = 0; i < WMT; ++i) {
@@ -108,18 +119,19 @@ __global__ void __launch_bounds__(256) taylor_kernel(TaylorArgs a) {
 #pragma unroll
           for (int j = 0; j < NTMAX; ++j) {
             if (j < NT) {
-              // divide (not multiply by reciprocal) as the reference does: Temp = VHS.dot(Temp) / n
-              const double vr = acc[i][j][0] / (double)n, vi = acc[i][j][1] / (double)n;
-              *reinterpret_cast<double2*>(Ts + ((size_t)kc2 * NT + j) * 32 + t2 * 8 + 2 * t) =
-                  make_double2(vr, vi);
               const int ol = 4 * j + t;
-              if (ol < no) {
-                double2* dst = reinterpret_cast<double2*>(
-                    a.phi + (((size_t)wg * d.ne + o0 + ol) * d.KC + kc2) * 32 + wl * 8 + t2 * 2);
-                double2 cur = *dst;
-                cur.x += vr;
-                cur.y += vi;
-                *dst = cur;
+              double2* gp = reinterpret_cast<double2*>(
+                  a.phi + (((size_t)wg * d.ne + o0 + min(ol, no - 1)) * d.KC + kc2) * 32 + wl * 8 + t2 * 2);
+              double2 p0 = make_double2(0.0, 0.0);
+              if (ol < no) p0 = *gp;
+              // the reference divides (Temp = VHS.dot(Temp) / n); so do we
+              const double vr = p0.x + acc[i][j][0] / (double)n;
+              const double vi = p0.y + acc[i][j][1] / (double)n;
+              if (n > 1) {
+                *reinterpret_cast<double2*>(Ts + ((size_t)kc2 * NT + j) * 32 + tb_off(t2, 2 * t)) =
+                    make_double2(vr, vi);
+              } else if (ol < no) {
+                *gp = make_double2(vr, vi);
               }
             }
           }
