@@ -2,6 +2,7 @@
 #include "../../include/pauxy_b200.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -10,6 +11,7 @@
 #include "pxb_common.cuh"
 #include "pxb_exchange.cuh"
 #include "pxb_gemm.cuh"
+#include "pxb_greens.cuh"
 #include "pxb_small.cuh"
 #include "pxb_taylor.cuh"
 
@@ -24,7 +26,7 @@ struct Region {
 enum ArenaId {
   A_LF, A_RF, A_BF, A_PSIT, A_H1ROT, A_VBAR,
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
-  A_EXX, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG,
+  A_EXX, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -44,6 +46,7 @@ struct pxb_context {
   long long launches = 0;  // kernels launched through this handle
   // Theta / overlap / e1b (A_THETA, A_E1B) correspond to the current walkers; X to the current Theta
   bool theta_valid = false, x_valid = false;
+  bool gemm_tma = true;  // TMA-fed persistent GEMM (PXB_GEMM=direct selects the L1/L2-streaming one)
   std::string err;
 
   template <class T>
@@ -105,26 +108,45 @@ CopyArgs copy_args(pxb_handle h) {
 }
 
 // ---- stage launchers ---------------------------------------------------------
+template <int NMT>
+int launch_greens(pxb_handle h, const GreensArgs& a, size_t smem, cudaStream_t st) {
+  PXB_CUDA(h, cudaFuncSetAttribute(greens_kernel<NMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  PXB_CUDA(h, cudaFuncSetAttribute(greens_kernel<NMT>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                   (int)cudaSharedmemCarveoutMaxShared));
+  ++h->launches;
+  greens_kernel<NMT><<<2 * h->d.Wp, GR_THREADS, smem, st>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
 int run_greens(pxb_handle h, const double* phi, bool want_theta, double2* ovlp_out, bool with_e1b,
                cudaStream_t st) {
   const Dims& d = h->d;
   GreensArgs a;
   a.phi = phi;
   a.theta = h->ptr<double>(A_THETA);
-  a.psiT = h->ptr<double>(A_PSIT);
+  a.PF = h->ptr<double>(A_PF);
   a.h1rot = h->ptr<double2>(A_H1ROT);
-  a.ovlp_out = ovlp_out;
-  a.e1b_out = (with_e1b || want_theta) ? h->ptr<double2>(A_E1B) : nullptr;
+  a.slog = h->ptr<double>(A_SLOG);
+  a.e1b_part = h->ptr<double2>(A_E1BP);
   a.d = d;
   a.want_theta = want_theta ? 1 : 0;
-  const int nth = 256;
-  const size_t smem = greens_smem_bytes(d, nth);
+  const size_t smem = greens_smem_bytes(d);
   if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "greens: problem too large for shared memory");
-  PXB_CUDA(h, cudaFuncSetAttribute(greens_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PXB_CUDA(h, cudaFuncSetAttribute(greens_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   (int)cudaSharedmemCarveoutMaxShared));
+  const int nmt = ((d.na > d.nb ? d.na : d.nb) + 7) >> 3;
+  int rc;
+  if (nmt <= 1) rc = launch_greens<1>(h, a, smem, st);
+  else if (nmt <= 2) rc = launch_greens<2>(h, a, smem, st);
+  else if (nmt <= 3) rc = launch_greens<3>(h, a, smem, st);
+  else if (nmt <= 4) rc = launch_greens<4>(h, a, smem, st);
+  else if (nmt <= 5) rc = launch_greens<5>(h, a, smem, st);
+  else if (nmt <= 6) rc = launch_greens<6>(h, a, smem, st);
+  else if (nmt <= 8) rc = launch_greens<8>(h, a, smem, st);
+  else return fail(h, PXB_ERR_ARG, "greens: more than 64 occupied orbitals per spin");
+  if (rc) return rc;
   ++h->launches;
-  greens_kernel<<<d.Wp, nth, smem, st>>>(a);
+  greens_combine_kernel<<<(d.Wp + 255) / 256, 256, 0, st>>>(
+      a.slog, a.e1b_part, ovlp_out, (want_theta || with_e1b) ? h->ptr<double2>(A_E1B) : nullptr, d.Wp);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -150,7 +172,11 @@ int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
     g.NTiles = d.WG;
     g.KS = ns * d.KC;
     ++h->launches;
-    PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
+    // 16 x 8 tile blocks: 4 * WG/8 work units keep the 148 persistent CTAs balanced (XG is only ~63)
+    if (h->gemm_tma)
+      PXB_CUDA(h, (launch_gemm_tma<4, 4, 4, 2>(g, epi, 1, h->sm_count, st)));
+    else
+      PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
   }
   return PXB_OK;
 }
@@ -169,7 +195,10 @@ int run_vhs_gemm(pxb_handle h, cudaStream_t st) {
   g.KS = d.NKC;
   EpiVHS epi{h->ptr<double>(A_VF), d.KC, d.MT, d.sqrt_dt, vf_walker(d)};
   ++h->launches;
-  PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
+  if (h->gemm_tma)
+    PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
+  else
+    PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
   return PXB_OK;
 }
 
@@ -189,23 +218,28 @@ int run_one_body(pxb_handle h, const double* in, double* out, const int* active,
     g.NTiles = d.WG * ns;
     g.KS = d.KC;
     EpiOF epi{out, active, d.ne, d.KC, ioff, ns};
+    ++h->launches;
     if (d.MT % 7 == 0) {
-      ++h->launches;
-      PXB_CUDA(h, (launch_gemm<7, 4, 2, 4>(g, epi, 1, st)));
+      if (h->gemm_tma)
+        PXB_CUDA(h, (launch_gemm_tma<7, 4, 2, 4>(g, epi, 1, h->sm_count, st)));
+      else
+        PXB_CUDA(h, (launch_gemm<7, 4, 2, 4>(g, epi, 1, st)));
     } else {
-      ++h->launches;
-      PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
+      if (h->gemm_tma)
+        PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
+      else
+        PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
     }
   }
   return PXB_OK;
 }
 
-template <int WMT, int NTMAX, int NWARPS, int MINB>
-int launch_taylor(pxb_handle h, TaylorArgs& a, int NT, int nwarps, cudaStream_t st) {
+template <int WMT, int NT, int NWARPS, int MINB>
+int launch_taylor(pxb_handle h, TaylorArgs& a, int nwarps, cudaStream_t st) {
   const Dims& d = h->d;
   const size_t smem = (size_t)d.KC * NT * 32 * sizeof(double);
   if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "taylor: tile too large for shared memory");
-  auto kern = taylor_kernel<WMT, NTMAX, NWARPS, MINB>;
+  auto kern = taylor_kernel<WMT, NT, NWARPS, MINB>;
   PXB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PXB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    (int)cudaSharedmemCarveoutMaxShared));
@@ -226,7 +260,6 @@ int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   int nchunks = (d.ne + 47) / 48;
   int ochunk = round_up((d.ne + nchunks - 1) / nchunks, 4);
   nchunks = (d.ne + ochunk - 1) / ochunk;
-  a.ochunk = ochunk;
   a.nchunks = nchunks;
   const int NT = ochunk / 4;
   // m-tiles per warp: 2 when that fits in 8 warps, else as many as needed
@@ -234,16 +267,26 @@ int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   if (wmt < 2 && d.MT >= 2) wmt = 2;
   if (wmt > 4) return fail(h, PXB_ERR_ARG, "taylor: nbasis > 256 not supported in this version");
   const int nwarps = (d.MT + wmt - 1) / wmt;
-#define PXB_TAYLOR_CASE(W_, N_, NW_, MB_) \
-  if (wmt == W_ && NT <= N_ && nwarps <= NW_) return launch_taylor<W_, N_, NW_, MB_>(h, a, NT, nwarps, st);
+  // n-tiles are a compile-time constant: the chunk is padded with zero orbitals up to it
+#define PXB_TAYLOR_CASE(W_, N_, NW_, MB_)                   \
+  if (wmt == W_ && NT <= N_ && nwarps <= NW_) {            \
+    a.ochunk = ochunk;                                     \
+    return launch_taylor<W_, N_, NW_, MB_>(h, a, nwarps, st); \
+  }
+  PXB_TAYLOR_CASE(1, 2, 8, 2)
   PXB_TAYLOR_CASE(1, 4, 8, 2)
+  PXB_TAYLOR_CASE(1, 8, 8, 2)
   PXB_TAYLOR_CASE(1, 12, 8, 2)
+  PXB_TAYLOR_CASE(2, 2, 8, 2)
   PXB_TAYLOR_CASE(2, 4, 8, 2)
+  PXB_TAYLOR_CASE(2, 6, 8, 2)
   PXB_TAYLOR_CASE(2, 8, 8, 2)
+  PXB_TAYLOR_CASE(2, 10, 8, 2)
   PXB_TAYLOR_CASE(2, 11, 7, 2)
-  PXB_TAYLOR_CASE(2, 12, 7, 2)
   PXB_TAYLOR_CASE(2, 12, 8, 1)
+  PXB_TAYLOR_CASE(3, 10, 8, 1)
   PXB_TAYLOR_CASE(3, 12, 8, 1)
+  PXB_TAYLOR_CASE(4, 10, 8, 1)
   PXB_TAYLOR_CASE(4, 12, 8, 1)
 #undef PXB_TAYLOR_CASE
   return fail(h, PXB_ERR_ARG, "taylor: no kernel instance for this shape");
@@ -314,6 +357,10 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   pxb_context* h = new (std::nothrow) pxb_context();
   if (!h) return PXB_ERR_ARG;
   h->cfg = *cfg;
+  {
+    const char* g = getenv("PXB_GEMM");
+    if (g && strcmp(g, "direct") == 0) h->gemm_tma = false;
+  }
   Dims& d = h->d;
   d.M = cfg->nbasis;
   d.na = cfg->nup;
@@ -375,6 +422,10 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_GWS, Wt * 8);
   add(A_CPROBS, Wt * 8);
   add(A_FLAG, 256);
+  add(A_PF, (size_t)(((d.na + 7) >> 3) + ((d.nb + 7) >> 3)) * d.KC * 32 * 8);
+  add(A_SLOG, W * 8 * 8);
+  add(A_E1BP, W * 2 * 16);
+  add(A_QRLD, W * 2 * 8);
   add(A_FIELD0 + PXB_F_WEIGHT, W * 8);
   add(A_FIELD0 + PXB_F_UNSCALED_WEIGHT, W * 8);
   add(A_FIELD0 + PXB_F_OT, W * 16);
@@ -450,6 +501,9 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
       static_cast<const double2*>(psi), static_cast<const double2*>(h1rot),
       static_cast<const double2*>(mf_shift), h->ptr<double>(A_PSIT), h->ptr<double2>(A_H1ROT),
       h->ptr<double2>(A_VBAR), d, flag);
+  ++h->launches;
+  pack_pf_kernel<<<grid_for((size_t)d.ne * d.Mp), 256, 0, st>>>(static_cast<const double2*>(psi),
+                                                                h->ptr<double>(A_PF), d);
   PXB_CUDA(h, cudaGetLastError());
   int hflag = 0;
   PXB_CUDA(h, cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
@@ -577,21 +631,25 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
 int pxb_orthogonalise(pxb_handle h, void* stream) {
   PXB_REQUIRE_READY(h);
   const Dims& d = h->d;
+  cudaStream_t st = S(stream);
   QrArgs a;
   a.phi = h->phi();
-  a.ot = h->field<double2>(PXB_F_OT);
-  a.detR = h->field<double>(PXB_F_DETR);
-  a.log_detR = h->field<double>(PXB_F_LOG_DETR);
+  a.logdet = h->ptr<double>(A_QRLD);
   a.d = d;
-  const int nth = 256;
-  const size_t smem = qr_smem_bytes(d, nth);
+  const size_t smem = qr_smem_bytes(d);
   if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "qr: problem too large for shared memory");
   PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                    (int)cudaSharedmemCarveoutMaxShared));
   ++h->launches;
-  qr_kernel<<<d.Wp, nth, smem, S(stream)>>>(a);
+  qr_kernel<<<2 * d.Wp, GR_THREADS, smem, st>>>(a);
   PXB_CUDA(h, cudaGetLastError());
+  ++h->launches;
+  qr_combine_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(a.logdet, h->field<double2>(PXB_F_OT),
+                                                       h->field<double>(PXB_F_DETR),
+                                                       h->field<double>(PXB_F_LOG_DETR), d.W);
+  PXB_CUDA(h, cudaGetLastError());
+  // Theta = O^-1 phi^T is invariant under phi -> phi R^-1: it stays valid (to rounding)
   return PXB_OK;
 }
 

@@ -138,4 +138,155 @@ inline cudaError_t launch_gemm(const GemmArgs& a, const Epi& epi, int batch, cud
   return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------
+// TMA-fed version: persistent CTAs, one producer warp streaming both operands
+// into a shared-memory ring with 1-D bulk copies (cp.async.bulk -> SASS UBLKCP,
+// completion on mbarriers), CWM x CWN consumer warps issuing DMMA from
+// conflict-free 256 B fragment reads.  The fragment-major HBM layout makes every
+// (tile, k-range) a contiguous run, so no tensor map is needed.
+// ----------------------------------------------------------------------------
+constexpr int GT_STAGES = 3;  // ring depth
+constexpr int GT_KS = 8;      // k-steps per stage (2 KB per tile row and stage)
+
+template <int WM, int WN, int CWM, int CWN>
+constexpr size_t gemm_tma_smem_bytes() {
+  return (size_t)GT_STAGES * (WM * CWM + WN * CWN) * GT_KS * 32 * sizeof(double) + 2 * GT_STAGES * 8 + 128;
+}
+
+template <int WM, int WN, int CWM, int CWN, class Epi>
+__global__ void __launch_bounds__((CWM * CWN + 1) * 32, 1)
+    gemm_tma_kernel(GemmArgs a, Epi epi, int tiles_m, int tiles_n, int batch) {
+  constexpr int TM = WM * CWM, TN = WN * CWN, NCW = CWM * CWN;
+  constexpr int A_STAGE = TM * GT_KS * 32, B_STAGE = TN * GT_KS * 32;  // doubles
+  extern __shared__ __align__(128) double gt_smem[];
+  double* As = gt_smem;
+  double* Bs = gt_smem + GT_STAGES * A_STAGE;
+  uint64_t* full = reinterpret_cast<uint64_t*>(Bs + GT_STAGES * B_STAGE);
+  uint64_t* empty = full + GT_STAGES;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < GT_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCW);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  const int per_z = tiles_m * tiles_n;
+  const int ntiles = per_z * batch;
+  const int nkstage = (a.KS + GT_KS - 1) / GT_KS;
+
+  if (warp == NCW) {
+    // ---------------- producer: lane L streams row L of the stage (A rows, then B rows) -----------
+    static_assert(TM + TN <= 32, "one producer lane per tile row");
+    unsigned it = 0;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+      const int z = tile / per_z, r = tile % per_z;
+      const int mt0 = (r % tiles_m) * TM, nt0 = (r / tiles_m) * TN;
+      const int rows_m = min(TM, a.MTiles - mt0), rows_n = min(TN, a.NTiles - nt0);
+      const double* src = nullptr;
+      int dst_off = 0;
+      bool isA = lane < TM;
+      if (isA) {
+        if (lane < rows_m) src = a.A + (size_t)z * a.strideAz + (size_t)(mt0 + lane) * a.KS * 32;
+        dst_off = lane * GT_KS * 32;
+      } else if (lane < TM + TN) {
+        const int j = lane - TM;
+        if (j < rows_n) {
+          const int nt = nt0 + j;
+          src = a.B + (size_t)z * a.strideBz + (size_t)(nt / a.ntInner) * a.strideBO +
+                (size_t)(nt % a.ntInner) * a.strideBI;
+        }
+        dst_off = j * GT_KS * 32;
+      }
+      for (int ks = 0; ks < nkstage; ++ks, ++it) {
+        const unsigned s = it % GT_STAGES, ph = (it / GT_STAGES) & 1u;
+        mbar_wait(&empty[s], ph ^ 1u);
+        const int k0 = ks * GT_KS, nk = min(GT_KS, a.KS - k0);
+        const unsigned rowbytes = (unsigned)nk * 256u;
+        if (lane == 0) mbar_expect_tx(&full[s], (unsigned)(rows_m + rows_n) * rowbytes);
+        __syncwarp();
+        if (src != nullptr) {
+          double* dst = (isA ? As + (size_t)s * A_STAGE : Bs + (size_t)s * B_STAGE) + dst_off;
+          tma_bulk_g2s(dst, src + (size_t)k0 * 32, rowbytes, &full[s]);
+        }
+      }
+    }
+    return;
+  }
+  // ---------------- consumers ----------------
+  const int wm = warp % CWM, wn = warp / CWM;
+  const int g = lane >> 2, t = lane & 3;
+  const int boff = b_lane_offset(lane);
+  unsigned it = 0;
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    const int z = tile / per_z, r = tile % per_z;
+    const int mt0 = (r % tiles_m) * TM + wm * WM, nt0 = (r / tiles_m) * TN + wn * WN;
+    double acc[WM][WN][2];
+#pragma unroll
+    for (int i = 0; i < WM; ++i)
+#pragma unroll
+      for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int ks = 0; ks < nkstage; ++ks, ++it) {
+      const unsigned s = it % GT_STAGES, ph = (it / GT_STAGES) & 1u;
+      mbar_wait(&full[s], ph);
+      const double* as = As + (size_t)s * A_STAGE + (size_t)wm * WM * GT_KS * 32 + lane;
+      const double* bs = Bs + (size_t)s * B_STAGE + (size_t)wn * WN * GT_KS * 32 + boff;
+      const int nk = min(GT_KS, a.KS - ks * GT_KS);
+      if (nk == GT_KS) {
+#pragma unroll
+        for (int kk = 0; kk < GT_KS; ++kk) {
+          double af[WM], bf[WN];
+#pragma unroll
+          for (int i = 0; i < WM; ++i) af[i] = as[(i * GT_KS + kk) * 32];
+#pragma unroll
+          for (int j = 0; j < WN; ++j) bf[j] = bs[(j * GT_KS + kk) * 32];
+#pragma unroll
+          for (int i = 0; i < WM; ++i)
+#pragma unroll
+            for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      } else {
+        for (int kk = 0; kk < nk; ++kk) {
+          double af[WM], bf[WN];
+#pragma unroll
+          for (int i = 0; i < WM; ++i) af[i] = as[(i * GT_KS + kk) * 32];
+#pragma unroll
+          for (int j = 0; j < WN; ++j) bf[j] = bs[(j * GT_KS + kk) * 32];
+#pragma unroll
+          for (int i = 0; i < WM; ++i)
+#pragma unroll
+            for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+#pragma unroll
+    for (int i = 0; i < WM; ++i) {
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        if (mt0 + i < a.MTiles && nt0 + j < a.NTiles)
+          epi(mt0 + i, nt0 + j, z, g, t, acc[i][j][0], acc[i][j][1]);
+      }
+    }
+  }
+}
+
+template <int WM, int WN, int CWM, int CWN, class Epi>
+inline cudaError_t launch_gemm_tma(const GemmArgs& a, const Epi& epi, int batch, int sm_count,
+                                   cudaStream_t st) {
+  constexpr int TM = WM * CWM, TN = WN * CWN;
+  const int tiles_m = (a.MTiles + TM - 1) / TM, tiles_n = (a.NTiles + TN - 1) / TN;
+  const int ntiles = tiles_m * tiles_n * batch;
+  const size_t smem = gemm_tma_smem_bytes<WM, WN, CWM, CWN>();
+  auto kern = gemm_tma_kernel<WM, WN, CWM, CWN, Epi>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  const int grid = ntiles < sm_count ? ntiles : sm_count;
+  kern<<<grid, (CWM * CWN + 1) * 32, smem, st>>>(a, epi, tiles_m, tiles_n, batch);
+  return cudaGetLastError();
+}
+
 }  // namespace pxb

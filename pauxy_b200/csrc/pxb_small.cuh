@@ -98,6 +98,26 @@ __global__ void pack_small_kernel(const double2* __restrict__ psi, const double2
   for (int n = tid; n < d.Np; n += nth) vbar[n] = n < d.N ? mf[n] : make_double2(0.0, 0.0);
 }
 
+// psi as DMMA B-fragments for the overlap GEMM: PF[s][jt][pc][lane=(g,t)] = psi[4pc+t][ioff_s + 8jt+g]
+__global__ void pack_pf_kernel(const double2* __restrict__ psi, double* __restrict__ PF, Dims d) {
+  const int jt0 = (d.na + 7) >> 3, jt1 = (d.nb + 7) >> 3;
+  const size_t total = (size_t)(jt0 + jt1) * d.KC * 32;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int lane = idx & 31, g = lane >> 2, t = lane & 3;
+    size_t r = idx >> 5;
+    const int pc = r % d.KC;
+    int jt = r / d.KC, s = 0;
+    if (jt >= jt0) {
+      s = 1;
+      jt -= jt0;
+    }
+    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
+    const int p = 4 * pc + t, j = 8 * jt + g;
+    PF[idx] = (p < d.M && j < ns) ? psi[(size_t)p * d.ne + ioff + j].x : 0.0;
+  }
+}
+
 // ============================================================================
 // walker matrix packing: reference layout [W][M][ne] complex <-> OF
 // ============================================================================
@@ -152,311 +172,6 @@ __global__ void vf_to_natural_kernel(const double* __restrict__ VF, double2* __r
                       (p & 7) * 4 + (q & 3);
     out[idx] = make_double2(b[0], b[32]);
   }
-}
-
-// ============================================================================
-// K1: overlap matrix, LU (partial pivoting), slogdet, Theta = O^-1 phi^T, e1b
-//   walkers/single_det.py:295-321 (greens_function) and :170-199 (calc_overlap)
-// One CTA per walker, both spins.
-// ============================================================================
-struct GreensArgs {
-  const double* phi;    // OF
-  double* theta;        // OF (may be null when mode == overlap only)
-  const double* psiT;   // [ne][Mp] real
-  const double2* h1rot; // [ne][Mp]
-  double2* ovlp_out;    // [Wp]
-  double2* e1b_out;     // [Wp] or null
-  Dims d;
-  int want_theta;
-};
-
-__device__ __forceinline__ double cabs1(cplx z) { return fabs(z.re) + fabs(z.im); }
-
-// warp-level arg-max of (value, index): largest value, lowest index on ties (as LAPACK izamax)
-__device__ __forceinline__ void warp_argmax(double& v, int& idx) {
-#pragma unroll
-  for (int m = 16; m > 0; m >>= 1) {
-    const double ov = __shfl_xor_sync(0xffffffffu, v, m);
-    const int oi = __shfl_xor_sync(0xffffffffu, idx, m);
-    if (ov > v || (ov == v && oi < idx)) {
-      v = ov;
-      idx = oi;
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256) greens_kernel(GreensArgs a) {
-  extern __shared__ __align__(16) unsigned char gs_raw[];
-  const Dims& d = a.d;
-  const int w = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int LD = d.Mp + 1;
-  const int nmax = max(d.na, d.nb);
-  cplx* ph = reinterpret_cast<cplx*>(gs_raw);          // [ne][LD]
-  cplx* lu = ph + (size_t)d.ne * LD;                   // [2][nmax*nmax]
-  cplx* rdiag = lu + 2 * nmax * nmax;                  // [2][nmax] reciprocal of U diagonal
-  double* red = reinterpret_cast<double*>(rdiag + 2 * nmax);  // [2*nth] reduction scratch
-  int* piv = reinterpret_cast<int*>(red + 2 * nth);    // [2][nmax] pivot rows, then [2] permutation sign
-  int* psign = piv + 2 * nmax;
-  const int wg = w >> 2, wl = w & 3;
-
-  // 1. phi -> shared, orbital-major
-  for (int idx = tid; idx < d.ne * d.Mp; idx += nth) {
-    const int p = idx % d.Mp, i = idx / d.Mp;
-    double2 v = *reinterpret_cast<const double2*>(a.phi + (((size_t)wg * d.ne + i) * d.KC + (p >> 2)) * 32 +
-                                                  wl * 8 + (p & 3) * 2);
-    ph[i * LD + p] = {v.x, v.y};
-  }
-  __syncthreads();
-
-  // 2. O_s[i][j] = sum_p phi[p, i] psi[p, j]     (psi real, stored [p][j]: lanes read consecutive j)
-  const int npair = d.na * d.na + d.nb * d.nb;
-  for (int idx = tid; idx < npair; idx += nth) {
-    int s = 0, r = idx;
-    if (idx >= d.na * d.na) {
-      s = 1;
-      r = idx - d.na * d.na;
-    }
-    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
-    const int i = r / ns, j = r % ns;
-    const cplx* pr = ph + (size_t)(ioff + i) * LD;
-    const double* ps = a.psiT + ioff + j;  // psiT is [Mp][ne] here
-    double sr = 0.0, si = 0.0;
-#pragma unroll 4
-    for (int p = 0; p < d.M; ++p) {
-      const double c = __ldg(ps + (size_t)p * d.ne);
-      sr += pr[p].re * c;
-      si += pr[p].im * c;
-    }
-    lu[s * nmax * nmax + i * ns + j] = {sr, si};
-  }
-  __syncthreads();
-
-  // 3. LU with partial pivoting: one warp per spin, no block-level barriers
-  if (warp < 2) {
-    const int s = warp, ns = s ? d.nb : d.na;
-    cplx* L = lu + s * nmax * nmax;
-    int sign = 1;
-    for (int k = 0; k < ns; ++k) {
-      double bv = -1.0;
-      int bi = k;
-      for (int i = k + lane; i < ns; i += 32) {
-        const double v = cabs1(L[i * ns + k]);
-        if (v > bv) {
-          bv = v;
-          bi = i;
-        }
-      }
-      warp_argmax(bv, bi);
-      if (lane == 0) piv[s * nmax + k] = bi;
-      if (bi != k) {
-        sign = -sign;
-        for (int j = lane; j < ns; j += 32) {
-          const cplx tmp = L[k * ns + j];
-          L[k * ns + j] = L[bi * ns + j];
-          L[bi * ns + j] = tmp;
-        }
-      }
-      __syncwarp();
-      const cplx ukk = L[k * ns + k];
-      const cplx rk = cdiv({1.0, 0.0}, ukk);
-      if (lane == 0) rdiag[s * nmax + k] = rk;
-      for (int i = k + 1 + lane; i < ns; i += 32) L[i * ns + k] = cdiv(L[i * ns + k], ukk);
-      __syncwarp();
-      const int m = ns - k - 1;
-      for (int idx = lane; idx < m * m; idx += 32) {
-        const int i = k + 1 + idx / m, j = k + 1 + idx % m;
-        L[i * ns + j] = csub(L[i * ns + j], cmul(L[i * ns + k], L[k * ns + j]));
-      }
-      __syncwarp();
-    }
-    if (lane == 0) psign[s] = sign;
-  }
-  __syncthreads();
-
-  // 4. sign * exp(logdet)  (numpy.linalg.slogdet semantics)
-  if (tid == 0) {
-    cplx sign = {1.0, 0.0};
-    double logdet = 0.0;
-    for (int s = 0; s < 2; ++s) {
-      const int ns = s ? d.nb : d.na;
-      const cplx* L = lu + s * nmax * nmax;
-      if (ns > 0 && psign[s] < 0) sign = {-sign.re, -sign.im};
-      for (int k = 0; k < ns; ++k) {
-        const cplx u = L[k * ns + k];
-        const double au = hypot(u.re, u.im);
-        sign = cmul(sign, {u.re / au, u.im / au});
-        logdet += log(au);
-      }
-    }
-    const double e = exp(logdet);
-    a.ovlp_out[w] = make_double2(sign.re * e, sign.im * e);
-  }
-  if (!a.want_theta) return;
-
-  // 5. solve L U Theta = P phi^T, one right-hand-side column p per thread (the row
-  //    interchanges are applied to the thread's own column first)
-  for (int idx = tid; idx < 2 * d.Mp; idx += nth) {
-    const int s = idx / d.Mp, p = idx % d.Mp;
-    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
-    const cplx* L = lu + s * nmax * nmax;
-    cplx* col = ph + (size_t)ioff * LD + p;
-    for (int k = 0; k < ns; ++k) {
-      const int pk = piv[s * nmax + k];
-      if (pk != k) {
-        const cplx tmp = col[k * LD];
-        col[k * LD] = col[pk * LD];
-        col[pk * LD] = tmp;
-      }
-    }
-    for (int i = 1; i < ns; ++i) {
-      cplx acc = col[i * LD];
-      for (int j = 0; j < i; ++j) acc = csub(acc, cmul(L[i * ns + j], col[j * LD]));
-      col[i * LD] = acc;
-    }
-    for (int i = ns - 1; i >= 0; --i) {
-      cplx acc = col[i * LD];
-      for (int j = i + 1; j < ns; ++j) acc = csub(acc, cmul(L[i * ns + j], col[j * LD]));
-      col[i * LD] = cmul(acc, rdiag[s * nmax + i]);
-    }
-  }
-  __syncthreads();
-
-  // 6. Theta -> OF, e1b = sum h1rot * Theta
-  double er = 0.0, ei = 0.0;
-  for (int idx = tid; idx < d.ne * d.Mp; idx += nth) {
-    const int p = idx % d.Mp, i = idx / d.Mp;
-    cplx v = ph[i * LD + p];
-    if (p >= d.M) v = {0.0, 0.0};
-    *reinterpret_cast<double2*>(a.theta + (((size_t)wg * d.ne + i) * d.KC + (p >> 2)) * 32 + wl * 8 +
-                                (p & 3) * 2) = make_double2(v.re, v.im);
-    if (a.e1b_out != nullptr) {
-      const double2 h = a.h1rot[idx];
-      er += h.x * v.re - h.y * v.im;
-      ei += h.x * v.im + h.y * v.re;
-    }
-  }
-  if (a.e1b_out != nullptr) {
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) {
-      er += __shfl_xor_sync(0xffffffffu, er, m);
-      ei += __shfl_xor_sync(0xffffffffu, ei, m);
-    }
-    if (lane == 0) {
-      red[warp] = er;
-      red[32 + warp] = ei;
-    }
-    __syncthreads();
-    if (tid == 0) {
-      double sr = 0.0, si = 0.0;
-      for (int k = 0; k < (nth >> 5); ++k) {
-        sr += red[k];
-        si += red[32 + k];
-      }
-      a.e1b_out[w] = make_double2(sr, si);
-    }
-  }
-}
-
-inline size_t greens_smem_bytes(const Dims& d, int nth) {
-  const int nmax = d.na > d.nb ? d.na : d.nb;
-  return sizeof(cplx) * ((size_t)d.ne * (d.Mp + 1) + 2 * nmax * nmax + 2 * nmax) +
-         sizeof(double) * 2 * nth + (2 * nmax + 4) * sizeof(int) + 16;
-}
-
-// ============================================================================
-// K8: re-orthogonalisation (walkers/single_det.py:215-255).  QR with R_ii > 0
-// by modified Gram-Schmidt, one CTA per walker (both spins).
-// ============================================================================
-struct QrArgs {
-  double* phi;  // OF, in place
-  double2* ot;
-  double* detR;
-  double* log_detR;
-  Dims d;
-};
-
-__global__ void __launch_bounds__(256) qr_kernel(QrArgs a) {
-  extern __shared__ __align__(16) unsigned char qs_raw[];
-  const Dims& d = a.d;
-  const int w = blockIdx.x, tid = threadIdx.x, nth = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5, nwarp = nth >> 5;
-  const int LD = d.Mp + 1;
-  cplx* ph = reinterpret_cast<cplx*>(qs_raw);           // [ne][LD]
-  double* red = reinterpret_cast<double*>(ph + (size_t)d.ne * LD);  // [nwarp]
-  __shared__ double s_norm;
-  const int wg = w >> 2, wl = w & 3;
-  for (int idx = tid; idx < d.ne * d.Mp; idx += nth) {
-    const int p = idx % d.Mp, i = idx / d.Mp;
-    double2 v = *reinterpret_cast<const double2*>(a.phi + (((size_t)wg * d.ne + i) * d.KC + (p >> 2)) * 32 +
-                                                  wl * 8 + (p & 3) * 2);
-    ph[i * LD + p] = {v.x, v.y};
-  }
-  __syncthreads();
-  double logdet = 0.0;
-  for (int s = 0; s < 2; ++s) {
-    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
-    for (int k = 0; k < ns; ++k) {
-      cplx* vk = ph + (size_t)(ioff + k) * LD;
-      // norm of column k
-      double part = 0.0;
-      for (int p = tid; p < d.M; p += nth) part += vk[p].re * vk[p].re + vk[p].im * vk[p].im;
-#pragma unroll
-      for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
-      if (lane == 0) red[warp] = part;
-      __syncthreads();
-      if (tid == 0) {
-        double tot = 0.0;
-        for (int i = 0; i < nwarp; ++i) tot += red[i];
-        s_norm = sqrt(tot);
-      }
-      __syncthreads();
-      const double nrm = s_norm;
-      logdet += log(nrm);
-      for (int p = tid; p < d.M; p += nth) {
-        vk[p].re /= nrm;
-        vk[p].im /= nrm;
-      }
-      __syncthreads();
-      // orthogonalise the later columns against v_k: one warp per column
-      for (int j = k + 1 + warp; j < ns; j += nwarp) {
-        cplx* vj = ph + (size_t)(ioff + j) * LD;
-        double rr = 0.0, ri = 0.0;  // r = v_k^H v_j
-        for (int p = lane; p < d.M; p += 32) {
-          rr += vk[p].re * vj[p].re + vk[p].im * vj[p].im;
-          ri += vk[p].re * vj[p].im - vk[p].im * vj[p].re;
-        }
-#pragma unroll
-        for (int m = 16; m > 0; m >>= 1) {
-          rr += __shfl_xor_sync(0xffffffffu, rr, m);
-          ri += __shfl_xor_sync(0xffffffffu, ri, m);
-        }
-        for (int p = lane; p < d.M; p += 32) {
-          vj[p].re -= rr * vk[p].re - ri * vk[p].im;
-          vj[p].im -= rr * vk[p].im + ri * vk[p].re;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (int idx = tid; idx < d.ne * d.Mp; idx += nth) {
-    const int p = idx % d.Mp, i = idx / d.Mp;
-    const cplx v = ph[i * LD + p];
-    *reinterpret_cast<double2*>(a.phi + (((size_t)wg * d.ne + i) * d.KC + (p >> 2)) * 32 + wl * 8 +
-                                (p & 3) * 2) = make_double2(v.re, v.im);
-  }
-  if (tid == 0 && w < d.W) {
-    // detR = exp(log_det - detR_shift[=0]); log_detR += log(detR); ot = ot / detR
-    const double detR = exp(logdet);
-    a.detR[w] = detR;
-    a.log_detR[w] += log(detR);
-    double2 o = a.ot[w];
-    a.ot[w] = make_double2(o.x / detR, o.y / detR);
-  }
-}
-
-inline size_t qr_smem_bytes(const Dims& d, int nth) {
-  return sizeof(cplx) * (size_t)d.ne * (d.Mp + 1) + sizeof(double) * (nth / 32) + 16;
 }
 
 // ============================================================================

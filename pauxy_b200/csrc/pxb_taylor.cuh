@@ -30,8 +30,9 @@ struct TaylorArgs {
 // half warp (g < 4 or g >= 4) read 16 consecutive doubles -> no bank conflicts
 __device__ __forceinline__ int tb_off(int k, int n) { return (n >> 2) * 16 + k * 4 + (n & 3); }
 
-// WMT m-tiles per warp, NTMAX >= n-tiles per CTA, NWARPS warps per CTA
-template <int WMT, int NTMAX, int NWARPS, int MINB>
+// WMT m-tiles per warp, NT n-tiles per CTA (compile time: no predication around the DMMAs;
+// orbitals beyond the chunk are zero columns), NWARPS warps per CTA
+template <int WMT, int NT, int NWARPS, int MINB>
 __global__ void __launch_bounds__(NWARPS * 32, MINB) taylor_kernel(TaylorArgs a) {
   extern __shared__ __align__(16) double Ts[];  // [KC][NT][32]
   const Dims& d = a.d;
@@ -39,7 +40,6 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) taylor_kernel(TaylorArgs a)
   if (a.active != nullptr && a.active[w] == 0) return;
   const int o0 = chunk * a.ochunk;
   const int no = min(a.ochunk, d.ne - o0);
-  const int NT = (no + 3) >> 2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   const int wg = w >> 2, wl = w & 3;
@@ -65,11 +65,11 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) taylor_kernel(TaylorArgs a)
   const double sgn = (g & 1) ? 1.0 : -1.0;  // (i B)^: (re, im) -> (-im, re)
 
   for (int n = d.exp_order; n >= 1; --n) {
-    double acc[WMT][NTMAX][2];
+    double acc[WMT][NT][2];
 #pragma unroll
     for (int i = 0; i < WMT; ++i)
 #pragma unroll
-      for (int j = 0; j < NTMAX; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+      for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     if (warp_active) {
       const double* Ap[WMT];
@@ -90,15 +90,13 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) taylor_kernel(TaylorArgs a)
         }
         const double* Tk = Ts + (size_t)kc * NT * 32;
 #pragma unroll
-        for (int j = 0; j < NTMAX; ++j) {
-          if (j < NT) {
-            const double b = Tk[j * 32 + boff];
-            const double bq = sgn * Tk[j * 32 + boffp];
+        for (int j = 0; j < NT; ++j) {
+          const double b = Tk[j * 32 + boff];
+          const double bq = sgn * Tk[j * 32 + boffp];
 #pragma unroll
-            for (int i = 0; i < WMT; ++i) {
-              dmma(acc[i][j][0], acc[i][j][1], ar[i], b);
-              dmma(acc[i][j][0], acc[i][j][1], ai[i], bq);
-            }
+          for (int i = 0; i < WMT; ++i) {
+            dmma(acc[i][j][0], acc[i][j][1], ar[i], b);
+            dmma(acc[i][j][0], acc[i][j][1], ai[i], bq);
           }
         }
 #pragma unroll
@@ -117,22 +115,20 @@ __global__ void __launch_bounds__(NWARPS * 32, MINB) taylor_kernel(TaylorArgs a)
         const int kc2 = p >> 2, t2 = p & 3;
         if (mt < d.MT && kc2 < d.KC) {
 #pragma unroll
-          for (int j = 0; j < NTMAX; ++j) {
-            if (j < NT) {
-              const int ol = 4 * j + t;
-              double2* gp = reinterpret_cast<double2*>(
-                  a.phi + (((size_t)wg * d.ne + o0 + min(ol, no - 1)) * d.KC + kc2) * 32 + wl * 8 + t2 * 2);
-              double2 p0 = make_double2(0.0, 0.0);
-              if (ol < no) p0 = *gp;
-              // the reference divides (Temp = VHS.dot(Temp) / n); so do we
-              const double vr = p0.x + acc[i][j][0] / (double)n;
-              const double vi = p0.y + acc[i][j][1] / (double)n;
-              if (n > 1) {
-                *reinterpret_cast<double2*>(Ts + ((size_t)kc2 * NT + j) * 32 + tb_off(t2, 2 * t)) =
-                    make_double2(vr, vi);
-              } else if (ol < no) {
-                *gp = make_double2(vr, vi);
-              }
+          for (int j = 0; j < NT; ++j) {
+            const int ol = 4 * j + t;
+            double2* gp = reinterpret_cast<double2*>(
+                a.phi + (((size_t)wg * d.ne + o0 + min(ol, no - 1)) * d.KC + kc2) * 32 + wl * 8 + t2 * 2);
+            double2 p0 = make_double2(0.0, 0.0);
+            if (ol < no) p0 = *gp;
+            // the reference divides (Temp = VHS.dot(Temp) / n); so do we
+            const double vr = p0.x + acc[i][j][0] / (double)n;
+            const double vi = p0.y + acc[i][j][1] / (double)n;
+            if (n > 1) {
+              *reinterpret_cast<double2*>(Ts + ((size_t)kc2 * NT + j) * 32 + tb_off(t2, 2 * t)) =
+                  make_double2(vr, vi);
+            } else if (ol < no) {
+              *gp = make_double2(vr, vi);
             }
           }
         }

@@ -1,0 +1,82 @@
+"""Two-device parity: an N-device run must reproduce the ONE-rank reference run
+ -- selection bit-exact, values <= 1e-10.  Needs 2 GPUs."""
+import os
+
+import numpy
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _worker(rank, world, port, name, pop, q):
+    import torch
+    import torch.distributed as dist
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=torch.device('cuda', rank))
+    from pauxy_b200.comm import TorchComm
+    from pauxy_b200.systems import Generic
+    from pauxy_b200.qmc import AFQMC
+    g = dict(numpy.load(os.path.join(GOLD, name + '.npz')))
+    nelec = tuple(int(x) for x in g['nelec'])
+    system = Generic(nelec=nelec, h1e=numpy.array([g['h1e'], g['h1e']]), chol=g['hs_pot'],
+                     ecore=float(g['ecore']))
+    opts = {'qmc': {'timestep': float(g['dt']), 'steps': int(g['steps']), 'blocks': int(g['blocks']),
+                    'rng_seed': int(g['seed']), 'num_walkers': int(g['nwalkers']),
+                    'stabilise_freq': int(g['stab']), 'pop_control_freq': int(g['popc'])},
+            'estimates': {'mixed': {'energy_eval_freq': 1, 'verbose': False}}}
+    if pop == 'pair_branch':
+        opts['walkers'] = {'population_control': 'pair_branch', 'min_weight': float(g['min_weight']),
+                           'max_weight': float(g['max_weight'])}
+    comm = TorchComm()
+    afqmc = AFQMC(comm=comm, options=opts, system=system, verbose=0, device=torch.device('cuda', rank))
+    hist = {k: [] for k in ('weight', 'ot', 'eloc', 'parent_ix')}
+
+    def obs(step, a):
+        e = a.engine
+        hist['weight'].append(e.weight.cpu().numpy().copy())
+        hist['ot'].append(e.ot.cpu().numpy().copy())
+        hist['eloc'].append(e.eloc.cpu().numpy().copy())
+        hist['parent_ix'].append(e.parent_ix.cpu().numpy().copy())
+    afqmc.run(comm=comm, verbose=0, observer=obs)
+    rows = afqmc.estimators.rows() if rank == 0 else None
+    q.put((rank, {k: numpy.array(v) for k, v in hist.items()}, rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def _run_two(name, pop):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 1000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, pop, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=600) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(120)
+    return res
+
+
+@pytest.mark.parametrize('name,pop', [('stress_comb', 'comb'), ('c1', 'comb'),
+                                      ('stress_pair_branch', 'pair_branch')])
+def test_two_devices_reproduce_one_rank_reference(name, pop):
+    res = _run_two(name, pop)
+    g = dict(numpy.load(os.path.join(GOLD, name + '.npz')))
+    weight = numpy.concatenate([res[0][1]['weight'], res[1][1]['weight']], axis=1)
+    ot = numpy.concatenate([res[0][1]['ot'], res[1][1]['ot']], axis=1)
+    eloc = numpy.concatenate([res[0][1]['eloc'], res[1][1]['eloc']], axis=1)
+    if pop == 'comb':
+        assert numpy.array_equal(res[0][1]['parent_ix'], g['parent_ix'])
+        assert numpy.array_equal(res[1][1]['parent_ix'], g['parent_ix'])
+    numpy.testing.assert_allclose(weight, g['weight'], rtol=1e-10, atol=1e-13)
+    numpy.testing.assert_allclose(ot, g['ot'], rtol=1e-10)
+    numpy.testing.assert_allclose(eloc, g['eloc'], rtol=1e-10, atol=1e-10)
+    numpy.testing.assert_allclose(res[0][2][:, :10], g['rows'][:, :10], rtol=1e-10, atol=1e-10)

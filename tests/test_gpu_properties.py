@@ -1,0 +1,141 @@
+"""Size-independent properties at BASELINE's full sizes, device RNG and
+population control on the GPU."""
+import numpy
+import pytest
+import torch
+
+from oracle import afqmc_oracle as orc
+from helpers import host_setup, make_engine, oracle_ham, random_walkers, relerr
+from pauxy_b200.hamiltonians import make_config_hamiltonian, synthetic_cholesky_hamiltonian
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(name, W, total=None):
+    h1e, hs, ecore, nelec = make_config_hamiltonian(name)
+    system, trial, prop = host_setup(h1e, hs, ecore, nelec, 0.005)
+    ham = oracle_ham(h1e, hs, ecore, nelec, 0.005)
+    return make_engine(system, trial, prop, W, 0.005, total_walkers=total), ham
+
+
+def test_full_size_c4_replicated_walkers():
+    """8192 walkers at c4 = 8 distinct walkers tiled: every copy must reproduce its
+    representative (same arithmetic whatever the tile position), and the
+    representatives must match the oracle (propagation + local energy)."""
+    W, R = 8192, 8
+    eng, ham = _engine('c4', W)
+    base = random_walkers(ham, R, seed=3)
+    rs = numpy.random.RandomState(4)
+    xib = rs.normal(size=(R, ham.nchol))
+    reps = numpy.arange(W) % R
+    eng.set_phi(torch.as_tensor(base).to(eng.device)[torch.as_tensor(reps).to(eng.device)].contiguous())
+    eng.ot.copy_(torch.as_tensor(orc.calc_overlap(ham, base)[reps]))
+    xi = torch.as_tensor(xib).to(eng.device)[torch.as_tensor(reps).to(eng.device)].contiguous()
+    eng.propagate(xi, eshift=0.0, step=1)
+    eng.local_energy()
+    eng.synchronize()
+    phi = eng.get_phi().cpu().numpy()
+    eloc = eng.eloc.cpu().numpy()
+    wt = eng.weight.cpu().numpy()
+    # copies identical to their representative
+    assert numpy.array_equal(phi, phi[reps])
+    assert numpy.array_equal(eloc, eloc[reps])
+    assert numpy.array_equal(wt, wt[reps])
+    # representatives against the oracle
+    tha, thb, ovlp_old = orc.greens_function(ham, base)
+    p1 = orc.kinetic_real(ham, base)
+    xbar, _ = orc.force_bias(ham, tha, thb)
+    x, cmf, cfb, _ = orc.shift_fields(ham, xib, xbar)
+    p3 = orc.kinetic_real(ham, orc.apply_exponential(p1, orc.construct_vhs(ham, x)))
+    assert relerr(phi[:R], p3) < 1e-11
+    t2a, t2b, ovlp_new = orc.greens_function(ham, p3)
+    assert relerr(eloc[:R], orc.local_energy(ham, t2a, t2b)) < 1e-11
+    assert relerr(eng.ot.cpu().numpy()[:R], ovlp_new) < 1e-11
+    for i in range(R):
+        wr, _, _, _ = orc.update_weight_hybrid(ham, 1.0, complex(ovlp_old[i]), complex(ovlp_new[i]),
+                                               0j, complex(cfb[i]), complex(cmf[i]), 0.0)
+        assert abs(wt[i] - wr) < 1e-11 * abs(wr)
+
+
+def test_philox_fields():
+    """Device RNG: N(0,1) statistics, determinism, and invariance of the stream of a
+    GLOBAL walker index under the split of walkers over devices."""
+    W = 1024
+    eng, ham = _engine('c2', W)
+    N = ham.nchol
+    eng.propagate(None, step=3, seed=11)
+    xi_a = (eng.xshifted + eng.xbar).cpu().numpy()
+    assert numpy.abs(xi_a.imag).max() < 1e-12
+    xi_a = xi_a.real
+    n = xi_a.size
+    assert abs(xi_a.mean()) < 5.0 / numpy.sqrt(n)
+    assert abs(xi_a.var() - 1.0) < 5.0 * numpy.sqrt(2.0 / n)
+    assert abs((xi_a ** 4).mean() - 3.0) < 0.15
+    assert abs(numpy.corrcoef(xi_a[:, 0], xi_a[:, 1])[0, 1]) < 0.2
+    # same (seed, step) -> same fields; other step -> different
+    eng2, _ = _engine('c2', W)
+    eng2.propagate(None, step=3, seed=11)
+    assert numpy.array_equal((eng2.xshifted + eng2.xbar).cpu().numpy().real, xi_a)
+    eng2.propagate(None, step=4, seed=11)
+    assert not numpy.array_equal((eng2.xshifted + eng2.xbar).cpu().numpy().real[:8], xi_a[:8])
+    # second half of the population on "another device": same fields for the same global index
+    eng3, _ = _engine('c2', W // 2, total=W)
+    eng3.propagate(None, step=3, seed=11, walker_offset=W // 2)
+    xi_b = (eng3.xshifted + eng3.xbar).cpu().numpy().real
+    numpy.testing.assert_allclose(xi_b, xi_a[W // 2:], rtol=0, atol=1e-12)
+
+
+def test_device_comb_bit_exact_large():
+    """Comb over 8192 walkers on the device against the oracle's sequential restatement
+    (walkers/handler.py:271-301): parent_ix bit-exact, clones copied onto kills."""
+    W = 8192
+    eng, ham = _engine('c1', W)
+    rs = numpy.random.RandomState(8)
+    phi = random_walkers(ham, W, seed=5)
+    eng.set_phi(phi)
+    w0 = numpy.abs(1.0 + 0.5 * rs.normal(size=W))
+    w0[rs.randint(0, W, 40)] = 0.0
+    eng.weight.copy_(torch.as_tensor(w0))
+    marks = rs.normal(size=W) + 1j * rs.normal(size=W)
+    eng.hybrid_energy.copy_(torch.as_tensor(marks))
+    r = 0.6180339887
+    eng.pop_control_comb(r)
+    eng.synchronize()
+    total = sum(w0)
+    gw = w0 / (total / W)
+    parents = orc.comb_parents(gw, r, W)
+    assert numpy.array_equal(eng.parent_ix.cpu().numpy()[:W], parents)
+    assert eng.total_weight.item() == total
+    expect_unscaled = w0.copy()          # the clone's whole buffer lands on the killed walker
+    for c, k in orc.comb_pairs(parents):
+        expect_unscaled[k] = w0[c]
+    assert numpy.array_equal(eng.unscaled_weight.cpu().numpy(), expect_unscaled)
+    assert numpy.all(eng.weight.cpu().numpy() == 1.0)
+    out = eng.get_phi().cpu().numpy()
+    eh = eng.hybrid_energy.cpu().numpy()
+    expect_phi, expect_eh = phi.copy(), marks.copy()
+    for c, k in orc.comb_pairs(parents):
+        expect_phi[k] = phi[c]
+        expect_eh[k] = marks[c]
+    assert numpy.array_equal(out, expect_phi)
+    assert numpy.array_equal(eh, expect_eh)
+
+
+def test_theta_travels_with_walkers():
+    """After population control the stored Theta of a cloned walker must equal a fresh
+    Green's function of its (copied) phi: the estimator reuses it."""
+    W = 64
+    eng, ham = _engine('c2', W)
+    rs = numpy.random.RandomState(2)
+    eng.set_phi(random_walkers(ham, W, seed=6))
+    xi = rs.normal(size=(W, ham.nchol))
+    eng.propagate(xi, step=1)
+    w0 = numpy.abs(1.0 + 0.8 * rs.normal(size=W))
+    eng.weight.copy_(torch.as_tensor(w0))
+    eng.pop_control_comb(0.3)
+    eng.local_energy()            # uses the Theta that travelled
+    e_reuse = eng.eloc.cpu().numpy().copy()
+    phi = eng.get_phi().cpu().numpy()
+    assert (eng.parent_ix.cpu().numpy()[:W] != 1).any()
+    tha, thb, _ = orc.greens_function(ham, phi)
+    assert relerr(e_reuse, orc.local_energy(ham, tha, thb)) < 1e-11

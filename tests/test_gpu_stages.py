@@ -38,10 +38,13 @@ def _case(name):
     if name == 'c4':
         h1e, hs, ecore = synthetic_cholesky_hamiltonian(108, 500, 1004)
         return h1e, hs, ecore, (21, 21), 0.005, None
+    if name == 'c5':
+        h1e, hs, ecore = synthetic_cholesky_hamiltonian(200, 1000, 1005)
+        return h1e, hs, ecore, (40, 40), 0.005, None
     raise KeyError(name)
 
 
-CASES = [('c1', 13), ('odd', 7), ('c2', 18), ('c3', 9), ('c4', 6)]
+CASES = [('c1', 13), ('odd', 7), ('c2', 18), ('c3', 9), ('c4', 6), ('c5', 3)]
 
 
 @pytest.fixture(scope='module', params=CASES, ids=[c[0] for c in CASES])
