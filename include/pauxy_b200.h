@@ -32,7 +32,7 @@ extern "C" {
 #define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
 #define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
 
-#define PXB_ABI_VERSION 1
+#define PXB_ABI_VERSION 2
 
 typedef struct pxb_context* pxb_handle;
 
@@ -49,7 +49,20 @@ typedef struct {
   int32_t device;     /* CUDA device ordinal */
   int32_t total_walkers; /* walkers over ALL devices (0: == nwalkers) */
   double dt;
+  int32_t exchange_mode; /* PXB_EXCHANGE_*: how pxb_local_energy evaluates the exchange term */
+  int32_t reserved;
 } pxb_config;
+
+/* Exchange energy of estimators/generic.py:198-214.  Both forms give the same number to
+ * rounding (the ERI is rebuilt from the same Cholesky vectors):
+ *   CHOLESKY  T[x] = R[x] Theta^T per Cholesky vector, fused trace   4 N ns^2 M flop / walker / spin
+ *   ERI       quadratic form Theta . K . Theta in the half-rotated ERI (the contraction of
+ *             local_energy_generic_opt, estimators/generic.py:133-150), K symmetric,
+ *             2 (ns M)^2 flop / walker / spin, K = (ns M)^2 doubles per spin in the arena
+ *   AUTO      ERI when K (both spins) fits in 16 GiB, else CHOLESKY */
+#define PXB_EXCHANGE_AUTO 0
+#define PXB_EXCHANGE_CHOLESKY 1
+#define PXB_EXCHANGE_ERI 2
 
 /* Walker-state fields living in the arena; pxb_field() gives their location
  * so the host can view them (e.g. as torch tensors over the arena).  They are

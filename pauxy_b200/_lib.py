@@ -10,6 +10,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libpauxy_b200.so')
 
 PXB_OK = 0
+ABI_VERSION = 2
+EXCHANGE_MODES = {'auto': 0, 'cholesky': 1, 'eri': 2}
 ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_ERR_UNSUPPORTED'}
 
 # enum pxb_field_id
@@ -22,7 +24,8 @@ class PxbConfig(ctypes.Structure):
     _fields_ = [('nbasis', ctypes.c_int32), ('nup', ctypes.c_int32), ('ndown', ctypes.c_int32),
                 ('nchol', ctypes.c_int32), ('nwalkers', ctypes.c_int32),
                 ('exp_order', ctypes.c_int32), ('device', ctypes.c_int32),
-                ('total_walkers', ctypes.c_int32), ('dt', ctypes.c_double)]
+                ('total_walkers', ctypes.c_int32), ('dt', ctypes.c_double),
+                ('exchange_mode', ctypes.c_int32), ('reserved', ctypes.c_int32)]
 
 
 class PxbError(RuntimeError):
@@ -91,7 +94,7 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.pxb_abi_version() != 1:
+    if lib.pxb_abi_version() != ABI_VERSION:
         raise ImportError("pauxy_b200: ABI version mismatch")
     _lib = lib
     return lib

@@ -1,6 +1,7 @@
 // C-ABI of the B200 AFQMC hot path (see include/pauxy_b200.h).
 #include "../../include/pauxy_b200.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -9,6 +10,7 @@
 #include <vector>
 
 #include "pxb_common.cuh"
+#include "pxb_eri.cuh"
 #include "pxb_exchange.cuh"
 #include "pxb_gemm.cuh"
 #include "pxb_greens.cuh"
@@ -26,7 +28,7 @@ struct Region {
 enum ArenaId {
   A_LF, A_RF, A_BF, A_PSIT, A_H1ROT, A_VBAR,
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
-  A_EXX, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
+  A_EXX, A_KF0, A_KF1, A_EPART, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -47,6 +49,9 @@ struct pxb_context {
   // Theta / overlap / e1b (A_THETA, A_E1B) correspond to the current walkers; X to the current Theta
   bool theta_valid = false, x_valid = false;
   bool gemm_tma = true;  // TMA-fed persistent GEMM (PXB_GEMM=direct selects the L1/L2-streaming one)
+  bool exx_eri = false;  // exchange through the half-rotated ERI quadratic form (pxb_eri.cuh)
+  bool kf_shared = false;  // both spins use the K of spin 0 (identical half-rotated Cholesky blocks)
+  int eri_nslot = 0;
   std::string err;
 
   template <class T>
@@ -292,8 +297,32 @@ int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   return fail(h, PXB_ERR_ARG, "taylor: no kernel instance for this shape");
 }
 
+int run_exchange_eri(pxb_handle h, cudaStream_t st) {
+  const Dims& d = h->d;
+  EriArgs a;
+  a.KF[0] = h->ptr<double>(A_KF0);
+  a.KF[1] = h->kf_shared ? h->ptr<double>(A_KF0) : h->ptr<double>(A_KF1);
+  a.theta = h->ptr<double>(A_THETA);
+  a.part = h->ptr<double2>(A_EPART);
+  a.d = d;
+  a.nslot = h->eri_nslot;
+  const int nrb = std::max(eri_rowblocks(d, 0), eri_rowblocks(d, 1));
+  const int nwb = (d.WG + EQ_TN - 1) / EQ_TN;
+  const int nitems = nrb * 2 * nwb;
+  const size_t smem = eri_smem_bytes();
+  PXB_CUDA(h, cudaFuncSetAttribute(exx_eri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ++h->launches;
+  exx_eri_kernel<<<std::min(nitems, h->sm_count), (EQ_CWM * EQ_CWN + 1) * 32, smem, st>>>(a, nitems, nwb);
+  PXB_CUDA(h, cudaGetLastError());
+  ++h->launches;
+  exx_eri_reduce_kernel<<<(2 * d.Wp + 255) / 256, 256, 0, st>>>(a.part, h->ptr<double2>(A_EXX), d, a.nslot);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
 int run_exchange(pxb_handle h, cudaStream_t st) {
   const Dims& d = h->d;
+  if (h->exx_eri) return run_exchange_eri(h, st);
   ExArgs a;
   a.RF = h->ptr<double>(A_RF);
   a.theta = h->ptr<double>(A_THETA);
@@ -395,6 +424,21 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
     h->max_smem_optin = 227 * 1024;
   }
 
+  {
+    const size_t kbytes = (eri_kf_doubles(d, 0) + eri_kf_doubles(d, 1)) * 8;
+    if (cfg->exchange_mode == PXB_EXCHANGE_ERI)
+      h->exx_eri = true;
+    else if (cfg->exchange_mode == PXB_EXCHANGE_CHOLESKY)
+      h->exx_eri = false;
+    else if (cfg->exchange_mode == PXB_EXCHANGE_AUTO)
+      h->exx_eri = kbytes <= ((size_t)16 << 30);
+    else {
+      delete h;
+      return PXB_ERR_ARG;
+    }
+    h->eri_nslot = std::max(eri_rowblocks(d, 0), eri_rowblocks(d, 1)) * EQ_CWM;
+  }
+
   size_t off = 0;
   auto add = [&](int id, size_t bytes) {
     h->reg[id].off = off;
@@ -415,6 +459,9 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_XF, xf_size(d) * 8);
   add(A_VF, (size_t)W * vf_walker(d) * 8);
   add(A_EXX, 2 * W * 16);
+  add(A_KF0, h->exx_eri ? eri_kf_doubles(d, 0) * 8 : 0);
+  add(A_KF1, h->exx_eri ? eri_kf_doubles(d, 1) * 8 : 0);
+  add(A_EPART, h->exx_eri ? (size_t)2 * h->eri_nslot * W * 16 : 0);
   add(A_E1B, W * 16);
   add(A_OVLP_OLD, W * 16);
   add(A_ACTIVE, W * 4);
@@ -505,9 +552,33 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
   pack_pf_kernel<<<grid_for((size_t)d.ne * d.Mp), 256, 0, st>>>(static_cast<const double2*>(psi),
                                                                 h->ptr<double>(A_PF), d);
   PXB_CUDA(h, cudaGetLastError());
+  if (h->exx_eri) {
+    // identical spin blocks of R (RHF-type trial): one K serves both spins
+    const bool cmp = d.na == d.nb && d.nb > 0;
+    if (cmp) {
+      ++h->launches;
+      rf_spin_compare_kernel<<<grid_for(rf_spin_base(d, 1)), 256, 0, st>>>(h->ptr<double>(A_RF), rf_spin_base(d, 1),
+                                                                         rf_spin_base(d, 1), flag);
+    }
+    int f2 = 0;
+    PXB_CUDA(h, cudaMemcpyAsync(&f2, flag, 4, cudaMemcpyDeviceToHost, st));
+    PXB_CUDA(h, cudaStreamSynchronize(st));
+    h->kf_shared = cmp && (f2 & 8) == 0;
+    for (int s = 0; s < (h->kf_shared ? 1 : 2); ++s) {
+      const int ns = s ? d.nb : d.na;
+      if (ns == 0) continue;
+      double* KF = h->ptr<double>(s ? A_KF1 : A_KF0);
+      PXB_CUDA(h, cudaMemsetAsync(KF, 0, eri_kf_doubles(d, s) * 8, st));
+      const int tiles = (d.M + 31) / 32;
+      ++h->launches;
+      eri_build_kernel<<<dim3(tiles * tiles, ns, ns), 1024, 0, st>>>(static_cast<const double2*>(rchol), KF, d, s);
+      PXB_CUDA(h, cudaGetLastError());
+    }
+  }
   int hflag = 0;
   PXB_CUDA(h, cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
   PXB_CUDA(h, cudaStreamSynchronize(st));
+  hflag &= 7;  // bit 3 is the spin-block comparison of the ERI setup
   if (hflag != 0) {
     char buf[160];
     snprintf(buf, sizeof buf,

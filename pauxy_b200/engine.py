@@ -24,7 +24,7 @@ class Engine(object):
     """
 
     def __init__(self, nbasis, nup, ndown, nchol, nwalkers, dt, exp_order=6, device=None,
-                 total_walkers=None):
+                 total_walkers=None, exchange='auto'):
         if not torch.cuda.is_available():
             raise RuntimeError("pauxy_b200.Engine needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -38,7 +38,7 @@ class Engine(object):
         self.Wp = _round_up(nwalkers, 4)
         self.Np = _round_up(nchol, 8)
         cfg = L.PxbConfig(nbasis, nup, ndown, nchol, nwalkers, exp_order,
-                          self.device.index or 0, self.Wtot, dt)
+                          self.device.index or 0, self.Wtot, dt, L.EXCHANGE_MODES[exchange], 0)
         self._h = ctypes.c_void_p()
         rc = self.lib.pxb_create(ctypes.byref(self._h), ctypes.byref(cfg))
         if rc != 0:

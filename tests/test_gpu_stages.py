@@ -162,6 +162,30 @@ def test_local_energy(setup):
     assert relerr(eloc, ref) < TOL
 
 
+@pytest.mark.parametrize('mode', ['cholesky', 'eri'])
+def test_exchange_modes(setup, mode):
+    """Both evaluations of the exchange term (fused Cholesky T-trace, half-rotated-ERI
+    quadratic form) against the oracle's estimators/generic.py:198-214 restatement."""
+    phi, ham = setup['phi'], setup['ham']
+    h1e, hs, ecore, nelec, dt, psi = _case(setup['name'])
+    system, trial, prop = host_setup(h1e, hs, ecore, nelec, dt, psi)
+    eng = make_engine(system, trial, prop, setup['W'], dt, exchange=mode)
+    eng.set_phi(phi)
+    eng.stage_exchange()
+    exx = eng.get_exx().cpu().numpy()
+    tha, thb, _ = orc.greens_function(ham, phi)
+    na, M = ham.nup, ham.nbasis
+    ra = ham.rchol[:na * M].real.reshape(na, M, -1)
+    rb = ham.rchol[na * M:].real.reshape(ham.ndown, M, -1)
+    Ta = numpy.einsum('ipx,wjp->wxij', ra, tha, optimize=True)
+    Tb = numpy.einsum('ipx,wjp->wxij', rb, thb, optimize=True)
+    ref = numpy.array([numpy.einsum('wxij,wxji->w', Ta, Ta), numpy.einsum('wxij,wxji->w', Tb, Tb)])
+    assert relerr(exx, ref) < TOL
+    eng.local_energy()
+    assert relerr(eng.eloc.cpu().numpy(), orc.local_energy(ham, tha, thb)) < TOL
+    eng.close()
+
+
 def test_reortho(setup):
     eng, phi, ham, W = setup['eng'], setup['phi'], setup['ham'], setup['W']
     import torch

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "missing export %s" % name
     assert declared == set(_lib.declared_symbols())
-    assert _lib.load().pxb_abi_version() == 1
+    assert _lib.load().pxb_abi_version() == _lib.ABI_VERSION
 
 
 def test_create_validates_arguments_without_gpu():
