@@ -26,27 +26,37 @@ if ROOT not in sys.path:
 import numpy  # noqa: E402
 
 
-def algorithmic_flops(M, na, nb, N, order=6):
-    """Per walker-step, SURVEY.md section 8(d): real-Cholesky MAC = 4 flop,
-    complex MAC = 8 flop, full-G build excluded, no padding counted."""
+def algorithmic_flops(M, na, nb, N, order=6, exchange='eri'):
+    """Algorithmic flops per walker and per CALL of each stage (SURVEY.md section 8(d)
+    conventions: real x complex MAC = 4 flop, complex MAC = 8 flop, no padding counted).
+    The exchange is counted in the form it is evaluated in: the symmetric quadratic form in
+    the half-rotated ERI needs 2 D (D + 1) flop per spin, D = ns M; the Cholesky form
+    4 N ns^2 M + 8 N ns^2."""
+    ne = na + nb
+    st = {
+        'greens': sum(8.0 * (2 * n * n * M + 4 * n ** 3 / 3.0) for n in (na, nb)),
+        'xgemm': 4.0 * N * ne * M,
+        'vhs': 4.0 * M * M * N,
+        'one_body': 4.0 * M * M * ne,
+        'taylor': 8.0 * order * M * M * ne,
+        'exchange': (sum(2.0 * n * M * (n * M + 1) for n in (na, nb)) if exchange == 'eri' else
+                     sum(4.0 * N * n * n * M + 8.0 * N * n * n for n in (na, nb))),
+        'energy': 3 * 8.0 * N,
+        'qr': sum(32.0 * (M * n * n - n ** 3 / 3.0) for n in (na, nb)),
+    }
+    return st
+
+
+def survey_flops_per_walker_step(M, na, nb, N, order=6):
+    """The SURVEY.md section 8(d) table (Cholesky-form exchange, Green's function counted twice,
+    overlap separately): 267.24 MFLOP at c4.  Only used to relate walker-steps/s to the
+    north-star phrasing; it is NOT what the kernels execute."""
     ne = na + nb
     g = sum(8.0 * (2 * n * n * M + 4 * n ** 3 / 3.0) for n in (na, nb))
     ov = sum(8.0 * (n * n * M + n ** 3 / 3.0) for n in (na, nb))
-    st = {
-        'greens_prop': g,
-        'one_body_x2': 8.0 * M * M * ne,
-        'force_bias': 4.0 * N * ne * M,
-        'vhs': 4.0 * M * M * N,
-        'taylor': 8.0 * order * M * M * ne,
-        'overlap': ov,
-        'greens_est': g,
-        'coulomb': 4.0 * N * ne * M,
-        'exchange': 4.0 * N * (na * na + nb * nb) * M,
-        'exchange_trace': 8.0 * N * (na * na + nb * nb),
-        'e1b': 8.0 * ne * M,
-    }
-    st['total'] = sum(st.values())
-    return st
+    return (2 * g + ov + 8.0 * M * M * ne + 8.0 * N * ne * M + 4.0 * M * M * N +
+            8.0 * order * M * M * ne + 4.0 * N * (na * na + nb * nb) * M +
+            8.0 * N * (na * na + nb * nb) + 8.0 * ne * M)
 
 
 class ClockSampler(threading.Thread):
@@ -280,36 +290,61 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    # per-stage CUDA events on the launch stream, live inside the timed region
+    eng.stage_times(reset=True)
+    eng.profile(True)
     ms_total = timed(args.steps, False)
+    stage = eng.stage_times(reset=True)
+    eng.profile(False)
     launches = eng.launch_count() - launches0
     ms_e2e = timed(args.steps, True)
     clocks = sampler.stop() if sampler else None
-
-    # dominant kernel: fused exchange (71 % of the algorithmic flops at c4)
-    eng.stage_greens(with_e1b=True)
-    torch.cuda.synchronize()
-    evs = []
-    for _ in range(max(3, args.steps)):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        eng.stage_exchange()
-        b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    ex_ms = float(numpy.mean([a.elapsed_time(b) for a, b in evs]))
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return 0
 
-    fl = algorithmic_flops(M, na, nb, N, afqmc.propagators.exp_nmax)
+    exchange = 'eri' if eng.exchange_is_eri() else 'cholesky'
+    fl = algorithmic_flops(M, na, nb, N, afqmc.propagators.exp_nmax, exchange)
     peak = measure_fp64_peak(torch, dev)
-    ex_flops = (fl['exchange'] + fl['exchange_trace']) * wpg
     ws_total = wpg * world * args.steps
     value = ws_total / (ms_total * 1e-3)
     e2e_value = ws_total / (ms_e2e * 1e-3)
-    achieved = ex_flops / (ex_ms * 1e-3) * 1e-12
+    # stage table: ms per step, launches per step, achieved TFLOP/s on the stage's algorithmic flops
+    stages = {}
+    step_flops = 0.0
+    for name, (ms, calls) in stage.items():
+        if calls == 0:
+            continue
+        per_call_ms = ms / calls
+        row = {'ms_per_step': ms / args.steps, 'calls_per_step': calls / float(args.steps)}
+        if name in fl:
+            row['mflop_per_walker_call'] = fl[name] * 1e-6
+            row['tflops'] = fl[name] * wpg / (per_call_ms * 1e-3) * 1e-12
+            row['frac_of_peak'] = row['tflops'] / peak
+            step_flops += fl[name] * calls / float(args.steps)
+        stages[name] = row
+    tensor_stages = [k for k in stages if k in ('xgemm', 'vhs', 'one_body', 'taylor', 'exchange')]
+    dom = max(tensor_stages, key=lambda k: stages[k]['ms_per_step'])
+    kernel_names = {'taylor': 'taylor_kernel (exp(VHS) phi, DMMA, Horner)',
+                    'vhs': 'gemm_tma_kernel<EpiVHS> (VHS = i sqrt(dt) L x)',
+                    'exchange': ('exx_eri_kernel (Theta.K.Theta, symmetric half-rotated ERI)'
+                                 if exchange == 'eri' else 'exchange_kernel (fused T = R Theta^T + trace)'),
+                    'xgemm': 'gemm_tma_kernel<EpiX> (X = R^T Theta)',
+                    'one_body': 'gemm_tma_kernel<EpiOF> (phi = BH1 phi)'}
+    dom_ms = stage[dom][0] / stage[dom][1]
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.isfile(tpath):
+        try:
+            tj = json.load(open(tpath))
+            ent = tj.get(args.config, {}).get(dom)
+            if ent:       # bytes per launch measured by ncu at ent['walkers'] walkers, scaled to wpg
+                traffic = ent['dram_bytes'] * (float(wpg) / ent['walkers'])
+        except Exception:
+            traffic = None
+    survey_mflop = survey_flops_per_walker_step(M, na, nb, N, afqmc.propagators.exp_nmax) * 1e-6
     line = {
         'metric': 'walker-steps/sec incl. local energy', 'value': value, 'unit': 'walker-steps/s',
         'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
@@ -321,14 +356,23 @@ def main():
                 'h2d_bytes_per_step': wpg * N * 8, 'd2h_bytes_per_step': 160 + wpg * 8,
                 'ms_per_step': ms_e2e / args.steps},
         'gpu_launches': int(launches),
-        'roofline': {'bound': 'tensor', 'kernel': 'exchange_kernel (fused T = R Theta^T + trace)',
-                     'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s', 'frac': achieved / peak,
-                     'traffic': None,
+        'roofline': {'bound': 'tensor', 'kernel': kernel_names[dom],
+                     'achieved': stages[dom]['tflops'], 'peak': peak, 'unit': 'TFLOP/s',
+                     'frac': stages[dom]['tflops'] / peak, 'traffic': traffic,
                      'peak_source': 'cuBLAS DGEMM 8192^3 measured in this run (MEASURED_PEAKS.json '
                                     'has no FP64 entry)',
-                     'kernel_ms': ex_ms,
-                     'whole_step_tflops': fl['total'] * wpg / (ms_total / args.steps * 1e-3) * 1e-12,
-                     'mflop_per_walker_step': fl['total'] * 1e-6},
+                     'kernel_ms': dom_ms,
+                     'algorithmic_mflop_per_walker': fl[dom] * 1e-6,
+                     'exchange_form': exchange,
+                     'stages': stages,
+                     'whole_step': {
+                         'mflop_per_walker_step_executed_form': step_flops * 1e-6,
+                         'tflops': step_flops * wpg / (ms_total / args.steps * 1e-3) * 1e-12,
+                         'frac_of_peak': step_flops * wpg / (ms_total / args.steps * 1e-3) * 1e-12 / peak,
+                         'survey_table_mflop_per_walker_step': survey_mflop,
+                         'survey_equivalent_tflops': survey_mflop * 1e6 * value / world * 1e-12,
+                         'note': 'survey_equivalent counts the Cholesky-form exchange of SURVEY.md '
+                                 '8(d) that the ERI quadratic form does not execute'}},
     }
     if not args.no_cpu_baseline and world == 1:
         v, cores, sample = cpu_port_throughput(args.config)

@@ -91,6 +91,28 @@ int pxb_abi_version(void);
 /* number of CUDA kernels launched through this handle so far (bench.py gpu_launches) */
 long long pxb_launch_count(pxb_handle h);
 
+/* Optional per-stage timing: with profiling enabled every stage of the hot path is bracketed by
+ * CUDA events on the stream it is launched on.  pxb_stage_times waits for the recorded events
+ * and returns the accumulated milliseconds / call counts per PXB_STAGE_* (arrays of n entries). */
+enum pxb_stage_id {
+  PXB_STAGE_GREENS = 0,     /* overlap, inverse, Theta, e1b          (single_det.py:295-321)   */
+  PXB_STAGE_XGEMM = 1,      /* X = R^T Theta, force bias == Coulomb  (generic.py:130-152)      */
+  PXB_STAGE_FIELD = 2,      /* xbar clip, x = xi - xbar, cmf, cfb    (continuous.py:133-158)   */
+  PXB_STAGE_VHS = 3,        /* VHS = i sqrt(dt) L x                  (generic.py:164-179)      */
+  PXB_STAGE_ONE_BODY = 4,   /* phi = BH1 phi, both half steps        (operations.py:29-52)     */
+  PXB_STAGE_TAYLOR = 5,     /* exp(VHS) phi                          (continuous.py:82-111)    */
+  PXB_STAGE_WEIGHT = 6,     /* hybrid weight update + cap            (continuous.py:264-292)   */
+  PXB_STAGE_EXCHANGE = 7,   /* exchange energy                       (estimators/generic.py:198-214) */
+  PXB_STAGE_ENERGY = 8,     /* Coulomb + assembly of (E, E1, E2)     (estimators/generic.py:187-221) */
+  PXB_STAGE_QR = 9,         /* re-orthogonalisation                  (single_det.py:215-255)   */
+  PXB_STAGE_POP_CONTROL = 10, /* comb on one device                  (handler.py:225-338)      */
+  PXB_STAGE_ACCUMULATE = 11,  /* Mixed.update sums                   (mixed.py:211-225)        */
+  PXB_STAGE_COUNT = 12
+};
+int pxb_exchange_mode(pxb_handle h); /* PXB_EXCHANGE_CHOLESKY or PXB_EXCHANGE_ERI in effect */
+int pxb_profile(pxb_handle h, int enable);
+int pxb_stage_times(pxb_handle h, double* ms, long long* calls, int n, int reset);
+
 /* ---- lifecycle -------------------------------------------------------- */
 int pxb_create(pxb_handle* out, const pxb_config* cfg);
 int pxb_destroy(pxb_handle h);

@@ -20,6 +20,10 @@ F_WEIGHT, F_UNSCALED_WEIGHT, F_OT, F_HYBRID_ENERGY, F_ELOC, F_DETR, F_LOG_DETR, 
     F_TOTAL_WEIGHT, F_PAIRS, F_COUNT = range(17)
 
 
+STAGES = ['greens', 'xgemm', 'field', 'vhs', 'one_body', 'taylor', 'weight', 'exchange', 'energy',
+          'qr', 'pop_control', 'accumulate']
+
+
 class PxbConfig(ctypes.Structure):
     _fields_ = [('nbasis', ctypes.c_int32), ('nup', ctypes.c_int32), ('ndown', ctypes.c_int32),
                 ('nchol', ctypes.c_int32), ('nwalkers', ctypes.c_int32),
@@ -39,6 +43,10 @@ _PROTOS = {
     'pxb_abi_version': (ctypes.c_int, []),
     'pxb_launch_count': (ctypes.c_longlong, [_vp]),
     'pxb_stage_exchange': (ctypes.c_int, [_vp, _vp]),
+    'pxb_profile': (ctypes.c_int, [_vp, ctypes.c_int]),
+    'pxb_exchange_mode': (ctypes.c_int, [_vp]),
+    'pxb_stage_times': (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double),
+                                       ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, ctypes.c_int]),
     'pxb_create': (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(PxbConfig)]),
     'pxb_destroy': (ctypes.c_int, [_vp]),
     'pxb_last_error': (ctypes.c_char_p, [_vp]),

@@ -16,6 +16,7 @@
 #include "pxb_greens.cuh"
 #include "pxb_small.cuh"
 #include "pxb_taylor.cuh"
+#include "pxb_taylor2.cuh"
 
 using namespace pxb;
 
@@ -49,6 +50,14 @@ struct pxb_context {
   // Theta / overlap / e1b (A_THETA, A_E1B) correspond to the current walkers; X to the current Theta
   bool theta_valid = false, x_valid = false;
   bool gemm_tma = true;  // TMA-fed persistent GEMM (PXB_GEMM=direct selects the L1/L2-streaming one)
+  // optional per-stage timing with CUDA events on the launch stream (pxb_profile / pxb_stage_times)
+  bool prof = false;
+  struct Pending { int stage; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> evpool;
+  double stage_ms[PXB_STAGE_COUNT] = {0};
+  long long stage_calls[PXB_STAGE_COUNT] = {0};
+  bool taylor_tma = true;  // persistent TMA-fed Taylor kernel (PXB_TAYLOR=direct selects the per-walker-CTA one)
   bool exx_eri = false;  // exchange through the half-rotated ERI quadratic form (pxb_eri.cuh)
   bool kf_shared = false;  // both spins use the K of spin 0 (identical half-rotated Cholesky blocks)
   int eri_nslot = 0;
@@ -89,6 +98,35 @@ int fail(pxb_handle h, int code, const std::string& msg) {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// brackets the launches of one stage with events when profiling is on
+struct StageTimer {
+  pxb_handle h;
+  cudaStream_t st;
+  int stage;
+  cudaEvent_t a = nullptr, b = nullptr;
+  static cudaEvent_t get(pxb_handle h) {
+    cudaEvent_t e = nullptr;
+    if (!h->evpool.empty()) {
+      e = h->evpool.back();
+      h->evpool.pop_back();
+    } else if (cudaEventCreate(&e) != cudaSuccess) {
+      e = nullptr;
+    }
+    return e;
+  }
+  StageTimer(pxb_handle h_, int stage_, cudaStream_t st_) : h(h_), st(st_), stage(stage_) {
+    if (!h->prof) return;
+    a = get(h);
+    b = get(h);
+    if (a) cudaEventRecord(a, st);
+  }
+  ~StageTimer() {
+    if (!a || !b) return;
+    cudaEventRecord(b, st);
+    h->pending.push_back({stage, a, b});
+  }
+};
+
 inline int grid_for(size_t n, int block = 256, int cap = 148 * 16) {
   size_t g = (n + block - 1) / block;
   if (g > (size_t)cap) g = cap;
@@ -126,6 +164,7 @@ int launch_greens(pxb_handle h, const GreensArgs& a, size_t smem, cudaStream_t s
 
 int run_greens(pxb_handle h, const double* phi, bool want_theta, double2* ovlp_out, bool with_e1b,
                cudaStream_t st) {
+  StageTimer timer__(h, PXB_STAGE_GREENS, st);
   const Dims& d = h->d;
   GreensArgs a;
   a.phi = phi;
@@ -158,6 +197,7 @@ int run_greens(pxb_handle h, const double* phi, bool want_theta, double2* ovlp_o
 
 // X_s[w][n] = sum_{i,p} R_s[(i,p), n] Theta_s[w][i][p]
 int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
+  StageTimer timer__(h, PXB_STAGE_XGEMM, st);
   const Dims& d = h->d;
   for (int s = 0; s < 2; ++s) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
@@ -187,6 +227,7 @@ int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
 }
 
 int run_vhs_gemm(pxb_handle h, cudaStream_t st) {
+  StageTimer timer__(h, PXB_STAGE_VHS, st);
   const Dims& d = h->d;
   GemmArgs g;
   g.A = h->ptr<double>(A_LF);
@@ -208,6 +249,7 @@ int run_vhs_gemm(pxb_handle h, cudaStream_t st) {
 }
 
 int run_one_body(pxb_handle h, const double* in, double* out, const int* active, cudaStream_t st) {
+  StageTimer timer__(h, PXB_STAGE_ONE_BODY, st);
   const Dims& d = h->d;
   for (int s = 0; s < 2; ++s) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
@@ -254,7 +296,65 @@ int launch_taylor(pxb_handle h, TaylorArgs& a, int nwarps, cudaStream_t st) {
   return PXB_OK;
 }
 
+template <int WMX, int WNX>
+int launch_taylor2(pxb_handle h, const Taylor2Args& a, size_t smem, int grid, cudaStream_t st) {
+  auto kern = taylor2_kernel<WMX, WNX>;
+  PXB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ++h->launches;
+  kern<<<grid, T2_THREADS, smem, st>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+// returns 1 if the shape is not covered by the persistent kernel (caller falls back), else status
+int run_taylor2(pxb_handle h, double* phi, const int* active, int ochunk, int nchunks, cudaStream_t st) {
+  const Dims& d = h->d;
+  const int NT = ochunk / 4;
+  if (d.MT < 4 || d.MT > 28 || NT < 2 || NT > 12) return 1;
+  Taylor2Args a;
+  a.VF = h->ptr<double>(A_VF);
+  a.phi = phi;
+  a.active = active;
+  a.d = d;
+  a.ochunk = ochunk;
+  a.nchunks = nchunks;
+  a.NT = NT;
+  const int base = d.MT / 4, rem = d.MT % 4;
+  a.m_off[0] = 0;
+  for (int g = 0; g < 4; ++g) a.m_off[g + 1] = a.m_off[g] + base + (g < rem ? 1 : 0);
+  const int nbig = (NT + 1) / 2;
+  a.n_off[0] = 0;
+  a.n_off[1] = nbig;
+  a.n_off[2] = NT;
+  const int wmx = base + (rem ? 1 : 0), wnx = nbig;
+  // shared memory: two iterate buffers when a >= 3-deep ring still fits, else one
+  const size_t budget = (size_t)h->max_smem_optin;
+  a.nbuf = 0;
+  for (int nbuf = 2; nbuf >= 1 && a.nbuf == 0; --nbuf)
+    for (int nstage = 6; nstage >= 3; --nstage)
+      if (taylor2_smem_bytes(d, NT, nbuf, nstage) <= budget) {
+        a.nbuf = nbuf;
+        a.nstage = nstage;
+        break;
+      }
+  if (a.nbuf == 0) return 1;
+  const size_t smem = taylor2_smem_bytes(d, NT, a.nbuf, a.nstage);
+  const int grid = std::min(d.W * nchunks, h->sm_count);
+#define PXB_T2(WM_, WN_) \
+  if (wmx == WM_ && wnx == WN_) return launch_taylor2<WM_, WN_>(h, a, smem, grid, st);
+  PXB_T2(1, 1) PXB_T2(1, 2) PXB_T2(1, 3) PXB_T2(1, 4) PXB_T2(1, 5) PXB_T2(1, 6)
+  PXB_T2(2, 1) PXB_T2(2, 2) PXB_T2(2, 3) PXB_T2(2, 4) PXB_T2(2, 5) PXB_T2(2, 6)
+  PXB_T2(3, 1) PXB_T2(3, 2) PXB_T2(3, 3) PXB_T2(3, 4) PXB_T2(3, 5) PXB_T2(3, 6)
+  PXB_T2(4, 1) PXB_T2(4, 2) PXB_T2(4, 3) PXB_T2(4, 4) PXB_T2(4, 5) PXB_T2(4, 6)
+  PXB_T2(5, 1) PXB_T2(5, 2) PXB_T2(5, 3) PXB_T2(5, 4) PXB_T2(5, 5) PXB_T2(5, 6)
+  PXB_T2(6, 1) PXB_T2(6, 2) PXB_T2(6, 3) PXB_T2(6, 4) PXB_T2(6, 5) PXB_T2(6, 6)
+  PXB_T2(7, 1) PXB_T2(7, 2) PXB_T2(7, 3) PXB_T2(7, 4) PXB_T2(7, 5) PXB_T2(7, 6)
+#undef PXB_T2
+  return 1;
+}
+
 int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
+  StageTimer timer__(h, PXB_STAGE_TAYLOR, st);
   const Dims& d = h->d;
   TaylorArgs a;
   a.VF = h->ptr<double>(A_VF);
@@ -267,6 +367,10 @@ int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   nchunks = (d.ne + ochunk - 1) / ochunk;
   a.nchunks = nchunks;
   const int NT = ochunk / 4;
+  if (h->taylor_tma) {
+    const int rc2 = run_taylor2(h, phi, active, ochunk, nchunks, st);
+    if (rc2 != 1) return rc2;
+  }
   // m-tiles per warp: 2 when that fits in 8 warps, else as many as needed
   int wmt = (d.MT + 7) / 8;
   if (wmt < 2 && d.MT >= 2) wmt = 2;
@@ -321,6 +425,7 @@ int run_exchange_eri(pxb_handle h, cudaStream_t st) {
 }
 
 int run_exchange(pxb_handle h, cudaStream_t st) {
+  StageTimer timer__(h, PXB_STAGE_EXCHANGE, st);
   const Dims& d = h->d;
   if (h->exx_eri) return run_exchange_eri(h, st);
   ExArgs a;
@@ -375,6 +480,41 @@ int pxb_abi_version(void) { return PXB_ABI_VERSION; }
 
 long long pxb_launch_count(pxb_handle h) { return h ? h->launches : -1; }
 
+int pxb_exchange_mode(pxb_handle h) {
+  if (!h) return PXB_ERR_ARG;
+  return h->exx_eri ? PXB_EXCHANGE_ERI : PXB_EXCHANGE_CHOLESKY;
+}
+
+int pxb_profile(pxb_handle h, int enable) {
+  if (!h) return PXB_ERR_ARG;
+  h->prof = enable != 0;
+  return PXB_OK;
+}
+
+int pxb_stage_times(pxb_handle h, double* ms, long long* calls, int n, int reset) {
+  if (!h) return PXB_ERR_ARG;
+  for (auto& p : h->pending) {
+    float t = 0.f;
+    PXB_CUDA(h, cudaEventSynchronize(p.b));
+    PXB_CUDA(h, cudaEventElapsedTime(&t, p.a, p.b));
+    h->stage_ms[p.stage] += t;
+    h->stage_calls[p.stage] += 1;
+    h->evpool.push_back(p.a);
+    h->evpool.push_back(p.b);
+  }
+  h->pending.clear();
+  for (int i = 0; i < n && i < PXB_STAGE_COUNT; ++i) {
+    if (ms) ms[i] = h->stage_ms[i];
+    if (calls) calls[i] = h->stage_calls[i];
+  }
+  if (reset)
+    for (int i = 0; i < PXB_STAGE_COUNT; ++i) {
+      h->stage_ms[i] = 0.0;
+      h->stage_calls[i] = 0;
+    }
+  return PXB_OK;
+}
+
 const char* pxb_last_error(pxb_handle h) { return h ? h->err.c_str() : "null handle"; }
 
 int pxb_create(pxb_handle* out, const pxb_config* cfg) {
@@ -389,6 +529,8 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   {
     const char* g = getenv("PXB_GEMM");
     if (g && strcmp(g, "direct") == 0) h->gemm_tma = false;
+    const char* t = getenv("PXB_TAYLOR");
+    if (t && strcmp(t, "direct") == 0) h->taylor_tma = false;
   }
   Dims& d = h->d;
   d.M = cfg->nbasis;
@@ -495,6 +637,13 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
 }
 
 int pxb_destroy(pxb_handle h) {
+  if (h) {
+    for (auto& p : h->pending) {
+      cudaEventDestroy(p.a);
+      cudaEventDestroy(p.b);
+    }
+    for (auto e : h->evpool) cudaEventDestroy(e);
+  }
   delete h;
   return PXB_OK;
 }
@@ -666,8 +815,11 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   f.seed = rng_seed;
   f.step = (uint64_t)step;
   f.walker_offset = walker_offset;
-  ++h->launches;
-  field_kernel<<<(d.Wp + 7) / 8, 256, 0, st>>>(f);
+  {
+    StageTimer timer__(h, PXB_STAGE_FIELD, st);
+    ++h->launches;
+    field_kernel<<<(d.Wp + 7) / 8, 256, 0, st>>>(f);
+  }
   PXB_CUDA(h, cudaGetLastError());
   if ((rc = run_vhs_gemm(h, st))) return rc;
   double* work = h->phi_other();
@@ -693,8 +845,11 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   wa.d = d;
   wa.eshift = eshift;
   wa.step = step;
-  ++h->launches;
-  weight_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(wa);
+  {
+    StageTimer timer__(h, PXB_STAGE_WEIGHT, st);
+    ++h->launches;
+    weight_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(wa);
+  }
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -703,6 +858,7 @@ int pxb_orthogonalise(pxb_handle h, void* stream) {
   PXB_REQUIRE_READY(h);
   const Dims& d = h->d;
   cudaStream_t st = S(stream);
+  StageTimer timer__(h, PXB_STAGE_QR, st);
   QrArgs a;
   a.phi = h->phi();
   a.logdet = h->ptr<double>(A_QRLD);
@@ -738,8 +894,11 @@ int pxb_local_energy(pxb_handle h, void* stream) {
   e.e1b = h->ptr<double2>(A_E1B);
   e.eloc = h->field<double2>(PXB_F_ELOC);
   e.d = d;
-  ++h->launches;
-  energy_kernel<<<(d.W + 7) / 8, 256, 0, st>>>(e);
+  {
+    StageTimer timer__(h, PXB_STAGE_ENERGY, st);
+    ++h->launches;
+    energy_kernel<<<(d.W + 7) / 8, 256, 0, st>>>(e);
+  }
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -755,6 +914,7 @@ int pxb_accumulate(pxb_handle h, int with_energy, void* stream) {
   a.estimates = h->field<double2>(PXB_F_ESTIMATES);
   a.d = h->d;
   a.with_energy = with_energy;
+  StageTimer timer__(h, PXB_STAGE_ACCUMULATE, S(stream));
   ++h->launches;
   accumulate_kernel<<<1, 1024, 0, S(stream)>>>(a);
   PXB_CUDA(h, cudaGetLastError());
@@ -817,6 +977,7 @@ int pxb_pop_control_comb(pxb_handle h, double r, void* stream) {
   if (d.Wtot != d.W) return fail(h, PXB_ERR_ARG, "pxb_pop_control_comb is the single-device path");
   if (d.W == 1) return PXB_OK;  // handler.py:226-227
   cudaStream_t st = S(stream);
+  StageTimer timer__(h, PXB_STAGE_POP_CONTROL, st);
   double* gw = h->ptr<double>(A_GW);
   ++h->launches;
   abs_weight_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(h->field<double>(PXB_F_WEIGHT), gw, d.W);

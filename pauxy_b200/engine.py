@@ -250,6 +250,21 @@ class Engine(object):
         with torch.cuda.device(self.device):
             self._check(self.lib.pxb_stage_exchange(self._h, self._stream()))
 
+    def exchange_is_eri(self):
+        return bool(self.lib.pxb_exchange_mode(self._h) == L.EXCHANGE_MODES['eri'])
+
+    def profile(self, enable=True):
+        """Bracket every stage with CUDA events on the launch stream (see stage_times)."""
+        self._check(self.lib.pxb_profile(self._h, 1 if enable else 0))
+
+    def stage_times(self, reset=True):
+        """{stage: (milliseconds, calls)} accumulated since the last reset (waits for the GPU)."""
+        n = len(L.STAGES)
+        ms = (ctypes.c_double * n)()
+        calls = (ctypes.c_longlong * n)()
+        self._check(self.lib.pxb_stage_times(self._h, ms, calls, n, 1 if reset else 0))
+        return dict((L.STAGES[i], (ms[i], calls[i])) for i in range(n))
+
     def launch_count(self):
         return int(self.lib.pxb_launch_count(self._h))
 
