@@ -26,7 +26,7 @@ if ROOT not in sys.path:
 import numpy  # noqa: E402
 
 
-def algorithmic_flops(M, na, nb, N, order=6, exchange='eri'):
+def algorithmic_flops(M, na, nb, N, order=6, exchange='eri', vhs_sym=False):
     """Algorithmic flops per walker and per CALL of each stage (SURVEY.md section 8(d)
     conventions: real x complex MAC = 4 flop, complex MAC = 8 flop, no padding counted).
     The exchange is counted in the form it is evaluated in: the symmetric quadratic form in
@@ -36,7 +36,8 @@ def algorithmic_flops(M, na, nb, N, order=6, exchange='eri'):
     st = {
         'greens': sum(8.0 * (2 * n * n * M + 4 * n ** 3 / 3.0) for n in (na, nb)),
         'xgemm': 4.0 * N * ne * M,
-        'vhs': 4.0 * M * M * N,
+        # symmetric L (real orbitals): only the upper triangle of VHS is a product, the rest a copy
+        'vhs': 4.0 * N * (M * (M + 1) / 2.0 if vhs_sym else M * M),
         'one_body': 4.0 * M * M * ne,
         'taylor': 8.0 * order * M * M * ne,
         'exchange': (sum(2.0 * n * M * (n * M + 1) for n in (na, nb)) if exchange == 'eri' else
@@ -306,7 +307,7 @@ def main():
         return 0
 
     exchange = 'eri' if eng.exchange_is_eri() else 'cholesky'
-    fl = algorithmic_flops(M, na, nb, N, afqmc.propagators.exp_nmax, exchange)
+    fl = algorithmic_flops(M, na, nb, N, afqmc.propagators.exp_nmax, exchange, eng.vhs_is_symmetric())
     peak = measure_fp64_peak(torch, dev)
     ws_total = wpg * world * args.steps
     value = ws_total / (ms_total * 1e-3)
@@ -327,8 +328,9 @@ def main():
         stages[name] = row
     tensor_stages = [k for k in stages if k in ('xgemm', 'vhs', 'one_body', 'taylor', 'exchange')]
     dom = max(tensor_stages, key=lambda k: stages[k]['ms_per_step'])
-    kernel_names = {'taylor': 'taylor_kernel (exp(VHS) phi, DMMA, Horner)',
+    kernel_names = {'taylor': 'taylor2_kernel (exp(VHS) phi: persistent, TMA-fed DMMA, Horner)',
                     'vhs': 'gemm_tma_kernel<EpiVHS> (VHS = i sqrt(dt) L x)',
+                    'taylor2': 'taylor2_kernel',
                     'exchange': ('exx_eri_kernel (Theta.K.Theta, symmetric half-rotated ERI)'
                                  if exchange == 'eri' else 'exchange_kernel (fused T = R Theta^T + trace)'),
                     'xgemm': 'gemm_tma_kernel<EpiX> (X = R^T Theta)',
@@ -363,7 +365,7 @@ def main():
                                     'has no FP64 entry)',
                      'kernel_ms': dom_ms,
                      'algorithmic_mflop_per_walker': fl[dom] * 1e-6,
-                     'exchange_form': exchange,
+                     'exchange_form': exchange, 'vhs_symmetric': eng.vhs_is_symmetric(),
                      'stages': stages,
                      'whole_step': {
                          'mflop_per_walker_step_executed_form': step_flops * 1e-6,

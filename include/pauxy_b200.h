@@ -110,6 +110,9 @@ enum pxb_stage_id {
   PXB_STAGE_COUNT = 12
 };
 int pxb_exchange_mode(pxb_handle h); /* PXB_EXCHANGE_CHOLESKY or PXB_EXCHANGE_ERI in effect */
+/* 1 if system.hs_pot was found symmetric in (p,q) (real orbitals): the VHS GEMM then computes the
+ * upper triangle only and mirrors it; 0 otherwise (after pxb_set_hamiltonian) */
+int pxb_vhs_symmetric(pxb_handle h);
 int pxb_profile(pxb_handle h, int enable);
 int pxb_stage_times(pxb_handle h, double* ms, long long* calls, int n, int reset);
 

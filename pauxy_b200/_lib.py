@@ -45,6 +45,7 @@ _PROTOS = {
     'pxb_stage_exchange': (ctypes.c_int, [_vp, _vp]),
     'pxb_profile': (ctypes.c_int, [_vp, ctypes.c_int]),
     'pxb_exchange_mode': (ctypes.c_int, [_vp]),
+    'pxb_vhs_symmetric': (ctypes.c_int, [_vp]),
     'pxb_stage_times': (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_double),
                                        ctypes.POINTER(ctypes.c_longlong), ctypes.c_int, ctypes.c_int]),
     'pxb_create': (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.POINTER(PxbConfig)]),

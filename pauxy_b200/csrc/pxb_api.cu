@@ -29,7 +29,7 @@ struct Region {
 enum ArenaId {
   A_LF, A_RF, A_BF, A_PSIT, A_H1ROT, A_VBAR,
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
-  A_EXX, A_KF0, A_KF1, A_EPART, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
+  A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -57,6 +57,9 @@ struct pxb_context {
   std::vector<cudaEvent_t> evpool;
   double stage_ms[PXB_STAGE_COUNT] = {0};
   long long stage_calls[PXB_STAGE_COUNT] = {0};
+  bool vhs_sym = false;  // L symmetric in (p,q): the VHS GEMM computes the upper triangle only
+  bool vhs_sym_allowed = true;
+  int rtu = 0;           // row tiles kept in that case
   bool taylor_tma = true;  // persistent TMA-fed Taylor kernel (PXB_TAYLOR=direct selects the per-walker-CTA one)
   bool exx_eri = false;  // exchange through the half-rotated ERI quadratic form (pxb_eri.cuh)
   bool kf_shared = false;  // both spins use the K of spin 0 (identical half-rotated Cholesky blocks)
@@ -236,10 +239,11 @@ int run_vhs_gemm(pxb_handle h, cudaStream_t st) {
   g.strideBO = (size_t)d.NKC * 32;
   g.strideBI = 0;
   g.ntInner = 1;
-  g.MTiles = d.RT;
+  g.MTiles = h->vhs_sym ? h->rtu : d.RT;
   g.NTiles = d.WG;
   g.KS = d.NKC;
-  EpiVHS epi{h->ptr<double>(A_VF), d.KC, d.MT, d.sqrt_dt, vf_walker(d)};
+  EpiVHS epi{h->ptr<double>(A_VF), d.KC, d.MT, d.sqrt_dt, vf_walker(d),
+             h->vhs_sym ? h->ptr<int>(A_RTMAP) : nullptr};
   ++h->launches;
   if (h->gemm_tma)
     PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
@@ -296,12 +300,12 @@ int launch_taylor(pxb_handle h, TaylorArgs& a, int nwarps, cudaStream_t st) {
   return PXB_OK;
 }
 
-template <int WMX, int WNX>
+template <int WMX, int WNX, int NG>
 int launch_taylor2(pxb_handle h, const Taylor2Args& a, size_t smem, int grid, cudaStream_t st) {
-  auto kern = taylor2_kernel<WMX, WNX>;
+  auto kern = taylor2_kernel<WMX, WNX, NG>;
   PXB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->launches;
-  kern<<<grid, T2_THREADS, smem, st>>>(a);
+  kern<<<grid, T2Cfg<NG>::threads, smem, st>>>(a);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -319,19 +323,55 @@ int run_taylor2(pxb_handle h, double* phi, const int* active, int ochunk, int nc
   a.ochunk = ochunk;
   a.nchunks = nchunks;
   a.NT = NT;
+  a.dbg = 0;
+  {
+    const char* e = getenv("PXB_TAYLOR_DBG");
+    if (e) a.dbg = atoi(e);
+  }
+  // 4 column groups (16 consumer warps, 112 registers) unless the m-groups are too tall for that budget
+  int NG = (NT >= 4 && (d.MT + 3) / 4 <= 4) ? 4 : 2;
+  {
+    const char* e = getenv("PXB_TAYLOR_GROUPS");
+    if (e && atoi(e) == 2) NG = 2;
+  }
+  // 4 m-groups and NG column groups, sizes differing by at most one, larger ones first
   const int base = d.MT / 4, rem = d.MT % 4;
+  int msize[4];
   a.m_off[0] = 0;
-  for (int g = 0; g < 4; ++g) a.m_off[g + 1] = a.m_off[g] + base + (g < rem ? 1 : 0);
-  const int nbig = (NT + 1) / 2;
+  for (int g = 0; g < 4; ++g) {
+    msize[g] = base + (g < rem ? 1 : 0);
+    a.m_off[g + 1] = a.m_off[g] + msize[g];
+  }
+  const int nbase = NT / NG, nrem = NT % NG;
+  int nsize[T2_MAXG] = {0, 0, 0, 0};
   a.n_off[0] = 0;
-  a.n_off[1] = nbig;
-  a.n_off[2] = NT;
-  const int wmx = base + (rem ? 1 : 0), wnx = nbig;
+  for (int g = 0; g < NG; ++g) {
+    nsize[g] = nbase + (g < nrem ? 1 : 0);
+    a.n_off[g + 1] = a.n_off[g] + nsize[g];
+  }
+  for (int g = NG; g < T2_MAXG; ++g) a.n_off[g + 1] = a.n_off[NG];
+  // m-group permutation per column group: the largest remaining m-group goes to the least loaded
+  // sub-partition (column groups are already in descending size)
+  int load[4] = {0, 0, 0, 0};
+  for (int g = 0; g < T2_MAXG; ++g) {
+    int order[4] = {0, 1, 2, 3};
+    std::sort(order, order + 4, [&](int x, int y) { return load[x] != load[y] ? load[x] < load[y] : x < y; });
+    for (int k = 0; k < 4; ++k) {
+      a.mperm[g][order[k]] = k;  // m-groups are sorted by descending size
+      if (g < NG) load[order[k]] += msize[k] * nsize[g];
+    }
+  }
+  const int wmx = base + (rem ? 1 : 0), wnx = nbase + (nrem ? 1 : 0);
   // shared memory: two iterate buffers when a >= 3-deep ring still fits, else one
   const size_t budget = (size_t)h->max_smem_optin;
   a.nbuf = 0;
-  for (int nbuf = 2; nbuf >= 1 && a.nbuf == 0; --nbuf)
-    for (int nstage = 6; nstage >= 3; --nstage)
+  int nbuf_max = 2;
+  {
+    const char* e = getenv("PXB_TAYLOR_NBUF");
+    if (e && atoi(e) == 1) nbuf_max = 1;
+  }
+  for (int nbuf = nbuf_max; nbuf >= 1 && a.nbuf == 0; --nbuf)
+    for (int nstage = 12; nstage >= 3; --nstage)
       if (taylor2_smem_bytes(d, NT, nbuf, nstage) <= budget) {
         a.nbuf = nbuf;
         a.nstage = nstage;
@@ -340,15 +380,17 @@ int run_taylor2(pxb_handle h, double* phi, const int* active, int ochunk, int nc
   if (a.nbuf == 0) return 1;
   const size_t smem = taylor2_smem_bytes(d, NT, a.nbuf, a.nstage);
   const int grid = std::min(d.W * nchunks, h->sm_count);
-#define PXB_T2(WM_, WN_) \
-  if (wmx == WM_ && wnx == WN_) return launch_taylor2<WM_, WN_>(h, a, smem, grid, st);
-  PXB_T2(1, 1) PXB_T2(1, 2) PXB_T2(1, 3) PXB_T2(1, 4) PXB_T2(1, 5) PXB_T2(1, 6)
-  PXB_T2(2, 1) PXB_T2(2, 2) PXB_T2(2, 3) PXB_T2(2, 4) PXB_T2(2, 5) PXB_T2(2, 6)
-  PXB_T2(3, 1) PXB_T2(3, 2) PXB_T2(3, 3) PXB_T2(3, 4) PXB_T2(3, 5) PXB_T2(3, 6)
-  PXB_T2(4, 1) PXB_T2(4, 2) PXB_T2(4, 3) PXB_T2(4, 4) PXB_T2(4, 5) PXB_T2(4, 6)
-  PXB_T2(5, 1) PXB_T2(5, 2) PXB_T2(5, 3) PXB_T2(5, 4) PXB_T2(5, 5) PXB_T2(5, 6)
-  PXB_T2(6, 1) PXB_T2(6, 2) PXB_T2(6, 3) PXB_T2(6, 4) PXB_T2(6, 5) PXB_T2(6, 6)
-  PXB_T2(7, 1) PXB_T2(7, 2) PXB_T2(7, 3) PXB_T2(7, 4) PXB_T2(7, 5) PXB_T2(7, 6)
+#define PXB_T2(WM_, WN_, NG_) \
+  if (wmx == WM_ && wnx == WN_ && NG == NG_) return launch_taylor2<WM_, WN_, NG_>(h, a, smem, grid, st);
+  PXB_T2(1, 1, 4) PXB_T2(1, 2, 4) PXB_T2(1, 3, 4)
+  PXB_T2(2, 1, 4) PXB_T2(2, 2, 4) PXB_T2(2, 3, 4)
+  PXB_T2(3, 1, 4) PXB_T2(3, 2, 4) PXB_T2(3, 3, 4)
+  PXB_T2(4, 1, 4) PXB_T2(4, 2, 4) PXB_T2(4, 3, 4)
+  PXB_T2(1, 1, 2) PXB_T2(1, 2, 2) PXB_T2(2, 1, 2) PXB_T2(2, 2, 2) PXB_T2(3, 1, 2) PXB_T2(3, 2, 2)
+  PXB_T2(4, 1, 2) PXB_T2(4, 2, 2) PXB_T2(4, 6, 2)
+  PXB_T2(5, 1, 2) PXB_T2(5, 2, 2) PXB_T2(5, 3, 2) PXB_T2(5, 4, 2) PXB_T2(5, 5, 2) PXB_T2(5, 6, 2)
+  PXB_T2(6, 1, 2) PXB_T2(6, 2, 2) PXB_T2(6, 3, 2) PXB_T2(6, 4, 2) PXB_T2(6, 5, 2) PXB_T2(6, 6, 2)
+  PXB_T2(7, 1, 2) PXB_T2(7, 2, 2) PXB_T2(7, 3, 2) PXB_T2(7, 4, 2) PXB_T2(7, 5, 2) PXB_T2(7, 6, 2)
 #undef PXB_T2
   return 1;
 }
@@ -485,6 +527,11 @@ int pxb_exchange_mode(pxb_handle h) {
   return h->exx_eri ? PXB_EXCHANGE_ERI : PXB_EXCHANGE_CHOLESKY;
 }
 
+int pxb_vhs_symmetric(pxb_handle h) {
+  if (!h) return PXB_ERR_ARG;
+  return h->vhs_sym ? 1 : 0;
+}
+
 int pxb_profile(pxb_handle h, int enable) {
   if (!h) return PXB_ERR_ARG;
   h->prof = enable != 0;
@@ -529,6 +576,8 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   {
     const char* g = getenv("PXB_GEMM");
     if (g && strcmp(g, "direct") == 0) h->gemm_tma = false;
+    const char* v = getenv("PXB_VHS");
+    if (v && strcmp(v, "full") == 0) h->vhs_sym_allowed = false;
     const char* t = getenv("PXB_TAYLOR");
     if (t && strcmp(t, "direct") == 0) h->taylor_tma = false;
   }
@@ -603,6 +652,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_EXX, 2 * W * 16);
   add(A_KF0, h->exx_eri ? eri_kf_doubles(d, 0) * 8 : 0);
   add(A_KF1, h->exx_eri ? eri_kf_doubles(d, 1) * 8 : 0);
+  add(A_RTMAP, (size_t)d.RT * 4);
   add(A_EPART, h->exx_eri ? (size_t)2 * h->eri_nslot * W * 16 : 0);
   add(A_E1B, W * 16);
   add(A_OVLP_OLD, W * 16);
@@ -685,7 +735,7 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
   int* flag = h->ptr<int>(A_FLAG);
   PXB_CUDA(h, cudaMemsetAsync(flag, 0, 4, st));
   ++h->launches;
-  pack_lf_kernel<<<grid_for(lf_size(d)), 256, 0, st>>>(hs_pot, h->ptr<double>(A_LF), d);
+  hs_symmetry_kernel<<<grid_for((size_t)d.M * d.M * d.N), 256, 0, st>>>(hs_pot, d, flag);
   ++h->launches;
   pack_rf_kernel<<<grid_for(rf_size(d)), 256, 0, st>>>(static_cast<const double2*>(rchol),
                                                        h->ptr<double>(A_RF), d, flag);
@@ -701,6 +751,30 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
   pack_pf_kernel<<<grid_for((size_t)d.ne * d.Mp), 256, 0, st>>>(static_cast<const double2*>(psi),
                                                                 h->ptr<double>(A_PF), d);
   PXB_CUDA(h, cudaGetLastError());
+  {
+    // symmetric Cholesky matrices (real orbitals): keep the row tiles (p pair, q chunk) that touch
+    // the upper triangle, 4 kc + 3 >= 2 pp; the GEMM epilogue mirrors them
+    int f1 = 0;
+    PXB_CUDA(h, cudaMemcpyAsync(&f1, flag, 4, cudaMemcpyDeviceToHost, st));
+    PXB_CUDA(h, cudaStreamSynchronize(st));
+    h->vhs_sym = h->vhs_sym_allowed && (f1 & 16) == 0;
+    const int* map = nullptr;
+    int nrt = d.RT;
+    if (h->vhs_sym) {
+      std::vector<int> m;
+      const int npp = (d.M + 1) / 2;
+      for (int pp = 0; pp < npp; ++pp)
+        for (int kc = 0; kc < d.KC; ++kc)
+          if (4 * kc + 3 >= 2 * pp) m.push_back(pp * d.KC + kc);
+      h->rtu = nrt = (int)m.size();
+      PXB_CUDA(h, cudaMemcpyAsync(h->ptr<int>(A_RTMAP), m.data(), m.size() * 4, cudaMemcpyHostToDevice, st));
+      PXB_CUDA(h, cudaStreamSynchronize(st));
+      map = h->ptr<int>(A_RTMAP);
+    }
+    ++h->launches;
+    pack_lf_kernel<<<grid_for((size_t)nrt * d.NKC * 32), 256, 0, st>>>(hs_pot, h->ptr<double>(A_LF), d, map, nrt);
+    PXB_CUDA(h, cudaGetLastError());
+  }
   if (h->exx_eri) {
     // identical spin blocks of R (RHF-type trial): one K serves both spins
     const bool cmp = d.na == d.nb && d.nb > 0;

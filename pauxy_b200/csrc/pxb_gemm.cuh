@@ -38,14 +38,27 @@ struct EpiVHS {  // VF[w][MT][KC][c][g][t]; row tile mt = (mtv*4+s)*KC + kc
   int KC, MT;
   double sqrt_dt;
   size_t walker_stride;
+  const int* rt_map;  // symmetric L: compact row-tile list (upper triangle); else null
   __device__ __forceinline__ void operator()(int rt, int nt, int z, int g, int t, double c0,
                                              double c1) const {
+    if (rt_map != nullptr) rt = rt_map[rt];
     int kc = rt % KC, ms = rt / KC, s = ms & 3, mtv = ms >> 2;
     int w = nt * 4 + t;
-    double* base = VF + (size_t)w * walker_stride + ((size_t)mtv * KC + kc) * 64 + 8 * s + g;
+    double* vw = VF + (size_t)w * walker_stride;
+    double* base = vw + ((size_t)mtv * KC + kc) * 64 + 8 * s + g;
     // VHS = i sqrt(dt) (S_re + i S_im)
-    base[0] = -sqrt_dt * c1;
-    base[32] = sqrt_dt * c0;
+    const double vr = -sqrt_dt * c1, vi = sqrt_dt * c0;
+    base[0] = vr;
+    base[32] = vi;
+    if (rt_map != nullptr) {
+      // mirror VHS[q][p] = VHS[p][q] (complex symmetric, no conjugation)
+      const int p = 8 * mtv + 2 * s + (g >> 2), q = 4 * kc + (g & 3);
+      if (q > p && (q >> 3) < MT) {
+        double* m = vw + ((size_t)(q >> 3) * KC + (p >> 2)) * 64 + (q & 7) * 4 + (p & 3);
+        m[0] = vr;
+        m[32] = vi;
+      }
+    }
   }
 };
 

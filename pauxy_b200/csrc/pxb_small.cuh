@@ -10,19 +10,38 @@ namespace pxb {
 // packing of the constant operands (setup)
 // ============================================================================
 // flag[0] |= 1 if a supposedly real input has a non-zero imaginary part
-__global__ void pack_lf_kernel(const double* __restrict__ hs_pot, double* __restrict__ LF, Dims d) {
-  const size_t total = lf_size(d);
+// rt_map (optional): compact list of the row tiles that are kept (upper triangle of a symmetric L)
+__global__ void pack_lf_kernel(const double* __restrict__ hs_pot, double* __restrict__ LF, Dims d,
+                               const int* __restrict__ rt_map, int nrt) {
+  const size_t total = (size_t)nrt * d.NKC * 32;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int tt = idx & 3, gp = (idx >> 2) & 7;
     const size_t r = idx >> 5;
     const int kcn = r % d.NKC;
-    const int rt = r / d.NKC;
+    const int rtc = r / d.NKC;
+    const int rt = rt_map != nullptr ? rt_map[rtc] : rtc;
     const int kc = rt % d.KC, ms = rt / d.KC, s = ms & 3, mtv = ms >> 2;
     const int p = 8 * mtv + 2 * s + (gp >> 2), q = 4 * kc + (gp & 3), n = 4 * kcn + tt;
     double v = 0.0;
     if (p < d.M && q < d.M && n < d.N) v = hs_pot[((size_t)p * d.M + q) * d.N + n];
     LF[idx] = v;
+  }
+}
+
+// flag |= 16 unless hs_pot[(p,q), n] == hs_pot[(q,p), n] for all p, q, n (then VHS is symmetric and
+// only its upper triangle is computed by the GEMM)
+__global__ void hs_symmetry_kernel(const double* __restrict__ hs_pot, Dims d, int* flag) {
+  const size_t total = (size_t)d.M * d.M * d.N;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int n = idx % d.N;
+    const size_t pq = idx / d.N;
+    const int q = pq % d.M, p = pq / d.M;
+    if (p < q && hs_pot[idx] != hs_pot[((size_t)q * d.M + p) * d.N + n]) {
+      atomicOr(flag, 16);
+      return;
+    }
   }
 }
 

@@ -18,13 +18,28 @@
 
 namespace pxb {
 
-constexpr int T2_KS = 2;         // k-steps per ring stage
-constexpr int T2_CONSUMERS = 8;  // consumer warps
-// 8 consumer warps (two warpgroups) + one producer warpgroup of which one warp works.  The CTA is
-// launched with 168 registers per thread (65536 / 384); setmaxnreg then moves registers from the
-// producer warpgroup (40) to the consumers (232) so that a 7 x 6 tile block of accumulators fits.
-constexpr int T2_THREADS = (T2_CONSUMERS + 4) * 32;
-constexpr int T2_REGS_PRODUCER = 40, T2_REGS_CONSUMER = 232;
+#ifndef T2_KS_OVERRIDE
+constexpr int T2_KS = 2;  // k-steps per ring stage
+#else
+constexpr int T2_KS = T2_KS_OVERRIDE;
+#endif
+// NG column groups of 4 consumer warps (one warp per SM sub-partition) + one producer warpgroup of
+// which one warp works.  The CTA is launched with 65536 / threads registers per thread; setmaxnreg
+// then moves registers from the producer warpgroup to the consumers.  setmaxnreg.inc can only take
+// what setmaxnreg.dec released inside the same CTA (it blocks otherwise), so with R0 registers at
+// launch  consumers * (Rc - R0) <= 4 * (R0 - Rp):
+//   NG = 2: R0 = 168 (384 threads), Rp = 40, Rc = 232: a 7 x 6 tile block of accumulators fits
+//   NG = 4: R0 =  96 (640 threads), Rp = 24, Rc = 112: 4 x 3 fits
+constexpr int T2_MAXG = 4;
+template <int NG>
+struct T2Cfg {
+  static constexpr int consumers = 4 * NG;
+  static constexpr int threads = (consumers + 4) * 32;
+  static constexpr int regs_producer = NG == 2 ? 40 : 24;
+  static constexpr int regs_consumer = NG == 2 ? 232 : 112;
+  static_assert(consumers * (regs_consumer - (65536 / threads) / 8 * 8) <= 4 * ((65536 / threads) / 8 * 8 - regs_producer),
+                "setmaxnreg.inc would block: more registers requested than the producer warpgroup releases");
+};
 
 struct Taylor2Args {
   const double* VF;
@@ -35,12 +50,17 @@ struct Taylor2Args {
   int NT;           // n-tiles per item (orbital slots / 4)
   int nbuf;         // 1 or 2 iterate buffers
   int nstage;       // ring depth
-  int m_off[5];     // m-group boundaries (4 groups)
-  int n_off[3];     // n-group boundaries (2 groups)
+  int m_off[5];                 // m-group boundaries (4 groups)
+  int n_off[T2_MAXG + 1];       // n-group (column group) boundaries
+  int mperm[T2_MAXG][4];        // m-group of the warp of column group g on sub-partition s
+  int dbg;                      // timing experiments only (PXB_TAYLOR_DBG): 1 no epilogue/barrier, 2 no phi reload
 };
 
-__device__ __forceinline__ void bar_sync_consumers() {
-  asm volatile("bar.sync 1, %0;" ::"n"(T2_CONSUMERS * 32) : "memory");
+// The column groups (warps 4g .. 4g+3) own disjoint orbital columns, i.e. independent Taylor
+// recursions: each synchronises on its own named barrier and they only meet at the VHS ring, so
+// one group's epilogue / barrier wait overlaps the other groups' DMMA streams on every sub-partition.
+__device__ __forceinline__ void bar_sync_group(int ng) {
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + ng) : "memory");
 }
 
 __device__ __forceinline__ double flip_sign_if(double v, unsigned mask) {
@@ -61,21 +81,40 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // (B-fragment order).  ASYNC: 16-byte cp.async copies (no registers, completes in the background).
 template <bool ASYNC>
 __device__ __forceinline__ void taylor2_load_tile(const Taylor2Args& a, double* Tl, int wg, int wl, int o0, int no,
-                                                  int ctid) {
+                                                  int gtid, int nt0, int ntn) {
   const Dims& d = a.d;
   const int NT = a.NT;
-  for (int idx = ctid; idx < d.KC * NT * 16; idx += T2_CONSUMERS * 32) {
-    const int oo = idx & 3, tt = (idx >> 2) & 3, r = idx >> 4;
-    const int nt = r % NT, kc = r / NT;
-    const int ol = 4 * nt + oo;
-    double2* dst = reinterpret_cast<double2*>(Tl + ((size_t)kc * NT + nt) * 32 + tb_off(tt, 2 * oo));
-    const double* src = a.phi + (((size_t)wg * d.ne + o0 + ol) * d.KC + kc) * 32 + wl * 8 + tt * 2;
-    if (ol >= no)
-      *dst = make_double2(0.0, 0.0);
-    else if (ASYNC)
-      cp_async_16(dst, src);
-    else
-      *dst = *reinterpret_cast<const double2*>(src);
+  constexpr int GT = 128;                // threads of a warp group
+  constexpr int U = 4;                   // independent loads in flight per thread (synchronous path)
+  const int total = d.KC * ntn * 16;
+  // the n-tiles [nt0, nt0 + ntn) of this warp group, by its 128 threads
+  for (int base = gtid; base < total; base += GT * U) {
+    double2 v[U];
+    double2* dst[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int idx = base + u * GT;
+      dst[u] = nullptr;
+      v[u] = make_double2(0.0, 0.0);
+      if (idx < total) {
+        const int oo = idx & 3, tt = (idx >> 2) & 3, r = idx >> 4;
+        const int nt = nt0 + r % ntn, kc = r / ntn;
+        const int ol = 4 * nt + oo;
+        dst[u] = reinterpret_cast<double2*>(Tl + ((size_t)kc * NT + nt) * 32 + tb_off(tt, 2 * oo));
+        const double* src = a.phi + (((size_t)wg * d.ne + o0 + ol) * d.KC + kc) * 32 + wl * 8 + tt * 2;
+        if (ol < no) {
+          if (ASYNC) {
+            cp_async_16(dst[u], src);
+            dst[u] = nullptr;
+          } else {
+            v[u] = *reinterpret_cast<const double2*>(src);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (dst[u] != nullptr) *dst[u] = v[u];
   }
 }
 
@@ -87,7 +126,7 @@ template <int WM, int WN>
 __device__ __forceinline__ void taylor2_orders(const Taylor2Args& a, double* Tbuf, const double* ring,
                                                uint64_t* full, uint64_t* empty, unsigned& itc, int& cur,
                                                int m0, int n0, int wg, int wl, int o0, int no, int lane,
-                                               int nwg, int nwl, int no0, int nno, int ctid) {
+                                               int nwg, int nwl, int no0, int nno, int gtid, int ng) {
   const Dims& d = a.d;
   const int g = lane >> 2, t = lane & 3;
   const int NT = a.NT;
@@ -122,7 +161,8 @@ __device__ __forceinline__ void taylor2_orders(const Taylor2Args& a, double* Tbu
     const double* Tcur = Tbuf + (size_t)cur * tsz;
     // during the last order the iterate buffer nobody reads receives the next item's phi tile
     if (n == 1 && a.nbuf == 2 && nwg >= 0)
-      taylor2_load_tile<true>(a, Tbuf + (size_t)(cur ^ 1) * tsz, nwg, nwl, no0, nno, ctid);
+      taylor2_load_tile<true>(a, Tbuf + (size_t)(cur ^ 1) * tsz, nwg, nwl, no0, nno, gtid, a.n_off[ng],
+                              a.n_off[ng + 1] - a.n_off[ng]);
     for (int ks = 0; ks < nks; ++ks, ++itc) {
       const unsigned s = itc % (unsigned)a.nstage, ph = (itc / (unsigned)a.nstage) & 1u;
       mbar_wait(&full[s], ph);
@@ -162,7 +202,8 @@ __device__ __forceinline__ void taylor2_orders(const Taylor2Args& a, double* Tbu
     // The reference divides by n (Temp = VHS.dot(Temp) / n); multiplying by the correctly rounded
     // reciprocal differs by at most one ulp per element.
     const double rn = 1.0 / (double)n;
-    if (a.nbuf == 1) bar_sync_consumers();  // everyone has finished reading S_n
+    if (a.dbg & 1) continue;
+    if (a.nbuf == 1) bar_sync_group(ng);  // the group has finished reading S_n
     double* Tnext = Tbuf + (size_t)(a.nbuf == 2 ? (cur ^ 1) : 0) * tsz;
 #pragma unroll
     for (int i = 0; i < WM; ++i) {
@@ -183,16 +224,17 @@ __device__ __forceinline__ void taylor2_orders(const Taylor2Args& a, double* Tbu
       }
     }
     if (n > 1) {
-      load_phi((double)(n - 1));  // in flight across the barrier
-      bar_sync_consumers();       // S_{n-1} complete
+      if (!(a.dbg & 2)) load_phi((double)(n - 1));  // in flight across the barrier
+      bar_sync_group(ng);         // S_{n-1} complete
       if (a.nbuf == 2) cur ^= 1;
     }
   }
 }
 
 // WMX = ceil(MT / 4), WNX = ceil(NT / 2): the largest warp rectangle; smaller groups use WMX-1 / WNX-1
-template <int WMX, int WNX>
-__global__ void __launch_bounds__(T2_THREADS, 1) taylor2_kernel(Taylor2Args a) {
+template <int WMX, int WNX, int NG>
+__global__ void __launch_bounds__(T2Cfg<NG>::threads, 1) taylor2_kernel(Taylor2Args a) {
+  constexpr int T2_CONSUMERS = T2Cfg<NG>::consumers;
   extern __shared__ __align__(128) double t2_smem[];
   const Dims& d = a.d;
   const int NT = a.NT;
@@ -215,7 +257,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) taylor2_kernel(Taylor2Args a) {
   const int nks = (d.KC + T2_KS - 1) / T2_KS;
 
   if (warp >= T2_CONSUMERS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2_REGS_PRODUCER));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2Cfg<NG>::regs_producer));
     if (warp != T2_CONSUMERS) return;
     // ---------------- producer: lane mt streams m-tile mt of the walker's VHS ----------------
     unsigned itc = 0;
@@ -241,15 +283,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) taylor2_kernel(Taylor2Args a) {
   }
 
   // ---------------- consumers ----------------
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2_REGS_CONSUMER));
-  // warp w < 4: m-group w, big n-group; warp w >= 4: m-group 7 - w, small n-group, so that the two
-  // warps of a sub-partition (w, w + 4) pair a big rectangle with a small one
-  const int mg = warp < 4 ? warp : 7 - warp, ng = warp < 4 ? 0 : 1;
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2Cfg<NG>::regs_consumer));
+  // warp w: column group w / 4 on sub-partition w % 4; the host permutes the m-groups per column
+  // group so that every sub-partition gets the same number of tile products
+  const int ng = warp >> 2, mg = a.mperm[ng][warp & 3];
   const int m0 = a.m_off[mg], wm = a.m_off[mg + 1] - m0;
   const int n0 = a.n_off[ng], wn = a.n_off[ng + 1] - n0;
   unsigned itc = 0;
   int cur = 0;
-  const int ctid = tid;  // 0..255
+  const int gtid = tid & 127;  // thread index inside the warp group
   // first active item of this CTA
   auto next_active = [&](int item) {
     while (item < nitems && a.active != nullptr && a.active[item / a.nchunks] == 0) item += gridDim.x;
@@ -276,15 +318,15 @@ __global__ void __launch_bounds__(T2_THREADS, 1) taylor2_kernel(Taylor2Args a) {
     if (prefetched) {
       cp_async_wait_all();  // issued during the previous item's last order
     } else {
-      if (a.nbuf == 1) bar_sync_consumers();
-      taylor2_load_tile<false>(a, Tbuf + (size_t)ld * tsz, wg, wl, o0, no, ctid);
+      if (a.nbuf == 1) bar_sync_group(ng);
+      taylor2_load_tile<false>(a, Tbuf + (size_t)ld * tsz, wg, wl, o0, no, gtid, n0, wn);
     }
-    bar_sync_consumers();
+    bar_sync_group(ng);
     cur = ld;
     prefetched = a.nbuf == 2 && nwg >= 0;
 #define PXB_T2_CASE(WM_, WN_)                                                                              \
   taylor2_orders<WM_, WN_>(a, Tbuf, ring, full, empty, itc, cur, m0, n0, wg, wl, o0, no, lane, nwg, nwl, no0, \
-                           nno, ctid)
+                           nno, gtid, ng)
     if (wm == WMX && wn == WNX) PXB_T2_CASE(WMX, WNX);
     else if (wm == WMX && wn == WNX - 1) PXB_T2_CASE(WMX, (WNX - 1));
     else if (wm == WMX - 1 && wn == WNX) PXB_T2_CASE((WMX - 1), WNX);

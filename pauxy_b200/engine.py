@@ -253,6 +253,9 @@ class Engine(object):
     def exchange_is_eri(self):
         return bool(self.lib.pxb_exchange_mode(self._h) == L.EXCHANGE_MODES['eri'])
 
+    def vhs_is_symmetric(self):
+        return bool(self.lib.pxb_vhs_symmetric(self._h) == 1)
+
     def profile(self, enable=True):
         """Bracket every stage with CUDA events on the launch stream (see stage_times)."""
         self._check(self.lib.pxb_profile(self._h, 1 if enable else 0))

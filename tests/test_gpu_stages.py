@@ -29,6 +29,13 @@ def _case(name):
         rs = numpy.random.RandomState(5)
         psi = rs.normal(size=(10, 6)).astype(numpy.complex128)
         return h1e, hs, enuc, (4, 2), 0.01, psi
+    if name == 'asym':  # Cholesky matrices NOT symmetric in (p,q): the full (non-mirrored) VHS GEMM
+        numpy.random.seed(11)
+        h1e, chol, enuc, _ = generate_hamiltonian(14, (5, 3))
+        hs = chol.reshape((-1, 196)).T.copy()
+        rs = numpy.random.RandomState(6)
+        hs = hs + 0.02 * rs.normal(size=hs.shape)
+        return h1e, hs, enuc, (5, 3), 0.005, None
     if name == 'c2':
         h1e, hs, ecore = synthetic_cholesky_hamiltonian(24, 120, 1002)
         return h1e, hs, ecore, (5, 5), 0.005, None
@@ -44,7 +51,7 @@ def _case(name):
     raise KeyError(name)
 
 
-CASES = [('c1', 13), ('odd', 7), ('c2', 18), ('c3', 9), ('c4', 6), ('c5', 3)]
+CASES = [('c1', 13), ('odd', 7), ('asym', 9), ('c2', 18), ('c3', 9), ('c4', 6), ('c5', 3)]
 
 
 @pytest.fixture(scope='module', params=CASES, ids=[c[0] for c in CASES])
