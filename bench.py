@@ -285,6 +285,7 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    comm.warmup(dev)
     for _ in range(max(args.warmup, 3)):
         one_step(False)
     launches0 = eng.launch_count()

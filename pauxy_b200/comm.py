@@ -29,6 +29,9 @@ class SingleComm(object):
     def exchange(self, sends, recvs):
         assert not sends and not recvs
 
+    def warmup(self, device=None):
+        pass
+
 
 class TorchComm(object):
     """One process per GPU; rank r owns global walkers [r*nw, (r+1)*nw)."""
@@ -44,6 +47,19 @@ class TorchComm(object):
         self.dist.barrier(self.group)
 
     Barrier = barrier
+
+    def warmup(self, device):
+        """Open every channel the hot path can use (all-gather, all-reduce, send/recv with every
+        peer) so that connection set-up does not land inside a timed or latency-sensitive step."""
+        t = torch.zeros(8, dtype=torch.float64, device=device)
+        self.allgather_tensor(t)
+        self.allreduce_sum_(t)
+        for shift in range(1, self.size):
+            to, frm = (self.rank + shift) % self.size, (self.rank - shift) % self.size
+            r = torch.empty(8, dtype=torch.float64, device=device)
+            self.exchange([(to, t)], [(frm, r)])
+        if device is not None and torch.device(device).type == 'cuda':
+            torch.cuda.synchronize(device)
 
     def bcast(self, obj, root=0):
         box = [obj]

@@ -14,6 +14,7 @@
 #include "pxb_exchange.cuh"
 #include "pxb_gemm.cuh"
 #include "pxb_greens.cuh"
+#include "pxb_greens2.cuh"
 #include "pxb_small.cuh"
 #include "pxb_taylor.cuh"
 #include "pxb_taylor2.cuh"
@@ -29,7 +30,7 @@ struct Region {
 enum ArenaId {
   A_LF, A_RF, A_BF, A_PSIT, A_H1ROT, A_VBAR,
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
-  A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
+  A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_OB, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -57,6 +58,7 @@ struct pxb_context {
   std::vector<cudaEvent_t> evpool;
   double stage_ms[PXB_STAGE_COUNT] = {0};
   long long stage_calls[PXB_STAGE_COUNT] = {0};
+  bool greens_split = true;  // batched overlap GEMM + warp-per-walker inverse/Theta (PXB_GREENS=fused: one CTA per walker)
   bool vhs_sym = false;  // L symmetric in (p,q): the VHS GEMM computes the upper triangle only
   bool vhs_sym_allowed = true;
   int rtu = 0;           // row tiles kept in that case
@@ -165,6 +167,50 @@ int launch_greens(pxb_handle h, const GreensArgs& a, size_t smem, cudaStream_t s
   return PXB_OK;
 }
 
+template <int NMT>
+int launch_greens2(pxb_handle h, const double* phi, cudaStream_t st) {
+  const Dims& d = h->d;
+  const int nmax = d.na > d.nb ? d.na : d.nb;
+  const int nld = nmax | 1, nsq = nmax * nld;
+  // 1. O_s = phi_s^T psi_s for all walkers
+  for (int s = 0; s < 2; ++s) {
+    const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
+    if (ns == 0) continue;
+    GemmArgs g;
+    g.A = h->ptr<double>(A_PF) + (s ? (size_t)((d.na + 7) >> 3) * d.KC * 32 : 0);
+    g.B = phi + (size_t)ioff * d.KC * 32;
+    g.strideAz = g.strideBz = 0;
+    g.strideBO = (size_t)d.ne * d.KC * 32;
+    g.strideBI = (size_t)d.KC * 32;
+    g.ntInner = ns;
+    g.MTiles = (ns + 7) >> 3;
+    g.NTiles = d.WG * ns;
+    g.KS = d.KC;
+    EpiO epi{h->ptr<double2>(A_OB), ns, s, nld, nsq};
+    ++h->launches;
+    PXB_CUDA(h, (launch_gemm_tma<NMT, 4, 1, 6>(g, epi, 1, h->sm_count, st)));
+  }
+  // 2. inverse, slogdet, Theta, e1b: one warp per (walker, spin)
+  ThetaArgs a;
+  a.OB = h->ptr<double2>(A_OB);
+  a.phi = phi;
+  a.theta = h->ptr<double>(A_THETA);
+  a.h1rot = h->ptr<double2>(A_H1ROT);
+  a.slog = h->ptr<double>(A_SLOG);
+  a.e1b_part = h->ptr<double2>(A_E1BP);
+  a.d = d;
+  a.nld = nld;
+  a.nsq = nsq;
+  const size_t spw = theta_smem_per_warp(nmax);
+  const size_t smem = spw * TH_WARPS;
+  if (smem > (size_t)h->max_smem_optin) return 1;
+  PXB_CUDA(h, cudaFuncSetAttribute(theta_kernel<NMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ++h->launches;
+  theta_kernel<NMT><<<(2 * d.Wp + TH_WARPS - 1) / TH_WARPS, TH_WARPS * 32, smem, st>>>(a, (int)spw);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
 int run_greens(pxb_handle h, const double* phi, bool want_theta, double2* ovlp_out, bool with_e1b,
                cudaStream_t st) {
   StageTimer timer__(h, PXB_STAGE_GREENS, st);
@@ -181,8 +227,19 @@ int run_greens(pxb_handle h, const double* phi, bool want_theta, double2* ovlp_o
   const size_t smem = greens_smem_bytes(d);
   if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "greens: problem too large for shared memory");
   const int nmt = ((d.na > d.nb ? d.na : d.nb) + 7) >> 3;
-  int rc;
-  if (nmt <= 1) rc = launch_greens<1>(h, a, smem, st);
+  int rc = 1;
+  if (h->greens_split && want_theta) {
+    if (nmt <= 1) rc = launch_greens2<1>(h, phi, st);
+    else if (nmt <= 2) rc = launch_greens2<2>(h, phi, st);
+    else if (nmt <= 3) rc = launch_greens2<3>(h, phi, st);
+    else if (nmt <= 4) rc = launch_greens2<4>(h, phi, st);
+    else if (nmt <= 5) rc = launch_greens2<5>(h, phi, st);
+    else if (nmt <= 6) rc = launch_greens2<6>(h, phi, st);
+    else if (nmt <= 8) rc = launch_greens2<8>(h, phi, st);
+  }
+  if (rc != 1) {
+    if (rc) return rc;
+  } else if (nmt <= 1) rc = launch_greens<1>(h, a, smem, st);
   else if (nmt <= 2) rc = launch_greens<2>(h, a, smem, st);
   else if (nmt <= 3) rc = launch_greens<3>(h, a, smem, st);
   else if (nmt <= 4) rc = launch_greens<4>(h, a, smem, st);
@@ -576,6 +633,8 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   {
     const char* g = getenv("PXB_GEMM");
     if (g && strcmp(g, "direct") == 0) h->gemm_tma = false;
+    const char* gr = getenv("PXB_GREENS");
+    if (gr && strcmp(gr, "fused") == 0) h->greens_split = false;
     const char* v = getenv("PXB_VHS");
     if (v && strcmp(v, "full") == 0) h->vhs_sym_allowed = false;
     const char* t = getenv("PXB_TAYLOR");
@@ -653,6 +712,10 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_KF0, h->exx_eri ? eri_kf_doubles(d, 0) * 8 : 0);
   add(A_KF1, h->exx_eri ? eri_kf_doubles(d, 1) * 8 : 0);
   add(A_RTMAP, (size_t)d.RT * 4);
+  {
+    const size_t nmax = d.na > d.nb ? d.na : d.nb;
+    add(A_OB, W * 2 * nmax * (nmax | 1) * 16);
+  }
   add(A_EPART, h->exx_eri ? (size_t)2 * h->eri_nslot * W * 16 : 0);
   add(A_E1B, W * 16);
   add(A_OVLP_OLD, W * 16);

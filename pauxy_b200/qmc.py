@@ -118,6 +118,7 @@ class AFQMC(object):
                                      self.propagators.BT_BP, verbose, engine=self.engine)
         self.psi = Walkers(self.system, self.trial, self.qmc, self.engine, walker_opts=wlk_opts,
                            verbose=verbose, comm=comm)
+        comm.warmup(self.engine.device)
         self.setup_timers()
         self.sync_timers = bool(options.get('sync_timers', False))
         if verbose:

@@ -137,6 +137,7 @@ def _gloo_worker(rank, world, port, q):
     dist.init_process_group('gloo', rank=rank, world_size=world)
     from pauxy_b200.comm import TorchComm
     comm = TorchComm()
+    comm.warmup(torch.device('cpu'))
     nw = 4
     w = torch.arange(nw, dtype=torch.float64) + 10 * rank
     gw = comm.allgather_tensor(w)
