@@ -50,7 +50,7 @@ inline size_t theta_smem_per_warp(int nmax) {
 
 // NMT: 8-row tiles over the occupied orbitals of one spin (ceil(ns/8) <= NMT)
 template <int NMT>
-__global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a, int smem_per_warp) {
+__global__ void __launch_bounds__(TH_WARPS * 32, NMT <= 3 ? 7 : 1) theta_kernel(ThetaArgs a, int smem_per_warp) {
   extern __shared__ __align__(16) unsigned char th_raw[];
   const Dims& d = a.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -178,34 +178,61 @@ __global__ void __launch_bounds__(TH_WARPS * 32) theta_kernel(ThetaArgs a, int s
   const double* phis = a.phi + ((size_t)wg * d.ne + ioff) * d.KC * 32 + wl * 8 + g;
   const unsigned smask = (g & 1) ? 0u : 0x80000000u;  // (i B)^: (re, im) -> (-im, re)
   double er = 0.0, ei = 0.0;
+  // B fragments of one iteration (two basis chunks x all k-steps) are loaded together: one
+  // global-load latency per iteration instead of one per k-step.  For the larger shapes, where few
+  // warps fit on an SM, they are also loaded one iteration ahead (costs 4 NMT more registers).
+  constexpr int KSM = 2 * NMT;  // >= ceil(ns / 4)
+  constexpr bool AHEAD = NMT >= 4;
+  const double* bptr[KSM];
+#pragma unroll
+  for (int ks = 0; ks < KSM; ++ks) {
+    const int i = min(4 * ks + t, ns - 1);  // clamped: the matching A entries are zero
+    bptr[ks] = phis + (size_t)i * d.KC * 32;
+  }
+  double bn[KSM][2];
+  auto load_b = [&](int pc0) {
+    const bool one = pc0 < d.KC, two = pc0 + 1 < d.KC;
+#pragma unroll
+    for (int ks = 0; ks < KSM; ++ks) {
+      bn[ks][0] = (one && ks < KS) ? ldg_nc(bptr[ks] + (size_t)pc0 * 32) : 0.0;
+      bn[ks][1] = (two && ks < KS) ? ldg_nc(bptr[ks] + (size_t)pc0 * 32 + 32) : 0.0;
+    }
+  };
+  if (AHEAD) load_b(0);
   for (int pc0 = 0; pc0 < d.KC; pc0 += 2) {
-    const bool two = pc0 + 1 < d.KC;
+    if (!AHEAD) load_b(pc0);
+    double b[KSM][2];
+#pragma unroll
+    for (int ks = 0; ks < KSM; ++ks) {
+      b[ks][0] = bn[ks][0];
+      b[ks][1] = bn[ks][1];
+    }
+    if (AHEAD) load_b(pc0 + 2);
     double acc[NMT][2][2];
 #pragma unroll
     for (int m = 0; m < NMT; ++m)
 #pragma unroll
       for (int q = 0; q < 2; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
-    for (int ks = 0; ks < KS; ++ks) {
-      const int i = min(4 * ks + t, ns - 1);  // clamped: the matching A entries are zero
-      const double* bp = phis + ((size_t)i * d.KC + pc0) * 32;
-      double b[2], bq[2];
-      b[0] = ldg_nc(bp);
-      b[1] = two ? ldg_nc(bp + 32) : 0.0;
 #pragma unroll
-      for (int q = 0; q < 2; ++q) {
-        const double o = __shfl_xor_sync(0xffffffffu, b[q], 4);
-        bq[q] = __hiloint2double(__double2hiint(o) ^ (int)smask, __double2loint(o));
-      }
-      const bool iv = 4 * ks + t < ns;
+    for (int ks = 0; ks < KSM; ++ks) {
+      if (ks < KS) {
+        double bq[2];
 #pragma unroll
-      for (int m = 0; m < NMT; ++m) {
-        if (m < nmt) {
-          const int ar = 8 * m + g;
-          const cplx av = (iv && ar < ns) ? A[(size_t)ar * lda + 4 * ks + t] : cplx{0.0, 0.0};
+        for (int q = 0; q < 2; ++q) {
+          const double o = __shfl_xor_sync(0xffffffffu, b[ks][q], 4);
+          bq[q] = __hiloint2double(__double2hiint(o) ^ (int)smask, __double2loint(o));
+        }
+        const bool iv = 4 * ks + t < ns;
 #pragma unroll
-          for (int q = 0; q < 2; ++q) {
-            dmma(acc[m][q][0], acc[m][q][1], av.re, b[q]);
-            dmma(acc[m][q][0], acc[m][q][1], av.im, bq[q]);
+        for (int m = 0; m < NMT; ++m) {
+          if (m < nmt) {
+            const int ar = 8 * m + g;
+            const cplx av = (iv && ar < ns) ? A[(size_t)ar * lda + 4 * ks + t] : cplx{0.0, 0.0};
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+              dmma(acc[m][q][0], acc[m][q][1], av.re, b[ks][q]);
+              dmma(acc[m][q][0], acc[m][q][1], av.im, bq[q]);
+            }
           }
         }
       }
