@@ -207,6 +207,13 @@ def update_weight_hybrid(ham, weight, ot_old, ot_new, ehyb_old, cfb, cmf, eshift
     return weight, ot, eh, trig
 
 
+def update_weight_free(ham, weight, phase, cmf, eshift):
+    """propagation/continuous.py:194-198 (free projection): the constant terms go into the
+    walker's weight and phase.  Returns (weight, phase)."""
+    magn, dtheta = cmath.polar(cmath.exp(cmf + ham.dt * eshift))
+    return weight * magn, phase * cmath.exp(1j * dtheta)
+
+
 def reortho(ham, phi):
     """walkers/single_det.py:215-255.  Returns (phi_new, detR [W], log_det [W])."""
     na = ham.nup
@@ -323,7 +330,7 @@ class OracleAFQMC(object):
     def __init__(self, ham, nwalkers, nsteps=10, nblocks=10, nstblz=10,
                  npop_control=1, energy_eval_freq=1, exp_order=6,
                  pop_control='comb', min_weight=0.1, max_weight=4.0,
-                 verbose_step0=False):
+                 verbose_step0=False, free_projection=False, force_bias=True):
         self.ham = ham
         W = nwalkers
         self.W = W
@@ -338,6 +345,10 @@ class OracleAFQMC(object):
         self.weight = numpy.ones(W)
         self.unscaled_weight = numpy.ones(W)
         self.hybrid_energy = numpy.zeros(W, dtype=numpy.complex128)
+        self.phase = numpy.ones(W, dtype=numpy.complex128)
+        self.free_projection = free_projection
+        # continuous.py:30-33: free projection switches the force bias off
+        self.force_bias = force_bias and not free_projection
         self.ot = calc_overlap(ham, self.phi).astype(numpy.complex128)
         self.detR = numpy.ones(W)
         self.log_detR = numpy.zeros(W)
@@ -366,7 +377,10 @@ class OracleAFQMC(object):
             phi = self.phi[idx]
             tha, thb, ovlp_old = greens_function(ham, phi)
             phi = kinetic_real(ham, phi)
-            xbar, _ = force_bias(ham, tha, thb)
+            if self.force_bias:
+                xbar, _ = force_bias(ham, tha, thb)
+            else:
+                xbar = numpy.zeros(xi_active.shape, dtype=numpy.complex128)  # continuous.py:136-138
             x, cmf, cfb, ntrig = shift_fields(ham, xi_active, xbar)
             self.nfb_trig += ntrig
             vhs = construct_vhs(ham, x)
@@ -375,6 +389,13 @@ class OracleAFQMC(object):
             ovlp_new = calc_overlap(ham, phi)
             self.phi[idx] = phi
             for k, iw in enumerate(idx):
+                if self.free_projection:
+                    # continuous.py:175-200 (xbar == 0 here: continuous.py:30-33)
+                    self.weight[iw], self.phase[iw] = update_weight_free(
+                        ham, float(self.weight[iw]), complex(self.phase[iw]), complex(cmf[k]),
+                        self.eshift)
+                    self.ot[iw] = ovlp_new[k]
+                    continue
                 w, ot, eh, trig = update_weight_hybrid(
                     ham, float(self.weight[iw]), complex(ovlp_old[k]), complex(ovlp_new[k]),
                     complex(self.hybrid_energy[iw]), complex(cfb[k]), complex(cmf[k]),
@@ -421,6 +442,7 @@ class OracleAFQMC(object):
             self.unscaled_weight[k] = self.unscaled_weight[c]
             self.ot[k] = self.ot[c]
             self.hybrid_energy[k] = self.hybrid_energy[c]
+            self.phase[k] = self.phase[c]
             self.detR[k] = self.detR[c]
             self.log_detR[k] = self.log_detR[c]
             self.eloc[k] = self.eloc[c]
@@ -434,6 +456,20 @@ class OracleAFQMC(object):
             self.eloc = local_energy(self.ham, tha, thb)
         for iw in range(self.W):
             w = self.weight[iw]
+            if self.free_projection:
+                # estimators/mixed.py:151-177
+                wfac = w * self.ot[iw] * self.phase[iw]
+                if step % self.energy_eval_freq == 0:
+                    E, T, V = self.eloc[iw]
+                    es[2] += wfac * E
+                    es[5] += wfac * T
+                    es[6] += wfac * V
+                    es[3] += wfac
+                es[0] += self.unscaled_weight[iw]
+                es[1] += wfac
+                es[7] += wfac * self.hybrid_energy[iw]
+                es[8] += w * abs(self.ot[iw])
+                continue
             if step % self.energy_eval_freq == 0:
                 E, T, V = self.eloc[iw]
                 es[2] += w * E.real
@@ -474,6 +510,10 @@ class OracleAFQMC(object):
             self.detR = detR
             self.log_detR = self.log_detR + numpy.log(detR)
             self.ot = self.ot / detR
+            if self.free_projection:
+                # walkers/handler.py:178-181: polar(detR), detR real positive
+                self.weight = self.weight * numpy.abs(detR)
+                self.phase = self.phase * numpy.exp(1j * numpy.angle(detR))
         active = numpy.abs(self.weight) > 1e-8
         self.propagate(xi_active, active)
         if step % self.npop_control == 0:

@@ -36,6 +36,8 @@ def options(nwalkers, dt, steps, blocks, seed, stab=10, popc=1, walkers=None):
 
 def save(name, meta, tr, setup=None, keep_xi=True, keep_phi=True, extra=None):
     out = dict(meta)
+    if 'phase' in tr:
+        out['phase'] = tr['phase']
     for k in ('weight_prop', 'weight', 'unscaled_weight', 'ot', 'hybrid_energy', 'eloc',
               'parent_ix', 'comb_r', 'eshift', 'estimates', 'detR', 'total_weight',
               'init_ot', 'init_estimates', 'nfb_trig', 'nhe_trig', 'rows', 'active'):
@@ -91,6 +93,24 @@ def case_c1():
     meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array((4, 4)), dt=0.005,
                 nwalkers=32, steps=10, blocks=4, seed=8, stab=5, popc=1)
     save('c1', meta, tr, setup=rh.reference_setup_arrays(a))
+
+
+def case_free(name, free, force_bias, pop='comb', walkers=None):
+    """Free projection (propagation/continuous.py:175-200, walkers/handler.py:178-181,
+    estimators/mixed.py:151-177; the reference switches the force bias off there,
+    continuous.py:30-33) and the phaseless walk without force bias (continuous.py:136-138)."""
+    numpy.random.seed(7)
+    h1e, chol, enuc, _ = generate_hamiltonian(12, (4, 4), cplx=False)
+    hs = 4.0 * chol.reshape((-1, 144)).T.copy()   # scaled: comb / pair-branch events must fire
+    opts = options(16, 0.01, 5, 6, 8, stab=4, popc=1, walkers=walkers)
+    opts['propagator'] = {'free_projection': free, 'force_bias': force_bias}
+    a, tr = rh.run_reference_traced(h1e, hs, enuc, (4, 4), opts)
+    meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array((4, 4)), dt=0.01,
+                nwalkers=16, steps=5, blocks=6, seed=8, stab=4, popc=1,
+                free_projection=free, force_bias=force_bias, pop_control=pop,
+                min_weight=(walkers or {}).get('min_weight', 0.1),
+                max_weight=(walkers or {}).get('max_weight', 4.0))
+    save(name, meta, tr, setup=rh.reference_setup_arrays(a))
 
 
 def case_stress(name, pop, walkers=None, scale_chol=6.0, dt=0.02):
@@ -151,7 +171,13 @@ def case_local_energy():
 
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ['tg', 'c1', 'stress', 'pb', 'le', 'c2s', 'c3s', 'c4s']
+    which = sys.argv[1:] or ['tg', 'c1', 'stress', 'pb', 'le', 'c2s', 'c3s', 'c4s', 'free']
+    if 'free' in which:
+        case_free('free_comb', True, True)
+        case_free('free_pair_branch', True, False, pop='pair_branch',
+                  walkers={'population_control': 'pair_branch', 'min_weight': 0.9,
+                           'max_weight': 1.1})
+        case_free('phaseless_nofb', False, False)
     if 'tg' in which:
         case_test_generic()
     if 'c1' in which:

@@ -88,7 +88,7 @@ def run_reference_traced(h1e, hs_pot, ecore, nelec, options, nsteps_total=None):
 
     tr = {k: [] for k in ('xi', 'active', 'weight_prop', 'weight', 'unscaled_weight',
                           'ot', 'hybrid_energy', 'eloc', 'parent_ix', 'comb_r',
-                          'eshift', 'estimates', 'detR', 'total_weight')}
+                          'eshift', 'estimates', 'detR', 'total_weight', 'phase')}
 
     # record fields and the comb's random number through the real RNG calls
     real_normal = numpy.random.normal
@@ -168,6 +168,7 @@ def run_reference_traced(h1e, hs_pot, ecore, nelec, options, nsteps_total=None):
             tr['hybrid_energy'].append(numpy.array([w.hybrid_energy for w in psi.walkers],
                                                    dtype=numpy.complex128))
             tr['detR'].append(numpy.array([w.detR for w in psi.walkers]))
+            tr['phase'].append(numpy.array([w.phase for w in psi.walkers], dtype=numpy.complex128))
             tr['total_weight'].append(psi.walkers[0].total_weight)
             tr['eloc'].append(eloc_now.copy())
     finally:

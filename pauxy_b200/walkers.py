@@ -202,7 +202,7 @@ class Walkers(object):
         self._check_total_weight()
         npairs = int(pairs[0])
         pl = pairs[1:1 + 2 * npairs].reshape(npairs, 2)
-        self._move(comm, [(int(c), int(k)) for c, k in pl])
+        self._move(comm, pl)
         eng.set_weights(1.0)
 
     def pair_branch(self, comm):
@@ -264,17 +264,23 @@ def plan_moves(pairs, nw, rank):
     live (rank = index // nw, slot = index % nw, handler.py:303-321).
     Returns (local [(src_slot, dst_slot)], out {peer: [src_slot]}, inc {peer:
     [dst_slot]}); per peer the two slot lists are in the same pair order on
-    both sides, so packed buffers line up."""
-    lo = rank * nw
+    both sides, so packed buffers line up.  Vectorised: the pair list has a few
+    thousand entries per step at 8 x 8192 walkers."""
+    p = numpy.asarray(pairs, dtype=numpy.int64).reshape(-1, 2)
     local, out, inc = [], {}, {}
-    for c, k in pairs:
-        rc, rk = c // nw, k // nw
-        if rc == rank and rk == rank:
-            local.append((c - lo, k - lo))
-        elif rc == rank:
-            out.setdefault(rk, []).append(c - lo)
-        elif rk == rank:
-            inc.setdefault(rc, []).append(k - lo)
+    if p.shape[0] == 0:
+        return local, out, inc
+    c, k = p[:, 0], p[:, 1]
+    rc, rk = c // nw, k // nw
+    lo = rank * nw
+    here = (rc == rank) & (rk == rank)
+    local = list(zip((c[here] - lo).tolist(), (k[here] - lo).tolist()))
+    so = (rc == rank) & (rk != rank)
+    for peer in numpy.unique(rk[so]).tolist():
+        out[int(peer)] = (c[so & (rk == peer)] - lo).tolist()
+    si = (rk == rank) & (rc != rank)
+    for peer in numpy.unique(rc[si]).tolist():
+        inc[int(peer)] = (k[si & (rc == peer)] - lo).tolist()
     return local, out, inc
 
 
