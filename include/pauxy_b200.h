@@ -32,7 +32,7 @@ extern "C" {
 #define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
 #define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
 
-#define PXB_ABI_VERSION 2
+#define PXB_ABI_VERSION 3
 
 typedef struct pxb_context* pxb_handle;
 
@@ -211,6 +211,30 @@ int pxb_pack_walkers(pxb_handle h, const int32_t* dev_slots, int n, double* dev_
 int pxb_unpack_walkers(pxb_handle h, const int32_t* dev_slots, int n, const double* dev_buffer,
                        void* stream);
 int pxb_set_weights(pxb_handle h, double value, void* stream); /* handler.py:337-338 */
+
+/* Peer-memory comb for several devices of one node (walkers/handler.py:225-338 with the
+ * Isend/Recv of handler.py:301-334 replaced by direct NVLink reads).  The reference moves a cloned
+ * walker with MPI point-to-point messages whose sizes the host has to know; here every device maps
+ * the arenas of its peers (CUDA IPC) and pulls the clones of its own killed walkers with one
+ * kernel, so a pop-control step needs no host synchronisation at all.
+ *  pxb_peer_export : IPC handle (PXB_IPC_HANDLE_BYTES bytes) of the cudaMalloc block holding the
+ *                    arena and the arena's offset inside it; exchange them between the ranks
+ *                    (e.g. an all-gather), then
+ *  pxb_peer_attach : map every peer's arena.  handles: [nranks][PXB_IPC_HANDLE_BYTES] bytes,
+ *                    offsets: [nranks].  All ranks must use the same pxb_config except `device`.
+ *  pxb_pop_control_comb_peers : total weight, comb plan (identical on every rank from the
+ *                    all-gathered |weights|, r = the caller's uniform) and the pull of the clones.
+ *                    The caller must run a cross-device barrier ON THE STREAM (e.g. a 1-element
+ *                    all-reduce) between this call and
+ *  pxb_pop_control_finish : unscaled_weight = weight, weight = 1 (handler.py:247-248, :337-338);
+ *                    nothing that writes walker state may be enqueued before that barrier. */
+#define PXB_IPC_HANDLE_BYTES 64
+int pxb_peer_export(pxb_handle h, void* handle_out, uint64_t* offset_out);
+int pxb_peer_attach(pxb_handle h, int rank, int nranks, const void* handles,
+                    const uint64_t* offsets);
+int pxb_pop_control_comb_peers(pxb_handle h, const double* dev_global_abs_weights, int64_t wtot,
+                               double r, void* stream);
+int pxb_pop_control_finish(pxb_handle h, void* stream);
 
 /* Host helpers (pure C, no device): bit-exact restatements used by the host
  * mirror when the selection has to happen on the host. */

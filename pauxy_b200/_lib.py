@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libpauxy_b200.so')
 
 PXB_OK = 0
-ABI_VERSION = 2
+ABI_VERSION = 3
 EXCHANGE_MODES = {'auto': 0, 'cholesky': 1, 'eri': 2}
 ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_ERR_UNSUPPORTED'}
 
@@ -73,6 +73,10 @@ _PROTOS = {
     'pxb_pack_walkers': (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
     'pxb_unpack_walkers': (ctypes.c_int, [_vp, _vp, ctypes.c_int, _vp, _vp]),
     'pxb_set_weights': (ctypes.c_int, [_vp, ctypes.c_double, _vp]),
+    'pxb_peer_export': (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_uint64)]),
+    'pxb_peer_attach': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp]),
+    'pxb_pop_control_comb_peers': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_double, _vp]),
+    'pxb_pop_control_finish': (ctypes.c_int, [_vp, _vp]),
     'pxb_comb_plan_host': (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_double, _vp]),
     'pxb_stage_greens': (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     'pxb_stage_force_bias_gemm': (ctypes.c_int, [_vp, _vp]),

@@ -29,6 +29,9 @@ class SingleComm(object):
     def exchange(self, sends, recvs):
         assert not sends and not recvs
 
+    def stream_barrier(self, device=None):
+        pass
+
     def warmup(self, device=None):
         pass
 
@@ -60,6 +63,13 @@ class TorchComm(object):
             self.exchange([(to, t)], [(frm, r)])
         if device is not None and torch.device(device).type == 'cuda':
             torch.cuda.synchronize(device)
+
+    def stream_barrier(self, device):
+        """Cross-device barrier in STREAM order (no host wait): a 1-element all-reduce.  Work
+        enqueued after it on any rank starts only when every rank's earlier work has finished."""
+        if getattr(self, '_flag', None) is None or self._flag.device != torch.device(device):
+            self._flag = torch.zeros(1, dtype=torch.float64, device=device)
+        self.dist.all_reduce(self._flag, op=self.dist.ReduceOp.SUM, group=self.group)
 
     def bcast(self, obj, root=0):
         box = [obj]

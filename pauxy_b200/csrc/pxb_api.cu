@@ -66,6 +66,10 @@ struct pxb_context {
   bool exx_eri = false;  // exchange through the half-rotated ERI quadratic form (pxb_eri.cuh)
   bool kf_shared = false;  // both spins use the K of spin 0 (identical half-rotated Cholesky blocks)
   int eri_nslot = 0;
+  // peer-memory population control: arena bases of all ranks mapped through CUDA IPC
+  int peer_rank = -1, peer_n = 0;
+  unsigned char* peer_base[PXB_MAX_PEERS] = {nullptr};
+  void* peer_map[PXB_MAX_PEERS] = {nullptr};  // what cudaIpcOpenMemHandle returned (to close)
   std::string err;
 
   template <class T>
@@ -756,6 +760,8 @@ int pxb_destroy(pxb_handle h) {
       cudaEventDestroy(p.b);
     }
     for (auto e : h->evpool) cudaEventDestroy(e);
+    for (int r = 0; r < PXB_MAX_PEERS; ++r)
+      if (h->peer_map[r]) cudaIpcCloseMemHandle(h->peer_map[r]);
   }
   delete h;
   return PXB_OK;
@@ -1064,10 +1070,11 @@ int pxb_zero_estimates(pxb_handle h, void* stream) {
   return PXB_OK;
 }
 
-int pxb_pop_rescale(pxb_handle h, const double* gw, int64_t wtot, void* stream) {
+static int pop_rescale_impl(pxb_handle h, const double* gw, int64_t wtot, int write_local, void* stream) {
   PXB_REQUIRE_READY(h);
   if (wtot != h->d.Wtot) return fail(h, PXB_ERR_ARG, "wtot != total_walkers given at create");
   RescaleArgs a;
+  a.write_local = write_local;
   a.gw = gw;
   a.gws = h->ptr<double>(A_GWS);
   a.weight = h->field<double>(PXB_F_WEIGHT);
@@ -1080,6 +1087,10 @@ int pxb_pop_rescale(pxb_handle h, const double* gw, int64_t wtot, void* stream) 
   pop_rescale_kernel<<<1, 1024, 0, S(stream)>>>(a);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
+}
+
+int pxb_pop_rescale(pxb_handle h, const double* gw, int64_t wtot, void* stream) {
+  return pop_rescale_impl(h, gw, wtot, 1, stream);
 }
 
 int pxb_comb_plan(pxb_handle h, const double* gw, int64_t wtot, double r, void* stream) {
@@ -1127,6 +1138,88 @@ int pxb_pop_control_comb(pxb_handle h, double r, void* stream) {
   PXB_CUDA(h, cudaGetLastError());
   h->x_valid = false;  // Theta and e1b travel with the walkers, X does not
   return pxb_set_weights(h, 1.0, stream);
+}
+
+// ---- peer-memory comb (multi-device, no host round trip) ----------------------
+int pxb_peer_export(pxb_handle h, void* handle_out, uint64_t* offset_out) {
+  if (!h || !handle_out || !offset_out) return PXB_ERR_ARG;
+  if (!h->arena) return fail(h, PXB_ERR_STATE, "arena not bound");
+  static_assert(sizeof(cudaIpcMemHandle_t) == PXB_IPC_HANDLE_BYTES, "IPC handle size");
+  PXB_CUDA(h, cudaSetDevice(h->cfg.device));
+  // the arena may sit inside a larger cudaMalloc block (caching allocators): the IPC handle
+  // names the block, so the offset of the arena inside it travels with the handle
+  typedef int (*get_range_fn)(unsigned long long*, size_t*, unsigned long long);
+  void* fp = nullptr;
+  cudaDriverEntryPointQueryResult qr;
+  PXB_CUDA(h, cudaGetDriverEntryPoint("cuMemGetAddressRange", &fp, cudaEnableDefault, &qr));
+  if (!fp || qr != cudaDriverEntryPointSuccess) return fail(h, PXB_ERR_CUDA, "cuMemGetAddressRange not found");
+  unsigned long long base = 0;
+  size_t size = 0;
+  if (reinterpret_cast<get_range_fn>(fp)(&base, &size, (unsigned long long)(uintptr_t)h->arena) != 0)
+    return fail(h, PXB_ERR_CUDA, "cuMemGetAddressRange failed");
+  cudaIpcMemHandle_t mh;
+  PXB_CUDA(h, cudaIpcGetMemHandle(&mh, reinterpret_cast<void*>((uintptr_t)base)));
+  std::memcpy(handle_out, &mh, sizeof(mh));
+  *offset_out = (uint64_t)((uintptr_t)h->arena - (uintptr_t)base);
+  return PXB_OK;
+}
+
+int pxb_peer_attach(pxb_handle h, int rank, int nranks, const void* handles, const uint64_t* offsets) {
+  if (!h || !handles || !offsets) return PXB_ERR_ARG;
+  if (!h->arena) return fail(h, PXB_ERR_STATE, "arena not bound");
+  if (nranks < 1 || nranks > PXB_MAX_PEERS || rank < 0 || rank >= nranks)
+    return fail(h, PXB_ERR_ARG, "pxb_peer_attach: bad rank / nranks");
+  if ((long long)nranks * h->d.W != h->d.Wtot)
+    return fail(h, PXB_ERR_ARG, "pxb_peer_attach: nranks * nwalkers != total_walkers");
+  PXB_CUDA(h, cudaSetDevice(h->cfg.device));
+  const unsigned char* hb = static_cast<const unsigned char*>(handles);
+  for (int r = 0; r < nranks; ++r) {
+    if (r == rank) {
+      h->peer_base[r] = h->arena;
+      continue;
+    }
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, hb + (size_t)r * PXB_IPC_HANDLE_BYTES, sizeof(mh));
+    void* p = nullptr;
+    PXB_CUDA(h, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_map[r] = p;
+    h->peer_base[r] = static_cast<unsigned char*>(p) + offsets[r];
+  }
+  h->peer_rank = rank;
+  h->peer_n = nranks;
+  return PXB_OK;
+}
+
+int pxb_pop_control_comb_peers(pxb_handle h, const double* gw, int64_t wtot, double r, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  if (h->peer_n < 1) return fail(h, PXB_ERR_STATE, "pxb_peer_attach has not been called");
+  cudaStream_t st = S(stream);
+  StageTimer timer__(h, PXB_STAGE_POP_CONTROL, st);
+  int rc;
+  if ((rc = pop_rescale_impl(h, gw, wtot, 0, stream))) return rc;
+  if ((rc = pxb_comb_plan(h, gw, wtot, r, stream))) return rc;
+  PeerArgs p;
+  for (int i = 0; i < PXB_MAX_PEERS; ++i) p.base[i] = h->peer_base[i];
+  p.rank = h->peer_rank;
+  p.nranks = h->peer_n;
+  p.nw = d.W;
+  ++h->launches;
+  pull_pairs_kernel<<<4 * h->sm_count, 256, 0, st>>>(copy_args(h), p, h->field<int>(PXB_F_PAIRS));
+  PXB_CUDA(h, cudaGetLastError());
+  h->x_valid = false;
+  return PXB_OK;
+}
+
+int pxb_pop_control_finish(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  StageTimer timer__(h, PXB_STAGE_POP_CONTROL, S(stream));
+  ++h->launches;
+  pop_finish_kernel<<<(d.W + 255) / 256, 256, 0, S(stream)>>>(
+      h->field<double>(PXB_F_WEIGHT), h->field<double>(PXB_F_UNSCALED_WEIGHT), 1.0, d.W);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
 }
 
 int pxb_payload_doubles(pxb_handle h, size_t* n) {

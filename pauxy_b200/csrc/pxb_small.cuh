@@ -527,6 +527,7 @@ struct RescaleArgs {
   double* total_weight; // [1]
   long long* counters;
   int W, Wtot;
+  int write_local;      // 0: leave weight / unscaled alone (peer-memory comb: peers may still read them)
 };
 
 __global__ void __launch_bounds__(1024) pop_rescale_kernel(RescaleArgs a) {
@@ -554,6 +555,7 @@ __global__ void __launch_bounds__(1024) pop_rescale_kernel(RescaleArgs a) {
   const double scale = __ddiv_rn(total, (double)a.Wtot);
   if (tid == 0) a.total_weight[0] = total;
   for (int i = tid; i < a.Wtot; i += 1024) a.gws[i] = __ddiv_rn(a.gw[i], scale);
+  if (!a.write_local) return;
   for (int i = tid; i < a.W; i += 1024) {
     const double wt = a.weight[i];
     a.unscaled[i] = wt;
@@ -723,6 +725,69 @@ __global__ void __launch_bounds__(256) copy_list_kernel(CopyArgs a, const int* s
       a.log_detR[dst] = a.log_detR[src];
       for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)dst + k] = a.eloc[3 * (size_t)src + k];
     }
+  }
+}
+
+// Comb data movement over peer memory (handler.py:301-334 without the Isend/Recv): every
+// device runs the same plan; for each (clone, kill) pair whose KILL slot lives here the clone's
+// payload is read straight out of the owning device's arena (NVLink P2P loads through the
+// IPC-mapped base pointers; plain loads when the clone is local) and written into the local
+// slot.  Clone slots (parent_ix > 1) are never kill slots (parent_ix == 0), so sources are
+// read-only during this phase on every device; the caller brackets the phase with collectives
+// (all-gather of the weights before, a barrier after).  weight[dst] receives the clone's RAW
+// weight: pop_finish_kernel turns it into unscaled_weight afterwards.
+constexpr int PXB_MAX_PEERS = 16;
+struct PeerArgs {
+  const unsigned char* base[PXB_MAX_PEERS];  // arena base of every rank (own entry: local arena)
+  int rank, nranks, nw;
+};
+
+template <class T>
+__device__ __forceinline__ const T* rebase(const T* local, const unsigned char* local_base,
+                                           const unsigned char* peer_base) {
+  return reinterpret_cast<const T*>(peer_base + (reinterpret_cast<const unsigned char*>(local) - local_base));
+}
+
+__global__ void __launch_bounds__(256) pull_pairs_kernel(CopyArgs a, PeerArgs p, const int* pairs) {
+  const Dims& d = a.d;
+  const int np = pairs[0];
+  const unsigned char* lb = p.base[p.rank];
+  for (int pi = blockIdx.x; pi < np; pi += gridDim.x) {
+    const int c = pairs[1 + 2 * pi], k = pairs[2 + 2 * pi];
+    if (k / p.nw != p.rank) continue;
+    const int dst = k - p.rank * p.nw;
+    const int sr = c / p.nw, src = c - sr * p.nw;
+    const unsigned char* pb = p.base[sr];
+    const double* sphi = rebase(a.phi, lb, pb);
+    const double* sth = rebase(a.theta, lb, pb);
+    const int n8 = d.ne * d.KC;
+    for (int idx = threadIdx.x; idx < n8 * 4; idx += blockDim.x) {
+      const int r = idx >> 2, q = idx & 3;
+      const size_t so = ((size_t)(src >> 2) * n8 + r) * 32 + (src & 3) * 8 + q * 2;
+      const size_t dn = ((size_t)(dst >> 2) * n8 + r) * 32 + (dst & 3) * 8 + q * 2;
+      *reinterpret_cast<double2*>(a.phi + dn) = *reinterpret_cast<const double2*>(sphi + so);
+      *reinterpret_cast<double2*>(a.theta + dn) = *reinterpret_cast<const double2*>(sth + so);
+    }
+    if (threadIdx.x == 0) {
+      a.e1b[dst] = rebase(a.e1b, lb, pb)[src];
+      a.weight[dst] = rebase(a.weight, lb, pb)[src];
+      a.ot[dst] = rebase(a.ot, lb, pb)[src];
+      a.ehyb[dst] = rebase(a.ehyb, lb, pb)[src];
+      a.detR[dst] = rebase(a.detR, lb, pb)[src];
+      a.log_detR[dst] = rebase(a.log_detR, lb, pb)[src];
+      const double2* se = rebase(a.eloc, lb, pb);
+      for (int j = 0; j < 3; ++j) a.eloc[3 * (size_t)dst + j] = se[3 * (size_t)src + j];
+    }
+  }
+}
+
+// after the barrier that follows pull_pairs_kernel: unscaled_weight = weight (handler.py:247-248,
+// copied clone -> kill by the comb), then every weight = value (handler.py:337-338)
+__global__ void pop_finish_kernel(double* weight, double* unscaled, double value, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    unscaled[i] = weight[i];
+    weight[i] = value;
   }
 }
 

@@ -55,6 +55,7 @@ class Engine(object):
         self._make_views()
         self._xi_pinned = None
         self._xi_dev = None
+        self.peers_attached = False
 
     # ------------------------------------------------------------------ utils
     def _stream(self):
@@ -205,6 +206,45 @@ class Engine(object):
             self._check(self.lib.pxb_comb_plan(self._h, global_abs_weights.data_ptr(),
                                                int(global_abs_weights.numel()), float(r),
                                                self._stream()))
+
+    # peer-memory comb (several devices of one node)
+    def attach_peers(self, comm):
+        """Exchange CUDA IPC handles of the arenas over `comm` and map every peer's arena
+        (pxb_peer_export / pxb_peer_attach).  Returns True when the peer path is usable."""
+        self.peers_attached = False
+        if comm is None or comm.size == 1:
+            return False
+        hbuf = (ctypes.c_ubyte * 64)()
+        off = ctypes.c_uint64()
+        with torch.cuda.device(self.device):
+            rc = self.lib.pxb_peer_export(self._h, hbuf, ctypes.byref(off))
+            mine = numpy.zeros(80, dtype=numpy.uint8)
+            if rc == 0:
+                mine[:64] = numpy.frombuffer(bytes(hbuf), dtype=numpy.uint8)
+                mine[64:72] = numpy.frombuffer(int(off.value).to_bytes(8, 'little'), dtype=numpy.uint8)
+                mine[72] = 1
+            allh = comm.allgather_tensor(torch.from_numpy(mine).to(self.device)).cpu().numpy()
+            allh = allh.reshape(comm.size, 80)
+            if not bool(allh[:, 72].all()):
+                return False
+            handles = numpy.ascontiguousarray(allh[:, :64])
+            offsets = numpy.ascontiguousarray(allh[:, 64:72]).view(numpy.uint64).reshape(-1).copy()
+            rc = self.lib.pxb_peer_attach(self._h, comm.rank, comm.size, handles.ctypes.data,
+                                          offsets.ctypes.data)
+            ok = torch.tensor([1.0 if rc == 0 else 0.0], dtype=torch.float64, device=self.device)
+            ok = comm.allgather_tensor(ok).cpu().numpy()
+            self.peers_attached = bool((ok > 0).all())
+        return self.peers_attached
+
+    def pop_control_comb_peers(self, global_abs_weights, r):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_pop_control_comb_peers(
+                self._h, global_abs_weights.data_ptr(), int(global_abs_weights.numel()), float(r),
+                self._stream()))
+
+    def pop_control_finish(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_pop_control_finish(self._h, self._stream()))
 
     def payload_doubles(self):
         n = ctypes.c_size_t()

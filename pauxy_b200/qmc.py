@@ -161,6 +161,8 @@ class AFQMC(object):
                                    self.propagators.free_projection)
             self.testim += self._tick() - start
             self.estimators.print_step(comm, comm.size, step)
+            if step % self.qmc.nsteps == 0:
+                self.psi.check_total_weight()   # handler.py:236-241, polled once per block
             if step < self.qmc.neqlb:
                 eshift = mixed.get_shift(self.propagators.hybrid)
             else:

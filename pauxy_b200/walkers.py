@@ -131,9 +131,13 @@ class Walkers(object):
         self.pcont_method = get_input_value(walker_opts, 'population_control', default='comb')
         self.min_weight = walker_opts.get('min_weight', 0.1)
         self.max_weight = walker_opts.get('max_weight', 4.0)
+        # several devices: pull clones straight from peer memory (False: NCCL send/recv)
+        self.peer_copy = walker_opts.get('peer_copy', True)
         self.target_weight = qmc.ntot_walkers
         self.nw = qmc.nwalkers
         engine.init_walkers(trial.init, qmc.ntot_walkers)
+        if self.peer_copy and comm is not None and comm.size > 1:
+            engine.attach_peers(comm)
         self.walkers = [SingleDetWalker(self, i) for i in range(self.nwalkers)]
         self.buff_size = engine.payload_doubles()
         self._phi_cache = None
@@ -183,6 +187,11 @@ class Walkers(object):
             raise ValueError("Unknown population control method.")
         self._phi_cache = None
 
+    def check_total_weight(self):
+        """Deferred form of the reference's exit on a vanishing population (handler.py:236-241):
+        the device paths only raise a flag; the driver polls it once per block."""
+        self._check_total_weight()
+
     def _check_total_weight(self):
         if int(self.engine.counters[3].item()) < 0:
             # the reference prints and sys.exit()s (handler.py:236-241)
@@ -196,6 +205,13 @@ class Walkers(object):
             eng.pop_control_comb(r)
             return
         gw = comm.allgather_tensor(torch.abs(eng.weight))
+        if self.peer_copy and eng.peers_attached:
+            # clones are pulled out of the peers' arenas over NVLink: no host round trip
+            # (total weight < 1e-8 is flagged in counters[3], see check_total_weight)
+            eng.pop_control_comb_peers(gw, r)
+            comm.stream_barrier(eng.device)
+            eng.pop_control_finish()
+            return
         eng.pop_rescale(gw)
         eng.comb_plan(gw, r)
         pairs = eng.pairs.cpu().numpy()

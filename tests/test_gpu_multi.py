@@ -10,7 +10,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 
 
-def _worker(rank, world, port, name, pop, q):
+def _worker(rank, world, port, name, pop, peer, q):
     import torch
     import torch.distributed as dist
     os.environ['MASTER_ADDR'] = '127.0.0.1'
@@ -28,35 +28,40 @@ def _worker(rank, world, port, name, pop, q):
                     'rng_seed': int(g['seed']), 'num_walkers': int(g['nwalkers']),
                     'stabilise_freq': int(g['stab']), 'pop_control_freq': int(g['popc'])},
             'estimates': {'mixed': {'energy_eval_freq': 1, 'verbose': False}}}
+    opts['walkers'] = {'peer_copy': peer}
     if pop == 'pair_branch':
-        opts['walkers'] = {'population_control': 'pair_branch', 'min_weight': float(g['min_weight']),
-                           'max_weight': float(g['max_weight'])}
+        opts['walkers'].update({'population_control': 'pair_branch',
+                                'min_weight': float(g['min_weight']),
+                                'max_weight': float(g['max_weight'])})
     comm = TorchComm()
     afqmc = AFQMC(comm=comm, options=opts, system=system, verbose=0, device=torch.device('cuda', rank))
-    hist = {k: [] for k in ('weight', 'ot', 'eloc', 'parent_ix')}
+    hist = {k: [] for k in ('weight', 'ot', 'eloc', 'parent_ix', 'unscaled_weight')}
 
     def obs(step, a):
         e = a.engine
         hist['weight'].append(e.weight.cpu().numpy().copy())
+        hist['unscaled_weight'].append(e.unscaled_weight.cpu().numpy().copy())
         hist['ot'].append(e.ot.cpu().numpy().copy())
         hist['eloc'].append(e.eloc.cpu().numpy().copy())
         hist['parent_ix'].append(e.parent_ix.cpu().numpy().copy())
     afqmc.run(comm=comm, verbose=0, observer=obs)
     rows = afqmc.estimators.rows() if rank == 0 else None
-    q.put((rank, {k: numpy.array(v) for k, v in hist.items()}, rows))
+    q.put((rank, {k: numpy.array(v) for k, v in hist.items()}, rows,
+           bool(afqmc.engine.peers_attached)))
     dist.barrier()
     dist.destroy_process_group()
 
 
-def _run_two(name, pop):
+def _run_two(name, pop, peer=True):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    port = 29600 + (os.getpid() % 1000)
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, pop, q)) for r in range(2)]
+    _run_two.calls = getattr(_run_two, 'calls', 0) + 1
+    port = 29600 + (os.getpid() * 7 + _run_two.calls) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, pop, peer, q)) for r in range(2)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in procs], key=lambda x: x[0])
@@ -65,10 +70,18 @@ def _run_two(name, pop):
     return res
 
 
-@pytest.mark.parametrize('name,pop', [('stress_comb', 'comb'), ('c1', 'comb'),
-                                      ('stress_pair_branch', 'pair_branch')])
-def test_two_devices_reproduce_one_rank_reference(name, pop):
-    res = _run_two(name, pop)
+@pytest.mark.parametrize('name,pop,peer', [('stress_comb', 'comb', True), ('c1', 'comb', True),
+                                           ('stress_comb', 'comb', False),
+                                           ('stress_pair_branch', 'pair_branch', False)])
+def test_two_devices_reproduce_one_rank_reference(name, pop, peer):
+    """peer=True: clones are pulled out of the other device's arena over NVLink
+    (pxb_pop_control_comb_peers); peer=False: packed NCCL send/recv planned on the host."""
+    res = _run_two(name, pop, peer)
+    if peer:
+        assert res[0][3] and res[1][3], "CUDA IPC peer mapping of the arenas failed"
+    unscaled = numpy.concatenate([res[0][1]['unscaled_weight'], res[1][1]['unscaled_weight']], axis=1)
+    numpy.testing.assert_allclose(unscaled, numpy.load(os.path.join(GOLD, name + '.npz'))['unscaled_weight'],
+                                  rtol=1e-10, atol=1e-13)
     g = dict(numpy.load(os.path.join(GOLD, name + '.npz')))
     weight = numpy.concatenate([res[0][1]['weight'], res[1][1]['weight']], axis=1)
     ot = numpy.concatenate([res[0][1]['ot'], res[1][1]['ot']], axis=1)
