@@ -32,7 +32,7 @@ extern "C" {
 #define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
 #define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
 
-#define PXB_ABI_VERSION 3
+#define PXB_ABI_VERSION 4
 
 typedef struct pxb_context* pxb_handle;
 
@@ -50,8 +50,15 @@ typedef struct {
   int32_t total_walkers; /* walkers over ALL devices (0: == nwalkers) */
   double dt;
   int32_t exchange_mode; /* PXB_EXCHANGE_*: how pxb_local_energy evaluates the exchange term */
-  int32_t reserved;
+  int32_t flags;         /* PXB_FLAG_* */
 } pxb_config;
+
+/* propagator options of pauxy/propagation/continuous.py:14-33 */
+#define PXB_FLAG_FREE_PROJECTION 1 /* propagate_walker_free (continuous.py:175-200), the free-projection
+                                      branches of Walkers.orthogonalise (handler.py:178-181) and of
+                                      Mixed.update (mixed.py:151-177); implies NO_FORCE_BIAS like the
+                                      reference (continuous.py:30-33) */
+#define PXB_FLAG_NO_FORCE_BIAS 2   /* force_bias = False: xbar = 0 (continuous.py:136-138) */
 
 /* Exchange energy of estimators/generic.py:198-214.  Both forms give the same number to
  * rounding (the ERI is rebuilt from the same Cholesky vectors):
@@ -84,7 +91,8 @@ enum pxb_field_id {
   PXB_F_OVLP_NEW = 13,       /* c128 [W]    overlap after the last propagate */
   PXB_F_TOTAL_WEIGHT = 14,   /* f64  [1]    walker.total_weight (same for all walkers) */
   PXB_F_PAIRS = 15,          /* i32  [1+2*Wtot] n_pairs then (clone, kill) global indices */
-  PXB_F_COUNT = 16
+  PXB_F_PHASE = 16,          /* c128 [W]    walker.phase (free projection; 1 otherwise) */
+  PXB_F_COUNT = 17
 };
 
 int pxb_abi_version(void);

@@ -10,14 +10,15 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libpauxy_b200.so')
 
 PXB_OK = 0
-ABI_VERSION = 3
+ABI_VERSION = 4
 EXCHANGE_MODES = {'auto': 0, 'cholesky': 1, 'eri': 2}
 ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_ERR_UNSUPPORTED'}
 
 # enum pxb_field_id
 F_WEIGHT, F_UNSCALED_WEIGHT, F_OT, F_HYBRID_ENERGY, F_ELOC, F_DETR, F_LOG_DETR, \
     F_ESTIMATES, F_COUNTERS, F_PARENT_IX, F_XBAR, F_XSHIFTED, F_CMF_CFB, F_OVLP_NEW, \
-    F_TOTAL_WEIGHT, F_PAIRS, F_COUNT = range(17)
+    F_TOTAL_WEIGHT, F_PAIRS, F_PHASE, F_COUNT = range(18)
+FLAG_FREE_PROJECTION, FLAG_NO_FORCE_BIAS = 1, 2
 
 
 STAGES = ['greens', 'xgemm', 'field', 'vhs', 'one_body', 'taylor', 'weight', 'exchange', 'energy',
@@ -29,7 +30,7 @@ class PxbConfig(ctypes.Structure):
                 ('nchol', ctypes.c_int32), ('nwalkers', ctypes.c_int32),
                 ('exp_order', ctypes.c_int32), ('device', ctypes.c_int32),
                 ('total_walkers', ctypes.c_int32), ('dt', ctypes.c_double),
-                ('exchange_mode', ctypes.c_int32), ('reserved', ctypes.c_int32)]
+                ('exchange_mode', ctypes.c_int32), ('flags', ctypes.c_int32)]
 
 
 class PxbError(RuntimeError):

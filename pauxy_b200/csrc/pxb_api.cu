@@ -155,6 +155,7 @@ CopyArgs copy_args(pxb_handle h) {
   c.eloc = h->field<double2>(PXB_F_ELOC);
   c.detR = h->field<double>(PXB_F_DETR);
   c.log_detR = h->field<double>(PXB_F_LOG_DETR);
+  c.phase = h->field<double2>(PXB_F_PHASE);
   c.d = h->d;
   return c;
 }
@@ -663,6 +664,8 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   d.NKC = d.Np / 4;
   d.RT = ((d.M + 1) / 2) * d.KC;
   d.exp_order = cfg->exp_order;
+  d.flags = cfg->flags;
+  if (d.flags & FLAG_FREE_PROJECTION) d.flags |= FLAG_NO_FORCE_BIAS;  // continuous.py:30-33
   d.dt = cfg->dt;
   d.sqrt_dt = sqrt(cfg->dt);
   d.ebound = sqrt(2.0 / cfg->dt);
@@ -748,6 +751,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_FIELD0 + PXB_F_OVLP_NEW, W * 16);
   add(A_FIELD0 + PXB_F_TOTAL_WEIGHT, 8);
   add(A_FIELD0 + PXB_F_PAIRS, (1 + 2 * Wt) * 4);
+  add(A_FIELD0 + PXB_F_PHASE, W * 16);
   h->arena_bytes = off;
   *out = h;
   return PXB_OK;
@@ -920,7 +924,8 @@ int pxb_init_walkers(pxb_handle h, const void* dev_init_phi, double total_walker
   init_scalars_kernel<<<(d.Wp + 255) / 256, 256, 0, st>>>(
       h->field<double>(PXB_F_WEIGHT), h->field<double>(PXB_F_UNSCALED_WEIGHT), h->field<double2>(PXB_F_OT),
       h->ptr<double2>(A_OVLP_OLD), h->field<double2>(PXB_F_HYBRID_ENERGY), h->field<double>(PXB_F_DETR),
-      h->field<double>(PXB_F_LOG_DETR), h->field<double>(PXB_F_TOTAL_WEIGHT), total_walkers, d);
+      h->field<double>(PXB_F_LOG_DETR), h->field<double>(PXB_F_TOTAL_WEIGHT),
+      h->field<double2>(PXB_F_PHASE), total_walkers, d);
   PXB_CUDA(h, cudaGetLastError());
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ESTIMATES), 0, 160, st));
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_COUNTERS), 0, 64, st));
@@ -978,6 +983,7 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   // (f) weights
   WeightArgs wa;
   wa.weight = h->field<double>(PXB_F_WEIGHT);
+  wa.phase = h->field<double2>(PXB_F_PHASE);
   wa.ot = h->field<double2>(PXB_F_OT);
   wa.ehyb = h->field<double2>(PXB_F_HYBRID_ENERGY);
   wa.ovlp_new = h->field<double2>(PXB_F_OVLP_NEW);
@@ -1017,7 +1023,10 @@ int pxb_orthogonalise(pxb_handle h, void* stream) {
   ++h->launches;
   qr_combine_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(a.logdet, h->field<double2>(PXB_F_OT),
                                                        h->field<double>(PXB_F_DETR),
-                                                       h->field<double>(PXB_F_LOG_DETR), d.W);
+                                                       h->field<double>(PXB_F_LOG_DETR),
+                                                       (d.flags & FLAG_FREE_PROJECTION)
+                                                           ? h->field<double>(PXB_F_WEIGHT) : nullptr,
+                                                       d.W);
   PXB_CUDA(h, cudaGetLastError());
   // Theta = O^-1 phi^T is invariant under phi -> phi R^-1: it stays valid (to rounding)
   return PXB_OK;
@@ -1050,6 +1059,7 @@ int pxb_accumulate(pxb_handle h, int with_energy, void* stream) {
   PXB_REQUIRE_READY(h);
   AccArgs a;
   a.weight = h->field<double>(PXB_F_WEIGHT);
+  a.phase = h->field<double2>(PXB_F_PHASE);
   a.unscaled = h->field<double>(PXB_F_UNSCALED_WEIGHT);
   a.ot = h->field<double2>(PXB_F_OT);
   a.ehyb = h->field<double2>(PXB_F_HYBRID_ENERGY);
@@ -1059,7 +1069,10 @@ int pxb_accumulate(pxb_handle h, int with_energy, void* stream) {
   a.with_energy = with_energy;
   StageTimer timer__(h, PXB_STAGE_ACCUMULATE, S(stream));
   ++h->launches;
-  accumulate_kernel<<<1, 1024, 0, S(stream)>>>(a);
+  if (h->d.flags & FLAG_FREE_PROJECTION)
+    accumulate_free_kernel<<<1, 1024, 0, S(stream)>>>(a);
+  else
+    accumulate_kernel<<<1, 1024, 0, S(stream)>>>(a);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }

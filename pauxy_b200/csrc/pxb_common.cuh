@@ -34,8 +34,11 @@ struct Dims {
   int NKC;  // Np / 4        k-steps over the Cholesky index
   int RT;   // ceil(M/2)*KC  active row tiles of the VHS GEMM
   int exp_order;
+  int flags;  // PXB_FLAG_* of pxb_config
   double dt, sqrt_dt, ebound, ecore;
 };
+constexpr int FLAG_FREE_PROJECTION = 1;  // == PXB_FLAG_FREE_PROJECTION
+constexpr int FLAG_NO_FORCE_BIAS = 2;    // == PXB_FLAG_NO_FORCE_BIAS
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 

@@ -340,7 +340,8 @@ inline size_t qr_smem_bytes(const Dims& d) {
 
 // detR = exp(log_det - detR_shift[=0]); log_detR += log(detR); ot = ot / detR (single_det.py:245-254)
 __global__ void qr_combine_kernel(const double* __restrict__ logdet, double2* __restrict__ ot,
-                                  double* __restrict__ detR, double* __restrict__ log_detR, int n) {
+                                  double* __restrict__ detR, double* __restrict__ log_detR,
+                                  double* __restrict__ weight_free, int n) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n) return;
   const double dr = exp(logdet[2 * w] + logdet[2 * w + 1]);
@@ -348,6 +349,9 @@ __global__ void qr_combine_kernel(const double* __restrict__ logdet, double2* __
   log_detR[w] += log(dr);
   const double2 o = ot[w];
   ot[w] = make_double2(o.x / dr, o.y / dr);
+  // free projection (handler.py:178-181): polar(detR) with detR real and positive -> the
+  // magnitude goes into the weight, the phase factor is exactly 1
+  if (weight_free != nullptr) weight_free[w] *= dr;
 }
 
 }  // namespace pxb

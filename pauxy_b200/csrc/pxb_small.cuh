@@ -270,16 +270,19 @@ __global__ void __launch_bounds__(256) field_kernel(FieldArgs a) {
       const int n = n0 + u;
       double xr = 0.0, xi_ = 0.0, br = 0.0, bi = 0.0;
       if (live && n < d.N) {
-        const double2 va = Xa[n], vb = Xb[n], mf = a.vbar[n];
-        const double vr = va.x + vb.x, vi = va.y + vb.y;
-        // xbar = -sqrt_dt * (1j*V - vbar)
-        br = -d.sqrt_dt * (-vi - mf.x);
-        bi = -d.sqrt_dt * (vr - mf.y);
-        const double ab = hypot(br, bi);
-        if (ab > 1.0) {
-          br /= ab;
-          bi /= ab;
-          ++ntrig;
+        const double2 mf = a.vbar[n];
+        if (!(d.flags & FLAG_NO_FORCE_BIAS)) {   // continuous.py:136-138: xbar = 0 otherwise
+          const double2 va = Xa[n], vb = Xb[n];
+          const double vr = va.x + vb.x, vi = va.y + vb.y;
+          // xbar = -sqrt_dt * (1j*V - vbar)
+          br = -d.sqrt_dt * (-vi - mf.x);
+          bi = -d.sqrt_dt * (vr - mf.y);
+          const double ab = hypot(br, bi);
+          if (ab > 1.0) {
+            br /= ab;
+            bi /= ab;
+            ++ntrig;
+          }
         }
         xr = z[u] - br;
         xi_ = -bi;
@@ -334,6 +337,7 @@ __global__ void active_kernel(const double* __restrict__ weight, int* __restrict
 // ============================================================================
 struct WeightArgs {
   double* weight;
+  double2* phase;  // free projection only
   double2* ot;
   double2* ehyb;
   const double2* ovlp_new;
@@ -351,7 +355,20 @@ __global__ void weight_kernel(WeightArgs a) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= d.W) return;
   double wt = a.weight[w];
-  if (a.active[w]) {
+  if (a.active[w] && (d.flags & FLAG_FREE_PROJECTION)) {
+    // propagate_walker_free (continuous.py:194-200): the constant terms go into weight and phase
+    const double2 cmf = a.cmfcfb[2 * w];
+    const double er = exp(cmf.x + d.dt * a.eshift);
+    double sn, cs;
+    sincos(cmf.y, &sn, &cs);
+    const double magn = hypot(er * cs, er * sn);
+    const double dtheta = atan2(er * sn, er * cs);
+    wt = wt * magn;
+    sincos(dtheta, &sn, &cs);
+    const double2 ph = a.phase[w];
+    a.phase[w] = make_double2(ph.x * cs - ph.y * sn, ph.x * sn + ph.y * cs);
+    a.ot[w] = a.ovlp_new[w];
+  } else if (a.active[w]) {
     // ovlp_old == walker.ot: the overlap of the walker before this step (single_det.py:321 equals
     // the stored ot up to rounding; after a re-orthogonalisation ot was divided by detR)
     const double2 oo = a.ot[w], on = a.ovlp_new[w];
@@ -450,6 +467,7 @@ __global__ void __launch_bounds__(256) energy_kernel(EnergyArgs a) {
 // ============================================================================
 struct AccArgs {
   const double* weight;
+  const double2* phase;
   const double* unscaled;
   const double2* ot;
   const double2* ehyb;
@@ -508,12 +526,104 @@ __global__ void __launch_bounds__(1024) accumulate_kernel(AccArgs a) {
   }
 }
 
+// free projection (estimators/mixed.py:151-177): every sum carries the complex factor
+// wfac = weight * ot * phase
+__global__ void __launch_bounds__(1024) accumulate_free_kernel(AccArgs a) {
+  __shared__ double red[14][32];
+  const Dims& d = a.d;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double v[14];
+#pragma unroll
+  for (int k = 0; k < 14; ++k) v[k] = 0.0;
+  for (int w = tid; w < d.W; w += 1024) {
+    const double wt = a.weight[w];
+    const double2 o = a.ot[w], ph = a.phase[w];
+    const double fr = wt * o.x, fi = wt * o.y;          // weight * ot
+    const double wr = fr * ph.x - fi * ph.y, wi = fr * ph.y + fi * ph.x;  // ... * phase
+    if (a.with_energy) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const double2 e = a.eloc[3 * (size_t)w + k];
+        v[2 * k] += wr * e.x - wi * e.y;
+        v[2 * k + 1] += wr * e.y + wi * e.x;
+      }
+      v[6] += wr;
+      v[7] += wi;
+    }
+    v[8] += a.unscaled[w];
+    v[9] += wr;
+    v[10] += wi;
+    const double2 eh = a.ehyb[w];
+    v[11] += wr * eh.x - wi * eh.y;
+    v[12] += wr * eh.y + wi * eh.x;
+    v[13] += wt * hypot(o.x, o.y);
+  }
+#pragma unroll
+  for (int k = 0; k < 14; ++k) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], m);
+    if (lane == 0) red[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 14; ++k) {
+      double x = red[k][lane];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
+      v[k] = x;
+    }
+    if (lane == 0) {
+      a.estimates[2].x += v[0];
+      a.estimates[2].y += v[1];
+      a.estimates[5].x += v[2];
+      a.estimates[5].y += v[3];
+      a.estimates[6].x += v[4];
+      a.estimates[6].y += v[5];
+      a.estimates[3].x += v[6];
+      a.estimates[3].y += v[7];
+      a.estimates[0].x += v[8];
+      a.estimates[1].x += v[9];
+      a.estimates[1].y += v[10];
+      a.estimates[7].x += v[11];
+      a.estimates[7].y += v[12];
+      a.estimates[8].x += v[13];
+    }
+  }
+}
+
 // ============================================================================
 // K10: population control (walkers/handler.py:225-338)
 // ============================================================================
 __global__ void abs_weight_kernel(const double* __restrict__ weight, double* __restrict__ out, int n) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = fabs(weight[i]);
+}
+
+// sequential (index-order) running sum of m shared-memory values by ONE thread; the loads of a
+// block of 16 are issued before the dependent DADD chain so that only the adds are serial
+template <bool STORE>
+__device__ __forceinline__ double serial_sum16(double run, double* chunk, int m) {
+  int i = 0;
+  for (; i + 16 <= m; i += 16) {
+    double v[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) v[j] = chunk[i + j];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      run = __dadd_rn(run, v[j]);
+      v[j] = run;
+    }
+    if (STORE) {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) chunk[i + j] = v[j];
+    }
+  }
+  for (; i < m; ++i) {
+    run = __dadd_rn(run, chunk[i]);
+    if (STORE) chunk[i] = run;
+  }
+  return run;
 }
 
 // total = python-style sequential sum of the global |weights| (handler.py:233);
@@ -538,10 +648,7 @@ __global__ void __launch_bounds__(1024) pop_rescale_kernel(RescaleArgs a) {
   for (int base = 0; base < a.Wtot; base += 1024) {
     if (base + tid < a.Wtot) chunk[tid] = a.gw[base + tid];
     __syncthreads();
-    if (tid == 0) {
-      const int m = min(1024, a.Wtot - base);
-      for (int i = 0; i < m; ++i) total = __dadd_rn(total, chunk[i]);
-    }
+    if (tid == 0) total = serial_sum16<false>(total, chunk, min(1024, a.Wtot - base));
     __syncthreads();
   }
   if (tid == 0) s_total = total;
@@ -576,79 +683,95 @@ struct CombArgs {
   double r;
 };
 
+// number of comb teeth (i + r) * spacing, i in [0, n), that lie below c -- evaluated with the
+// reference's own floating-point expression around the analytic estimate, so the result is
+// exactly what the two-pointer sweep of handler.py:277-286 counts
+__device__ __forceinline__ int teeth_below(double c, double r, double spacing, int n) {
+  double e = floor(c / spacing - r);
+  int ic = e < 0.0 ? 0 : (e > (double)n ? n : (int)e);
+  while (ic > 0 && !(__dmul_rn(__dadd_rn((double)(ic - 1), r), spacing) < c)) --ic;
+  while (ic < n && __dmul_rn(__dadd_rn((double)ic, r), spacing) < c) ++ic;
+  return ic;
+}
+
 __global__ void __launch_bounds__(1024) comb_plan_kernel(CombArgs a) {
   __shared__ double chunk[1024];
   __shared__ double s_total;
-  __shared__ int s_cnt[2][1024];
-  __shared__ int s_base[2];
-  const int tid = threadIdx.x, n = a.Wtot;
+  __shared__ int s_warp[2][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = a.Wtot;
   double run = 0.0;
   for (int base = 0; base < n; base += 1024) {
     if (base + tid < n) chunk[tid] = a.gws[base + tid];
     __syncthreads();
-    if (tid == 0) {
-      const int m = min(1024, n - base);
-      for (int i = 0; i < m; ++i) {
-        run = __dadd_rn(run, chunk[i]);
-        chunk[i] = run;
-      }
-    }
+    if (tid == 0) run = serial_sum16<true>(run, chunk, min(1024, n - base));
     __syncthreads();
     if (base + tid < n) a.cprobs[base + tid] = chunk[tid];
     __syncthreads();
   }
   if (tid == 0) s_total = run;
-  for (int i = tid; i < n; i += 1024) a.parent_ix[i] = 0;
   __syncthreads();
   __threadfence_block();
   const double spacing = __ddiv_rn(s_total, (double)n);
-  for (int ic = tid; ic < n; ic += 1024) {
-    const double tooth = __dmul_rn(__dadd_rn((double)ic, a.r), spacing);
-    int lo = 0, hi = n;  // first iw with tooth < cprobs[iw]
-    while (lo < hi) {
-      const int mid = (lo + hi) >> 1;
-      if (tooth < a.cprobs[mid])
-        hi = mid;
-      else
-        lo = mid + 1;
+  if (!(spacing > 0.0)) {  // vanished population: flagged by pop_rescale_kernel, nothing to plan
+    for (int i = tid; i < n; i += 1024) a.parent_ix[i] = 1;
+    if (tid == 0) a.pairs[0] = 0;
+    return;
+  }
+  // parent_ix[iw] = teeth in [cprobs[iw-1], cprobs[iw]); teeth past the last walker stay with it
+  // (the reference would raise IndexError there).  Each thread owns a contiguous segment, so the
+  // kill (parent == 0) / clone (parent > 1) lists come out ascending, zipped position-wise.
+  const int seg = (n + 1023) / 1024;
+  const int i0 = min(tid * seg, n), i1 = min(i0 + seg, n);
+  int nk = 0, nc = 0;
+  {
+    int below = (i0 == 0) ? 0 : teeth_below(a.cprobs[i0 - 1], a.r, spacing, n);
+    for (int i = i0; i < i1; ++i) {
+      const int upto = (i == n - 1) ? n : teeth_below(a.cprobs[i], a.r, spacing, n);
+      const int p = upto - below;
+      below = upto;
+      a.parent_ix[i] = p;
+      nk += (p == 0);
+      nc += (p > 1);
     }
-    if (lo >= n) lo = n - 1;  // the reference would raise IndexError here
-    atomicAdd(&a.parent_ix[lo], 1);
+  }
+  // exclusive block scan of (nk, nc)
+  int sk = nk, sc = nc;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int vk = __shfl_up_sync(0xffffffffu, sk, off), vc = __shfl_up_sync(0xffffffffu, sc, off);
+    if (lane >= off) {
+      sk += vk;
+      sc += vc;
+    }
+  }
+  if (lane == 31) {
+    s_warp[0][warp] = sk;
+    s_warp[1][warp] = sc;
   }
   __syncthreads();
-  // ascending kill (parent == 0) and clone (parent > 1) lists, zipped position-wise
-  if (tid < 2) s_base[tid] = 0;
-  __syncthreads();
-  for (int base = 0; base < n; base += 1024) {
-    const int i = base + tid;
-    const int p = (i < n) ? a.parent_ix[i] : 1;
-    const int isk = (p == 0), isc = (p > 1);
-    s_cnt[0][tid] = isk;
-    s_cnt[1][tid] = isc;
-    __syncthreads();
-    // inclusive scan (Hillis-Steele) on both flags
-    for (int off = 1; off < 1024; off <<= 1) {
-      int vk = 0, vc = 0;
-      if (tid >= off) {
-        vk = s_cnt[0][tid - off];
-        vc = s_cnt[1][tid - off];
+  if (warp == 0) {
+    int wk = s_warp[0][lane], wc = s_warp[1][lane];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int vk = __shfl_up_sync(0xffffffffu, wk, off), vc = __shfl_up_sync(0xffffffffu, wc, off);
+      if (lane >= off) {
+        wk += vk;
+        wc += vc;
       }
-      __syncthreads();
-      s_cnt[0][tid] += vk;
-      s_cnt[1][tid] += vc;
-      __syncthreads();
     }
-    if (isk) a.pairs[1 + 2 * (s_base[0] + s_cnt[0][tid] - 1) + 1] = i;
-    if (isc) a.pairs[1 + 2 * (s_base[1] + s_cnt[1][tid] - 1)] = i;
-    __syncthreads();
-    if (tid == 0) {
-      s_base[0] += s_cnt[0][1023];
-      s_base[1] += s_cnt[1][1023];
-    }
-    __syncthreads();
+    s_warp[0][lane] = wk;
+    s_warp[1][lane] = wc;
+  }
+  __syncthreads();
+  int ok = sk - nk + (warp ? s_warp[0][warp - 1] : 0);
+  int oc = sc - nc + (warp ? s_warp[1][warp - 1] : 0);
+  for (int i = i0; i < i1; ++i) {
+    const int p = a.parent_ix[i];
+    if (p == 0) a.pairs[1 + 2 * (ok++) + 1] = i;
+    if (p > 1) a.pairs[1 + 2 * (oc++)] = i;
   }
   if (tid == 0) {
-    const int np = min(s_base[0], s_base[1]);
+    const int np = min(s_warp[0][31], s_warp[1][31]);
     a.pairs[0] = np;
     a.counters[3] += np;
   }
@@ -666,6 +789,7 @@ struct CopyArgs {
   double2* eloc;
   double* detR;
   double* log_detR;
+  double2* phase;
   Dims d;
 };
 
@@ -695,6 +819,7 @@ __global__ void __launch_bounds__(256) copy_pairs_kernel(CopyArgs a, const int* 
       a.unscaled[dst] = a.unscaled[src];
       a.ot[dst] = a.ot[src];
       a.ehyb[dst] = a.ehyb[src];
+      a.phase[dst] = a.phase[src];
       a.detR[dst] = a.detR[src];
       a.log_detR[dst] = a.log_detR[src];
       for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)dst + k] = a.eloc[3 * (size_t)src + k];
@@ -721,6 +846,7 @@ __global__ void __launch_bounds__(256) copy_list_kernel(CopyArgs a, const int* s
       a.unscaled[dst] = a.unscaled[src];
       a.ot[dst] = a.ot[src];
       a.ehyb[dst] = a.ehyb[src];
+      a.phase[dst] = a.phase[src];
       a.detR[dst] = a.detR[src];
       a.log_detR[dst] = a.log_detR[src];
       for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)dst + k] = a.eloc[3 * (size_t)src + k];
@@ -773,6 +899,7 @@ __global__ void __launch_bounds__(256) pull_pairs_kernel(CopyArgs a, PeerArgs p,
       a.weight[dst] = rebase(a.weight, lb, pb)[src];
       a.ot[dst] = rebase(a.ot, lb, pb)[src];
       a.ehyb[dst] = rebase(a.ehyb, lb, pb)[src];
+      a.phase[dst] = rebase(a.phase, lb, pb)[src];
       a.detR[dst] = rebase(a.detR, lb, pb)[src];
       a.log_detR[dst] = rebase(a.log_detR, lb, pb)[src];
       const double2* se = rebase(a.eloc, lb, pb);
@@ -826,6 +953,7 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
         a.log_detR[w] = s[7];
         for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)w + k] = make_double2(s[8 + 2 * k], s[9 + 2 * k]);
         a.e1b[w] = make_double2(s[14], s[15]);
+        a.phase[w] = make_double2(s[16], s[17]);
       } else {
         s[0] = a.weight[w];
         s[1] = a.unscaled[w];
@@ -841,7 +969,8 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
         }
         s[14] = a.e1b[w].x;
         s[15] = a.e1b[w].y;
-        s[16] = s[17] = 0.0;
+        s[16] = a.phase[w].x;
+        s[17] = a.phase[w].y;
       }
     }
   }
@@ -854,7 +983,7 @@ __global__ void fill_kernel(double* p, double v, int n) {
 
 __global__ void init_scalars_kernel(double* weight, double* unscaled, double2* ot, const double2* ovlp,
                                     double2* ehyb, double* detR, double* log_detR, double* total_weight,
-                                    double total, Dims d) {
+                                    double2* phase, double total, Dims d) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w == 0) total_weight[0] = total;
   if (w >= d.Wp) return;
@@ -863,6 +992,7 @@ __global__ void init_scalars_kernel(double* weight, double* unscaled, double2* o
   unscaled[w] = real ? 1.0 : 0.0;
   ot[w] = ovlp[w];
   ehyb[w] = make_double2(0.0, 0.0);
+  phase[w] = make_double2(1.0, 0.0);
   detR[w] = 1.0;
   log_detR[w] = 0.0;
 }

@@ -24,7 +24,7 @@ class Engine(object):
     """
 
     def __init__(self, nbasis, nup, ndown, nchol, nwalkers, dt, exp_order=6, device=None,
-                 total_walkers=None, exchange='auto'):
+                 total_walkers=None, exchange='auto', free_projection=False, force_bias=True):
         if not torch.cuda.is_available():
             raise RuntimeError("pauxy_b200.Engine needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -38,7 +38,9 @@ class Engine(object):
         self.Wp = _round_up(nwalkers, 4)
         self.Np = _round_up(nchol, 8)
         cfg = L.PxbConfig(nbasis, nup, ndown, nchol, nwalkers, exp_order,
-                          self.device.index or 0, self.Wtot, dt, L.EXCHANGE_MODES[exchange], 0)
+                          self.device.index or 0, self.Wtot, dt, L.EXCHANGE_MODES[exchange],
+                          (L.FLAG_FREE_PROJECTION if free_projection else 0) |
+                          (0 if force_bias else L.FLAG_NO_FORCE_BIAS))
         self._h = ctypes.c_void_p()
         rc = self.lib.pxb_create(ctypes.byref(self._h), ctypes.byref(cfg))
         if rc != 0:
@@ -92,6 +94,7 @@ class Engine(object):
         self.ovlp_new = self._view(L.F_OVLP_NEW, c128)[:W]
         self.total_weight = self._view(L.F_TOTAL_WEIGHT, f64)
         self.pairs = self._view(L.F_PAIRS, torch.int32)
+        self.phase = self._view(L.F_PHASE, c128)[:W]
 
     def _dev(self, a, dtype):
         t = torch.as_tensor(numpy.ascontiguousarray(a, dtype=dtype))

@@ -59,9 +59,7 @@ class Mixed(object):
 
     def update(self, system, qmc, trial, psi, step, free_projection=False):
         """mixed.py:211-225 for every walker of the device batch."""
-        if free_projection:
-            raise NotImplementedError("pauxy_b200: free projection is not built")
-        eng = self.engine
+        eng = self.engine   # free projection: PXB_FLAG_FREE_PROJECTION selects mixed.py:151-177
         evaluate = (step % self.energy_eval_freq == 0)
         if evaluate and self.eval_energy:
             eng.local_energy()

@@ -53,14 +53,11 @@ class Continuous(object):
         self.hybrid = options.get('hybrid', True)
         self.force_bias = options.get('force_bias', True)
         if self.free_projection:
-            raise NotImplementedError("pauxy_b200: free projection is a 'next' row "
-                                      "(SURVEY.md section 8f.4)")
+            self.force_bias = False     # continuous.py:30-33
         if not self.hybrid:
             raise NotImplementedError(
                 "pauxy_b200: the local-energy weight update crashes in the reference for "
                 "SingleDet + Generic (SURVEY.md row A8'), there is no oracle for it")
-        if not self.force_bias:
-            raise NotImplementedError("pauxy_b200: force_bias=False is not built")
         if options.get('stochastic_ri', False):
             raise NotImplementedError("pauxy_b200: stochastic RI is out of scope")
         self.exp_nmax = options.get('expansion_order', 6)

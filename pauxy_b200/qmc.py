@@ -108,7 +108,9 @@ class AFQMC(object):
         self.engine = Engine(s.nbasis, s.nup, s.ndown, s.nfields, self.qmc.nwalkers, self.qmc.dt,
                              exp_order=self.propagators.exp_nmax, device=device,
                              total_walkers=self.qmc.ntot_walkers,
-                             exchange=est_opts.get('mixed', {}).get('exchange', 'auto'))
+                             exchange=est_opts.get('mixed', {}).get('exchange', 'auto'),
+                             free_projection=self.propagators.free_projection,
+                             force_bias=self.propagators.force_bias)
         p = self.propagators.propagator
         self.engine.set_hamiltonian(s.hs_pot, self.trial._rchol, p.BH1,
                                     self.trial.half_rotated_h1(s), self.trial.psi, p.mf_shift,

@@ -31,7 +31,6 @@ class SingleDetWalker(object):
         self.nup = handler.system.nup
         self.ndown = handler.system.ndown
         self.le_oratio = 1.0
-        self.phase = 1 + 0j
         self.alive = 1
         self.field_configs = None
         self.stack = None
@@ -48,6 +47,8 @@ class SingleDetWalker(object):
     ovlp = ot
     hybrid_energy = property(lambda s: s._scalar('hybrid_energy'),
                              lambda s, v: s._h.engine.hybrid_energy.__setitem__(s._i, complex(v)))
+    phase = property(lambda s: s._scalar('phase'),
+                     lambda s, v: s._h.engine.phase.__setitem__(s._i, complex(v)))
     detR = property(lambda s: s._scalar('detR'))
     log_detR = property(lambda s: s._scalar('log_detR'))
     total_weight = property(lambda s: s._h.engine.total_weight[0].item())
@@ -170,8 +171,8 @@ class Walkers(object):
 
     # ------------------------------------------------------------ re-ortho
     def orthogonalise(self, trial, free_projection):
-        if free_projection:
-            raise NotImplementedError("pauxy_b200: free projection is not built")
+        """handler.py:166-181; the free-projection branch (weight *= |detR|) is selected by the
+        engine's PXB_FLAG_FREE_PROJECTION, set from the same propagator option."""
         self.engine.orthogonalise()
         self._phi_cache = None
 

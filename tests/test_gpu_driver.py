@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-10
 
 
-def _options(g, walkers=None):
+def _options(g, walkers=None, propagator=None):
     o = {'qmc': {'timestep': float(g['dt']), 'steps': int(g['steps']), 'blocks': int(g['blocks']),
                  'rng_seed': int(g['seed']), 'num_walkers': int(g['nwalkers']),
                  'stabilise_freq': int(g['stab']), 'pop_control_freq': int(g['popc'])},
@@ -23,15 +23,17 @@ def _options(g, walkers=None):
          'trial': {'name': 'MultiSlater'}}
     if walkers:
         o['walkers'] = walkers
+    if propagator:
+        o['propagator'] = propagator
     return o
 
 
-def _run(g, h1e, hs, ecore, walkers=None):
+def _run(g, h1e, hs, ecore, walkers=None, propagator=None):
     nelec = tuple(int(x) for x in g['nelec'])
     system = Generic(nelec=nelec, h1e=numpy.array([h1e, h1e]), chol=hs, ecore=ecore)
-    afqmc = AFQMC(options=_options(g, walkers), system=system, verbose=0)
+    afqmc = AFQMC(options=_options(g, walkers, propagator), system=system, verbose=0)
     hist = {k: [] for k in ('weight', 'unscaled_weight', 'ot', 'hybrid_energy', 'eloc',
-                            'parent_ix')}
+                            'parent_ix', 'phase')}
 
     def obs(step, a):
         e = a.engine
@@ -41,6 +43,7 @@ def _run(g, h1e, hs, ecore, walkers=None):
         hist['hybrid_energy'].append(e.hybrid_energy.cpu().numpy().copy())
         hist['eloc'].append(e.eloc.cpu().numpy().copy())
         hist['parent_ix'].append(e.parent_ix.cpu().numpy()[:e.W].copy())
+        hist['phase'].append(e.phase.cpu().numpy().copy())
     afqmc.run(verbose=0, observer=obs)
     return afqmc, {k: numpy.array(v) for k, v in hist.items()}
 
@@ -87,6 +90,33 @@ def test_pair_branch_matches_reference(golden):
     _close(h['ot'], g['ot'])
     _close(h['eloc'], g['eloc'], atol=1e-10)
     _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
+
+
+@pytest.mark.parametrize('name', ['free_comb', 'free_pair_branch', 'phaseless_nofb'])
+def test_free_projection_and_no_force_bias(golden, name):
+    """propagate_walker_free (continuous.py:175-200), the free-projection branches of
+    orthogonalise (handler.py:178-181) and Mixed.update (mixed.py:151-177), and the phaseless
+    walk with force_bias=False (continuous.py:136-138), against traces of the reference."""
+    g = golden(name)
+    walkers = None
+    if str(g['pop_control']) == 'pair_branch':
+        walkers = {'population_control': 'pair_branch', 'min_weight': float(g['min_weight']),
+                   'max_weight': float(g['max_weight'])}
+    afqmc, h = _run(g, g['h1e'], g['hs_pot'], float(g['ecore']), walkers=walkers,
+                    propagator={'free_projection': bool(g['free_projection']),
+                                'force_bias': bool(g['force_bias'])})
+    if walkers is None:
+        assert numpy.array_equal(h['parent_ix'], g['parent_ix'])
+    _close(h['weight'], g['weight'], atol=1e-13)
+    _close(h['unscaled_weight'], g['unscaled_weight'], atol=1e-13)
+    _close(h['ot'], g['ot'])
+    _close(h['phase'], g['phase'], atol=1e-12)
+    _close(h['hybrid_energy'], g['hybrid_energy'], rtol=1e-9, atol=1e-8)
+    _close(h['eloc'], g['eloc'], atol=1e-10)
+    assert afqmc.propagators.nhe_trig == int(g['nhe_trig'])
+    assert afqmc.propagators.nfb_trig == 0
+    _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
+    _close(afqmc.psi.phi_host(), g['phi_final'], atol=1e-11)
 
 
 @pytest.mark.parametrize('name', ['c2_shape', 'c3_shape', 'c4_shape'])

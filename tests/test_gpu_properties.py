@@ -121,6 +121,43 @@ def test_device_comb_bit_exact_large():
     assert numpy.array_equal(eh, expect_eh)
 
 
+@pytest.mark.parametrize('W,kind', [(2, 'skew'), (5, 'zeros'), (3000, 'wide'), (3000, 'zeros'),
+                                    (4097, 'skew'), (8192, 'equal')])
+def test_device_comb_selection_edge_cases(W, kind):
+    """parent_ix and the zipped (clone, kill) list for awkward weight vectors and uniforms
+    (walkers/handler.py:271-301): sizes off the block size, many dead walkers, a few walkers
+    holding most of the weight, all-equal weights, r at both ends of [0, 1)."""
+    eng, ham = _engine('c1', W)
+    rs = numpy.random.RandomState(W + len(kind))
+    for r in (0.0, 1e-300, 0.5, 0.9999999999999999, float(rs.rand())):
+        if kind == 'skew':
+            w0 = numpy.abs(rs.normal(size=W)) * 1e-3
+            w0[rs.randint(0, W, max(1, W // 500))] = 0.09 * W
+        elif kind == 'zeros':
+            w0 = numpy.abs(1.0 + rs.normal(size=W))
+            w0[rs.rand(W) < 0.6] = 0.0
+            w0[0] = 1.0
+        elif kind == 'wide':
+            w0 = 10.0 ** rs.uniform(-12, 2, size=W)
+        else:
+            w0 = numpy.ones(W)
+        eng.weight.copy_(torch.as_tensor(w0))
+        eng.pop_control_comb(r)
+        eng.synchronize()
+        total = sum(w0)
+        gw = w0 / (total / W)
+        try:
+            parents = orc.comb_parents(gw, r, W)
+        except IndexError:      # the reference's sweep runs off the end (last tooth >= total)
+            continue
+        assert numpy.array_equal(eng.parent_ix.cpu().numpy()[:W], parents)
+        pairs = eng.pairs.cpu().numpy()
+        expect = orc.comb_pairs(parents)
+        assert int(pairs[0]) == len(expect)
+        assert [tuple(x) for x in pairs[1:1 + 2 * len(expect)].reshape(-1, 2)] == \
+            [tuple(x) for x in expect]
+
+
 def test_theta_travels_with_walkers():
     """After population control the stored Theta of a cloned walker must equal a fresh
     Green's function of its (copied) phi: the estimator reuses it."""

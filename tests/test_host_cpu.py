@@ -108,9 +108,11 @@ def test_unsupported_modes_fail_loudly():
     class Q(object):
         dt = 0.01
         nstblz = 10
-    for opts in ({'free_projection': True}, {'hybrid': False}, {'optimised': False}):
+    for opts in ({'hybrid': False}, {'optimised': False}):
         with pytest.raises(NotImplementedError):
             Continuous(system, trial, Q(), options=opts)
+    # continuous.py:30-33: free projection switches the force bias off
+    assert Continuous(system, trial, Q(), options={'free_projection': True}).force_bias is False
 
 
 def test_plan_moves_partitions_pairs():
