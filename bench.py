@@ -231,7 +231,6 @@ def main():
     nbuf = 3
     xi_host = [torch.from_numpy(rs.normal(size=(wpg, N))).pin_memory() for _ in range(nbuf)]
     xi_dev = [x.to(dev) for x in xi_host]
-    xi_stage = torch.empty((wpg, N), dtype=torch.float64, device=dev)
     combr = rs.rand(4096)
     res_host = torch.empty(10, dtype=torch.complex128).pin_memory()
     w_host = torch.empty(wpg, dtype=torch.float64).pin_memory()
@@ -244,8 +243,13 @@ def main():
         if step % afqmc.qmc.nstblz == 0:
             psi.orthogonalise(afqmc.trial, False)
         if e2e:
-            xi_stage.copy_(xi_host[step % nbuf], non_blocking=True)     # H2D of this step's fields
-            eng.propagate(xi_stage, eshift=state['eshift'], step=step)
+            # H2D of this step's fields was started on the copy stream during the previous step
+            # (Engine.prefetch_xi); the first one of a timed region is issued here
+            xi_now = state.pop('xi_next', None)
+            if xi_now is None:
+                xi_now = eng.prefetch_xi(xi_host[step % nbuf])
+            eng.propagate(xi_now, eshift=state['eshift'], step=step)
+            state['xi_next'] = eng.prefetch_xi(xi_host[(step + 1) % nbuf])
         else:
             eng.propagate(xi_dev[step % nbuf], eshift=state['eshift'], step=step)
         if world == 1:
@@ -301,6 +305,7 @@ def main():
     stage = eng.stage_times(reset=True)
     eng.profile(False)
     launches = eng.launch_count() - launches0
+    state.pop('xi_next', None)
     ms_e2e = timed(args.steps, True)
     clocks = sampler.stop() if sampler else None
 

@@ -323,6 +323,42 @@ EST_NAMES = ['uweight', 'weight', 'enumer', 'edenom', 'eproj', 'e1b', 'e2b',
              'ehyb', 'ovlp', 'time']  # estimators/mixed.py:460-469
 
 
+def exponentiate_matrix(M, order=6):
+    """utils/linalg.py:163-170."""
+    T = numpy.copy(M)
+    out = numpy.identity(M.shape[0], dtype=M.dtype)
+    for n in range(1, order + 1):
+        out += T
+        T = M.dot(T) / (n + 1)
+    return out
+
+
+def back_propagate(ham, phi, configs, nstblz):
+    """propagation/generic.py:253-290 (back_propagate_generic) with the propagator matrix of
+    generic.py:180-213: for the stored field configurations in REVERSE order,
+    phi <- B(c)^dagger phi with B = BH1 exp6(i sqrt(dt) L.c) BH1, a QR re-orthogonalisation
+    (utils/linalg.py:82-105) every nstblz applications.  phi [M, ne] is changed in place."""
+    M, na = ham.nbasis, ham.nup
+    for i, c in enumerate(configs[::-1]):
+        vhs = 1j * ham.sqrt_dt * ham.hs_pot.dot(c).reshape(M, M)
+        e = exponentiate_matrix(vhs)
+        for s, sl in enumerate((slice(0, na), slice(na, ham.ne))):
+            B = ham.BH1[s].dot(e).dot(ham.BH1[s])
+            phi[:, sl] = numpy.dot(B.conj().T, phi[:, sl])
+        if i != 0 and i % nstblz == 0:
+            for sl in (slice(0, na), slice(na, ham.ne)):
+                if sl.stop > sl.start:
+                    Q, R = scipy.linalg.qr(phi[:, sl], mode='economic')
+                    phi[:, sl] = Q.dot(numpy.diag(numpy.sign(numpy.diag(R))))
+    return phi
+
+
+def gab(A, B):
+    """estimators/greens_function.py:5-38: B (A^dagger B)^-1 A^dagger."""
+    inv_o = scipy.linalg.inv((A.conj().T).dot(B))
+    return B.dot(inv_o.dot(A.conj().T))
+
+
 class OracleAFQMC(object):
     """qmc/afqmc.py:200-255 + walkers/handler.py:225-338 + estimators/mixed.py:
     180-289 on structure-of-arrays walker state (single rank)."""
@@ -330,7 +366,8 @@ class OracleAFQMC(object):
     def __init__(self, ham, nwalkers, nsteps=10, nblocks=10, nstblz=10,
                  npop_control=1, energy_eval_freq=1, exp_order=6,
                  pop_control='comb', min_weight=0.1, max_weight=4.0,
-                 verbose_step0=False, free_projection=False, force_bias=True):
+                 verbose_step0=False, free_projection=False, force_bias=True,
+                 nbp=0, nsplit=1, init_walker=False):
         self.ham = ham
         W = nwalkers
         self.W = W
@@ -363,6 +400,15 @@ class OracleAFQMC(object):
         self.step = 0
         self.last_parent_ix = numpy.ones(W, dtype='i')
         self.verbose_step0 = verbose_step0
+        # back propagation (estimators/back_propagation.py:55-76, walkers/walker.py:43,55-58)
+        self.nbp = nbp
+        self.init_walker = init_walker
+        self.bp_splits = [(i + 1) * (nbp // nsplit) for i in range(nsplit)] if nbp else []
+        self.phi_old = self.phi.copy()
+        self.configs = numpy.zeros((W, max(nbp, 1), ham.nchol), dtype=numpy.complex128)
+        self.cfg_step = numpy.zeros(W, dtype=int)
+        self.bp_estimates = numpy.zeros(1 + 2 * ham.nbasis * ham.nbasis, dtype=numpy.complex128)
+        self.bp_out = []          # (buff_ix, denominator, one_rdm [2, M, M]) per print
         self.estimator_update(0)
         if verbose_step0:
             self.print_step(0, nsteps=1)
@@ -383,6 +429,12 @@ class OracleAFQMC(object):
                 xbar = numpy.zeros(xi_active.shape, dtype=numpy.complex128)  # continuous.py:136-138
             x, cmf, cfb, ntrig = shift_fields(ham, xi_active, xbar)
             self.nfb_trig += ntrig
+            if self.nbp and not self.free_projection:
+                # continuous.py:288-289 -> FieldConfig.update (walkers/stack.py:52-79); a walker
+                # whose importance function is not finite skips the update (continuous.py:291-293)
+                for k, iw in enumerate(idx):
+                    self.configs[iw, self.cfg_step[iw]] = x[k]
+                    self.cfg_step[iw] += 1
             vhs = construct_vhs(ham, x)
             phi = apply_exponential(phi, vhs, self.exp_order)
             phi = kinetic_real(ham, phi)
@@ -446,6 +498,9 @@ class OracleAFQMC(object):
             self.detR[k] = self.detR[c]
             self.log_detR[k] = self.log_detR[c]
             self.eloc[k] = self.eloc[c]
+            self.phi_old[k] = self.phi_old[c]
+            self.configs[k] = self.configs[c]
+            self.cfg_step[k] = self.cfg_step[c]
 
     # -- estimators -----------------------------------------------------------
     def estimator_update(self, step):
@@ -499,6 +554,36 @@ class OracleAFQMC(object):
         self.rows.append(numpy.concatenate([[step], gs]))
         self.estimates[:] = 0
 
+    # -- back propagation -----------------------------------------------------
+    def bp_update(self):
+        """estimators/back_propagation.py:127-225 (update_uhf, BP-PhL weights, one_rdm only)
+        followed by print_step (:282-333): returns nothing, appends to bp_out."""
+        ham = self.ham
+        M, na = ham.nbasis, ham.nup
+        buff_ix = int(self.cfg_step[0])
+        if buff_ix not in self.bp_splits:
+            return
+        init = self.phi0 if (self.init_walker and hasattr(self, 'phi0')) else ham.psi
+        for iw in range(self.W):
+            phi_bp = init.copy()
+            back_propagate(ham, phi_bp, self.configs[iw, :self.cfg_step[iw]], self.nstblz)
+            G = numpy.zeros((2, M, M), dtype=numpy.complex128)
+            G[0] = gab(phi_bp[:, :na], self.phi_old[iw][:, :na]).T
+            if ham.ne > na:
+                G[1] = gab(phi_bp[:, na:], self.phi_old[iw][:, na:]).T
+            w = self.weight[iw]
+            self.bp_estimates[0] += w
+            self.bp_estimates[1:] += w * G.flatten()
+            if buff_ix == self.bp_splits[-1]:
+                # FieldConfig.reset (walkers/stack.py:122-125), nprop_tot == nbp
+                if self.cfg_step[iw] % self.nbp == 0:
+                    self.cfg_step[iw] = 0
+        if buff_ix == self.bp_splits[-1]:
+            self.phi_old = self.phi.copy()          # copy_historic_wfn (handler.py:200-203)
+        self.bp_out.append((buff_ix, self.bp_estimates[0],
+                            self.bp_estimates[1:].reshape(2, M, M).copy()))
+        self.bp_estimates[:] = 0
+
     # -- one driver step ------------------------------------------------------
     def do_step(self, xi_active, rand):
         """Loop body of afqmc.py:223-255.  xi_active: [n_active, N] normals for
@@ -519,6 +604,8 @@ class OracleAFQMC(object):
         if step % self.npop_control == 0:
             self.pop_control(rand)
         self.estimator_update(step)
+        if self.nbp:
+            self.bp_update()
         self.print_step(step)
         if step < self.neqlb:
             self.eshift = self.eshift_vec[0].real

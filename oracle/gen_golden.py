@@ -113,6 +113,27 @@ def case_free(name, free, force_bias, pop='comb', walkers=None):
     save(name, meta, tr, setup=rh.reference_setup_arrays(a))
 
 
+def case_bp(name, nmo, nelec, nwalkers, tau_bp, nsplit, stab, scale, dt=0.005, steps=10, blocks=3):
+    """Back propagation (estimators/back_propagation.py:127-225, propagation/generic.py:253-290,
+    walkers/stack.py:5-127).  'bp_ref' is the reference's own driver test
+    (qmc/tests/test_afqmc.py:232-278); 'bp_stress' re-orthogonalises inside the back
+    propagation, splits it in two and has comb events that move field histories."""
+    numpy.random.seed(7)
+    h1e, chol, enuc, _ = generate_hamiltonian(nmo, nelec, cplx=False)
+    hs = scale * chol.reshape((-1, nmo * nmo)).T.copy()
+    opts = options(nwalkers, dt, steps, blocks, 8, stab=stab, popc=1)
+    opts['estimator'] = {'back_propagated': {'tau_bp': tau_bp, 'one_rdm': True, 'nsplit': nsplit},
+                         'mixed': {'energy_eval_freq': 1, 'verbose': False}}
+    opts.pop('estimates', None)
+    a, tr = rh.run_reference_traced(h1e, hs, enuc, nelec, opts)
+    meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array(nelec), dt=dt,
+                nwalkers=nwalkers, steps=steps, blocks=blocks, seed=8, stab=stab, popc=1,
+                tau_bp=tau_bp, nsplit=nsplit)
+    extra = {k: tr[k] for k in ('bp_buff_ix', 'bp_denominator', 'bp_one_rdm', 'phi_old_final')}
+    print(name, 'bp prints', len(tr['bp_buff_ix']), 'buff_ix', tr['bp_buff_ix'][:6])
+    save(name, meta, tr, setup=rh.reference_setup_arrays(a), extra=extra)
+
+
 def case_stress(name, pop, walkers=None, scale_chol=6.0, dt=0.02):
     """Small case scaled so that the force-bias clip, the hybrid-energy bound,
     the weight cap and comb/pair-branch events all fire."""
@@ -171,13 +192,16 @@ def case_local_energy():
 
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ['tg', 'c1', 'stress', 'pb', 'le', 'c2s', 'c3s', 'c4s', 'free']
+    which = sys.argv[1:] or ['tg', 'c1', 'stress', 'pb', 'le', 'c2s', 'c3s', 'c4s', 'free', 'bp']
     if 'free' in which:
         case_free('free_comb', True, True)
         case_free('free_pair_branch', True, False, pop='pair_branch',
                   walkers={'population_control': 'pair_branch', 'min_weight': 0.9,
                            'max_weight': 1.1})
         case_free('phaseless_nofb', False, False)
+    if 'bp' in which:
+        case_bp('bp_ref', 11, (3, 3), 10, 0.025, 1, 10, 1.0, blocks=10)
+        case_bp('bp_stress', 12, (4, 4), 16, 0.12, 2, 2, 6.0, dt=0.02, steps=5, blocks=4)
     if 'tg' in which:
         case_test_generic()
     if 'c1' in which:

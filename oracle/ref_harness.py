@@ -115,6 +115,18 @@ def run_reference_traced(h1e, hs_pot, ecore, nelec, options, nsteps_total=None):
         return real_bcast(obj, root=root)
 
     comm.bcast = rec_bcast
+    # back-propagated estimates as BackPropagation.print_step reduces them
+    # (estimators/back_propagation.py:282-333), captured before they are zeroed
+    bp = afqmc.estimators.estimators.get('back_prop')
+    bp_rec = []
+    if bp is not None:
+        real_bp_print = bp.print_step
+
+        def rec_bp_print(comm_, nprocs, step, nsteps=1, free_projection=False):
+            if bp.accumulated:
+                bp_rec.append((int(bp.buff_ix), numpy.array(bp.estimates, copy=True)))
+            return real_bp_print(comm_, nprocs, step, nsteps, free_projection)
+        bp.print_step = rec_bp_print
     eloc_now = numpy.zeros((W, 3), dtype=numpy.complex128)
     real_local_energy = [w.local_energy for w in psi.walkers]
 
@@ -180,6 +192,14 @@ def run_reference_traced(h1e, hs_pot, ecore, nelec, options, nsteps_total=None):
     out['nfb_trig'] = numpy.array(prop.nfb_trig)
     out['nhe_trig'] = numpy.array(prop.nhe_trig)
     out['rows'] = estimator_rows(afqmc.estimators.filename)
+    if bp is not None:
+        M = system.nbasis
+        out['bp_buff_ix'] = numpy.array([b[0] for b in bp_rec])
+        out['bp_energies'] = numpy.array([b[1][:bp.nreg] for b in bp_rec])
+        out['bp_denominator'] = numpy.array([b[1][bp.nreg] for b in bp_rec])
+        out['bp_one_rdm'] = numpy.array([b[1][bp.nreg + 1:bp.nreg + 1 + 2 * M * M].reshape(2, M, M)
+                                         for b in bp_rec])
+        out['phi_old_final'] = numpy.array([w.phi_old for w in psi.walkers])
     return afqmc, out
 
 

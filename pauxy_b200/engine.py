@@ -165,18 +165,51 @@ class Engine(object):
         self._xi_event.record(torch.cuda.current_stream(self.device))
         return self._xi_dev
 
+    def prefetch_xi(self, xi_pinned):
+        """Start the host->device copy of the NEXT step's fields (pinned float64 [W, N]) on a
+        copy stream, double-buffered, so that it overlaps the step in flight.  Returns the device
+        tensor to hand to propagate(), which waits for the copy on the launch stream."""
+        if getattr(self, '_pf', None) is None:
+            with torch.cuda.device(self.device):
+                self._pf = {'buf': [torch.empty((self.W, self.N), dtype=torch.float64,
+                                                device=self.device) for _ in range(2)],
+                            'ready': [torch.cuda.Event(), torch.cuda.Event()],
+                            'free': [None, None], 'next': 0,
+                            'stream': torch.cuda.Stream(self.device)}
+        pf = self._pf
+        i = pf['next']
+        pf['next'] = 1 - i
+        with torch.cuda.device(self.device):
+            if pf['free'][i] is not None:
+                pf['stream'].wait_event(pf['free'][i])   # the step that read this buffer is done
+            with torch.cuda.stream(pf['stream']):
+                pf['buf'][i].copy_(xi_pinned, non_blocking=True)
+                pf['ready'][i].record(pf['stream'])
+        return pf['buf'][i]
+
     def propagate(self, xi=None, eshift=0.0, step=1, seed=0, walker_offset=0):
         """xi: None (device Philox), numpy [W,N] or cuda float64 tensor [W,N]."""
         with torch.cuda.device(self.device):
             ptr = None
+            slot = None
             if xi is not None:
                 if not torch.is_tensor(xi):
                     xi = self.stage_xi(xi)
                 assert xi.dtype == torch.float64 and tuple(xi.shape) == (self.W, self.N)
                 assert xi.is_contiguous()
                 ptr = xi.data_ptr()
+                pf = getattr(self, '_pf', None)
+                if pf is not None:
+                    for i in range(2):
+                        if pf['buf'][i].data_ptr() == ptr:
+                            slot = i
+                            torch.cuda.current_stream(self.device).wait_event(pf['ready'][i])
             self._check(self.lib.pxb_propagate(self._h, ptr, int(seed), int(walker_offset),
                                                float(eshift), int(step), self._stream()))
+            if slot is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(self.device))
+                self._pf['free'][slot] = ev
 
     def orthogonalise(self):
         with torch.cuda.device(self.device):
