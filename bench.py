@@ -189,6 +189,8 @@ def main():
     ap.add_argument('--config', default='c4')
     ap.add_argument('--walkers', type=int, default=0, help='walkers per GPU (default: config)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-prefetch', action='store_true',
+                    help='e2e leg: copy the fields on the launch stream instead of prefetching')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -231,6 +233,7 @@ def main():
     nbuf = 3
     xi_host = [torch.from_numpy(rs.normal(size=(wpg, N))).pin_memory() for _ in range(nbuf)]
     xi_dev = [x.to(dev) for x in xi_host]
+    xi_stage = torch.empty((wpg, N), dtype=torch.float64, device=dev)
     combr = rs.rand(4096)
     res_host = torch.empty(10, dtype=torch.complex128).pin_memory()
     w_host = torch.empty(wpg, dtype=torch.float64).pin_memory()
@@ -245,11 +248,15 @@ def main():
         if e2e:
             # H2D of this step's fields was started on the copy stream during the previous step
             # (Engine.prefetch_xi); the first one of a timed region is issued here
-            xi_now = state.pop('xi_next', None)
-            if xi_now is None:
-                xi_now = eng.prefetch_xi(xi_host[step % nbuf])
-            eng.propagate(xi_now, eshift=state['eshift'], step=step)
-            state['xi_next'] = eng.prefetch_xi(xi_host[(step + 1) % nbuf])
+            if args.no_prefetch:
+                xi_stage.copy_(xi_host[step % nbuf], non_blocking=True)
+                eng.propagate(xi_stage, eshift=state['eshift'], step=step)
+            else:
+                xi_now = state.pop('xi_next', None)
+                if xi_now is None:
+                    xi_now = eng.prefetch_xi(xi_host[step % nbuf])
+                eng.propagate(xi_now, eshift=state['eshift'], step=step)
+                state['xi_next'] = eng.prefetch_xi(xi_host[(step + 1) % nbuf])
         else:
             eng.propagate(xi_dev[step % nbuf], eshift=state['eshift'], step=step)
         if world == 1:
@@ -305,6 +312,8 @@ def main():
     stage = eng.stage_times(reset=True)
     eng.profile(False)
     launches = eng.launch_count() - launches0
+    for _ in range(2):          # warm the end-to-end path too (copy stream, pinned staging)
+        one_step(True)
     state.pop('xi_next', None)
     ms_e2e = timed(args.steps, True)
     clocks = sampler.stop() if sampler else None

@@ -32,7 +32,7 @@ extern "C" {
 #define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
 #define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
 
-#define PXB_ABI_VERSION 4
+#define PXB_ABI_VERSION 5
 
 typedef struct pxb_context* pxb_handle;
 
@@ -51,6 +51,9 @@ typedef struct {
   double dt;
   int32_t exchange_mode; /* PXB_EXCHANGE_*: how pxb_local_energy evaluates the exchange term */
   int32_t flags;         /* PXB_FLAG_* */
+  int32_t nbp;           /* back propagation: field configurations kept per walker
+                            (estimators/back_propagation.py:55 nmax = int(tau_bp/dt)); 0 = off */
+  int32_t reserved;
 } pxb_config;
 
 /* propagator options of pauxy/propagation/continuous.py:14-33 */
@@ -92,7 +95,10 @@ enum pxb_field_id {
   PXB_F_TOTAL_WEIGHT = 14,   /* f64  [1]    walker.total_weight (same for all walkers) */
   PXB_F_PAIRS = 15,          /* i32  [1+2*Wtot] n_pairs then (clone, kill) global indices */
   PXB_F_PHASE = 16,          /* c128 [W]    walker.phase (free projection; 1 otherwise) */
-  PXB_F_COUNT = 17
+  PXB_F_BP_RDM = 17,         /* c128 [2,M,M] sum_w weight_w G_w of the back-propagated estimator
+                                              (back_propagation.py:198-205), nbp > 0 only */
+  PXB_F_BP_DENOM = 18,       /* c128 [1]    sum_w weight_w (back_propagation.py:200) */
+  PXB_F_COUNT = 19
 };
 
 int pxb_abi_version(void);
@@ -243,6 +249,29 @@ int pxb_peer_attach(pxb_handle h, int rank, int nranks, const void* handles,
 int pxb_pop_control_comb_peers(pxb_handle h, const double* dev_global_abs_weights, int64_t wtot,
                                double r, void* stream);
 int pxb_pop_control_finish(pxb_handle h, void* stream);
+
+/* ---- back propagation (pxb_config.nbp > 0) ------------------
+ * pxb_propagate then keeps the shifted fields x of every step per walker (FieldConfig.update,
+ * walkers/stack.py:52-79 called from propagation/continuous.py:288-289); they and phi_old travel
+ * with the walker through population control.
+ *  pxb_bp_steps        : configurations stored since the last reset (field_configs.step).
+ *  pxb_back_propagate  : BackPropagation.update_uhf (estimators/back_propagation.py:127-225) for
+ *      all walkers: phi_bp = trial.psi (init_walker != 0: trial.init), then for the first `nsteps`
+ *      stored configurations in reverse order phi_bp <- B(c)^dagger phi_bp
+ *      (back_propagate_generic, propagation/generic.py:253-290; B of generic.py:180-213) with a QR
+ *      re-orthogonalisation after every nstblz applications, G = gab(phi_bp, phi_old)^T and
+ *      BP_RDM += weight * G, BP_DENOM += weight (BP-PhL weights).  Needs Cholesky matrices that are
+ *      symmetric to rounding (real orbitals): PXB_ERR_UNSUPPORTED otherwise; BH1 may be any real matrix.
+ *  pxb_bp_reset        : phi_old = phi for every walker, empty history (walkers/handler.py:200-203,
+ *      walkers/stack.py:122-125).
+ *  pxb_bp_zero         : BackPropagation.zero (back_propagation.py:335-338).
+ *  pxb_get_phi_bp      : c128 [W, M, ne] copy of the back-propagated (which = 0) or the historic
+ *      (which = 1) determinants (tests). */
+int pxb_bp_steps(pxb_handle h);
+int pxb_back_propagate(pxb_handle h, int nsteps, int nstblz, int init_walker, void* stream);
+int pxb_bp_reset(pxb_handle h, void* stream);
+int pxb_bp_zero(pxb_handle h, void* stream);
+int pxb_get_phi_bp(pxb_handle h, int which, void* dev_out, void* stream);
 
 /* Host helpers (pure C, no device): bit-exact restatements used by the host
  * mirror when the selection has to happen on the host. */

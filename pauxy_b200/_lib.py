@@ -10,14 +10,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libpauxy_b200.so')
 
 PXB_OK = 0
-ABI_VERSION = 4
+ABI_VERSION = 5
 EXCHANGE_MODES = {'auto': 0, 'cholesky': 1, 'eri': 2}
 ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_ERR_UNSUPPORTED'}
 
 # enum pxb_field_id
 F_WEIGHT, F_UNSCALED_WEIGHT, F_OT, F_HYBRID_ENERGY, F_ELOC, F_DETR, F_LOG_DETR, \
     F_ESTIMATES, F_COUNTERS, F_PARENT_IX, F_XBAR, F_XSHIFTED, F_CMF_CFB, F_OVLP_NEW, \
-    F_TOTAL_WEIGHT, F_PAIRS, F_PHASE, F_COUNT = range(18)
+    F_TOTAL_WEIGHT, F_PAIRS, F_PHASE, F_BP_RDM, F_BP_DENOM, F_COUNT = range(20)
 FLAG_FREE_PROJECTION, FLAG_NO_FORCE_BIAS = 1, 2
 
 
@@ -30,7 +30,8 @@ class PxbConfig(ctypes.Structure):
                 ('nchol', ctypes.c_int32), ('nwalkers', ctypes.c_int32),
                 ('exp_order', ctypes.c_int32), ('device', ctypes.c_int32),
                 ('total_walkers', ctypes.c_int32), ('dt', ctypes.c_double),
-                ('exchange_mode', ctypes.c_int32), ('flags', ctypes.c_int32)]
+                ('exchange_mode', ctypes.c_int32), ('flags', ctypes.c_int32), ('nbp', ctypes.c_int32),
+                ('reserved', ctypes.c_int32)]
 
 
 class PxbError(RuntimeError):
@@ -78,6 +79,11 @@ _PROTOS = {
     'pxb_peer_attach': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     'pxb_pop_control_comb_peers': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_double, _vp]),
     'pxb_pop_control_finish': (ctypes.c_int, [_vp, _vp]),
+    'pxb_bp_steps': (ctypes.c_int, [_vp]),
+    'pxb_back_propagate': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    'pxb_bp_reset': (ctypes.c_int, [_vp, _vp]),
+    'pxb_bp_zero': (ctypes.c_int, [_vp, _vp]),
+    'pxb_get_phi_bp': (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
     'pxb_comb_plan_host': (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_double, _vp]),
     'pxb_stage_greens': (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     'pxb_stage_force_bias_gemm': (ctypes.c_int, [_vp, _vp]),

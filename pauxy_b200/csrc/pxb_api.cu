@@ -10,6 +10,7 @@
 #include <vector>
 
 #include "pxb_common.cuh"
+#include "pxb_bp.cuh"
 #include "pxb_eri.cuh"
 #include "pxb_exchange.cuh"
 #include "pxb_gemm.cuh"
@@ -31,6 +32,7 @@ enum ArenaId {
   A_LF, A_RF, A_BF, A_PSIT, A_H1ROT, A_VBAR,
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
   A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_OB, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
+  A_FC, A_PHI_OLD, A_PHI_BP, A_PHI_BP2, A_THETA_BP, A_BP_PART, A_PSI_NAT, A_INIT_NAT, A_BFT,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -61,11 +63,16 @@ struct pxb_context {
   bool greens_split = true;  // batched overlap GEMM + warp-per-walker inverse/Theta (PXB_GREENS=fused: one CTA per walker)
   bool vhs_sym = false;  // L symmetric in (p,q): the VHS GEMM computes the upper triangle only
   bool vhs_sym_allowed = true;
+  bool hs_near_sym = false;  // L symmetric in (p,q) to rounding (needed by the back propagation)
   int rtu = 0;           // row tiles kept in that case
   bool taylor_tma = true;  // persistent TMA-fed Taylor kernel (PXB_TAYLOR=direct selects the per-walker-CTA one)
   bool exx_eri = false;  // exchange through the half-rotated ERI quadratic form (pxb_eri.cuh)
   bool kf_shared = false;  // both spins use the K of spin 0 (identical half-rotated Cholesky blocks)
   int eri_nslot = 0;
+  // back propagation: stored field configurations per walker (walkers/stack.py:5-127)
+  int nbp = 0;      // capacity (steps), 0: back propagation off
+  int bp_step = 0;  // configurations stored since the last pxb_bp_reset
+  int bp_chunks = 0;
   // peer-memory population control: arena bases of all ranks mapped through CUDA IPC
   int peer_rank = -1, peer_n = 0;
   unsigned char* peer_base[PXB_MAX_PEERS] = {nullptr};
@@ -156,6 +163,9 @@ CopyArgs copy_args(pxb_handle h) {
   c.detR = h->field<double>(PXB_F_DETR);
   c.log_detR = h->field<double>(PXB_F_LOG_DETR);
   c.phase = h->field<double2>(PXB_F_PHASE);
+  c.phi_old = h->nbp > 0 ? h->ptr<double>(A_PHI_OLD) : nullptr;
+  c.fc = h->nbp > 0 ? h->ptr<double>(A_FC) : nullptr;
+  c.fc_rows = (int)fc_rows(h->d, h->nbp);
   c.d = h->d;
   return c;
 }
@@ -171,6 +181,9 @@ int launch_greens(pxb_handle h, const GreensArgs& a, size_t smem, cudaStream_t s
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
+
+template <int NMT>
+int launch_theta(pxb_handle h, const double* phi, double* theta_out, cudaStream_t st);
 
 template <int NMT>
 int launch_greens2(pxb_handle h, const double* phi, cudaStream_t st) {
@@ -195,11 +208,19 @@ int launch_greens2(pxb_handle h, const double* phi, cudaStream_t st) {
     ++h->launches;
     PXB_CUDA(h, (launch_gemm_tma<NMT, 4, 1, 6>(g, epi, 1, h->sm_count, st)));
   }
-  // 2. inverse, slogdet, Theta, e1b: one warp per (walker, spin)
+  return launch_theta<NMT>(h, phi, h->ptr<double>(A_THETA), st);
+}
+
+// 2. inverse, slogdet, Theta, e1b: one warp per (walker, spin); Theta = OB^-1 phi^T -> theta_out
+template <int NMT>
+int launch_theta(pxb_handle h, const double* phi, double* theta_out, cudaStream_t st) {
+  const Dims& d = h->d;
+  const int nmax = d.na > d.nb ? d.na : d.nb;
+  const int nld = nmax | 1, nsq = nmax * nld;
   ThetaArgs a;
   a.OB = h->ptr<double2>(A_OB);
   a.phi = phi;
-  a.theta = h->ptr<double>(A_THETA);
+  a.theta = theta_out;
   a.h1rot = h->ptr<double2>(A_H1ROT);
   a.slog = h->ptr<double>(A_SLOG);
   a.e1b_part = h->ptr<double2>(A_E1BP);
@@ -314,14 +335,15 @@ int run_vhs_gemm(pxb_handle h, cudaStream_t st) {
   return PXB_OK;
 }
 
-int run_one_body(pxb_handle h, const double* in, double* out, const int* active, cudaStream_t st) {
+int run_one_body(pxb_handle h, const double* in, double* out, const int* active, cudaStream_t st,
+                 bool transposed = false) {
   StageTimer timer__(h, PXB_STAGE_ONE_BODY, st);
   const Dims& d = h->d;
   for (int s = 0; s < 2; ++s) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     if (ns == 0) continue;
     GemmArgs g;
-    g.A = h->ptr<double>(A_BF) + (size_t)s * d.MT * d.KC * 32;
+    g.A = h->ptr<double>(transposed ? A_BFT : A_BF) + (size_t)s * d.MT * d.KC * 32;
     g.B = in + (size_t)ioff * d.KC * 32;
     g.strideAz = g.strideBz = 0;
     g.strideBO = (size_t)d.ne * d.KC * 32;
@@ -752,6 +774,20 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_FIELD0 + PXB_F_TOTAL_WEIGHT, 8);
   add(A_FIELD0 + PXB_F_PAIRS, (1 + 2 * Wt) * 4);
   add(A_FIELD0 + PXB_F_PHASE, W * 16);
+  h->nbp = cfg->nbp > 0 ? cfg->nbp : 0;
+  const bool bp = h->nbp > 0;
+  h->bp_chunks = bp ? std::max(1, std::min(64, d.W / 16)) : 0;
+  add(A_FC, bp ? fc_size(d, h->nbp) * 8 : 0);
+  add(A_PHI_OLD, bp ? of_size(d) * 8 : 0);
+  add(A_PHI_BP, bp ? of_size(d) * 8 : 0);
+  add(A_PHI_BP2, bp ? of_size(d) * 8 : 0);
+  add(A_THETA_BP, bp ? of_size(d) * 8 : 0);
+  add(A_BP_PART, bp ? (size_t)h->bp_chunks * 2 * d.M * d.M * 16 : 0);
+  add(A_BFT, bp ? bf_size(d) * 8 : 0);
+  add(A_PSI_NAT, (size_t)d.M * d.ne * 16);
+  add(A_INIT_NAT, (size_t)d.M * d.ne * 16);
+  add(A_FIELD0 + PXB_F_BP_RDM, bp ? (size_t)2 * d.M * d.M * 16 : 0);
+  add(A_FIELD0 + PXB_F_BP_DENOM, 16);
   h->arena_bytes = off;
   *out = h;
   return PXB_OK;
@@ -814,7 +850,12 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
                                                        h->ptr<double>(A_RF), d, flag);
   ++h->launches;
   pack_bf_kernel<<<grid_for(bf_size(d)), 256, 0, st>>>(static_cast<const double2*>(bh1), h->ptr<double>(A_BF),
-                                                       d, flag);
+                                                       d, flag, 0);
+  if (h->nbp > 0) {  // BH1^T for the B^dagger chain of the back propagation
+    ++h->launches;
+    pack_bf_kernel<<<grid_for(bf_size(d)), 256, 0, st>>>(static_cast<const double2*>(bh1), h->ptr<double>(A_BFT),
+                                                         d, flag, 1);
+  }
   ++h->launches;
   pack_small_kernel<<<grid_for((size_t)d.ne * d.Mp), 256, 0, st>>>(
       static_cast<const double2*>(psi), static_cast<const double2*>(h1rot),
@@ -831,6 +872,7 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
     PXB_CUDA(h, cudaMemcpyAsync(&f1, flag, 4, cudaMemcpyDeviceToHost, st));
     PXB_CUDA(h, cudaStreamSynchronize(st));
     h->vhs_sym = h->vhs_sym_allowed && (f1 & 16) == 0;
+    h->hs_near_sym = (f1 & 32) == 0;
     const int* map = nullptr;
     int nrt = d.RT;
     if (h->vhs_sym) {
@@ -882,6 +924,7 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
              (hflag >> 1) & 1, (hflag >> 2) & 1);
     return fail(h, PXB_ERR_UNSUPPORTED, buf);
   }
+  PXB_CUDA(h, cudaMemcpyAsync(h->ptr<void>(A_PSI_NAT), psi, (size_t)d.M * d.ne * 16, cudaMemcpyDeviceToDevice, st));
   h->d.ecore = ecore;
   h->ham_set = true;
   h->theta_valid = h->x_valid = false;
@@ -930,6 +973,16 @@ int pxb_init_walkers(pxb_handle h, const void* dev_init_phi, double total_walker
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ESTIMATES), 0, 160, st));
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_COUNTERS), 0, 64, st));
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ELOC), 0, (size_t)d.Wp * 48, st));
+  PXB_CUDA(h, cudaMemcpyAsync(h->ptr<void>(A_INIT_NAT), dev_init_phi, (size_t)d.M * d.ne * 16,
+                              cudaMemcpyDeviceToDevice, st));
+  if (h->nbp > 0) {
+    // walker.phi_old = phi.copy() (walkers/walker.py:43), empty field history
+    PXB_CUDA(h, cudaMemcpyAsync(h->ptr<void>(A_PHI_OLD), h->phi(), of_size(d) * 8, cudaMemcpyDeviceToDevice, st));
+    PXB_CUDA(h, cudaMemsetAsync(h->ptr<void>(A_FC), 0, fc_size(d, h->nbp) * 8, st));
+    PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_BP_RDM), 0, (size_t)2 * d.M * d.M * 16, st));
+    PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_BP_DENOM), 0, 16, st));
+    h->bp_step = 0;
+  }
   return PXB_OK;
 }
 
@@ -969,6 +1022,15 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
     field_kernel<<<(d.Wp + 7) / 8, 256, 0, st>>>(f);
   }
   PXB_CUDA(h, cudaGetLastError());
+  if (h->nbp > 0 && !(d.flags & FLAG_FREE_PROJECTION)) {
+    // FieldConfig.update (walkers/stack.py:52-79, called from continuous.py:288-289): keep x
+    if (h->bp_step >= h->nbp)
+      return fail(h, PXB_ERR_STATE, "field history is full: call pxb_bp_reset after back propagating");
+    const size_t row = (size_t)d.NKC * 32 * 8;
+    PXB_CUDA(h, cudaMemcpy2DAsync(h->ptr<unsigned char>(A_FC) + (size_t)h->bp_step * row, row * h->nbp,
+                                  h->ptr<void>(A_XF), row, row, d.WG, cudaMemcpyDeviceToDevice, st));
+    ++h->bp_step;
+  }
   if ((rc = run_vhs_gemm(h, st))) return rc;
   double* work = h->phi_other();
   if ((rc = run_one_body(h, h->phi(), work, nullptr, st))) return rc;
@@ -1237,7 +1299,7 @@ int pxb_pop_control_finish(pxb_handle h, void* stream) {
 
 int pxb_payload_doubles(pxb_handle h, size_t* n) {
   if (!h || !n) return PXB_ERR_ARG;
-  *n = (size_t)2 * h->d.ne * h->d.KC * 8 + 18;
+  *n = payload_doubles(h->d, h->nbp > 0, (int)fc_rows(h->d, h->nbp));
   return PXB_OK;
 }
 
@@ -1294,6 +1356,118 @@ int pxb_comb_plan_host(const double* weights, int64_t n, double r, int32_t* pare
       if (iw >= n) return PXB_ERR_ARG;  // the reference raises IndexError here
     }
   }
+  return PXB_OK;
+}
+
+// ---- back propagation -----------------------------------------
+int pxb_bp_steps(pxb_handle h) { return h ? h->bp_step : 0; }
+
+int pxb_back_propagate(pxb_handle h, int nsteps, int nstblz, int init_walker, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  cudaStream_t st = S(stream);
+  if (h->nbp <= 0) return fail(h, PXB_ERR_STATE, "back propagation was not enabled (pxb_config.nbp == 0)");
+  if (nsteps < 0 || nsteps > h->bp_step) return fail(h, PXB_ERR_ARG, "pxb_back_propagate: nsteps exceeds the stored history");
+  if (nstblz < 1) return fail(h, PXB_ERR_ARG, "pxb_back_propagate: nstblz < 1");
+  if (!h->hs_near_sym)
+    return fail(h, PXB_ERR_UNSUPPORTED, "back propagation needs symmetric Cholesky matrices (real orbitals)");
+  double* phi_bp = h->ptr<double>(A_PHI_BP);
+  double* work = h->ptr<double>(A_PHI_BP2);
+  int rc;
+  // phi_bp = trial.psi (or trial.init) for every walker (back_propagation.py:150-153)
+  ++h->launches;
+  phi_to_of_kernel<<<grid_for((size_t)d.Wp * d.ne * d.Mp), 256, 0, st>>>(
+      h->ptr<double2>(init_walker ? A_INIT_NAT : A_PSI_NAT), phi_bp, d, 1);
+  PXB_CUDA(h, cudaGetLastError());
+  // propagation/generic.py:277-287: configurations in reverse order, B^dagger each
+  for (int i = 0; i < nsteps; ++i) {
+    const int s = nsteps - 1 - i;
+    ++h->launches;
+    bp_field_kernel<<<grid_for((size_t)d.WG * d.NKC * 16), 256, 0, st>>>(h->ptr<double>(A_FC), h->ptr<double>(A_XF),
+                                                                         d, h->nbp, s);
+    PXB_CUDA(h, cudaGetLastError());
+    if ((rc = run_vhs_gemm(h, st))) return rc;
+    if ((rc = run_one_body(h, phi_bp, work, nullptr, st, true))) return rc;
+    if ((rc = run_taylor(h, work, nullptr, st))) return rc;
+    if ((rc = run_one_body(h, work, phi_bp, nullptr, st, true))) return rc;
+    if (i != 0 && i % nstblz == 0) {
+      QrArgs q;
+      q.phi = phi_bp;
+      q.logdet = h->ptr<double>(A_QRLD);
+      q.d = d;
+      const size_t smem = qr_smem_bytes(d);
+      if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "qr: problem too large for shared memory");
+      PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      ++h->launches;
+      qr_kernel<<<2 * d.Wp, GR_THREADS, smem, st>>>(q);
+      PXB_CUDA(h, cudaGetLastError());
+    }
+  }
+  // G_s = gab(phi_bp_s, phi_old_s)^T = conj(phi_bp_s) (phi_old_s^T conj(phi_bp_s))^-1 phi_old_s^T
+  const int nmax = d.na > d.nb ? d.na : d.nb;
+  const int nld = nmax | 1, nsq = nmax * nld;
+  ++h->launches;
+  bp_overlap_kernel<<<2 * d.Wp, 128, 0, st>>>(h->ptr<double>(A_PHI_OLD), phi_bp, h->ptr<double2>(A_OB), d, nld, nsq);
+  PXB_CUDA(h, cudaGetLastError());
+  const int nmt = (nmax + 7) >> 3;
+  double* thbp = h->ptr<double>(A_THETA_BP);
+  const double* pold = h->ptr<double>(A_PHI_OLD);
+  rc = 1;
+  if (nmt <= 1) rc = launch_theta<1>(h, pold, thbp, st);
+  else if (nmt <= 2) rc = launch_theta<2>(h, pold, thbp, st);
+  else if (nmt <= 3) rc = launch_theta<3>(h, pold, thbp, st);
+  else if (nmt <= 4) rc = launch_theta<4>(h, pold, thbp, st);
+  else if (nmt <= 5) rc = launch_theta<5>(h, pold, thbp, st);
+  else if (nmt <= 6) rc = launch_theta<6>(h, pold, thbp, st);
+  else if (nmt <= 8) rc = launch_theta<8>(h, pold, thbp, st);
+  if (rc == 1) return fail(h, PXB_ERR_UNSUPPORTED, "back propagation: too many occupied orbitals for the Theta kernel");
+  if (rc) return rc;
+  // estimates += weight * G (back_propagation.py:198-205), BP-PhL weights
+  BpRdmArgs a;
+  a.phi_bp = phi_bp;
+  a.theta = thbp;
+  a.weight = h->field<double>(PXB_F_WEIGHT);
+  a.part = h->ptr<double2>(A_BP_PART);
+  a.d = d;
+  a.nchunks = h->bp_chunks;
+  a.wchunk = (d.W + a.nchunks - 1) / a.nchunks;
+  a.tiles = (d.M + BPR_T - 1) / BPR_T;
+  ++h->launches;
+  bp_rdm_kernel<<<a.tiles * a.tiles * 2 * a.nchunks, 256, 0, st>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  ++h->launches;
+  bp_reduce_kernel<<<std::min(grid_for((size_t)2 * d.M * d.M), 4 * h->sm_count), 256, 0, st>>>(
+      a.part, h->field<double2>(PXB_F_BP_RDM), h->field<double2>(PXB_F_BP_DENOM), a.weight, d, a.nchunks);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_bp_reset(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  if (h->nbp <= 0) return fail(h, PXB_ERR_STATE, "back propagation was not enabled (pxb_config.nbp == 0)");
+  // copy_historic_wfn (walkers/handler.py:200-203) + FieldConfig.reset (walkers/stack.py:122-125)
+  PXB_CUDA(h, cudaMemcpyAsync(h->ptr<void>(A_PHI_OLD), h->phi(), of_size(h->d) * 8, cudaMemcpyDeviceToDevice,
+                              S(stream)));
+  h->bp_step = 0;
+  return PXB_OK;
+}
+
+int pxb_bp_zero(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  if (h->nbp <= 0) return fail(h, PXB_ERR_STATE, "back propagation was not enabled (pxb_config.nbp == 0)");
+  PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_BP_RDM), 0, (size_t)2 * h->d.M * h->d.M * 16, S(stream)));
+  PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_BP_DENOM), 0, 16, S(stream)));
+  return PXB_OK;
+}
+
+int pxb_get_phi_bp(pxb_handle h, int which, void* dev_out, void* stream) {
+  PXB_REQUIRE_READY(h);
+  if (h->nbp <= 0) return fail(h, PXB_ERR_STATE, "back propagation was not enabled (pxb_config.nbp == 0)");
+  const Dims& d = h->d;
+  ++h->launches;
+  of_to_natural_kernel<<<grid_for((size_t)d.W * d.ne * d.M), 256, 0, S(stream)>>>(
+      h->ptr<double>(which ? A_PHI_OLD : A_PHI_BP), static_cast<double2*>(dev_out), d, 1);
+  PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
 

@@ -38,9 +38,12 @@ __global__ void hs_symmetry_kernel(const double* __restrict__ hs_pot, Dims d, in
     const int n = idx % d.N;
     const size_t pq = idx / d.N;
     const int q = pq % d.M, p = pq / d.M;
-    if (p < q && hs_pot[idx] != hs_pot[((size_t)q * d.M + p) * d.N + n]) {
-      atomicOr(flag, 16);
-      return;
+    if (p < q) {
+      const double a = hs_pot[idx], b = hs_pot[((size_t)q * d.M + p) * d.N + n];
+      if (a != b) {
+        // 16: not bit-symmetric; 32: not symmetric even to rounding (back propagation then needs L^T)
+        atomicOr(flag, fabs(a - b) > 1e-12 * (fabs(a) + fabs(b)) + 1e-14 ? 48 : 16);
+      }
     }
   }
 }
@@ -75,7 +78,7 @@ __global__ void pack_rf_kernel(const double2* __restrict__ rchol, double* __rest
 }
 
 __global__ void pack_bf_kernel(const double2* __restrict__ bh1, double* __restrict__ BF, Dims d,
-                               int* flag) {
+                               int* flag, int transpose) {
   const size_t total = bf_size(d);
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -87,7 +90,7 @@ __global__ void pack_bf_kernel(const double2* __restrict__ bh1, double* __restri
     const int p = 8 * mt + g, q = 4 * kc + tt;
     double v = 0.0;
     if (p < d.M && q < d.M) {
-      double2 z = bh1[((size_t)s * d.M + p) * d.M + q];
+      double2 z = transpose ? bh1[((size_t)s * d.M + q) * d.M + p] : bh1[((size_t)s * d.M + p) * d.M + q];
       v = z.x;
       if (z.y != 0.0) atomicOr(flag, 2);
     }
@@ -790,11 +793,37 @@ struct CopyArgs {
   double* detR;
   double* log_detR;
   double2* phase;
+  double* phi_old;  // back propagation only (else nullptr): walker.phi_old, OF layout
+  double* fc;       // back propagation only: field history, rows = nbp * NKC per walker group
+  int fc_rows;
   Dims d;
 };
 
-__device__ __forceinline__ size_t payload_doubles(const Dims& d) {
-  return (size_t)2 * d.ne * d.KC * 8 + 18;
+__device__ __host__ __forceinline__ size_t payload_doubles(const Dims& d, bool bp, int fc_rows) {
+  return (size_t)(bp ? 3 : 2) * d.ne * d.KC * 8 + (bp ? (size_t)fc_rows * 8 : 0) + 18;
+}
+
+// walker-interleaved arrays [W/4][rows][4 walkers][8 doubles]: copy the `rows` 64-byte pieces of
+// walker src (in sbase) to walker dst (in dbase)
+__device__ __forceinline__ void copy_rows(double* dbase, const double* sbase, int rows, int dst, int src) {
+  for (int idx = threadIdx.x; idx < rows * 4; idx += blockDim.x) {
+    const int r = idx >> 2, q = idx & 3;
+    const size_t so = ((size_t)(src >> 2) * rows + r) * 32 + (src & 3) * 8 + q * 2;
+    const size_t dn = ((size_t)(dst >> 2) * rows + r) * 32 + (dst & 3) * 8 + q * 2;
+    *reinterpret_cast<double2*>(dbase + dn) = *reinterpret_cast<const double2*>(sbase + so);
+  }
+}
+// same between walker w of an interleaved array and a contiguous buffer of rows * 8 doubles
+__device__ __forceinline__ void pack_rows(double* base, double* buf, int rows, int w, int unpack) {
+  for (int idx = threadIdx.x; idx < rows * 4; idx += blockDim.x) {
+    const int r = idx >> 2, q = idx & 3;
+    double2* g = reinterpret_cast<double2*>(base + ((size_t)(w >> 2) * rows + r) * 32 + (w & 3) * 8 + q * 2);
+    double2* l = reinterpret_cast<double2*>(buf + (size_t)r * 8 + q * 2);
+    if (unpack)
+      *g = *l;
+    else
+      *l = *g;
+  }
 }
 
 // pairs: device list [1 + 2*n] of GLOBAL indices; only pairs with both ends on
@@ -806,12 +835,11 @@ __global__ void __launch_bounds__(256) copy_pairs_kernel(CopyArgs a, const int* 
     const int src = pairs[1 + 2 * pi] - offset, dst = pairs[2 + 2 * pi] - offset;
     if (src < 0 || src >= d.W || dst < 0 || dst >= d.W) continue;
     const int n8 = d.ne * d.KC;
-    for (int idx = threadIdx.x; idx < n8 * 4; idx += blockDim.x) {
-      const int r = idx >> 2, q = idx & 3;
-      const size_t so = ((size_t)(src >> 2) * n8 + r) * 32 + (src & 3) * 8 + q * 2;
-      const size_t dn = ((size_t)(dst >> 2) * n8 + r) * 32 + (dst & 3) * 8 + q * 2;
-      *reinterpret_cast<double2*>(a.phi + dn) = *reinterpret_cast<const double2*>(a.phi + so);
-      *reinterpret_cast<double2*>(a.theta + dn) = *reinterpret_cast<const double2*>(a.theta + so);
+    copy_rows(a.phi, a.phi, n8, dst, src);
+    copy_rows(a.theta, a.theta, n8, dst, src);
+    if (a.phi_old != nullptr) {
+      copy_rows(a.phi_old, a.phi_old, n8, dst, src);
+      copy_rows(a.fc, a.fc, a.fc_rows, dst, src);
     }
     if (threadIdx.x == 0) {
       a.e1b[dst] = a.e1b[src];
@@ -833,12 +861,11 @@ __global__ void __launch_bounds__(256) copy_list_kernel(CopyArgs a, const int* s
   for (int pi = blockIdx.x; pi < n; pi += gridDim.x) {
     const int src = src_l[pi], dst = dst_l[pi];
     const int n8 = d.ne * d.KC;
-    for (int idx = threadIdx.x; idx < n8 * 4; idx += blockDim.x) {
-      const int r = idx >> 2, q = idx & 3;
-      const size_t so = ((size_t)(src >> 2) * n8 + r) * 32 + (src & 3) * 8 + q * 2;
-      const size_t dn = ((size_t)(dst >> 2) * n8 + r) * 32 + (dst & 3) * 8 + q * 2;
-      *reinterpret_cast<double2*>(a.phi + dn) = *reinterpret_cast<const double2*>(a.phi + so);
-      *reinterpret_cast<double2*>(a.theta + dn) = *reinterpret_cast<const double2*>(a.theta + so);
+    copy_rows(a.phi, a.phi, n8, dst, src);
+    copy_rows(a.theta, a.theta, n8, dst, src);
+    if (a.phi_old != nullptr) {
+      copy_rows(a.phi_old, a.phi_old, n8, dst, src);
+      copy_rows(a.fc, a.fc, a.fc_rows, dst, src);
     }
     if (threadIdx.x == 0) {
       a.e1b[dst] = a.e1b[src];
@@ -887,12 +914,11 @@ __global__ void __launch_bounds__(256) pull_pairs_kernel(CopyArgs a, PeerArgs p,
     const double* sphi = rebase(a.phi, lb, pb);
     const double* sth = rebase(a.theta, lb, pb);
     const int n8 = d.ne * d.KC;
-    for (int idx = threadIdx.x; idx < n8 * 4; idx += blockDim.x) {
-      const int r = idx >> 2, q = idx & 3;
-      const size_t so = ((size_t)(src >> 2) * n8 + r) * 32 + (src & 3) * 8 + q * 2;
-      const size_t dn = ((size_t)(dst >> 2) * n8 + r) * 32 + (dst & 3) * 8 + q * 2;
-      *reinterpret_cast<double2*>(a.phi + dn) = *reinterpret_cast<const double2*>(sphi + so);
-      *reinterpret_cast<double2*>(a.theta + dn) = *reinterpret_cast<const double2*>(sth + so);
+    copy_rows(a.phi, sphi, n8, dst, src);
+    copy_rows(a.theta, sth, n8, dst, src);
+    if (a.phi_old != nullptr) {
+      copy_rows(a.phi_old, rebase(a.phi_old, lb, pb), n8, dst, src);
+      copy_rows(a.fc, rebase(a.fc, lb, pb), a.fc_rows, dst, src);
     }
     if (threadIdx.x == 0) {
       a.e1b[dst] = rebase(a.e1b, lb, pb)[src];
@@ -922,28 +948,20 @@ __global__ void pop_finish_kernel(double* weight, double* unscaled, double value
 __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots, int n, double* buf,
                                                    int unpack) {
   const Dims& d = a.d;
-  const size_t pd = payload_doubles(d);
+  const bool bp = a.phi_old != nullptr;
+  const size_t pd = payload_doubles(d, bp, a.fc_rows);
   for (int pi = blockIdx.x; pi < n; pi += gridDim.x) {
     const int w = slots[pi];
     double* b = buf + (size_t)pi * pd;
     const int n8 = d.ne * d.KC;
-    for (int idx = threadIdx.x; idx < n8 * 4; idx += blockDim.x) {
-      const int r = idx >> 2, q = idx & 3;
-      const size_t go = ((size_t)(w >> 2) * n8 + r) * 32 + (w & 3) * 8 + q * 2;
-      double2* g = reinterpret_cast<double2*>(a.phi + go);
-      double2* gt = reinterpret_cast<double2*>(a.theta + go);
-      double2* l = reinterpret_cast<double2*>(b + (size_t)r * 8 + q * 2);
-      double2* lt = reinterpret_cast<double2*>(b + (size_t)n8 * 8 + (size_t)r * 8 + q * 2);
-      if (unpack) {
-        *g = *l;
-        *gt = *lt;
-      } else {
-        *l = *g;
-        *lt = *gt;
-      }
+    pack_rows(a.phi, b, n8, w, unpack);
+    pack_rows(a.theta, b + (size_t)n8 * 8, n8, w, unpack);
+    if (bp) {
+      pack_rows(a.phi_old, b + (size_t)2 * n8 * 8, n8, w, unpack);
+      pack_rows(a.fc, b + (size_t)3 * n8 * 8, a.fc_rows, w, unpack);
     }
     if (threadIdx.x == 0) {
-      double* s = b + (size_t)2 * n8 * 8;
+      double* s = b + pd - 18;
       if (unpack) {
         a.weight[w] = s[0];
         a.unscaled[w] = s[1];

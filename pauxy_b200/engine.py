@@ -24,7 +24,8 @@ class Engine(object):
     """
 
     def __init__(self, nbasis, nup, ndown, nchol, nwalkers, dt, exp_order=6, device=None,
-                 total_walkers=None, exchange='auto', free_projection=False, force_bias=True):
+                 total_walkers=None, exchange='auto', free_projection=False, force_bias=True,
+                 nbp=0):
         if not torch.cuda.is_available():
             raise RuntimeError("pauxy_b200.Engine needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -40,7 +41,8 @@ class Engine(object):
         cfg = L.PxbConfig(nbasis, nup, ndown, nchol, nwalkers, exp_order,
                           self.device.index or 0, self.Wtot, dt, L.EXCHANGE_MODES[exchange],
                           (L.FLAG_FREE_PROJECTION if free_projection else 0) |
-                          (0 if force_bias else L.FLAG_NO_FORCE_BIAS))
+                          (0 if force_bias else L.FLAG_NO_FORCE_BIAS), int(nbp or 0), 0)
+        self.nbp = int(nbp or 0)
         self._h = ctypes.c_void_p()
         rc = self.lib.pxb_create(ctypes.byref(self._h), ctypes.byref(cfg))
         if rc != 0:
@@ -95,6 +97,9 @@ class Engine(object):
         self.total_weight = self._view(L.F_TOTAL_WEIGHT, f64)
         self.pairs = self._view(L.F_PAIRS, torch.int32)
         self.phase = self._view(L.F_PHASE, c128)[:W]
+        if self.nbp > 0:
+            self.bp_rdm = self._view(L.F_BP_RDM, c128, (2, self.M, self.M))
+        self.bp_denom = self._view(L.F_BP_DENOM, c128)
 
     def _dev(self, a, dtype):
         t = torch.as_tensor(numpy.ascontiguousarray(a, dtype=dtype))
@@ -312,6 +317,30 @@ class Engine(object):
     def set_weights(self, value):
         with torch.cuda.device(self.device):
             self._check(self.lib.pxb_set_weights(self._h, float(value), self._stream()))
+
+    # ------------------------------------------------------- back propagation
+    def bp_steps(self):
+        return int(self.lib.pxb_bp_steps(self._h))
+
+    def back_propagate(self, nsteps, nstblz, init_walker=False):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_back_propagate(self._h, int(nsteps), int(nstblz),
+                                                    1 if init_walker else 0, self._stream()))
+
+    def bp_reset(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_bp_reset(self._h, self._stream()))
+
+    def bp_zero(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_bp_zero(self._h, self._stream()))
+
+    def get_phi_bp(self, historic=False):
+        with torch.cuda.device(self.device):
+            out = torch.empty((self.W, self.M, self.ne), dtype=torch.complex128, device=self.device)
+            self._check(self.lib.pxb_get_phi_bp(self._h, 1 if historic else 0, out.data_ptr(),
+                                                self._stream()))
+        return out
 
     # ------------------------------------------------------------ stage access
     def stage_greens(self, with_e1b=False):

@@ -104,21 +104,107 @@ class Mixed(object):
         self._t0 = time.time()
 
 
+def back_propagation_options(estimates):
+    """estimators/handler.py:84-86: the 'back_propagation' section, alias 'back_propagated'."""
+    estimates = estimates or {}
+    bp = estimates.get('back_propagation', None)
+    return bp if bp is not None else estimates.get('back_propagated', None)
+
+
+class BackPropagation(object):
+    """pauxy.estimators.back_propagation.BackPropagation (back_propagation.py:17-125 options,
+    :127-225 update_uhf, :282-333 print_step) for a single-determinant trial and the generic
+    Hamiltonian: back-propagated one-body density matrix with BP-PhL weights.  The walkers' field
+    histories and phi_old live on the device; one pxb_back_propagate call does every walker."""
+
+    def __init__(self, bp, root, filename, qmc, system, trial, dtype, BT2, engine=None):
+        self.tau_bp = bp.get('tau_bp', 0)
+        self.nmax = int(self.tau_bp / qmc.dt)
+        self.header = ['E', 'E1b', 'E2b']
+        self.calc_one_rdm = bp.get('one_rdm', True)
+        self.init_walker = bp.get('init_walker', False)
+        self.nsplit = bp.get('nsplit', 1)
+        self.splits = numpy.array([(i + 1) * (self.nmax // self.nsplit) for i in range(self.nsplit)])
+        self.nreg = len(self.header)
+        self.accumulated = False
+        self.eval_energy = bp.get('evaluate_energy', False)
+        for key, off in (('two_rdm', None), ('evaluate_ekt', False), ('restore_weights', None),
+                         ('evaluate_energy', False)):
+            if bp.get(key, off) not in (off,):
+                raise NotImplementedError("pauxy_b200: back_propagated option %r is not built "
+                                          "(one_rdm with BP-PhL weights is)" % key)
+        if self.nmax < 1:
+            raise ValueError("back_propagated: tau_bp < timestep")
+        if trial.ndets != 1:
+            raise NotImplementedError("pauxy_b200: back propagation needs a single-determinant trial")
+        self.nstblz = qmc.nstblz
+        self.BT2 = BT2
+        self.dt = qmc.dt
+        self.engine = engine
+        self.G = numpy.zeros((2, system.nbasis, system.nbasis), dtype=numpy.complex128)
+        self.buff_ix = 0
+        # what the reference pushes to estimates.h5 under back_propagated/ (in memory here)
+        self.output = {'denominator': {}, 'one_rdm': {}}
+
+    def update(self, system, qmc, trial, psi, step, free_projection=False):
+        eng = self.engine
+        buff_ix = eng.bp_steps()
+        if buff_ix not in self.splits:
+            return
+        eng.back_propagate(buff_ix, self.nstblz, self.init_walker)
+        if buff_ix == self.splits[-1]:
+            eng.bp_reset()
+        self.accumulated = True
+        self.buff_ix = buff_ix
+
+    def print_step(self, comm, nprocs, step, nsteps=1, free_projection=False):
+        if not self.accumulated:
+            return
+        eng = self.engine
+        if comm is not None and comm.size > 1:
+            comm.allreduce_sum_(eng.bp_rdm)
+            comm.allreduce_sum_(eng.bp_denom)
+        if comm is None or comm.rank == 0:
+            weight = complex(eng.bp_denom.cpu().numpy()[0])
+            self.output['denominator'].setdefault(self.buff_ix, []).append(weight)
+            if self.calc_one_rdm:
+                self.output['one_rdm'].setdefault(self.buff_ix, []).append(eng.bp_rdm.cpu().numpy().copy())
+        self.accumulated = False
+        self.zero()
+
+    def zero(self):
+        self.engine.bp_zero()
+
+    def one_rdm(self, buff_ix=None):
+        """Normalised back-propagated density matrices [nprints, 2, M, M] (what
+        pauxy.analysis.extraction.extract_rdm returns)."""
+        ix = self.splits[-1] if buff_ix is None else buff_ix
+        rdm = numpy.array(self.output['one_rdm'].get(ix, []))
+        den = numpy.array(self.output['denominator'].get(ix, []))
+        return rdm / den[:, None, None, None]
+
+
 class Estimators(object):
     """pauxy/estimators/handler.py:18-162, mixed estimator only."""
 
     def __init__(self, estimates, root, qmc, system, trial, BT2, verbose=False, engine=None):
         estimates = estimates or {}
-        for key in ('back_propagation', 'back_propagated', 'itcf'):
-            if estimates.get(key) is not None:
-                raise NotImplementedError("pauxy_b200: %s is a 'next' row (SURVEY 8f.1)" % key)
+        if estimates.get('itcf') is not None:
+            raise NotImplementedError("pauxy_b200: imaginary-time correlation functions are not built")
         self.basename = estimates.get('basename', 'estimates')
         self.filename = estimates.get('filename', None)
         self.estimators = {'mixed': Mixed(estimates.get('mixed', {}), system, root, self.filename,
                                           qmc, trial, complex, engine=engine)}
-        self.back_propagation = False
-        self.nprop_tot = None
-        self.nbp = None
+        bp = back_propagation_options(estimates)
+        self.back_propagation = bp is not None
+        if self.back_propagation:
+            self.estimators['back_prop'] = BackPropagation(bp, root, self.filename, qmc, system,
+                                                           trial, complex, BT2, engine=engine)
+            self.nprop_tot = self.estimators['back_prop'].nmax
+            self.nbp = self.estimators['back_prop'].nmax
+        else:
+            self.nprop_tot = None
+            self.nbp = None
         self.calc_itcf = False
 
     def update(self, system, qmc, trial, psi, step, free_projection=False):

@@ -12,7 +12,7 @@ import torch
 
 from .comm import SingleComm
 from .engine import Engine
-from .estimators import Estimators
+from .estimators import Estimators, back_propagation_options
 from .propagation import get_propagator_driver
 from .trial import get_trial_wavefunction
 from .walkers import Walkers, get_input_value
@@ -105,12 +105,14 @@ class AFQMC(object):
             self.qmc.nwalkers = 1
         self.qmc.ntot_walkers = self.qmc.nwalkers * comm.size
         s = self.system
+        bp_opt = back_propagation_options(est_opts)
+        nbp = int(bp_opt.get('tau_bp', 0) / self.qmc.dt) if bp_opt is not None else 0
         self.engine = Engine(s.nbasis, s.nup, s.ndown, s.nfields, self.qmc.nwalkers, self.qmc.dt,
                              exp_order=self.propagators.exp_nmax, device=device,
                              total_walkers=self.qmc.ntot_walkers,
                              exchange=est_opts.get('mixed', {}).get('exchange', 'auto'),
                              free_projection=self.propagators.free_projection,
-                             force_bias=self.propagators.force_bias)
+                             force_bias=self.propagators.force_bias, nbp=nbp)
         p = self.propagators.propagator
         self.engine.set_hamiltonian(s.hs_pot, self.trial._rchol, p.BH1,
                                     self.trial.half_rotated_h1(s), self.trial.psi, p.mf_shift,
@@ -119,7 +121,8 @@ class AFQMC(object):
         self.estimators = Estimators(est_opts, self.root, self.qmc, self.system, self.trial,
                                      self.propagators.BT_BP, verbose, engine=self.engine)
         self.psi = Walkers(self.system, self.trial, self.qmc, self.engine, walker_opts=wlk_opts,
-                           verbose=verbose, comm=comm)
+                           verbose=verbose, comm=comm, nprop_tot=self.estimators.nprop_tot,
+                           nbp=self.estimators.nbp)
         comm.warmup(self.engine.device)
         self.setup_timers()
         self.sync_timers = bool(options.get('sync_timers', False))

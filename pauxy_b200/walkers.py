@@ -65,6 +65,11 @@ class SingleDetWalker(object):
         self._h._phi_cache = None
 
     @property
+    def phi_old(self):
+        """walker.phi_old (walkers/walker.py:43), kept on the device when back propagating."""
+        return self._h.engine.get_phi_bp(historic=True)[self._i].cpu().numpy()
+
+    @property
     def E_L(self):
         return self._h.engine.eloc[self._i, 0].item().real
 
@@ -113,8 +118,8 @@ class Walkers(object):
     def __init__(self, system, trial, qmc, engine, walker_opts=None, verbose=False, comm=None,
                  nprop_tot=None, nbp=None):
         walker_opts = walker_opts or {}
-        if nbp is not None:
-            raise NotImplementedError("pauxy_b200: back propagation is a 'next' row (SURVEY 8f.1)")
+        if nbp is not None and int(nbp) != engine.nbp:
+            raise ValueError("Walkers: nbp differs from the engine's field-history capacity")
         self.system = system
         self.engine = engine
         self.nwalkers = qmc.nwalkers

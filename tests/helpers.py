@@ -27,10 +27,10 @@ def host_setup(h1e, hs_pot, ecore, nelec, dt, psi=None):
 
 
 def make_engine(system, trial, prop, nwalkers, dt, total_walkers=None, exp_order=6,
-                exchange='auto'):
+                exchange='auto', nbp=0):
     from pauxy_b200.engine import Engine
     eng = Engine(system.nbasis, system.nup, system.ndown, system.nfields, nwalkers, dt,
-                 exp_order=exp_order, total_walkers=total_walkers, exchange=exchange)
+                 exp_order=exp_order, total_walkers=total_walkers, exchange=exchange, nbp=nbp)
     eng.set_hamiltonian(system.hs_pot, trial._rchol, prop.BH1, trial.half_rotated_h1(system),
                         trial.psi, prop.mf_shift, system.ecore)
     eng.init_walkers(trial.init, total_walkers or nwalkers)

@@ -15,7 +15,7 @@ pytestmark = pytest.mark.gpu
 RTOL = 1e-10
 
 
-def _options(g, walkers=None, propagator=None):
+def _options(g, walkers=None, propagator=None, back_propagated=None):
     o = {'qmc': {'timestep': float(g['dt']), 'steps': int(g['steps']), 'blocks': int(g['blocks']),
                  'rng_seed': int(g['seed']), 'num_walkers': int(g['nwalkers']),
                  'stabilise_freq': int(g['stab']), 'pop_control_freq': int(g['popc'])},
@@ -25,13 +25,16 @@ def _options(g, walkers=None, propagator=None):
         o['walkers'] = walkers
     if propagator:
         o['propagator'] = propagator
+    if back_propagated:
+        o['estimates']['back_propagated'] = back_propagated
     return o
 
 
-def _run(g, h1e, hs, ecore, walkers=None, propagator=None):
+def _run(g, h1e, hs, ecore, walkers=None, propagator=None, back_propagated=None):
     nelec = tuple(int(x) for x in g['nelec'])
     system = Generic(nelec=nelec, h1e=numpy.array([h1e, h1e]), chol=hs, ecore=ecore)
-    afqmc = AFQMC(options=_options(g, walkers, propagator), system=system, verbose=0)
+    afqmc = AFQMC(options=_options(g, walkers, propagator, back_propagated), system=system,
+                  verbose=0)
     hist = {k: [] for k in ('weight', 'unscaled_weight', 'ot', 'hybrid_energy', 'eloc',
                             'parent_ix', 'phase')}
 
@@ -117,6 +120,41 @@ def test_free_projection_and_no_force_bias(golden, name):
     assert afqmc.propagators.nfb_trig == 0
     _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
     _close(afqmc.psi.phi_host(), g['phi_final'], atol=1e-11)
+
+
+@pytest.mark.parametrize('name', ['bp_ref', 'bp_stress'])
+def test_back_propagation(golden, name):
+    """Back-propagated one-body density matrices (estimators/back_propagation.py:127-225,
+    propagation/generic.py:180-213,253-290, walkers/stack.py:5-127) against traces of the
+    reference; bp_ref is the reference's own driver test (qmc/tests/test_afqmc.py:232-278),
+    bp_stress re-orthogonalises inside the back propagation, splits it in two and moves field
+    histories between walkers in the comb."""
+    g = golden(name)
+    afqmc, h = _run(g, g['h1e'], g['hs_pot'], float(g['ecore']),
+                    back_propagated={'tau_bp': float(g['tau_bp']), 'nsplit': int(g['nsplit']),
+                                     'one_rdm': True})
+    assert numpy.array_equal(h['parent_ix'], g['parent_ix'])
+    _close(h['weight'], g['weight'], atol=1e-13)
+    _close(h['ot'], g['ot'], rtol=1e-10 if name == 'bp_ref' else 2e-9)   # stress walk amplifies rounding
+    bp = afqmc.estimators.estimators['back_prop']
+    ix = list(g['bp_buff_ix'])
+    got_den = numpy.zeros(len(ix), dtype=numpy.complex128)
+    got_rdm = numpy.zeros((len(ix),) + g['bp_one_rdm'].shape[1:], dtype=numpy.complex128)
+    seen = {}
+    for n, b in enumerate(ix):
+        k = seen.get(b, 0)
+        got_den[n] = bp.output['denominator'][b][k]
+        got_rdm[n] = bp.output['one_rdm'][b][k]
+        seen[b] = k + 1
+    assert all(len(bp.output['denominator'][b]) == seen[b] for b in seen)
+    _close(got_den, g['bp_denominator'], rtol=1e-12)
+    _close(got_rdm, g['bp_one_rdm'], rtol=1e-9, atol=1e-9)
+    _close(afqmc.engine.get_phi_bp(historic=True).cpu().numpy(), g['phi_old_final'], atol=1e-9)
+    if name == 'bp_ref':
+        rdm = bp.one_rdm()
+        assert rdm[0, 0].trace().real == pytest.approx(3.0)
+        assert rdm[0, 1].trace().real == pytest.approx(3.0)
+        assert rdm[11, 0, 1, 3].real == pytest.approx(-0.121883381144845, rel=1e-8)
 
 
 @pytest.mark.parametrize('name', ['c2_shape', 'c3_shape', 'c4_shape'])

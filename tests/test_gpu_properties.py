@@ -11,11 +11,11 @@ from pauxy_b200.hamiltonians import make_config_hamiltonian, synthetic_cholesky_
 pytestmark = pytest.mark.gpu
 
 
-def _engine(name, W, total=None):
+def _engine(name, W, total=None, nbp=0):
     h1e, hs, ecore, nelec = make_config_hamiltonian(name)
     system, trial, prop = host_setup(h1e, hs, ecore, nelec, 0.005)
     ham = oracle_ham(h1e, hs, ecore, nelec, 0.005)
-    return make_engine(system, trial, prop, W, 0.005, total_walkers=total), ham
+    return make_engine(system, trial, prop, W, 0.005, total_walkers=total, nbp=nbp), ham
 
 
 def test_full_size_c4_replicated_walkers():
@@ -156,6 +156,46 @@ def test_device_comb_selection_edge_cases(W, kind):
         assert int(pairs[0]) == len(expect)
         assert [tuple(x) for x in pairs[1:1 + 2 * len(expect)].reshape(-1, 2)] == \
             [tuple(x) for x in expect]
+
+
+@pytest.mark.parametrize('name,W', [('c2', 37), ('c4', 12)])
+def test_back_propagation_at_config_shapes(name, W):
+    """pxb_back_propagate at BASELINE shapes (M = 24 and M = 108: one and several output tiles,
+    ragged walker count) against the oracle's restatement of propagation/generic.py:253-290 and
+    estimators/back_propagation.py:150-205: back-propagated determinants and sum_w w G_w."""
+    nbp, nstblz = 4, 2
+    eng, ham = _engine(name, W, nbp=nbp)
+    rs = numpy.random.RandomState(17)
+    phi0 = random_walkers(ham, W, seed=9)
+    eng.set_phi(phi0)
+    eng.bp_reset()                      # phi_old = the walkers we start from
+    xs = []
+    for step in range(1, nbp + 1):
+        eng.propagate(rs.normal(size=(W, ham.nchol)), eshift=0.0, step=step)
+        xs.append(eng.xshifted.cpu().numpy().copy())
+    assert eng.bp_steps() == nbp
+    wts = numpy.abs(1.0 + 0.3 * rs.normal(size=W))
+    wts[3] = 0.0
+    eng.weight.copy_(torch.as_tensor(wts))
+    eng.back_propagate(nbp, nstblz)
+    got_bp = eng.get_phi_bp().cpu().numpy()
+    numpy.testing.assert_array_equal(eng.get_phi_bp(historic=True).cpu().numpy(), phi0)
+    xs = numpy.array(xs)                # [step, W, N]
+    M, na = ham.nbasis, ham.nup
+    rdm = numpy.zeros((2, M, M), dtype=numpy.complex128)
+    for w in range(W):
+        phi_bp = ham.psi.copy()
+        orc.back_propagate(ham, phi_bp, xs[:, w], nstblz)
+        assert relerr(got_bp[w], phi_bp) < 1e-11
+        rdm[0] += wts[w] * orc.gab(phi_bp[:, :na], phi0[w][:, :na]).T
+        rdm[1] += wts[w] * orc.gab(phi_bp[:, na:], phi0[w][:, na:]).T
+    assert relerr(eng.bp_rdm.cpu().numpy(), rdm) < 1e-11
+    assert abs(eng.bp_denom.cpu().numpy()[0] - wts.sum()) < 1e-12 * W
+    # a second call accumulates, pxb_bp_zero clears
+    eng.back_propagate(nbp, nstblz)
+    assert relerr(eng.bp_rdm.cpu().numpy(), 2 * rdm) < 1e-11
+    eng.bp_zero()
+    assert float(eng.bp_rdm.abs().max()) == 0.0
 
 
 def test_theta_travels_with_walkers():
