@@ -542,7 +542,7 @@ int run_exchange_eri(pxb_handle h, cudaStream_t st) {
   const size_t smem = eri_smem_bytes();
   PXB_CUDA(h, cudaFuncSetAttribute(exx_eri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->launches;
-  exx_eri_kernel<<<std::min(nitems, h->sm_count), (EQ_CWM * EQ_CWN + 1) * 32, smem, st>>>(a, nitems, nwb);
+  exx_eri_kernel<<<std::min(nitems, h->sm_count), gemm_tma_threads<EQ_CWM * EQ_CWN>(), smem, st>>>(a, nitems, nwb);
   PXB_CUDA(h, cudaGetLastError());
   ++h->launches;
   exx_eri_reduce_kernel<<<(2 * d.Wp + 255) / 256, 256, 0, st>>>(a.part, h->ptr<double2>(A_EXX), d, a.nslot);

@@ -70,7 +70,8 @@ __device__ __forceinline__ EriItem eri_item(const Dims& d, int item, int nwb) {
   return it;
 }
 
-__global__ void __launch_bounds__((EQ_CWM * EQ_CWN + 1) * 32, 1) exx_eri_kernel(EriArgs a, int nitems, int nwb) {
+static_assert(EQ_CWM * EQ_CWN == 8, "register rebalancing below assumes two consumer warpgroups");
+__global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_eri_kernel(EriArgs a, int nitems, int nwb) {
   constexpr int TM = EQ_TM, TN = EQ_TN, NCW = EQ_CWM * EQ_CWN, WM = EQ_WM, WN = EQ_WN;
   constexpr int A_STAGE = TM * GT_KS * 32, B_STAGE = TN * GT_KS * 32;
   extern __shared__ __align__(128) double eq_smem[];
@@ -90,7 +91,9 @@ __global__ void __launch_bounds__((EQ_CWM * EQ_CWN + 1) * 32, 1) exx_eri_kernel(
   }
   __syncthreads();
 
-  if (warp == NCW) {
+  if (warp >= NCW) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GT_REGS_PRODUCER));
+    if (warp != NCW) return;
     // ---------------- producer: lane L streams row L of the stage (A rows, then B rows) -----------
     static_assert(TM + TN <= 32, "one producer lane per tile row");
     unsigned itc = 0;
@@ -126,6 +129,7 @@ __global__ void __launch_bounds__((EQ_CWM * EQ_CWN + 1) * 32, 1) exx_eri_kernel(
     return;
   }
   // ---------------- consumers ----------------
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GT_REGS_CONSUMER));
   const int wm = warp % EQ_CWM, wn = warp / EQ_CWM;
   const int g = lane >> 2, t = lane & 3;
   const int boff = b_lane_offset(lane);
@@ -140,16 +144,6 @@ __global__ void __launch_bounds__((EQ_CWM * EQ_CWN + 1) * 32, 1) exx_eri_kernel(
       for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
     for (int ks = 0; ks < it.nkstage; ++ks, ++itc) {
       const unsigned s = itc % GT_STAGES, ph = (itc / GT_STAGES) & 1u;
-      if (ks == EQ_DIAG_STAGES) {
-        // the diagonal block counts once, everything to its right twice (K symmetric)
-#pragma unroll
-        for (int i = 0; i < WM; ++i)
-#pragma unroll
-          for (int j = 0; j < WN; ++j) {
-            acc[i][j][0] *= 0.5;
-            acc[i][j][1] *= 0.5;
-          }
-      }
       mbar_wait(&full[s], ph);
       const double* as = As + (size_t)s * A_STAGE + (size_t)wm * WM * GT_KS * 32 + lane;
       const double* bs = Bs + (size_t)s * B_STAGE + (size_t)wn * WN * GT_KS * 32 + boff;
@@ -184,7 +178,10 @@ __global__ void __launch_bounds__((EQ_CWM * EQ_CWN + 1) * 32, 1) exx_eri_kernel(
       if (lane == 0) mbar_arrive(&empty[s]);
     }
     // quadratic-form epilogue: lane (g,t) of tile (i,j) holds Y[a = 8(mt0+i)+g] of walker 4(nt0+j)+t
-    const double factor = it.nkstage > EQ_DIAG_STAGES ? 2.0 : 1.0;
+    // the diagonal block counts once, everything to its right twice (K symmetric): KF stores the
+    // diagonal blocks pre-multiplied by 1/2 (exact), so one factor serves the whole row block and
+    // the accumulators are never touched between DMMAs
+    const double factor = 2.0;
     const int ioff = it.s ? d.na : 0;
     const int D = eri_dim(d, it.s);
     const int mtw = it.mt0 + wm * WM, ntw = it.nt0 + wn * WN;
@@ -265,7 +262,10 @@ __global__ void __launch_bounds__(1024) eri_build_kernel(const double2* __restri
   if (q < d.M && p < d.M) {
     const int arow = i * d.Mp + q;
     const int ks = j * d.KC + (p >> 2);
-    KF[((size_t)(arow >> 3) * KS + ks) * 32 + (arow & 7) * 4 + (p & 3)] = acc;
+    // diagonal block of the row block this row belongs to (columns [128 rb, 128 rb + 128)): x 1/2
+    const int rb = arow / (EQ_TM * 8);
+    const bool diag = ks >= rb * EQ_TM * 2 && ks < (rb + 1) * EQ_TM * 2;
+    KF[((size_t)(arow >> 3) * KS + ks) * 32 + (arow & 7) * 4 + (p & 3)] = diag ? 0.5 * acc : acc;
   }
 }
 

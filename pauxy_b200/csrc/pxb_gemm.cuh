@@ -166,10 +166,20 @@ constexpr size_t gemm_tma_smem_bytes() {
   return (size_t)GT_STAGES * (WM * CWM + WN * CWN) * GT_KS * 32 * sizeof(double) + 2 * GT_STAGES * 8 + 128;
 }
 
+// Register rebalancing for the 8-consumer-warp configurations: the SM sub-partition that hosts the
+// producer warp next to two consumer warps caps every thread at 168 registers (16384 / 3 warps),
+// which spills the 4 x 8 accumulator blocks.  Launching a full producer warpgroup (12 warps) and
+// moving registers with setmaxnreg (producer group 168 -> 40, consumers 168 -> 232; the increase
+// 8 * 64 equals what the 4 producer-group warps release) removes the spills.
+constexpr int GT_REGS_PRODUCER = 40, GT_REGS_CONSUMER = 232;
+template <int NCW>
+constexpr int gemm_tma_threads() { return NCW == 8 ? 12 * 32 : (NCW + 1) * 32; }
+
 template <int WM, int WN, int CWM, int CWN, class Epi>
-__global__ void __launch_bounds__((CWM * CWN + 1) * 32, 1)
+__global__ void __launch_bounds__(gemm_tma_threads<CWM * CWN>(), 1)
     gemm_tma_kernel(GemmArgs a, Epi epi, int tiles_m, int tiles_n, int batch) {
   constexpr int TM = WM * CWM, TN = WN * CWN, NCW = CWM * CWN;
+  constexpr bool REB = NCW == 8;
   constexpr int A_STAGE = TM * GT_KS * 32, B_STAGE = TN * GT_KS * 32;  // doubles
   extern __shared__ __align__(128) double gt_smem[];
   double* As = gt_smem;
@@ -190,7 +200,9 @@ __global__ void __launch_bounds__((CWM * CWN + 1) * 32, 1)
   const int ntiles = per_z * batch;
   const int nkstage = (a.KS + GT_KS - 1) / GT_KS;
 
-  if (warp == NCW) {
+  if (warp >= NCW) {
+    if constexpr (REB) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(GT_REGS_PRODUCER));
+    if (warp != NCW) return;
     // ---------------- producer: lane L streams row L of the stage (A rows, then B rows) -----------
     static_assert(TM + TN <= 32, "one producer lane per tile row");
     unsigned it = 0;
@@ -229,6 +241,7 @@ __global__ void __launch_bounds__((CWM * CWN + 1) * 32, 1)
     return;
   }
   // ---------------- consumers ----------------
+  if constexpr (REB) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(GT_REGS_CONSUMER));
   const int wm = warp % CWM, wn = warp / CWM;
   const int g = lane >> 2, t = lane & 3;
   const int boff = b_lane_offset(lane);
@@ -298,7 +311,7 @@ inline cudaError_t launch_gemm_tma(const GemmArgs& a, const Epi& epi, int batch,
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   const int grid = ntiles < sm_count ? ntiles : sm_count;
-  kern<<<grid, (CWM * CWN + 1) * 32, smem, st>>>(a, epi, tiles_m, tiles_n, batch);
+  kern<<<grid, gemm_tma_threads<CWM * CWN>(), smem, st>>>(a, epi, tiles_m, tiles_n, batch);
   return cudaGetLastError();
 }
 
