@@ -259,11 +259,8 @@ def main():
                 state['xi_next'] = eng.prefetch_xi(xi_host[(step + 1) % nbuf])
         else:
             eng.propagate(xi_dev[step % nbuf], eshift=state['eshift'], step=step)
-        if world == 1:
-            eng.pop_control_comb(combr[step % 4096])
-        else:
-            numpy.random.seed(step)     # same uniform on every rank
-            psi.pop_control(comm)
+        numpy.random.seed(step)         # same comb uniform on every rank
+        psi.pop_control(comm, overlap_energy=True)   # what AFQMC.run does with energy_eval_freq = 1
         est.update(afqmc.system, afqmc.qmc, afqmc.trial, psi, step, False)
         if e2e:
             res_host.copy_(eng.estimates, non_blocking=True)             # D2H of the step's result

@@ -32,7 +32,7 @@ extern "C" {
 #define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
 #define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
 
-#define PXB_ABI_VERSION 5
+#define PXB_ABI_VERSION 6
 
 typedef struct pxb_context* pxb_handle;
 
@@ -242,6 +242,24 @@ int pxb_set_weights(pxb_handle h, double value, void* stream); /* handler.py:337
  *                    all-reduce) between this call and
  *  pxb_pop_control_finish : unscaled_weight = weight, weight = 1 (handler.py:247-248, :337-338);
  *                    nothing that writes walker state may be enqueued before that barrier. */
+/* The same, split so that the host can overlap the plan with the local-energy evaluation (the plan
+ * needs only the weights; the energies of the walkers before the comb are the energies of their
+ * clones after it, and ELOC / X / Theta travel in the walker payload):
+ *   side stream  : [all-gather |w|]  pxb_pop_plan
+ *   launch stream: pxb_local_energy   ... wait for the side stream ...  pxb_pop_pull
+ *                  [stream barrier across devices]  pxb_pop_control_finish
+ * pxb_pop_plan    : total weight + comb plan, writes no walker state; dev_global_abs_weights may be
+ *                   NULL on one device.  pxb_pop_pull: the data movement of that plan (local
+ *                   copies, NVLink pulls for clones owned by peers; on one device no attach needed). */
+int pxb_pop_plan(pxb_handle h, const double* dev_global_abs_weights, int64_t wtot, double r,
+                 void* stream);
+int pxb_pop_pull(pxb_handle h, void* stream);
+/* The persistent kernels of pxb_local_energy (X GEMM, exchange) normally take one CTA per SM, which
+ * leaves no room for a side-stream kernel until they end.  pxb_reserve_sms(h, n) makes them leave n
+ * SMs free (n = 1 while a long comb plan -- tens of thousands of walkers over all devices -- runs
+ * beside them; 0 restores the default). */
+int pxb_reserve_sms(pxb_handle h, int n);
+
 #define PXB_IPC_HANDLE_BYTES 64
 int pxb_peer_export(pxb_handle h, void* handle_out, uint64_t* offset_out);
 int pxb_peer_attach(pxb_handle h, int rank, int nranks, const void* handles,

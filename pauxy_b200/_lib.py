@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libpauxy_b200.so')
 
 PXB_OK = 0
-ABI_VERSION = 5
+ABI_VERSION = 6
 EXCHANGE_MODES = {'auto': 0, 'cholesky': 1, 'eri': 2}
 ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_ERR_UNSUPPORTED'}
 
@@ -78,6 +78,9 @@ _PROTOS = {
     'pxb_peer_export': (ctypes.c_int, [_vp, _vp, ctypes.POINTER(ctypes.c_uint64)]),
     'pxb_peer_attach': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _vp, _vp]),
     'pxb_pop_control_comb_peers': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_double, _vp]),
+    'pxb_pop_plan': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_double, _vp]),
+    'pxb_pop_pull': (ctypes.c_int, [_vp, _vp]),
+    'pxb_reserve_sms': (ctypes.c_int, [_vp, ctypes.c_int]),
     'pxb_pop_control_finish': (ctypes.c_int, [_vp, _vp]),
     'pxb_bp_steps': (ctypes.c_int, [_vp]),
     'pxb_back_propagate': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),

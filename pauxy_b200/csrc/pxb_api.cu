@@ -48,10 +48,12 @@ struct pxb_context {
   bool ham_set = false;
   int phi_cur = 0;  // which of PHI_A / PHI_B holds the walkers
   int sm_count = 148;
+  int reserved_sms = 0;
   int max_smem_optin = 0;
   long long launches = 0;  // kernels launched through this handle
   // Theta / overlap / e1b (A_THETA, A_E1B) correspond to the current walkers; X to the current Theta
   bool theta_valid = false, x_valid = false;
+  bool eloc_valid = false;  // ELOC holds the local energies of the current walkers (travels with them)
   bool gemm_tma = true;  // TMA-fed persistent GEMM (PXB_GEMM=direct selects the L1/L2-streaming one)
   // optional per-stage timing with CUDA events on the launch stream (pxb_profile / pxb_stage_times)
   bool prof = false;
@@ -114,6 +116,10 @@ int fail(pxb_handle h, int code, const std::string& msg) {
 
 inline cudaStream_t S(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
+// CTAs of the persistent local-energy kernels: all SMs, minus the ones the caller reserved for a
+// concurrent side-stream kernel (pxb_reserve_sms; the serial comb plan needs one SM to itself)
+inline int persist_sms(pxb_handle h) { return std::max(1, h->sm_count - h->reserved_sms); }
+
 // brackets the launches of one stage with events when profiling is on
 struct StageTimer {
   pxb_handle h;
@@ -163,6 +169,7 @@ CopyArgs copy_args(pxb_handle h) {
   c.detR = h->field<double>(PXB_F_DETR);
   c.log_detR = h->field<double>(PXB_F_LOG_DETR);
   c.phase = h->field<double2>(PXB_F_PHASE);
+  c.X = h->ptr<double2>(A_X);
   c.phi_old = h->nbp > 0 ? h->ptr<double>(A_PHI_OLD) : nullptr;
   c.fc = h->nbp > 0 ? h->ptr<double>(A_FC) : nullptr;
   c.fc_rows = (int)fc_rows(h->d, h->nbp);
@@ -305,7 +312,7 @@ int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
     ++h->launches;
     // 16 x 8 tile blocks: 4 * WG/8 work units keep the 148 persistent CTAs balanced (XG is only ~63)
     if (h->gemm_tma)
-      PXB_CUDA(h, (launch_gemm_tma<4, 4, 4, 2>(g, epi, 1, h->sm_count, st)));
+      PXB_CUDA(h, (launch_gemm_tma<4, 4, 4, 2>(g, epi, 1, persist_sms(h), st)));
     else
       PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
   }
@@ -542,7 +549,7 @@ int run_exchange_eri(pxb_handle h, cudaStream_t st) {
   const size_t smem = eri_smem_bytes();
   PXB_CUDA(h, cudaFuncSetAttribute(exx_eri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->launches;
-  exx_eri_kernel<<<std::min(nitems, h->sm_count), gemm_tma_threads<EQ_CWM * EQ_CWN>(), smem, st>>>(a, nitems, nwb);
+  exx_eri_kernel<<<std::min(nitems, persist_sms(h)), gemm_tma_threads<EQ_CWM * EQ_CWN>(), smem, st>>>(a, nitems, nwb);
   PXB_CUDA(h, cudaGetLastError());
   ++h->launches;
   exx_eri_reduce_kernel<<<(2 * d.Wp + 255) / 256, 256, 0, st>>>(a.part, h->ptr<double2>(A_EXX), d, a.nslot);
@@ -563,7 +570,7 @@ int run_exchange(pxb_handle h, cudaStream_t st) {
   if ((nmax + 3) / 4 > EX_MAX_BLOCKS) return fail(h, PXB_ERR_ARG, "exchange: more than 64 occupied orbitals per spin");
   const size_t bbytes = (size_t)nmax * d.KC * 32 * 8;
   const size_t tail = exchange_tail_bytes();
-  const int grid = std::min(2 * d.WG, h->sm_count);
+  const int grid = std::min(2 * d.WG, persist_sms(h));
   if (bbytes + tail <= (size_t)h->max_smem_optin) {
     a.smem_b_doubles = (int)(bbytes / 8);
     PXB_CUDA(h, cudaFuncSetAttribute(exchange_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -820,9 +827,14 @@ int pxb_bind_arena(pxb_handle h, void* dev_arena, size_t bytes, void* stream) {
   PXB_CUDA(h, cudaSetDevice(h->cfg.device));
   PXB_CUDA(h, cudaMemsetAsync(dev_arena, 0, h->arena_bytes, S(stream)));
   h->arena = static_cast<unsigned char*>(dev_arena);
+  if (h->d.Wtot == h->d.W) {  // one device: the "peer" table is just this arena
+    h->peer_rank = 0;
+    h->peer_n = 1;
+    h->peer_base[0] = h->arena;
+  }
   h->ham_set = false;
   h->phi_cur = 0;
-  h->theta_valid = h->x_valid = false;
+  h->theta_valid = h->x_valid = h->eloc_valid = false;
   return PXB_OK;
 }
 
@@ -927,7 +939,7 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
   PXB_CUDA(h, cudaMemcpyAsync(h->ptr<void>(A_PSI_NAT), psi, (size_t)d.M * d.ne * 16, cudaMemcpyDeviceToDevice, st));
   h->d.ecore = ecore;
   h->ham_set = true;
-  h->theta_valid = h->x_valid = false;
+  h->theta_valid = h->x_valid = h->eloc_valid = false;
   return PXB_OK;
 }
 
@@ -938,7 +950,7 @@ int pxb_set_phi(pxb_handle h, const void* dev_phi, void* stream) {
   phi_to_of_kernel<<<grid_for((size_t)d.Wp * d.ne * d.Mp), 256, 0, S(stream)>>>(
       static_cast<const double2*>(dev_phi), h->phi(), d, 0);
   PXB_CUDA(h, cudaGetLastError());
-  h->theta_valid = h->x_valid = false;
+  h->theta_valid = h->x_valid = h->eloc_valid = false;
   return PXB_OK;
 }
 
@@ -960,7 +972,7 @@ int pxb_init_walkers(pxb_handle h, const void* dev_init_phi, double total_walker
   phi_to_of_kernel<<<grid_for((size_t)d.Wp * d.ne * d.Mp), 256, 0, st>>>(
       static_cast<const double2*>(dev_init_phi), h->phi(), d, 1);
   PXB_CUDA(h, cudaGetLastError());
-  h->theta_valid = h->x_valid = false;
+  h->theta_valid = h->x_valid = h->eloc_valid = false;
   int rc = ensure_theta(h, st);
   if (rc) return rc;
   ++h->launches;
@@ -1039,7 +1051,7 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   if ((rc = run_one_body(h, work, h->phi(), active, st))) return rc;
   // (e) Green's function of the propagated walkers: its determinant is the new overlap
   //     (single_det.py:170-199) and its Theta serves the estimator and the next step
-  h->theta_valid = h->x_valid = false;
+  h->theta_valid = h->x_valid = h->eloc_valid = false;
   if ((rc = run_greens(h, h->phi(), true, h->field<double2>(PXB_F_OVLP_NEW), true, st))) return rc;
   h->theta_valid = true;
   // (f) weights
@@ -1099,6 +1111,9 @@ int pxb_local_energy(pxb_handle h, void* stream) {
   const Dims& d = h->d;
   cudaStream_t st = S(stream);
   int rc;
+  // already evaluated for these walkers (e.g. before the population control: ELOC travels with
+  // the walker payload, so the estimator's call after it finds them in place)
+  if (h->theta_valid && h->x_valid && h->eloc_valid) return PXB_OK;
   if ((rc = ensure_theta(h, st))) return rc;
   if ((rc = ensure_x(h, st))) return rc;
   if ((rc = run_exchange(h, st))) return rc;
@@ -1114,6 +1129,7 @@ int pxb_local_energy(pxb_handle h, void* stream) {
     energy_kernel<<<(d.W + 7) / 8, 256, 0, st>>>(e);
   }
   PXB_CUDA(h, cudaGetLastError());
+  h->eloc_valid = true;
   return PXB_OK;
 }
 
@@ -1211,7 +1227,6 @@ int pxb_pop_control_comb(pxb_handle h, double r, void* stream) {
   ++h->launches;
   copy_pairs_kernel<<<std::min(d.W, 4 * h->sm_count), 256, 0, st>>>(copy_args(h), h->field<int>(PXB_F_PAIRS), 0);
   PXB_CUDA(h, cudaGetLastError());
-  h->x_valid = false;  // Theta and e1b travel with the walkers, X does not
   return pxb_set_weights(h, 1.0, stream);
 }
 
@@ -1265,15 +1280,35 @@ int pxb_peer_attach(pxb_handle h, int rank, int nranks, const void* handles, con
   return PXB_OK;
 }
 
-int pxb_pop_control_comb_peers(pxb_handle h, const double* gw, int64_t wtot, double r, void* stream) {
+// total weight + comb plan only (no walker state is written): may run on a side stream while
+// pxb_local_energy works on the launch stream; gw == NULL (one device): |weight| is taken locally
+int pxb_pop_plan(pxb_handle h, const double* gw, int64_t wtot, double r, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  cudaStream_t st = S(stream);
+  StageTimer timer__(h, PXB_STAGE_POP_CONTROL, st);
+  if (gw == nullptr) {
+    if (d.Wtot != d.W) return fail(h, PXB_ERR_ARG, "pxb_pop_plan: global weights needed with several devices");
+    double* lgw = h->ptr<double>(A_GW);
+    ++h->launches;
+    abs_weight_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(h->field<double>(PXB_F_WEIGHT), lgw, d.W);
+    PXB_CUDA(h, cudaGetLastError());
+    gw = lgw;
+    wtot = d.W;
+  }
+  int rc;
+  if ((rc = pop_rescale_impl(h, gw, wtot, 0, stream))) return rc;
+  return pxb_comb_plan(h, gw, wtot, r, stream);
+}
+
+// data movement of the plan: every killed slot of this device receives its clone (local copy or
+// NVLink pull from the owner's arena)
+int pxb_pop_pull(pxb_handle h, void* stream) {
   PXB_REQUIRE_READY(h);
   const Dims& d = h->d;
   if (h->peer_n < 1) return fail(h, PXB_ERR_STATE, "pxb_peer_attach has not been called");
   cudaStream_t st = S(stream);
   StageTimer timer__(h, PXB_STAGE_POP_CONTROL, st);
-  int rc;
-  if ((rc = pop_rescale_impl(h, gw, wtot, 0, stream))) return rc;
-  if ((rc = pxb_comb_plan(h, gw, wtot, r, stream))) return rc;
   PeerArgs p;
   for (int i = 0; i < PXB_MAX_PEERS; ++i) p.base[i] = h->peer_base[i];
   p.rank = h->peer_rank;
@@ -1282,7 +1317,18 @@ int pxb_pop_control_comb_peers(pxb_handle h, const double* gw, int64_t wtot, dou
   ++h->launches;
   pull_pairs_kernel<<<4 * h->sm_count, 256, 0, st>>>(copy_args(h), p, h->field<int>(PXB_F_PAIRS));
   PXB_CUDA(h, cudaGetLastError());
-  h->x_valid = false;
+  return PXB_OK;  // Theta, e1b, X and ELOC travel with the walkers: their validity is unchanged
+}
+
+int pxb_pop_control_comb_peers(pxb_handle h, const double* gw, int64_t wtot, double r, void* stream) {
+  int rc = pxb_pop_plan(h, gw, wtot, r, stream);
+  if (rc) return rc;
+  return pxb_pop_pull(h, stream);
+}
+
+int pxb_reserve_sms(pxb_handle h, int n) {
+  if (!h || n < 0) return PXB_ERR_ARG;
+  h->reserved_sms = n;
   return PXB_OK;
 }
 
@@ -1309,7 +1355,6 @@ int pxb_copy_walkers(pxb_handle h, const int32_t* src, const int32_t* dst, int n
   ++h->launches;
   copy_list_kernel<<<std::min(n, 4 * h->sm_count), 256, 0, S(stream)>>>(copy_args(h), src, dst, n);
   PXB_CUDA(h, cudaGetLastError());
-  h->x_valid = false;
   return PXB_OK;
 }
 
@@ -1329,7 +1374,6 @@ int pxb_unpack_walkers(pxb_handle h, const int32_t* slots, int n, const double* 
   pack_kernel<<<std::min(n, 4 * h->sm_count), 256, 0, S(stream)>>>(copy_args(h), slots, n,
                                                                   const_cast<double*>(buf), 1);
   PXB_CUDA(h, cudaGetLastError());
-  h->x_valid = false;
   return PXB_OK;
 }
 
@@ -1482,7 +1526,7 @@ int pxb_stage_exchange(pxb_handle h, void* stream) {
 int pxb_stage_greens(pxb_handle h, int with_e1b, void* stream) {
   PXB_REQUIRE_READY(h);
   (void)with_e1b;
-  h->theta_valid = h->x_valid = false;
+  h->theta_valid = h->x_valid = h->eloc_valid = false;
   return ensure_theta(h, S(stream));
 }
 

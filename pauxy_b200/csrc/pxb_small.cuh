@@ -793,6 +793,7 @@ struct CopyArgs {
   double* detR;
   double* log_detR;
   double2* phase;
+  double2* X;       // [2][Wp][Np] X_s = R_s^T Theta_s travels with the walker like Theta does
   double* phi_old;  // back propagation only (else nullptr): walker.phi_old, OF layout
   double* fc;       // back propagation only: field history, rows = nbp * NKC per walker group
   int fc_rows;
@@ -800,7 +801,15 @@ struct CopyArgs {
 };
 
 __device__ __host__ __forceinline__ size_t payload_doubles(const Dims& d, bool bp, int fc_rows) {
-  return (size_t)(bp ? 3 : 2) * d.ne * d.KC * 8 + (bp ? (size_t)fc_rows * 8 : 0) + 18;
+  return (size_t)(bp ? 3 : 2) * d.ne * d.KC * 8 + (bp ? (size_t)fc_rows * 8 : 0) + (size_t)4 * d.Np + 18;
+}
+
+// X rows of walker src (array sX) -> walker dst (array dX)
+__device__ __forceinline__ void copy_x(double2* dX, const double2* sX, const Dims& d, int dst, int src) {
+  for (int idx = threadIdx.x; idx < 2 * d.Np; idx += blockDim.x) {
+    const int s = idx / d.Np, n = idx - s * d.Np;
+    dX[((size_t)s * d.Wp + dst) * d.Np + n] = sX[((size_t)s * d.Wp + src) * d.Np + n];
+  }
 }
 
 // walker-interleaved arrays [W/4][rows][4 walkers][8 doubles]: copy the `rows` 64-byte pieces of
@@ -837,6 +846,7 @@ __global__ void __launch_bounds__(256) copy_pairs_kernel(CopyArgs a, const int* 
     const int n8 = d.ne * d.KC;
     copy_rows(a.phi, a.phi, n8, dst, src);
     copy_rows(a.theta, a.theta, n8, dst, src);
+    copy_x(a.X, a.X, d, dst, src);
     if (a.phi_old != nullptr) {
       copy_rows(a.phi_old, a.phi_old, n8, dst, src);
       copy_rows(a.fc, a.fc, a.fc_rows, dst, src);
@@ -863,6 +873,7 @@ __global__ void __launch_bounds__(256) copy_list_kernel(CopyArgs a, const int* s
     const int n8 = d.ne * d.KC;
     copy_rows(a.phi, a.phi, n8, dst, src);
     copy_rows(a.theta, a.theta, n8, dst, src);
+    copy_x(a.X, a.X, d, dst, src);
     if (a.phi_old != nullptr) {
       copy_rows(a.phi_old, a.phi_old, n8, dst, src);
       copy_rows(a.fc, a.fc, a.fc_rows, dst, src);
@@ -916,6 +927,7 @@ __global__ void __launch_bounds__(256) pull_pairs_kernel(CopyArgs a, PeerArgs p,
     const int n8 = d.ne * d.KC;
     copy_rows(a.phi, sphi, n8, dst, src);
     copy_rows(a.theta, sth, n8, dst, src);
+    copy_x(a.X, rebase(a.X, lb, pb), d, dst, src);
     if (a.phi_old != nullptr) {
       copy_rows(a.phi_old, rebase(a.phi_old, lb, pb), n8, dst, src);
       copy_rows(a.fc, rebase(a.fc, lb, pb), a.fc_rows, dst, src);
@@ -959,6 +971,17 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
     if (bp) {
       pack_rows(a.phi_old, b + (size_t)2 * n8 * 8, n8, w, unpack);
       pack_rows(a.fc, b + (size_t)3 * n8 * 8, a.fc_rows, w, unpack);
+    }
+    {
+      double2* xb = reinterpret_cast<double2*>(b + pd - 18 - (size_t)4 * d.Np);
+      for (int idx = threadIdx.x; idx < 2 * d.Np; idx += blockDim.x) {
+        const int sp = idx / d.Np, n = idx - sp * d.Np;
+        double2* gx = a.X + ((size_t)sp * d.Wp + w) * d.Np + n;
+        if (unpack)
+          *gx = xb[idx];
+        else
+          xb[idx] = *gx;
+      }
     }
     if (threadIdx.x == 0) {
       double* s = b + pd - 18;

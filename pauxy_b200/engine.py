@@ -283,6 +283,22 @@ class Engine(object):
                 self._h, global_abs_weights.data_ptr(), int(global_abs_weights.numel()), float(r),
                 self._stream()))
 
+    def pop_plan(self, global_abs_weights, r):
+        """Total weight + comb plan on the CURRENT stream (global_abs_weights None: one device)."""
+        with torch.cuda.device(self.device):
+            if global_abs_weights is None:
+                ptr, n = None, 0
+            else:
+                ptr, n = global_abs_weights.data_ptr(), int(global_abs_weights.numel())
+            self._check(self.lib.pxb_pop_plan(self._h, ptr, n, float(r), self._stream()))
+
+    def reserve_sms(self, n):
+        self._check(self.lib.pxb_reserve_sms(self._h, int(n)))
+
+    def pop_pull(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_pop_pull(self._h, self._stream()))
+
     def pop_control_finish(self):
         with torch.cuda.device(self.device):
             self._check(self.lib.pxb_pop_control_finish(self._h, self._stream()))

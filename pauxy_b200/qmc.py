@@ -159,7 +159,8 @@ class AFQMC(object):
             self.tprop += self._tick() - start
             if step % self.qmc.npop_control == 0:
                 start = self._tick()
-                self.psi.pop_control(comm)
+                self.psi.pop_control(comm, overlap_energy=(
+                    mixed.eval_energy and step % mixed.energy_eval_freq == 0))
                 self.tpopc += self._tick() - start
             start = self._tick()
             self.estimators.update(self.system, self.qmc, self.trial, self.psi, step,

@@ -139,6 +139,10 @@ class Walkers(object):
         self.max_weight = walker_opts.get('max_weight', 4.0)
         # several devices: pull clones straight from peer memory (False: NCCL send/recv)
         self.peer_copy = walker_opts.get('peer_copy', True)
+        # evaluate the local energy concurrently with the comb plan when the driver asks for it
+        self.overlap = walker_opts.get('overlap_energy', True)
+        self.reserve_sm_walkers = walker_opts.get('reserve_sm_walkers', 24576)
+        self._side = None
         self.target_weight = qmc.ntot_walkers
         self.nw = qmc.nwalkers
         engine.init_walkers(trial.init, qmc.ntot_walkers)
@@ -182,11 +186,16 @@ class Walkers(object):
         self._phi_cache = None
 
     # --------------------------------------------------- population control
-    def pop_control(self, comm):
+    def pop_control(self, comm, overlap_energy=False):
+        """handler.py:225-254.  overlap_energy: the driver is going to evaluate the local energy
+        right after this call (estimators/mixed.py:211-221); the comb then evaluates it for the
+        walkers BEFORE the copies, concurrently with the (serial) comb plan -- a cloned walker's
+        energy is its source's, and ELOC travels with the payload, so the estimator finds the
+        same numbers."""
         if self.ntot_walkers == 1:
             return
         if self.pcont_method == "comb":
-            self.comb(comm)
+            self.comb(comm, overlap_energy)
         elif self.pcont_method == "pair_branch":
             self.pair_branch(comm)
         else:
@@ -203,11 +212,39 @@ class Walkers(object):
             # the reference prints and sys.exit()s (handler.py:236-241)
             raise RuntimeError("# Warning: total walker weight < 1e-8. Something is seriously wrong.")
 
-    def comb(self, comm):
+    def comb(self, comm, overlap_energy=False):
         """handler.py:225-338.  One uniform draw from the global stream per call."""
         eng = self.engine
         r = numpy.random.random()
-        if comm is None or comm.size == 1:
+        multi = comm is not None and comm.size > 1
+        if overlap_energy and self.overlap and (not multi or (self.peer_copy and eng.peers_attached)):
+            main = torch.cuda.current_stream(eng.device)
+            if self._side is None:
+                self._side = torch.cuda.Stream(eng.device)
+            side = self._side
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                gw = comm.allgather_tensor(torch.abs(eng.weight)) if multi else None
+                eng.pop_plan(gw, r)             # serial sums + plan, needs only the weights
+            # the plan is one CTA of serial float64 sums (bit-exact with the reference): with tens of
+            # thousands of walkers it runs ~1 ms, so the persistent energy kernels leave it an SM
+            reserve = 1 if self.ntot_walkers >= self.reserve_sm_walkers else 0
+            if reserve:
+                eng.reserve_sms(reserve)
+            eng.local_energy()                  # X, exchange, ELOC of the walkers before the comb
+            if reserve:
+                eng.reserve_sms(0)
+            main.wait_stream(side)
+            if multi:
+                # the all-gather above only orders the peers' SIDE streams: their ELOC / X are
+                # final once their launch streams pass this barrier
+                comm.stream_barrier(eng.device)
+            eng.pop_pull()
+            if multi:
+                comm.stream_barrier(eng.device)   # nobody overwrites walker state while a peer pulls
+            eng.pop_control_finish()
+            return
+        if not multi:
             eng.pop_control_comb(r)
             return
         gw = comm.allgather_tensor(torch.abs(eng.weight))

@@ -72,6 +72,18 @@ def test_trace_matches_reference(golden, name):
     _close(afqmc.psi.phi_host(), g['phi_final'], atol=1e-11)
 
 
+def test_sequential_pop_control_path(golden):
+    """walkers.overlap_energy=False: comb first, energy afterwards on the copied walkers (the
+    reference's literal order); must give the same trace as the overlapped default."""
+    g = golden('stress_comb')
+    afqmc, h = _run(g, g['h1e'], g['hs_pot'], float(g['ecore']), walkers={'overlap_energy': False})
+    assert numpy.array_equal(h['parent_ix'], g['parent_ix'])
+    _close(h['unscaled_weight'], g['unscaled_weight'], atol=1e-13)
+    _close(h['ot'], g['ot'])
+    _close(h['eloc'], g['eloc'], atol=1e-10)
+    _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
+
+
 def test_reference_driver_goldens(golden):
     """The reference's own assertions (pauxy/qmc/tests/test_afqmc.py:227,229)."""
     g = golden('test_generic')
