@@ -1,6 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-for c in c5:2048 c3:4096 c2:1024 c1:32; do
+for c in c5:2048 c3:4096 c2:1024; do
 cfg=${c%%:*}; w=${c#*:}
 echo "== bench $cfg W=$w"; timeout 300 python bench.py --config $cfg --walkers $w --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_$cfg.log 2>&1; tail -1 gpurun_out/bench_$cfg.log | python -c "
 import json,sys
