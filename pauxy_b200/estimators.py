@@ -223,3 +223,26 @@ class Estimators(object):
         filename = filename or (self.basename + '.0.npy')
         numpy.save(filename, self.rows())
         return filename
+
+    def dump_datasets(self, filename=None, metadata=None):
+        """Everything the reference writes to estimates.<n>.h5, under the same dataset names
+        (estimators/utils.py:308-320 H5EstimatorHelper.push, estimators/mixed.py:368-371,
+        estimators/back_propagation.py:340-345, estimators/handler.py:119-121), in an .npz
+        container: 'basic/headers', 'basic/energies/%09d', 'back_propagated/denominator_<ix>/%09d',
+        'back_propagated/one_rdm_<ix>/%09d', 'metadata'."""
+        import json
+        filename = filename or (self.basename + '.0.npz')
+        out = {'basic/headers': numpy.array(self.estimators['mixed'].header[1:]).astype('S')}
+        for n, row in enumerate(self.estimators['mixed'].rows):
+            out['basic/energies/%09d' % n] = numpy.asarray(row[1:])
+        bp = self.estimators.get('back_prop')
+        if bp is not None:
+            for ix, vals in bp.output['denominator'].items():
+                for n, v in enumerate(vals):
+                    out['back_propagated/denominator_%d/%09d' % (ix, n)] = numpy.array([v])
+            for ix, vals in bp.output['one_rdm'].items():
+                for n, v in enumerate(vals):
+                    out['back_propagated/one_rdm_%d/%09d' % (ix, n)] = v
+        out['metadata'] = numpy.array(json.dumps(metadata or {}))
+        numpy.savez(filename, **out)
+        return filename

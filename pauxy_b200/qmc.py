@@ -167,6 +167,8 @@ class AFQMC(object):
                                    self.propagators.free_projection)
             self.testim += self._tick() - start
             self.estimators.print_step(comm, comm.size, step)
+            if self.psi.write_restart and step % self.psi.write_freq == 0:
+                self.psi.write_walkers(comm)
             if step % self.qmc.nsteps == 0:
                 self.psi.check_total_weight()   # handler.py:236-241, polled once per block
             if step < self.qmc.neqlb:

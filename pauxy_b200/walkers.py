@@ -126,10 +126,13 @@ class Walkers(object):
         self.ntot_walkers = qmc.ntot_walkers
         self.rank = 0 if comm is None else comm.rank
         self.walker_offset = self.rank * self.nwalkers  # global index rank*nw + i (handler.py:303-321)
+        # walker restart (handler.py:43-47,148-161,432-485): same options and the same per-walker
+        # record [weight, phase, ot, phi.ravel()] as the reference's 'walker_%d' datasets; the
+        # container is one .npy per rank instead of an MPI-IO HDF5 file (no h5py in this image)
         self.write_freq = walker_opts.get('write_freq', 0)
-        self.write_restart = False
-        if self.write_freq > 0:
-            raise NotImplementedError("pauxy_b200: walker restart files need HDF5 (SURVEY 8f.2)")
+        self.write_file = walker_opts.get('write_file', 'restart.h5')
+        self.read_file = walker_opts.get('read_file', None)
+        self.write_restart = self.write_freq > 0
         self.use_log_shift = walker_opts.get('use_log_shift', False)
         if self.use_log_shift:
             raise NotImplementedError("pauxy_b200: use_log_shift is not built")
@@ -149,6 +152,8 @@ class Walkers(object):
         if self.peer_copy and comm is not None and comm.size > 1:
             engine.attach_peers(comm)
         self.walkers = [SingleDetWalker(self, i) for i in range(self.nwalkers)]
+        if self.read_file is not None:
+            self.read_walkers(comm)
         self.buff_size = engine.payload_doubles()
         self._phi_cache = None
         self.last_parent_ix = None
@@ -313,6 +318,35 @@ class Walkers(object):
         comm.exchange(sends, recvs)
         for slots, buf in unpack:
             eng.unpack_walkers(slots, buf)
+
+    # ------------------------------------------------------------- restart
+    def _restart_name(self, base):
+        return '%s.rank%d.npy' % (base, self.rank)
+
+    def get_write_buffers(self):
+        """[nw, 3 + M*ne] complex: the reference's get_write_buffer (handler.py:432-435) for
+        every walker of this rank."""
+        eng = self.engine
+        phi = eng.get_phi().cpu().numpy().reshape(self.nwalkers, -1)
+        head = numpy.stack([eng.weight.cpu().numpy().astype(numpy.complex128),
+                            eng.phase.cpu().numpy(), eng.ot.cpu().numpy()], axis=1)
+        return numpy.concatenate([head, phi], axis=1)
+
+    def write_walkers(self, comm=None):
+        numpy.save(self._restart_name(self.write_file), self.get_write_buffers())
+
+    def read_walkers(self, comm=None):
+        """set_walker_from_buffer for every walker (handler.py:437-442, :477-485)."""
+        eng = self.engine
+        buff = numpy.load(self._restart_name(self.read_file))
+        if buff.shape != (self.nwalkers, 3 + eng.M * eng.ne):
+            raise ValueError("restart file %s does not match this walker population"
+                             % self._restart_name(self.read_file))
+        eng.set_phi(numpy.ascontiguousarray(buff[:, 3:].reshape(self.nwalkers, eng.M, eng.ne)))
+        eng.weight.copy_(torch.as_tensor(numpy.ascontiguousarray(buff[:, 0].real)))
+        eng.phase.copy_(torch.as_tensor(numpy.ascontiguousarray(buff[:, 1])))
+        eng.ot.copy_(torch.as_tensor(numpy.ascontiguousarray(buff[:, 2])))
+        self._phi_cache = None
 
     def set_total_weight(self, total_weight):
         self.engine.total_weight[0] = float(total_weight)

@@ -84,6 +84,33 @@ def test_sequential_pop_control_path(golden):
     _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
 
 
+def test_walker_restart_round_trip(golden, tmp_path):
+    """write_walkers / read_walkers (walkers/handler.py:432-485): a run continued from the restart
+    record of another run reproduces that run's walkers, overlaps and weights."""
+    g = golden('stress_comb')
+    base = str(tmp_path / 'restart.h5')
+    nelec = tuple(int(x) for x in g['nelec'])
+    system = Generic(nelec=nelec, h1e=numpy.array([g['h1e'], g['h1e']]), chol=g['hs_pot'],
+                     ecore=float(g['ecore']))
+    opts = _options(g, walkers={'write_freq': 7, 'write_file': base})
+    a = AFQMC(options=opts, system=system, verbose=0)
+    a.run(verbose=0)                    # 30 steps: restart written at 7, 14, 21, 28
+    rec = numpy.load(base + '.rank0.npy')
+    assert rec.shape == (int(g['nwalkers']), 3 + g['h1e'].shape[0] * sum(nelec))
+    b = AFQMC(options=_options(g, walkers={'read_file': base}), system=system, verbose=0)
+    numpy.testing.assert_array_equal(b.psi.get_write_buffers(), rec)
+    # the record is the state after step 28 of the first run
+    a2 = AFQMC(options=opts, system=system, verbose=0)
+    seen = {}
+    a2.run(verbose=0, observer=lambda step, q: seen.setdefault(step, q.psi.get_write_buffers())
+           if step == 28 else None)
+    numpy.testing.assert_array_equal(seen[28], rec)
+    out = a.estimators.dump_datasets(str(tmp_path / 'estimates.0.npz'), metadata={'qmc': opts['qmc']})
+    z = numpy.load(out)
+    assert [h.decode() for h in z['basic/headers']][:3] == ['WeightFactor', 'Weight', 'ENumer']
+    numpy.testing.assert_array_equal(z['basic/energies/%09d' % 2], a.estimators.rows()[2][1:])
+
+
 def test_reference_driver_goldens(golden):
     """The reference's own assertions (pauxy/qmc/tests/test_afqmc.py:227,229)."""
     g = golden('test_generic')
