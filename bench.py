@@ -329,6 +329,15 @@ def main():
     # stage table: ms per step, launches per step, achieved TFLOP/s on the stage's algorithmic flops
     stages = {}
     step_flops = 0.0
+    Np = (N + 7) // 8 * 8
+    # field_kernel: reads X (both spins) and xi, writes the VHS operand x and the parity copies of
+    # xbar and x; energy_kernel: reads X (both spins); 16 bytes per complex
+    mem_bytes = {'field': 2 * Np * 16 + N * 8 + 3 * Np * 16, 'energy': 2 * Np * 16 + 5 * 16}
+    hbm_peak = 6550.4
+    try:
+        hbm_peak = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
+    except Exception:
+        pass
     for name, (ms, calls) in stage.items():
         if calls == 0:
             continue
@@ -339,6 +348,10 @@ def main():
             row['tflops'] = fl[name] * wpg / (per_call_ms * 1e-3) * 1e-12
             row['frac_of_peak'] = row['tflops'] / peak
             step_flops += fl[name] * calls / float(args.steps)
+        if name in mem_bytes:
+            # memory-bound stages: algorithmic bytes per walker-step against the measured HBM peak
+            row['gbytes_per_s'] = mem_bytes[name] * wpg / (per_call_ms * 1e-3) * 1e-9
+            row['frac_of_hbm_peak'] = row['gbytes_per_s'] / hbm_peak
         if name == 'pop_control':
             row['note'] = ('comb plan runs on a side stream beside xgemm/exchange/energy; its events '
                            'include waiting for a free SM, it is not additive to the step')
