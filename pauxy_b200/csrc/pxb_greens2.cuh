@@ -128,9 +128,10 @@ __global__ void __launch_bounds__(TH_WARPS * 32, NMT <= 3 ? 7 : 1) theta_kernel(
     // column k (multipliers) aside, then row k scaled with the unit entry in place of the pivot
     for (int i = lane; i < ns; i += 32) colk[i] = A[(size_t)i * lda + k];
     __syncwarp();
-    cplx rk[2];
+    constexpr int NU = NMT > 4 ? 2 : 1;  // columns per lane: ns <= 8 NMT
+    cplx rk[NU];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < NU; ++u) {
       const int j = lane + 32 * u;
       rk[u] = {0.0, 0.0};
       if (j < ns) {
@@ -139,15 +140,33 @@ __global__ void __launch_bounds__(TH_WARPS * 32, NMT <= 3 ? 7 : 1) theta_kernel(
         A[(size_t)k * lda + j] = rk[u];
       }
     }
-    for (int i = 0; i < ns; ++i) {
-      if (i == k) continue;
-      const cplx f = colk[i];
+    if (NU == 1) {
+      // one column per lane: the lane predicate and the pivot-column test leave the row loop,
+      // which is unrolled so that several independent shared-memory round trips are in flight
+      if (lane < ns) {
+        cplx* aj = A + lane;
+        const cplx r0 = rk[0];
+        const bool isk = lane == k;
+#pragma unroll 4
+        for (int i = 0; i < ns; ++i) {
+          if (i == k) continue;
+          const cplx f = colk[i];
+          cplx v = aj[(size_t)i * lda];
+          if (isk) v = {0.0, 0.0};
+          aj[(size_t)i * lda] = csub(v, cmul(f, r0));
+        }
+      }
+    } else {
+      for (int i = 0; i < ns; ++i) {
+        if (i == k) continue;
+        const cplx f = colk[i];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int j = lane + 32 * u;
-        if (j < ns) {
-          const cplx v = (j == k) ? cplx{0.0, 0.0} : A[(size_t)i * lda + j];
-          A[(size_t)i * lda + j] = csub(v, cmul(f, rk[u]));
+        for (int u = 0; u < NU; ++u) {
+          const int j = lane + 32 * u;
+          if (j < ns) {
+            const cplx v = (j == k) ? cplx{0.0, 0.0} : A[(size_t)i * lda + j];
+            A[(size_t)i * lda + j] = csub(v, cmul(f, rk[u]));
+          }
         }
       }
     }
