@@ -32,7 +32,7 @@ extern "C" {
 #define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
 #define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
 
-#define PXB_ABI_VERSION 6
+#define PXB_ABI_VERSION 7
 
 typedef struct pxb_context* pxb_handle;
 
@@ -98,7 +98,9 @@ enum pxb_field_id {
   PXB_F_BP_RDM = 17,         /* c128 [2,M,M] sum_w weight_w G_w of the back-propagated estimator
                                               (back_propagation.py:198-205), nbp > 0 only */
   PXB_F_BP_DENOM = 18,       /* c128 [1]    sum_w weight_w (back_propagation.py:200) */
-  PXB_F_COUNT = 19
+  PXB_F_THETA_SUM = 19,      /* c128 [ne,M] sum_w weight_w Theta_w since the last pxb_zero_estimates: the mixed
+                                one-body density matrix is Re(conj(psi) THETA_SUM) (mixed.py:226-229) */
+  PXB_F_COUNT = 20
 };
 
 int pxb_abi_version(void);
@@ -190,6 +192,8 @@ int pxb_local_energy(pxb_handle h, void* stream);
  * with_energy != 0 adds the enumer/e1b/e2b/edenom terms from ELOC. */
 int pxb_accumulate(pxb_handle h, int with_energy, void* stream);
 int pxb_zero_estimates(pxb_handle h, void* stream);
+/* Mixed.update with one_rdm (estimators/mixed.py:226-229): THETA_SUM += sum_w weight_w Theta_w */
+int pxb_accumulate_theta(pxb_handle h, void* stream);
 
 /* ---- population control (walkers/handler.py:225-412) -------------------- */
 /* Single-device pop_control with the comb: total weight (sequential sum),

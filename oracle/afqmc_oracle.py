@@ -367,7 +367,7 @@ class OracleAFQMC(object):
                  npop_control=1, energy_eval_freq=1, exp_order=6,
                  pop_control='comb', min_weight=0.1, max_weight=4.0,
                  verbose_step0=False, free_projection=False, force_bias=True,
-                 nbp=0, nsplit=1, init_walker=False):
+                 nbp=0, nsplit=1, init_walker=False, one_rdm=False):
         self.ham = ham
         W = nwalkers
         self.W = W
@@ -400,6 +400,10 @@ class OracleAFQMC(object):
         self.step = 0
         self.last_parent_ix = numpy.ones(W, dtype='i')
         self.verbose_step0 = verbose_step0
+        # mixed one-body density matrix (estimators/mixed.py:76,226-229,279-283)
+        self.one_rdm = one_rdm
+        self.rdm_acc = numpy.zeros((2, ham.nbasis, ham.nbasis))
+        self.rdm_out = []
         # back propagation (estimators/back_propagation.py:55-76, walkers/walker.py:43,55-58)
         self.nbp = nbp
         self.init_walker = init_walker
@@ -509,6 +513,13 @@ class OracleAFQMC(object):
         if step % self.energy_eval_freq == 0:
             tha, thb, _ = greens_function(self.ham, self.phi)
             self.eloc = local_energy(self.ham, tha, thb)
+        if self.one_rdm and not self.free_projection:
+            # mixed.py:226-229: weight * Re(walker.G), G from the greens_function call above
+            # (fresh every step when energy_eval_freq == 1)
+            tha, thb, _ = greens_function(self.ham, self.phi)
+            Ga, Gb = full_greens_function(self.ham, tha, thb)
+            self.rdm_acc[0] += numpy.einsum('w,wpq->pq', self.weight, Ga.real)
+            self.rdm_acc[1] += numpy.einsum('w,wpq->pq', self.weight, Gb.real)
         for iw in range(self.W):
             w = self.weight[iw]
             if self.free_projection:
@@ -552,6 +563,9 @@ class OracleAFQMC(object):
         gs[8] /= gs[1]
         self.eshift_vec = numpy.array([gs[7], gs[4]])
         self.rows.append(numpy.concatenate([[step], gs]))
+        if self.one_rdm:
+            self.rdm_out.append(self.rdm_acc / nsteps / gs[1])     # mixed.py:279-283
+            self.rdm_acc[:] = 0
         self.estimates[:] = 0
 
     # -- back propagation -----------------------------------------------------

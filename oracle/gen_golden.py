@@ -134,6 +134,20 @@ def case_bp(name, nmo, nelec, nwalkers, tau_bp, nsplit, stab, scale, dt=0.005, s
     save(name, meta, tr, setup=rh.reference_setup_arrays(a), extra=extra)
 
 
+def case_mixed_rdm():
+    """Mixed one-body density matrix (estimators/mixed.py:226-229,279-283) on the stress walk."""
+    numpy.random.seed(11)
+    h1e, chol, enuc, _ = generate_hamiltonian(8, (3, 3), cplx=False)
+    hs = 6.0 * chol.reshape((-1, 64)).T.copy()
+    opts = options(16, 0.02, 5, 4, 21, stab=3, popc=1)
+    opts['estimates']['mixed']['one_rdm'] = True
+    a, tr = rh.run_reference_traced(h1e, hs, enuc, (3, 3), opts)
+    meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array((3, 3)), dt=0.02,
+                nwalkers=16, steps=5, blocks=4, seed=21, stab=3, popc=1)
+    save('mixed_rdm', meta, tr, setup=rh.reference_setup_arrays(a),
+         extra={'mixed_one_rdm': tr['mixed_one_rdm']})
+
+
 def case_stress(name, pop, walkers=None, scale_chol=6.0, dt=0.02):
     """Small case scaled so that the force-bias clip, the hybrid-energy bound,
     the weight cap and comb/pair-branch events all fire."""
@@ -192,13 +206,15 @@ def case_local_energy():
 
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
-    which = sys.argv[1:] or ['tg', 'c1', 'stress', 'pb', 'le', 'c2s', 'c3s', 'c4s', 'free', 'bp']
+    which = sys.argv[1:] or ['tg', 'c1', 'stress', 'pb', 'le', 'c2s', 'c3s', 'c4s', 'free', 'bp', 'rdm']
     if 'free' in which:
         case_free('free_comb', True, True)
         case_free('free_pair_branch', True, False, pop='pair_branch',
                   walkers={'population_control': 'pair_branch', 'min_weight': 0.9,
                            'max_weight': 1.1})
         case_free('phaseless_nofb', False, False)
+    if 'rdm' in which:
+        case_mixed_rdm()
     if 'bp' in which:
         case_bp('bp_ref', 11, (3, 3), 10, 0.025, 1, 10, 1.0, blocks=10)
         case_bp('bp_stress', 12, (4, 4), 16, 0.12, 2, 2, 6.0, dt=0.02, steps=5, blocks=4)

@@ -70,6 +70,14 @@ def estimator_rows(filename='estimates.0.h5'):
     return numpy.array([numpy.asarray(g[k]) for k in keys])
 
 
+def estimator_one_rdm(filename='estimates.0.h5'):
+    """'basic/one_rdm/%09d' pushed by Mixed.print_step (estimators/mixed.py:279-283)."""
+    import h5py
+    g = h5py._STORE[filename]
+    keys = sorted(k for k in g.keys() if k.startswith('basic/one_rdm/'))
+    return numpy.array([numpy.asarray(g[k]) for k in keys])
+
+
 def run_reference_traced(h1e, hs_pot, ecore, nelec, options, nsteps_total=None):
     """Re-run the loop body of AFQMC.run (/root/reference/pauxy/qmc/afqmc.py:
     200-255) calling the reference's own objects, recording per-step vectors.
@@ -192,6 +200,8 @@ def run_reference_traced(h1e, hs_pot, ecore, nelec, options, nsteps_total=None):
     out['nfb_trig'] = numpy.array(prop.nfb_trig)
     out['nhe_trig'] = numpy.array(prop.nhe_trig)
     out['rows'] = estimator_rows(afqmc.estimators.filename)
+    if mixed.calc_one_rdm:
+        out['mixed_one_rdm'] = estimator_one_rdm(afqmc.estimators.filename)
     if bp is not None:
         M = system.nbasis
         out['bp_buff_ix'] = numpy.array([b[0] for b in bp_rec])

@@ -795,6 +795,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_INIT_NAT, (size_t)d.M * d.ne * 16);
   add(A_FIELD0 + PXB_F_BP_RDM, bp ? (size_t)2 * d.M * d.M * 16 : 0);
   add(A_FIELD0 + PXB_F_BP_DENOM, 16);
+  add(A_FIELD0 + PXB_F_THETA_SUM, (size_t)d.ne * d.M * 16);
   h->arena_bytes = off;
   *out = h;
   return PXB_OK;
@@ -1155,8 +1156,22 @@ int pxb_accumulate(pxb_handle h, int with_energy, void* stream) {
   return PXB_OK;
 }
 
+int pxb_accumulate_theta(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  int rc = ensure_theta(h, S(stream));
+  if (rc) return rc;
+  StageTimer timer__(h, PXB_STAGE_ACCUMULATE, S(stream));
+  ++h->launches;
+  theta_wsum_kernel<<<d.ne * d.KC, 128, 0, S(stream)>>>(h->ptr<double>(A_THETA), h->field<double>(PXB_F_WEIGHT),
+                                                       h->field<double2>(PXB_F_THETA_SUM), d);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
 int pxb_zero_estimates(pxb_handle h, void* stream) {
   PXB_REQUIRE_READY(h);
+  PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_THETA_SUM), 0, (size_t)h->d.ne * h->d.M * 16, S(stream)));
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ESTIMATES), 0, 160, S(stream)));
   return PXB_OK;
 }

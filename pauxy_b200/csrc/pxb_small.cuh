@@ -529,6 +529,47 @@ __global__ void __launch_bounds__(1024) accumulate_kernel(AccArgs a) {
   }
 }
 
+// Mixed one-body density matrix (estimators/mixed.py:226-229): sum_w w Re(G_w) with
+// G_w = conj(psi) Theta_w is conj(psi) (sum_w w Theta_w), so the device only reduces Theta over the
+// walkers: out[i][p] += sum_w weight_w Theta_w[i][p].  One CTA per (orbital i, basis chunk kc) row
+// of the OF layout: every walker group contributes one contiguous 256-byte fragment.  Fixed
+// reduction order (deterministic).
+__global__ void __launch_bounds__(128) theta_wsum_kernel(const double* __restrict__ theta,
+                                                         const double* __restrict__ weight,
+                                                         double2* __restrict__ out, Dims d) {
+  __shared__ double2 red[128];
+  const int row = blockIdx.x;  // i * KC + kc
+  const int i = row / d.KC, kc = row % d.KC;
+  const int e = threadIdx.x & 15, sub = threadIdx.x >> 4;  // element (wl, t) of a fragment, 8 groups at a time
+  const int wl = e >> 2, t = e & 3;
+  double re = 0.0, im = 0.0;
+  for (int wg = sub; wg < d.WG; wg += 8) {
+    const int w = 4 * wg + wl;
+    if (w < d.W) {
+      const double2 v = *reinterpret_cast<const double2*>(theta + (((size_t)wg * d.ne + i) * d.KC + kc) * 32 + e * 2);
+      const double wt = weight[w];
+      re += wt * v.x;
+      im += wt * v.y;
+    }
+  }
+  red[threadIdx.x] = make_double2(re, im);
+  __syncthreads();
+  if (threadIdx.x < 4) {  // thread t sums its 4 walkers-in-group x 8 sub-slices in a fixed order
+    double sr = 0.0, si = 0.0;
+    for (int s2 = 0; s2 < 8; ++s2)
+      for (int l = 0; l < 4; ++l) {
+        const double2 v = red[s2 * 16 + l * 4 + threadIdx.x];
+        sr += v.x;
+        si += v.y;
+      }
+    const int p = 4 * kc + threadIdx.x;
+    if (p < d.M) {
+      out[(size_t)i * d.M + p].x += sr;
+      out[(size_t)i * d.M + p].y += si;
+    }
+  }
+}
+
 // free projection (estimators/mixed.py:151-177): every sum carries the complex factor
 // wfac = weight * ot * phase
 __global__ void __launch_bounds__(1024) accumulate_free_kernel(AccArgs a) {

@@ -100,6 +100,7 @@ class Engine(object):
         if self.nbp > 0:
             self.bp_rdm = self._view(L.F_BP_RDM, c128, (2, self.M, self.M))
         self.bp_denom = self._view(L.F_BP_DENOM, c128)
+        self.theta_sum = self._view(L.F_THETA_SUM, c128, (self.ne, self.M))
 
     def _dev(self, a, dtype):
         t = torch.as_tensor(numpy.ascontiguousarray(a, dtype=dtype))
@@ -227,6 +228,10 @@ class Engine(object):
     def accumulate(self, with_energy=True):
         with torch.cuda.device(self.device):
             self._check(self.lib.pxb_accumulate(self._h, 1 if with_energy else 0, self._stream()))
+
+    def accumulate_theta(self):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_accumulate_theta(self._h, self._stream()))
 
     def zero_estimates(self):
         with torch.cuda.device(self.device):

@@ -34,11 +34,19 @@ class Mixed(object):
     def __init__(self, mixed, system, root, filename, qmc, trial, dtype, engine=None):
         mixed = mixed or {}
         self.eval_energy = mixed.get('evaluate_energy', True)
-        if mixed.get('one_rdm', False) or mixed.get('two_rdm', None) is not None:
-            raise NotImplementedError("pauxy_b200: RDM accumulation is not built")
+        if mixed.get('two_rdm', None) is not None:
+            raise NotImplementedError("pauxy_b200: two-body RDM accumulation is not built")
+        self.calc_one_rdm = mixed.get('one_rdm', False)
         self.energy_eval_freq = mixed.get('energy_eval_freq', None)
         if self.energy_eval_freq is None:
             self.energy_eval_freq = qmc.nsteps
+        if self.calc_one_rdm and self.energy_eval_freq != 1:
+            # the reference then accumulates the Green's function left behind by the propagator
+            # (of the walker BEFORE the step); only the per-step evaluation is mirrored
+            raise NotImplementedError("pauxy_b200: mixed one_rdm needs energy_eval_freq = 1")
+        self.psi_trial = numpy.array(trial.psi)
+        self.nup = system.nup
+        self.one_rdm = []
         self.verbose = mixed.get('verbose', True)
         self.nsteps = qmc.nsteps
         self.header = list(HEADER)
@@ -66,6 +74,8 @@ class Mixed(object):
         elif evaluate:
             eng.eloc.zero_()
         eng.accumulate(with_energy=evaluate)
+        if self.calc_one_rdm and not free_projection:
+            eng.accumulate_theta()          # mixed.py:226-229
 
     def print_step(self, comm, nprocs, step, nsteps=None, free_projection=False):
         """mixed.py:252-289: block averages, reduction over ranks, eshift."""
@@ -77,6 +87,8 @@ class Mixed(object):
         dev = self.engine.estimates
         if comm is not None and comm.size > 1:
             comm.allreduce_sum_(dev)
+            if self.calc_one_rdm:
+                comm.allreduce_sum_(self.engine.theta_sum)
         gs = dev.cpu().numpy().copy()
         gs[ns.time] = (time.time() - self._t0) / nprocs
         gs[ns.uweight:ns.weight + 1] /= nsteps
@@ -91,6 +103,13 @@ class Mixed(object):
             if self.verbose:
                 print(format_fixed_width_floats([step] + list(gs[:ns.time + 1].real)))
             self.rows.append(numpy.array([step] + list(gs[:ns.time + 1])))
+            if self.calc_one_rdm:
+                # sum_w w Re(G_w), G_w = conj(psi) Theta_w  ->  Re(conj(psi) sum_w w Theta_w);
+                # block average and normalisation of mixed.py:279-283
+                th = self.engine.theta_sum.cpu().numpy()
+                na, psi = self.nup, self.psi_trial
+                G = numpy.array([psi[:, :na].conj().dot(th[:na]), psi[:, na:].conj().dot(th[na:])])
+                self.one_rdm.append(G.real / nsteps / gs[ns.weight])
         self.zero()
 
     def print_header(self, eol='', encode=False):

@@ -111,6 +111,21 @@ def test_walker_restart_round_trip(golden, tmp_path):
     numpy.testing.assert_array_equal(z['basic/energies/%09d' % 2], a.estimators.rows()[2][1:])
 
 
+def test_mixed_one_rdm(golden):
+    """Mixed one-body density matrix (estimators/mixed.py:226-229,279-283) against the reference."""
+    g = golden('mixed_rdm')
+    nelec = tuple(int(x) for x in g['nelec'])
+    system = Generic(nelec=nelec, h1e=numpy.array([g['h1e'], g['h1e']]), chol=g['hs_pot'],
+                     ecore=float(g['ecore']))
+    opts = _options(g)
+    opts['estimates']['mixed']['one_rdm'] = True
+    afqmc = AFQMC(options=opts, system=system, verbose=0)
+    afqmc.run(verbose=0)
+    _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
+    rdm = numpy.array(afqmc.estimators.estimators['mixed'].one_rdm)
+    _close(rdm, g['mixed_one_rdm'].real, rtol=1e-9, atol=1e-10)
+
+
 def test_reference_driver_goldens(golden):
     """The reference's own assertions (pauxy/qmc/tests/test_afqmc.py:227,229)."""
     g = golden('test_generic')
