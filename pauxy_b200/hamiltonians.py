@@ -13,56 +13,74 @@ needs an M^4 ERI tensor, which is 12.8 GB at M=200.
 import numpy
 
 
-def modified_cholesky(M, tol=1e-6, cmax=20):
-    """Pivoted incomplete Cholesky M ~= sum_n L_n L_n^dagger.
+def modified_cholesky(matrix, tol=1e-6, cmax=20):
+    """Pivoted, incomplete Cholesky factorisation  matrix ~= sum_n v_n v_n^dagger  of a Hermitian
+    positive semi-definite matrix, stopped when the largest residual diagonal drops below `tol`.
 
-    Follows /root/reference/pauxy/utils/linalg.py:112-161.
-    Returns an array of shape [nchol, dim].
+    Same algorithm AND the same floating-point evaluation order as the reference's test helper
+    (/root/reference/pauxy/utils/linalg.py:112-161: accumulated diagonal of the approximation,
+    residual recomputed from it, one matrix-vector product per new vector), because the synthetic
+    c1 Hamiltonian must come out bit-identical to the reference's.  Returns [nvec, dim].
     """
-    assert len(M.shape) == 2
-    delta = numpy.copy(M.diagonal())
-    nchol_max = int(cmax * M.shape[0] ** 0.5)
-    chol_vecs = numpy.zeros((nchol_max, M.shape[0]), dtype=M.dtype)
-    nu = numpy.argmax(numpy.abs(delta))
-    delta_max = delta[nu]
-    Mapprox = numpy.zeros(M.shape[0], dtype=M.dtype)
-    chol_vecs[0] = numpy.copy(M[:, nu]) / delta_max ** 0.5
-    nchol = 0
-    while abs(delta_max) > tol:
-        Mapprox += chol_vecs[nchol] * chol_vecs[nchol].conj()
-        delta = M.diagonal() - Mapprox
-        nu = numpy.argmax(numpy.abs(delta))
-        delta_max = numpy.abs(delta[nu])
-        nchol += 1
-        Munu0 = numpy.dot(chol_vecs[:nchol, nu].conj(), chol_vecs[:nchol, :])
-        chol_vecs[nchol] = (M[:, nu] - Munu0) / (delta_max) ** 0.5
-    return numpy.array(chol_vecs[:nchol])
+    if matrix.ndim != 2:
+        raise ValueError("modified_cholesky needs a matrix")
+    dim = matrix.shape[0]
+    diagonal = matrix.diagonal()
+    capacity = int(cmax * dim ** 0.5)
+    vectors = numpy.zeros((capacity, dim), dtype=matrix.dtype)
+    covered = numpy.zeros(dim, dtype=matrix.dtype)     # diagonal of sum_n v_n v_n^dagger so far
+    pivot = int(numpy.argmax(numpy.abs(diagonal)))
+    residual = diagonal[pivot]
+    vectors[0] = matrix[:, pivot] / residual ** 0.5
+    count = 0
+    while abs(residual) > tol:
+        covered += vectors[count] * vectors[count].conj()
+        remaining = diagonal - covered
+        pivot = int(numpy.argmax(numpy.abs(remaining)))
+        residual = numpy.abs(remaining[pivot])
+        count += 1
+        # column `pivot` of the current approximation, subtracted from the matrix column
+        overlap = numpy.dot(vectors[:count, pivot].conj(), vectors[:count, :])
+        vectors[count] = (matrix[:, pivot] - overlap) / residual ** 0.5
+    return vectors[:count].copy()
+
+
+def _random_block(shape, cplx, gaussian_scale=None):
+    """One real (or complex: real part first) block from the global legacy numpy stream."""
+    def draw():
+        if gaussian_scale is None:
+            return numpy.random.random(shape)
+        return numpy.random.normal(scale=gaussian_scale, size=shape)
+    block = draw()
+    if cplx:
+        block = block + 1j * draw()
+    return block
 
 
 def generate_hamiltonian(nmo, nelec, cplx=False, sym=8):
-    """Random Hamiltonian from the GLOBAL numpy stream (seed it first).
+    """Random test Hamiltonian drawn from the GLOBAL numpy stream (seed it first): uniform h1e,
+    Gaussian two-electron integrals symmetrised to 4- or 8-fold symmetry, made positive
+    semi-definite by squaring and factorised with modified_cholesky; then one uniform for the core
+    energy.  Draw order, symmetrisation order and tolerances are those of the reference's test
+    helper (/root/reference/pauxy/utils/testing.py:6-29) so that numpy.random.seed(7) gives the
+    inputs of the reference's own tests bit for bit.
 
-    Follows /root/reference/pauxy/utils/testing.py:6-29.
     Returns (h1e [M,M], chol [N,M,M], enuc, eri [M^2,M^2]).
     """
-    h1e = numpy.random.random((nmo, nmo))
-    if cplx:
-        h1e = h1e + 1j * numpy.random.random((nmo, nmo))
-    eri = numpy.random.normal(scale=0.01, size=(nmo, nmo, nmo, nmo))
-    if cplx:
-        eri = eri + 1j * numpy.random.normal(scale=0.01, size=(nmo, nmo, nmo, nmo))
+    h1e = _random_block((nmo, nmo), cplx)
+    eri = _random_block((nmo,) * 4, cplx, gaussian_scale=0.01)
     if sym >= 4:
-        eri = eri + eri.transpose(2, 3, 0, 1)
-        eri = eri + eri.transpose(3, 2, 1, 0).conj()
+        for perm, conjugate in (((2, 3, 0, 1), False), ((3, 2, 1, 0), True)):
+            partner = eri.transpose(perm)
+            eri = eri + (partner.conj() if conjugate else partner)
     if sym == 8:
         eri = eri + eri.transpose(1, 0, 2, 3)
-    eri = eri.transpose((0, 1, 3, 2))
-    eri = eri.reshape((nmo * nmo, nmo * nmo))
-    eri = numpy.dot(eri, eri.conj().T)
-    chol = modified_cholesky(eri, tol=1e-3, cmax=30)
-    chol = chol.reshape((-1, nmo, nmo))
+    # Hermitian super-matrix M[(i,k),(l,j)], squared to make it positive semi-definite
+    super_matrix = eri.transpose((0, 1, 3, 2)).reshape((nmo * nmo, nmo * nmo))
+    super_matrix = numpy.dot(super_matrix, super_matrix.conj().T)
+    chol = modified_cholesky(super_matrix, tol=1e-3, cmax=30).reshape((-1, nmo, nmo))
     enuc = numpy.random.rand()
-    return h1e, chol, enuc, eri
+    return h1e, chol, enuc, super_matrix
 
 
 def synthetic_cholesky_hamiltonian(nbasis, nchol, seed, scale=0.02, h1_scale=0.05,
