@@ -237,3 +237,5 @@ if __name__ == '__main__':
         case_shape('c3_shape', 60, 7, 300, 16, 6, 1003, 5)
     if 'c4s' in which:
         case_shape('c4_shape', 108, 21, 500, 16, 6, 1004, 5)
+    if 'c5s' in which:
+        case_shape('c5_shape', 200, 40, 1000, 4, 3, 1005, 2)

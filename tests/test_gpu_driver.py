@@ -211,7 +211,7 @@ def test_back_propagation(golden, name):
         assert rdm[11, 0, 1, 3].real == pytest.approx(-0.121883381144845, rel=1e-8)
 
 
-@pytest.mark.parametrize('name', ['c2_shape', 'c3_shape', 'c4_shape'])
+@pytest.mark.parametrize('name', ['c2_shape', 'c3_shape', 'c4_shape', 'c5_shape'])
 def test_shape_fixture_matches_reference(golden, name):
     g = golden(name)
     h1e, hs, ecore = synthetic_cholesky_hamiltonian(int(g['nbasis']), int(g['nchol']),

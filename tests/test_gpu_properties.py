@@ -18,12 +18,12 @@ def _engine(name, W, total=None, nbp=0):
     return make_engine(system, trial, prop, W, 0.005, total_walkers=total, nbp=nbp), ham
 
 
-def test_full_size_c4_replicated_walkers():
-    """8192 walkers at c4 = 8 distinct walkers tiled: every copy must reproduce its
-    representative (same arithmetic whatever the tile position), and the
-    representatives must match the oracle (propagation + local energy)."""
-    W, R = 8192, 8
-    eng, ham = _engine('c4', W)
+@pytest.mark.parametrize('cfg,W,R', [('c4', 8192, 8), ('c5', 2048, 4)])
+def test_full_size_replicated_walkers(cfg, W, R):
+    """BASELINE full sizes (c4: 8192 walkers; c5: the 2048-walker share of one of 8 GPUs) = R
+    distinct walkers tiled: every copy must reproduce its representative (same arithmetic whatever
+    the tile position), and the representatives must match the oracle (propagation + local energy)."""
+    eng, ham = _engine(cfg, W)
     base = random_walkers(ham, R, seed=3)
     rs = numpy.random.RandomState(4)
     xib = rs.normal(size=(R, ham.nchol))
