@@ -217,7 +217,10 @@ int pxb_comb_plan(pxb_handle h, const double* dev_global_abs_weights, int64_t wt
                   void* stream);
 /* Walker payload movement (Walker.get_buffer/set_buffer, walkers/walker.py:
  * 63-131): the fields that matter downstream -- phi, weight, unscaled_weight,
- * ot, hybrid_energy, eloc, detR, log_detR.
+ * ot, hybrid_energy, phase, eloc, detR, log_detR -- plus what this library keeps
+ * per walker so that nothing has to be recomputed after a copy: the rotated
+ * Green's function Theta with its one-body energy, X = R^T Theta, and with
+ * nbp > 0 phi_old and the field history (walker.field_configs).
  *  pxb_copy_walkers : local slot src[i] -> local slot dst[i], i < n (int32 dev lists)
  *  pxb_pack_walkers / pxb_unpack_walkers : to / from a contiguous buffer of
  *      n * pxb_payload_doubles() doubles, for send/recv between devices. */
@@ -250,8 +253,9 @@ int pxb_set_weights(pxb_handle h, double value, void* stream); /* handler.py:337
  * needs only the weights; the energies of the walkers before the comb are the energies of their
  * clones after it, and ELOC / X / Theta travel in the walker payload):
  *   side stream  : [all-gather |w|]  pxb_pop_plan
- *   launch stream: pxb_local_energy   ... wait for the side stream ...  pxb_pop_pull
- *                  [stream barrier across devices]  pxb_pop_control_finish
+ *   launch stream: pxb_local_energy   ... wait for the side stream ...
+ *                  [stream barrier across devices: the peers' ELOC / X are final]  pxb_pop_pull
+ *                  [stream barrier across devices: the peers have finished reading]  pxb_pop_control_finish
  * pxb_pop_plan    : total weight + comb plan, writes no walker state; dev_global_abs_weights may be
  *                   NULL on one device.  pxb_pop_pull: the data movement of that plan (local
  *                   copies, NVLink pulls for clones owned by peers; on one device no attach needed). */
