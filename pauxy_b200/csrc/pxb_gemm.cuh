@@ -22,14 +22,22 @@ struct GemmArgs {
   int MTiles, NTiles, KS;
 };
 
+// Epilogues.  A warp owns WM x WN tiles: everything that depends only on the tile row (mt) or only
+// on the tile column (nt) -- index divisions, map look-ups, base pointers -- is computed once per
+// row / column (row(), col()) and store() is left with an add and a store.  (Before this split the
+// one-body GEMM executed as many instructions in its epilogue as in its main loop: two integer
+// divisions per tile.)
 struct EpiX {  // X[z][w][n] complex128, ld = Np
   double* X;
   int Wp, Np;
-  __device__ __forceinline__ void operator()(int mt, int nt, int z, int g, int t, double c0,
-                                             double c1) const {
-    int w = nt * 4 + t, n = mt * 8 + g;
-    double2* dst = reinterpret_cast<double2*>(X) + ((size_t)z * Wp + w) * Np + n;
-    *dst = make_double2(c0, c1);
+  struct Row { int n; };
+  struct Col { double2* base; };
+  __device__ __forceinline__ Row row(int mt, int g) const { return {mt * 8 + g}; }
+  __device__ __forceinline__ Col col(int nt, int z, int t) const {
+    return {reinterpret_cast<double2*>(X) + ((size_t)z * Wp + nt * 4 + t) * Np};
+  }
+  __device__ __forceinline__ void store(const Row& r, const Col& c, double c0, double c1) const {
+    c.base[r.n] = make_double2(c0, c1);
   }
 };
 
@@ -39,25 +47,34 @@ struct EpiVHS {  // VF[w][MT][KC][c][g][t]; row tile mt = (mtv*4+s)*KC + kc
   double sqrt_dt;
   size_t walker_stride;
   const int* rt_map;  // symmetric L: compact row-tile list (upper triangle); else null
-  __device__ __forceinline__ void operator()(int rt, int nt, int z, int g, int t, double c0,
-                                             double c1) const {
+  struct Row { int off, moff; };  // element offsets inside a walker's VF block; moff < 0: no mirror
+  struct Col { double* vw; };
+  __device__ __forceinline__ Row row(int rt, int g) const {
     if (rt_map != nullptr) rt = rt_map[rt];
-    int kc = rt % KC, ms = rt / KC, s = ms & 3, mtv = ms >> 2;
-    int w = nt * 4 + t;
-    double* vw = VF + (size_t)w * walker_stride;
-    double* base = vw + ((size_t)mtv * KC + kc) * 64 + 8 * s + g;
-    // VHS = i sqrt(dt) (S_re + i S_im)
-    const double vr = -sqrt_dt * c1, vi = sqrt_dt * c0;
-    base[0] = vr;
-    base[32] = vi;
+    const int kc = rt % KC, ms = rt / KC, s = ms & 3, mtv = ms >> 2;
+    Row r;
+    r.off = (mtv * KC + kc) * 64 + 8 * s + g;
+    r.moff = -1;
     if (rt_map != nullptr) {
       // mirror VHS[q][p] = VHS[p][q] (complex symmetric, no conjugation)
       const int p = 8 * mtv + 2 * s + (g >> 2), q = 4 * kc + (g & 3);
-      if (q > p && (q >> 3) < MT) {
-        double* m = vw + ((size_t)(q >> 3) * KC + (p >> 2)) * 64 + (q & 7) * 4 + (p & 3);
-        m[0] = vr;
-        m[32] = vi;
-      }
+      if (q > p && (q >> 3) < MT) r.moff = ((q >> 3) * KC + (p >> 2)) * 64 + (q & 7) * 4 + (p & 3);
+    }
+    return r;
+  }
+  __device__ __forceinline__ Col col(int nt, int z, int t) const {
+    return {VF + (size_t)(nt * 4 + t) * walker_stride};
+  }
+  __device__ __forceinline__ void store(const Row& r, const Col& c, double c0, double c1) const {
+    // VHS = i sqrt(dt) (S_re + i S_im)
+    const double vr = -sqrt_dt * c1, vi = sqrt_dt * c0;
+    double* base = c.vw + r.off;
+    base[0] = vr;
+    base[32] = vi;
+    if (r.moff >= 0) {
+      double* m = c.vw + r.moff;
+      m[0] = vr;
+      m[32] = vi;
     }
   }
 };
@@ -66,15 +83,20 @@ struct EpiOF {  // out OF buffer; n-tile nt = wg*nInner + il, orbital i = ioff +
   double* out;
   const int* active;  // optional per-walker mask (skip store if 0)
   int ne, KC, ioff, nInner;
-  __device__ __forceinline__ void operator()(int mt, int nt, int z, int g, int t, double c0,
-                                             double c1) const {
-    int wg = nt / nInner, il = nt % nInner;
-    int pc = 2 * mt + (g >> 2);
-    if (pc >= KC) return;
-    if (active != nullptr && active[wg * 4 + t] == 0) return;
-    double2* dst = reinterpret_cast<double2*>(
-        out + (((size_t)wg * ne + ioff + il) * KC + pc) * 32 + t * 8 + (g & 3) * 2);
-    *dst = make_double2(c0, c1);
+  struct Row { int off; };        // < 0: padding rows beyond the basis
+  struct Col { double* base; };   // nullptr: inactive walker, nothing stored
+  __device__ __forceinline__ Row row(int mt, int g) const {
+    const int pc = 2 * mt + (g >> 2);
+    return {pc < KC ? pc * 32 + (g & 3) * 2 : -1};
+  }
+  __device__ __forceinline__ Col col(int nt, int z, int t) const {
+    const int wg = nt / nInner, il = nt - wg * nInner;
+    if (active != nullptr && active[wg * 4 + t] == 0) return {nullptr};
+    return {out + ((size_t)wg * ne + ioff + il) * KC * 32 + t * 8};
+  }
+  __device__ __forceinline__ void store(const Row& r, const Col& c, double c0, double c1) const {
+    if (r.off < 0 || c.base == nullptr) return;
+    *reinterpret_cast<double2*>(c.base + r.off) = make_double2(c0, c1);
   }
 };
 
@@ -132,12 +154,17 @@ __global__ void __launch_bounds__(CWM* CWN * 32)
   }
 
   const int g = lane >> 2, t = lane & 3;
+  typename Epi::Row er[WM];
+  typename Epi::Col ec[WN];
+#pragma unroll
+  for (int i = 0; i < WM; ++i) er[i] = epi.row(min(mt0 + i, a.MTiles - 1), g);
+#pragma unroll
+  for (int j = 0; j < WN; ++j) ec[j] = epi.col(min(nt0 + j, a.NTiles - 1), z, t);
 #pragma unroll
   for (int i = 0; i < WM; ++i) {
 #pragma unroll
     for (int j = 0; j < WN; ++j) {
-      if (mt0 + i < a.MTiles && nt0 + j < a.NTiles)
-        epi(mt0 + i, nt0 + j, z, g, t, acc[i][j][0], acc[i][j][1]);
+      if (mt0 + i < a.MTiles && nt0 + j < a.NTiles) epi.store(er[i], ec[j], acc[i][j][0], acc[i][j][1]);
     }
   }
 }
@@ -289,12 +316,17 @@ __global__ void __launch_bounds__(gemm_tma_threads<CWM * CWN>(), 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty[s]);
     }
+    typename Epi::Row er[WM];
+    typename Epi::Col ec[WN];
+#pragma unroll
+    for (int i = 0; i < WM; ++i) er[i] = epi.row(min(mt0 + i, a.MTiles - 1), g);
+#pragma unroll
+    for (int j = 0; j < WN; ++j) ec[j] = epi.col(min(nt0 + j, a.NTiles - 1), z, t);
 #pragma unroll
     for (int i = 0; i < WM; ++i) {
 #pragma unroll
       for (int j = 0; j < WN; ++j) {
-        if (mt0 + i < a.MTiles && nt0 + j < a.NTiles)
-          epi(mt0 + i, nt0 + j, z, g, t, acc[i][j][0], acc[i][j][1]);
+        if (mt0 + i < a.MTiles && nt0 + j < a.NTiles) epi.store(er[i], ec[j], acc[i][j][0], acc[i][j][1]);
       }
     }
   }

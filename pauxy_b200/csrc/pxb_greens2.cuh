@@ -21,12 +21,18 @@ namespace pxb {
 struct EpiO {  // O[(w, spin)][i][j] complex, row-major with leading dimension nld, slot stride nsq
   double2* OB;
   int ns, spin, nld, nsq;
-  __device__ __forceinline__ void operator()(int mt, int nt, int z, int g, int t, double c0, double c1) const {
-    const int wg = nt / ns, i = nt % ns;
+  struct Row { int j; };           // < 0: padding rows beyond the occupied orbitals
+  struct Col { double2* base; };
+  __device__ __forceinline__ Row row(int mt, int g) const {
     const int j = 8 * mt + g;
-    if (j >= ns) return;
-    const int w = 4 * wg + t;
-    OB[((size_t)w * 2 + spin) * nsq + (size_t)i * nld + j] = make_double2(c0, c1);
+    return {j < ns ? j : -1};
+  }
+  __device__ __forceinline__ Col col(int nt, int z, int t) const {
+    const int wg = nt / ns, i = nt - wg * ns;
+    return {OB + ((size_t)(4 * wg + t) * 2 + spin) * nsq + (size_t)i * nld};
+  }
+  __device__ __forceinline__ void store(const Row& r, const Col& c, double c0, double c1) const {
+    if (r.j >= 0) c.base[r.j] = make_double2(c0, c1);
   }
 };
 
