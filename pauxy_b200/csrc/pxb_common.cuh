@@ -82,6 +82,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 }
 
 __device__ __forceinline__ double ldg_nc(const double* p) { return __ldg(p); }
+__device__ __forceinline__ double2 ldg_nc2(const double* p) { return __ldg(reinterpret_cast<const double2*>(p)); }
 
 // ---- mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP) ---------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {

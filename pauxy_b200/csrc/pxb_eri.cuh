@@ -142,6 +142,26 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
     for (int i = 0; i < WM; ++i)
 #pragma unroll
       for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    // the Theta elements of the quadratic-form epilogue (one per accumulator) are requested now:
+    // their L2 latency is hidden behind the whole k-loop instead of sitting in front of the epilogue
+    const int ioff = it.s ? d.na : 0;
+    const int D = eri_dim(d, it.s);
+    const int mtw = it.mt0 + wm * WM, ntw = it.nt0 + wn * WN;
+    double2 th[WM][WN];
+    bool rowok[WM];
+#pragma unroll
+    for (int i = 0; i < WM; ++i) {
+      const int arow = 8 * (mtw + i) + g;
+      rowok[i] = (mtw + i < it.MT) && (arow < D);
+      const int orb = rowok[i] ? arow / d.Mp : 0;
+      const int q = rowok[i] ? arow - orb * d.Mp : 0;
+      const double* trow = a.theta + ((size_t)(ioff + orb) * d.KC + (q >> 2)) * 32 + t * 8 + (q & 3) * 2;
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        const int wg = min(ntw + j, d.WG - 1);
+        th[i][j] = rowok[i] ? ldg_nc2(trow + (size_t)wg * d.ne * d.KC * 32) : make_double2(0.0, 0.0);
+      }
+    }
     for (int ks = 0; ks < it.nkstage; ++ks, ++itc) {
       const unsigned s = itc % GT_STAGES, ph = (itc / GT_STAGES) & 1u;
       mbar_wait(&full[s], ph);
@@ -182,16 +202,6 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
     // diagonal blocks pre-multiplied by 1/2 (exact), so one factor serves the whole row block and
     // the accumulators are never touched between DMMAs
     const double factor = 2.0;
-    const int ioff = it.s ? d.na : 0;
-    const int D = eri_dim(d, it.s);
-    const int mtw = it.mt0 + wm * WM, ntw = it.nt0 + wn * WN;
-    int orb[WM], q[WM];
-#pragma unroll
-    for (int i = 0; i < WM; ++i) {
-      const int arow = 8 * (mtw + i) + g;
-      orb[i] = (mtw + i < it.MT && arow < D) ? arow / d.Mp : -1;
-      q[i] = arow - (orb[i] < 0 ? 0 : orb[i]) * d.Mp;
-    }
 #pragma unroll
     for (int j = 0; j < WN; ++j) {
       const int wg = ntw + j;
@@ -199,11 +209,9 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
       double sr = 0.0, si = 0.0;
 #pragma unroll
       for (int i = 0; i < WM; ++i) {
-        if (orb[i] >= 0) {
-          const double2 th = *reinterpret_cast<const double2*>(
-              a.theta + (((size_t)wg * d.ne + ioff + orb[i]) * d.KC + (q[i] >> 2)) * 32 + t * 8 + (q[i] & 3) * 2);
-          sr += th.x * acc[i][j][0] - th.y * acc[i][j][1];
-          si += th.x * acc[i][j][1] + th.y * acc[i][j][0];
+        if (rowok[i]) {
+          sr += th[i][j].x * acc[i][j][0] - th[i][j].y * acc[i][j][1];
+          si += th[i][j].x * acc[i][j][1] + th[i][j].y * acc[i][j][0];
         }
       }
 #pragma unroll
