@@ -541,7 +541,7 @@ __global__ void __launch_bounds__(128) theta_wsum_kernel(const double* __restric
   const int row = blockIdx.x;  // i * KC + kc
   const int i = row / d.KC, kc = row % d.KC;
   const int e = threadIdx.x & 15, sub = threadIdx.x >> 4;  // element (wl, t) of a fragment, 8 groups at a time
-  const int wl = e >> 2, t = e & 3;
+  const int wl = e >> 2;
   double re = 0.0, im = 0.0;
   for (int wg = sub; wg < d.WG; wg += 8) {
     const int w = 4 * wg + wl;
