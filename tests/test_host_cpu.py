@@ -5,6 +5,7 @@ import re
 
 import numpy
 import pytest
+import torch
 
 from oracle import afqmc_oracle as orc
 from helpers import host_setup
@@ -183,3 +184,108 @@ def test_two_rank_plumbing_gloo():
     for c, k in [(1, 6), (5, 2), (3, 0), (7, 4)]:
         expect[k] = orig[c]
     assert allstate == expect
+
+
+# --------------------------------------------------------------------------- estimator host logic
+class _FakeEngine(object):
+    """CPU stand-in for pauxy_b200.engine.Engine: just the buffers and call log the estimator
+    classes touch (the arithmetic of the real one is covered by the GPU tests)."""
+
+    def __init__(self, M, ne):
+        self.estimates = torch.zeros(10, dtype=torch.complex128)
+        self.theta_sum = torch.zeros((ne, M), dtype=torch.complex128)
+        self.bp_rdm = torch.zeros((2, M, M), dtype=torch.complex128)
+        self.bp_denom = torch.zeros(1, dtype=torch.complex128)
+        self.calls = []
+        self.steps = 0
+
+    def bp_steps(self):
+        return self.steps
+
+    def back_propagate(self, n, nstblz, init_walker=False):
+        self.calls.append(('bp', n, nstblz, init_walker))
+        self.bp_rdm += float(n)
+        self.bp_denom += 2.0
+
+    def bp_reset(self):
+        self.calls.append(('reset',))
+        self.steps = 0
+
+    def bp_zero(self):
+        self.bp_rdm.zero_()
+        self.bp_denom.zero_()
+
+    def zero_estimates(self):
+        self.estimates.zero_()
+        self.theta_sum.zero_()
+
+
+class _Qmc(object):
+    dt = 0.01
+    nsteps = 5
+    nstblz = 4
+
+
+def test_back_propagation_estimator_schedule():
+    """BackPropagation.update / print_step (estimators/back_propagation.py:127-225, :282-333):
+    back propagation at every split point with the configurations stored so far, history reset
+    and phi_old refresh at the last one, one output record per accumulated print."""
+    from pauxy_b200.estimators import BackPropagation
+    from pauxy_b200.comm import SingleComm
+    system, trial, prop = host_setup(numpy.eye(4), numpy.zeros((16, 3)), 0.0, (1, 1), 0.01)
+    eng = _FakeEngine(4, 2)
+    bp = BackPropagation({'tau_bp': 0.06, 'nsplit': 2}, True, None, _Qmc(), system, trial, complex,
+                         prop.BH1, engine=eng)
+    assert bp.nmax == 6 and list(bp.splits) == [3, 6]
+    comm = SingleComm()
+    for step in range(1, 13):
+        eng.steps += 1                       # what pxb_propagate does with nbp > 0
+        bp.update(system, _Qmc(), trial, None, step)
+        bp.print_step(comm, 1, step)
+    assert eng.calls == [('bp', 3, 4, False), ('bp', 6, 4, False), ('reset',)] * 2
+    assert sorted(bp.output['denominator']) == [3, 6]
+    assert [len(v) for v in bp.output['one_rdm'].values()] == [2, 2]
+    # accumulators are zeroed after every print: each record holds one back propagation only
+    assert bp.output['denominator'][6] == [2.0 + 0j, 2.0 + 0j]
+    assert float(bp.output['one_rdm'][3][0].real.max()) == 3.0
+    numpy.testing.assert_allclose(bp.one_rdm()[0], numpy.full((2, 4, 4), 3.0))
+    for bad in ({'restore_weights': 'full'}, {'evaluate_energy': True}, {'two_rdm': True}):
+        with pytest.raises(NotImplementedError):
+            BackPropagation(dict(tau_bp=0.06, **bad), True, None, _Qmc(), system, trial, complex,
+                            prop.BH1, engine=eng)
+
+
+def test_mixed_print_step_block_arithmetic():
+    """Mixed.print_step (estimators/mixed.py:252-289) on given accumulators: block averages,
+    projected energy, shift vector, and the one-RDM normalisation of mixed.py:279-283."""
+    from pauxy_b200.estimators import Mixed
+    from pauxy_b200.comm import SingleComm
+    from oracle import afqmc_oracle as orc
+    rs = numpy.random.RandomState(3)
+    M, nelec = 5, (2, 1)
+    h1e = rs.normal(size=(M, M))
+    h1e = h1e + h1e.T
+    hs = rs.normal(size=(M * M, 4))
+    system, trial, prop = host_setup(h1e, hs, 0.3, nelec, 0.01)
+    eng = _FakeEngine(M, 3)
+    mixed = Mixed({'energy_eval_freq': 1, 'one_rdm': True, 'verbose': False}, system, True, None,
+                  _Qmc(), trial, complex, engine=eng)
+    acc = rs.normal(size=10) + 1j * rs.normal(size=10)
+    acc[[0, 1, 3]] = numpy.abs(acc[[0, 1, 3]]) + 5.0          # weights / denominators
+    eng.estimates.copy_(torch.as_tensor(acc))
+    th = rs.normal(size=(3, M)) + 1j * rs.normal(size=(3, M))
+    eng.theta_sum.copy_(torch.as_tensor(th))
+    mixed.print_step(SingleComm(), 1, 5)
+    # the oracle's restatement of the same lines on the same accumulators
+    o = orc.OracleAFQMC.__new__(orc.OracleAFQMC)
+    o.nsteps, o.estimates, o.rows, o.one_rdm = 5, acc.copy(), [], False
+    o.print_step(5)
+    numpy.testing.assert_allclose(mixed.rows[0][1:10], o.rows[0][1:10], rtol=1e-14)
+    numpy.testing.assert_allclose(mixed.eshift, o.eshift_vec, rtol=1e-14)
+    gs_weight = acc[1] / 5
+    G = numpy.array([trial.psi[:, :2].conj().dot(th[:2]), trial.psi[:, 2:].conj().dot(th[2:])])
+    numpy.testing.assert_allclose(mixed.one_rdm[0], G.real / 5 / gs_weight, rtol=1e-13)
+    assert float(eng.estimates.abs().max()) == 0.0 and float(eng.theta_sum.abs().max()) == 0.0
+    with pytest.raises(NotImplementedError):
+        Mixed({'energy_eval_freq': 5, 'one_rdm': True}, system, True, None, _Qmc(), trial, complex,
+              engine=eng)
