@@ -148,30 +148,34 @@ def case_mixed_rdm():
          extra={'mixed_one_rdm': tr['mixed_one_rdm']})
 
 
-def case_stress(name, pop, walkers=None, scale_chol=6.0, dt=0.02):
+def case_stress(name, pop, walkers=None, scale_chol=6.0, dt=0.02, nwalkers=16, keep_xi=True):
     """Small case scaled so that the force-bias clip, the hybrid-energy bound,
-    the weight cap and comb/pair-branch events all fire."""
+    the weight cap and comb/pair-branch events all fire.  nwalkers=64 gives the multi-device
+    tests and the bench's N-rank self-check clones that cross several devices."""
     numpy.random.seed(11)
     h1e, chol, enuc, _ = generate_hamiltonian(8, (3, 3), cplx=False)
     hs = scale_chol * chol.reshape((-1, 64)).T.copy()
-    opts = options(16, dt, 5, 6, 21, stab=3, popc=1, walkers=walkers)
+    opts = options(nwalkers, dt, 5, 6, 21, stab=3, popc=1, walkers=walkers)
     a, tr = rh.run_reference_traced(h1e, hs, enuc, (3, 3), opts)
     meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array((3, 3)), dt=dt,
-                nwalkers=16, steps=5, blocks=6, seed=21, stab=3, popc=1,
+                nwalkers=nwalkers, steps=5, blocks=6, seed=21, stab=3, popc=1,
                 pop_control=pop, min_weight=(walkers or {}).get('min_weight', 0.1),
                 max_weight=(walkers or {}).get('max_weight', 4.0))
-    save(name, meta, tr, setup=rh.reference_setup_arrays(a))
+    save(name, meta, tr, setup=rh.reference_setup_arrays(a), keep_xi=keep_xi)
 
 
-def case_shape(name, M, na, N, W, steps, seed_h, stab):
-    """BASELINE c2/c3/c4 shapes at reduced walker count; inputs regenerate
-    from seeds, fields from the global legacy stream."""
-    h1e, hs, ecore = synthetic_cholesky_hamiltonian(M, N, seed_h)
-    opts = options(W, 0.005, steps, 1, 8, stab=stab, popc=1)
+def case_shape(name, M, na, N, W, steps, seed_h, stab, blocks=1, dt=0.005, scale=0.02, ramp=0.05):
+    """BASELINE c2..c5 shapes at reduced walker count; inputs regenerate from seeds, fields from
+    the global legacy stream.  The `*_shape` fixtures use the benchmark's benign Hamiltonian
+    (no branch fires); the `*_stress` ones scale the Cholesky vectors, the orbital-energy ramp
+    and the time step so that the force-bias clip, the hybrid-energy bound (armed from block 2
+    on, when eshift != 0), comb events and re-orthogonalisations all occur AT those shapes."""
+    h1e, hs, ecore = synthetic_cholesky_hamiltonian(M, N, seed_h, scale=scale, ramp=ramp)
+    opts = options(W, dt, steps, blocks, 8, stab=stab, popc=1)
     a, tr = rh.run_reference_traced(h1e, hs, ecore, (na, na), opts)
-    meta = dict(nbasis=M, nelec=numpy.array((na, na)), nchol=N, dt=0.005, nwalkers=W,
-                steps=steps, blocks=1, seed=8, stab=stab, popc=1, seed_h=seed_h,
-                h1e_checksum=h1e.sum(), hs_checksum=hs.sum())
+    meta = dict(nbasis=M, nelec=numpy.array((na, na)), nchol=N, dt=dt, nwalkers=W,
+                steps=steps, blocks=blocks, seed=8, stab=stab, popc=1, seed_h=seed_h,
+                scale=scale, ramp=ramp, h1e_checksum=h1e.sum(), hs_checksum=hs.sum())
     save(name, meta, tr, keep_xi=False, keep_phi=False)
 
 
@@ -224,6 +228,12 @@ if __name__ == '__main__':
         case_c1()
     if 'stress' in which:
         case_stress('stress_comb', 'comb')
+    if 'stress64' in which:
+        case_stress('stress_comb64', 'comb', nwalkers=64, keep_xi=False)
+        case_stress('stress_pair_branch64', 'pair_branch',
+                    walkers={'population_control': 'pair_branch',
+                             'min_weight': 0.9, 'max_weight': 1.1},
+                    scale_chol=3.0, dt=0.01, nwalkers=64, keep_xi=False)
     if 'pb' in which:
         case_stress('stress_pair_branch', 'pair_branch',
                     walkers={'population_control': 'pair_branch',
@@ -237,5 +247,13 @@ if __name__ == '__main__':
         case_shape('c3_shape', 60, 7, 300, 16, 6, 1003, 5)
     if 'c4s' in which:
         case_shape('c4_shape', 108, 21, 500, 16, 6, 1004, 5)
+    if 'c2st' in which:
+        case_shape('c2_stress', 24, 5, 120, 32, 10, 1002, 5, blocks=3, dt=0.02, scale=0.4, ramp=0.2)
+    if 'c3st' in which:
+        case_shape('c3_stress', 60, 7, 300, 16, 10, 1003, 5, blocks=2, dt=0.02, scale=0.35, ramp=0.2)
+    if 'c4st' in which:
+        case_shape('c4_stress', 108, 21, 500, 32, 10, 1004, 5, blocks=2, dt=0.02, scale=0.25, ramp=0.2)
+    if 'c5st' in which:
+        case_shape('c5_stress', 200, 40, 1000, 8, 3, 1005, 2, blocks=2, dt=0.02, scale=0.3, ramp=0.2)
     if 'c5s' in which:
         case_shape('c5_shape', 200, 40, 1000, 4, 3, 1005, 2)

@@ -1012,6 +1012,10 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   PXB_CUDA(h, cudaGetLastError());
   // (a) Theta of the current walkers (normally still valid from the previous step's
   //     closing Green's function / the estimator); ovlp_old is walker.ot
+  // the reference recomputes the overlap at the top of propagate_walker_phaseless
+  // (continuous.py:245); walker.ot stands in for it only while Theta is current -- after
+  // pxb_set_phi / a restart read the freshly computed overlap (A_OVLP_OLD) is used instead
+  const bool ot_stale = !h->theta_valid;
   if ((rc = ensure_theta(h, st))) return rc;
   // (c1) force bias GEMM X_s = R_s^T Theta_s (shared with the Coulomb term of the estimator)
   if ((rc = ensure_x(h, st))) return rc;
@@ -1062,6 +1066,7 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   wa.ot = h->field<double2>(PXB_F_OT);
   wa.ehyb = h->field<double2>(PXB_F_HYBRID_ENERGY);
   wa.ovlp_new = h->field<double2>(PXB_F_OVLP_NEW);
+  wa.ovlp_old = ot_stale ? h->ptr<double2>(A_OVLP_OLD) : h->field<double2>(PXB_F_OT);
   wa.cmfcfb = h->field<double2>(PXB_F_CMF_CFB);
   wa.active = active;
   wa.total_weight = h->field<double>(PXB_F_TOTAL_WEIGHT);
@@ -1220,7 +1225,8 @@ int pxb_comb_plan(pxb_handle h, const double* gw, int64_t wtot, double r, void* 
 int pxb_set_weights(pxb_handle h, double value, void* stream) {
   PXB_REQUIRE_READY(h);
   ++h->launches;
-  fill_kernel<<<(h->d.W + 255) / 256, 256, 0, S(stream)>>>(h->field<double>(PXB_F_WEIGHT), value, h->d.W);
+  fill_kernel<<<(h->d.W + 255) / 256, 256, 0, S(stream)>>>(h->field<double>(PXB_F_WEIGHT), value, h->d.W,
+                                                           h->field<long long>(PXB_F_COUNTERS) + 4);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -1353,7 +1359,8 @@ int pxb_pop_control_finish(pxb_handle h, void* stream) {
   StageTimer timer__(h, PXB_STAGE_POP_CONTROL, S(stream));
   ++h->launches;
   pop_finish_kernel<<<(d.W + 255) / 256, 256, 0, S(stream)>>>(
-      h->field<double>(PXB_F_WEIGHT), h->field<double>(PXB_F_UNSCALED_WEIGHT), 1.0, d.W);
+      h->field<double>(PXB_F_WEIGHT), h->field<double>(PXB_F_UNSCALED_WEIGHT), 1.0, d.W,
+      h->field<long long>(PXB_F_COUNTERS));
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }

@@ -344,6 +344,7 @@ struct WeightArgs {
   double2* ot;
   double2* ehyb;
   const double2* ovlp_new;
+  const double2* ovlp_old;  // walker.ot, or the overlap recomputed at the top of the step when ot was stale
   const double2* cmfcfb;
   const int* active;
   const double* total_weight;
@@ -374,7 +375,7 @@ __global__ void weight_kernel(WeightArgs a) {
   } else if (a.active[w]) {
     // ovlp_old == walker.ot: the overlap of the walker before this step (single_det.py:321 equals
     // the stored ot up to rounding; after a re-orthogonalisation ot was divided by detR)
-    const double2 oo = a.ot[w], on = a.ovlp_new[w];
+    const double2 oo = a.ovlp_old[w], on = a.ovlp_new[w];
     const cplx ratio = cdiv({on.x, on.y}, {oo.x, oo.y});
     const double2 cmf = a.cmfcfb[2 * w], cfb = a.cmfcfb[2 * w + 1];
     // cmath.log: principal branch
@@ -698,9 +699,12 @@ __global__ void __launch_bounds__(1024) pop_rescale_kernel(RescaleArgs a) {
   if (tid == 0) s_total = total;
   __syncthreads();
   total = s_total;
-  if (total < 1e-8) {
-    // the reference exits here (handler.py:236-241); we flag and leave weights untouched
-    if (tid == 0) a.counters[3] = -1;
+  if (total < 1e-8 || a.counters[4] != 0) {
+    // the reference exits here (handler.py:236-241); counters[4] is a STICKY flag that nothing else
+    // writes: the comb plan, the copies and the weight reset all become no-ops once it is set, and
+    // the driver raises when it polls it (Walkers.check_total_weight)
+    if (tid == 0) a.counters[4] = 1;
+    for (int i = tid; i < a.Wtot; i += 1024) a.gws[i] = 0.0;
     return;
   }
   const double scale = __ddiv_rn(total, (double)a.Wtot);
@@ -756,7 +760,7 @@ __global__ void __launch_bounds__(1024) comb_plan_kernel(CombArgs a) {
   __syncthreads();
   __threadfence_block();
   const double spacing = __ddiv_rn(s_total, (double)n);
-  if (!(spacing > 0.0)) {  // vanished population: flagged by pop_rescale_kernel, nothing to plan
+  if (!(spacing > 0.0) || a.counters[4] != 0) {  // vanished population (sticky flag): nothing to plan
     for (int i = tid; i < n; i += 1024) a.parent_ix[i] = 1;
     if (tid == 0) a.pairs[0] = 0;
     return;
@@ -989,8 +993,10 @@ __global__ void __launch_bounds__(256) pull_pairs_kernel(CopyArgs a, PeerArgs p,
 
 // after the barrier that follows pull_pairs_kernel: unscaled_weight = weight (handler.py:247-248,
 // copied clone -> kill by the comb), then every weight = value (handler.py:337-338)
-__global__ void pop_finish_kernel(double* weight, double* unscaled, double value, int n) {
+__global__ void pop_finish_kernel(double* weight, double* unscaled, double value, int n,
+                                  const long long* counters) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (counters[4] != 0) return;  // vanished population: the weights stay as they are
   if (i < n) {
     unscaled[i] = weight[i];
     weight[i] = value;
@@ -1058,8 +1064,10 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
   }
 }
 
-__global__ void fill_kernel(double* p, double v, int n) {
+// skip_flag (optional): nothing is written when *skip_flag != 0 (vanished population)
+__global__ void fill_kernel(double* p, double v, int n, const long long* skip_flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (skip_flag != nullptr && *skip_flag != 0) return;
   if (i < n) p[i] = v;
 }
 

@@ -72,7 +72,20 @@ class Continuous(object):
         self.BT_BP = self.propagator.BH1
         self.nstblz = qmc.nstblz
         self.ebound = (2.0 / self.dt) ** 0.5
-        self.rng = options.get('rng', 'host')  # 'host': numpy legacy stream (parity); 'philox': device
+        # Source of the auxiliary fields xi ~ N(0,1) (continuous.py:133):
+        #   'host'   the reference's global legacy numpy stream, drawn on the host in global walker
+        #            order (bit-identical fields: parity runs; every rank draws the whole block)
+        #   'philox' counter-based Philox4x32-10 + Box-Muller inside field_kernel, keyed by (seed,
+        #            step, global walker index, field): the production default for several devices --
+        #            no host work, no H2D traffic, results independent of the device count
+        # `field_source` (callable step -> pinned float64 host tensor [nwalkers, nfields]) overrides
+        # both: externally supplied fields (replaying a recorded walk, a host-side generator), copied
+        # to the device on a copy stream one step ahead (Engine.prefetch_xi).
+        self.rng = options.get('rng', 'host')
+        if self.rng not in ('host', 'philox'):
+            raise ValueError("propagator.rng must be 'host' or 'philox'")
+        self.field_source = None
+        self._xi_ahead = None
         self.rng_seed = 0
         self.verbose = verbose
         self._nfb_base = 0
@@ -95,7 +108,14 @@ class Continuous(object):
         device batch: propagate_walker_phaseless for every walker with
         |weight| > 1e-8, then the 10 % weight cap."""
         eng = self.engine
-        if self.rng == 'host':
+        if self.field_source is not None:
+            ahead = self._xi_ahead
+            xi = ahead[1] if (ahead is not None and ahead[0] == step) else \
+                eng.prefetch_xi(self.field_source(step))
+            eng.propagate(xi, eshift=eshift, step=step)
+            nxt = self.field_source(step + 1)
+            self._xi_ahead = (step + 1, eng.prefetch_xi(nxt)) if nxt is not None else None
+        elif self.rng == 'host':
             xi = psi.draw_fields(system.nfields, comm)
             eng.propagate(xi, eshift=eshift, step=step)
         else:

@@ -125,6 +125,7 @@ class AFQMC(object):
                            nbp=self.estimators.nbp)
         comm.warmup(self.engine.device)
         self.setup_timers()
+        self.eshift = 0
         self.sync_timers = bool(options.get('sync_timers', False))
         if verbose:
             self.estimators.estimators['mixed'].print_header()
@@ -147,38 +148,47 @@ class AFQMC(object):
                      self.propagators.free_projection)
         if verbose:
             mixed.print_step(comm, comm.size, 0, 1)
+        self.eshift = eshift
         for step in range(1, self.qmc.total_steps + 1):
-            start_step = self._tick()
-            if step % self.qmc.nstblz == 0:
-                start = self._tick()
-                self.psi.orthogonalise(self.trial, self.propagators.free_projection)
-                self.tortho += self._tick() - start
-            start = self._tick()
-            self.propagators.propagate_walkers(self.psi, self.system, self.trial, eshift, step,
-                                               comm=comm)
-            self.tprop += self._tick() - start
-            if step % self.qmc.npop_control == 0:
-                start = self._tick()
-                self.psi.pop_control(comm, overlap_energy=(
-                    mixed.eval_energy and step % mixed.energy_eval_freq == 0))
-                self.tpopc += self._tick() - start
-            start = self._tick()
-            self.estimators.update(self.system, self.qmc, self.trial, self.psi, step,
-                                   self.propagators.free_projection)
-            self.testim += self._tick() - start
-            self.estimators.print_step(comm, comm.size, step)
-            if self.psi.write_restart and step % self.psi.write_freq == 0:
-                self.psi.write_walkers(comm)
-            if step % self.qmc.nsteps == 0:
-                self.psi.check_total_weight()   # handler.py:236-241, polled once per block
-            if step < self.qmc.neqlb:
-                eshift = mixed.get_shift(self.propagators.hybrid)
-            else:
-                eshift += (mixed.get_shift() - eshift)
-            self.tstep += self._tick() - start_step
+            self.step(step, comm)
             if observer is not None:
                 observer(step, self)
         self.engine.synchronize()
+
+    def step(self, step, comm=None):
+        """One pass of the loop body of pauxy/qmc/afqmc.py:223-255 for the device batch (what
+        `run` iterates and what bench.py times): re-orthogonalisation every `stabilise_freq`
+        steps, propagation, population control, estimator update, block output + energy shift."""
+        comm = comm if comm is not None else self.comm
+        mixed = self.estimators.estimators['mixed']
+        start_step = self._tick()
+        if step % self.qmc.nstblz == 0:
+            start = self._tick()
+            self.psi.orthogonalise(self.trial, self.propagators.free_projection)
+            self.tortho += self._tick() - start
+        start = self._tick()
+        self.propagators.propagate_walkers(self.psi, self.system, self.trial, self.eshift, step,
+                                           comm=comm)
+        self.tprop += self._tick() - start
+        if step % self.qmc.npop_control == 0:
+            start = self._tick()
+            self.psi.pop_control(comm, overlap_energy=(
+                mixed.eval_energy and step % mixed.energy_eval_freq == 0))
+            self.tpopc += self._tick() - start
+        start = self._tick()
+        self.estimators.update(self.system, self.qmc, self.trial, self.psi, step,
+                               self.propagators.free_projection)
+        self.testim += self._tick() - start
+        self.estimators.print_step(comm, comm.size, step)
+        if self.psi.write_restart and step % self.psi.write_freq == 0:
+            self.psi.write_walkers(comm)
+        if step % self.qmc.nsteps == 0:
+            self.psi.check_total_weight()   # handler.py:236-241, polled once per block
+        if step < self.qmc.neqlb:
+            self.eshift = mixed.get_shift(self.propagators.hybrid)
+        else:
+            self.eshift += (mixed.get_shift() - self.eshift)
+        self.tstep += self._tick() - start_step
 
     def finalise(self, verbose=False):
         if self.root and verbose:

@@ -213,7 +213,7 @@ class Walkers(object):
         self._check_total_weight()
 
     def _check_total_weight(self):
-        if int(self.engine.counters[3].item()) < 0:
+        if int(self.engine.counters[4].item()) != 0:
             # the reference prints and sys.exit()s (handler.py:236-241)
             raise RuntimeError("# Warning: total walker weight < 1e-8. Something is seriously wrong.")
 
@@ -255,7 +255,7 @@ class Walkers(object):
         gw = comm.allgather_tensor(torch.abs(eng.weight))
         if self.peer_copy and eng.peers_attached:
             # clones are pulled out of the peers' arenas over NVLink: no host round trip
-            # (total weight < 1e-8 is flagged in counters[3], see check_total_weight)
+            # (total weight < 1e-8 raises the sticky flag counters[4], see check_total_weight)
             eng.pop_control_comb_peers(gw, r)
             comm.stream_barrier(eng.device)
             eng.pop_control_finish()
