@@ -254,6 +254,6 @@ if __name__ == '__main__':
     if 'c4st' in which:
         case_shape('c4_stress', 108, 21, 500, 32, 10, 1004, 5, blocks=2, dt=0.02, scale=0.25, ramp=0.2)
     if 'c5st' in which:
-        case_shape('c5_stress', 200, 40, 1000, 8, 3, 1005, 2, blocks=2, dt=0.02, scale=0.3, ramp=0.2)
+        case_shape('c5_stress', 200, 40, 1000, 8, 4, 1005, 3, blocks=2, dt=0.02, scale=0.35, ramp=0.2)
     if 'c5s' in which:
         case_shape('c5_shape', 200, 40, 1000, 4, 3, 1005, 2)

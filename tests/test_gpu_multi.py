@@ -1,5 +1,7 @@
-"""Two-device parity: an N-device run must reproduce the ONE-rank reference run
- -- selection bit-exact, values <= 1e-10.  Needs 2 GPUs."""
+"""Multi-device parity: an N-device run must reproduce the ONE-rank reference run
+ -- selection bit-exact, values <= 1e-10.  Needs 2 GPUs (4 / 8 for the
+wider cases; the driver's test box has one, so the kept evidence is profiles/r02/
+pytest_gpu_multi_n*.log and the `parity_nranks` block of every multi-GPU bench line)."""
 import os
 
 import numpy
@@ -57,16 +59,17 @@ def _worker(rank, world, port, name, pop, peer, q):
     dist.destroy_process_group()
 
 
-def _run_two(name, pop, peer=True):
+def _run_n(name, pop, peer=True, world=2):
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs")
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs %d GPUs" % world)
     import torch.multiprocessing as mp
     ctx = mp.get_context('spawn')
     q = ctx.Queue()
-    _run_two.calls = getattr(_run_two, 'calls', 0) + 1
-    port = 29600 + (os.getpid() * 7 + _run_two.calls) % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, name, pop, peer, q)) for r in range(2)]
+    _run_n.calls = getattr(_run_n, 'calls', 0) + 1
+    port = 29600 + (os.getpid() * 7 + _run_n.calls) % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, pop, peer, q))
+             for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=600) for _ in procs], key=lambda x: x[0])
@@ -75,29 +78,35 @@ def _run_two(name, pop, peer=True):
     return res
 
 
-@pytest.mark.parametrize('name,pop,peer', [('stress_comb', 'comb', True), ('c1', 'comb', True),
-                                           ('stress_comb', 'comb', False),
-                                           ('bp_stress', 'comb', True), ('bp_stress', 'comb', False),
-                                           ('stress_pair_branch', 'pair_branch', False)])
-def test_two_devices_reproduce_one_rank_reference(name, pop, peer):
+@pytest.mark.parametrize('world,name,pop,peer', [
+    (2, 'stress_comb', 'comb', True), (2, 'c1', 'comb', True), (2, 'stress_comb', 'comb', False),
+    (2, 'bp_stress', 'comb', True), (2, 'bp_stress', 'comb', False),
+    (2, 'stress_pair_branch', 'pair_branch', False),
+    # 64 walkers: clones cross several devices (stress_comb64: 1153 comb events in 30 steps)
+    (2, 'stress_comb64', 'comb', True), (2, 'stress_pair_branch64', 'pair_branch', False),
+    (4, 'stress_comb64', 'comb', True), (4, 'stress_comb64', 'comb', False),
+    (4, 'stress_pair_branch64', 'pair_branch', False), (4, 'bp_stress', 'comb', True),
+    (8, 'stress_comb64', 'comb', True), (8, 'stress_comb64', 'comb', False),
+    (8, 'stress_pair_branch64', 'pair_branch', False)])
+def test_devices_reproduce_one_rank_reference(world, name, pop, peer):
     """peer=True: clones are pulled out of the other device's arena over NVLink
     (pxb_pop_control_comb_peers); peer=False: packed NCCL send/recv planned on the host."""
-    res = _run_two(name, pop, peer)
+    res = _run_n(name, pop, peer, world)
     if peer:
-        assert res[0][3] and res[1][3], "CUDA IPC peer mapping of the arenas failed"
+        assert all(r[3] for r in res), "CUDA IPC peer mapping of the arenas failed"
     # bp_stress is a deliberately stiff walk (Cholesky vectors x 6, dt = 0.02, 12 orbitals): it
     # amplifies rounding differences to ~4e-9 within its 20 steps on one device as well
     tol = 1e-8 if name == 'bp_stress' else 1e-10
-    unscaled = numpy.concatenate([res[0][1]['unscaled_weight'], res[1][1]['unscaled_weight']], axis=1)
+    unscaled = numpy.concatenate([r[1]['unscaled_weight'] for r in res], axis=1)
     numpy.testing.assert_allclose(unscaled, numpy.load(os.path.join(GOLD, name + '.npz'))['unscaled_weight'],
                                   rtol=tol, atol=1e-13)
     g = dict(numpy.load(os.path.join(GOLD, name + '.npz')))
-    weight = numpy.concatenate([res[0][1]['weight'], res[1][1]['weight']], axis=1)
-    ot = numpy.concatenate([res[0][1]['ot'], res[1][1]['ot']], axis=1)
-    eloc = numpy.concatenate([res[0][1]['eloc'], res[1][1]['eloc']], axis=1)
+    weight = numpy.concatenate([r[1]['weight'] for r in res], axis=1)
+    ot = numpy.concatenate([r[1]['ot'] for r in res], axis=1)
+    eloc = numpy.concatenate([r[1]['eloc'] for r in res], axis=1)
     if pop == 'comb':
-        assert numpy.array_equal(res[0][1]['parent_ix'], g['parent_ix'])
-        assert numpy.array_equal(res[1][1]['parent_ix'], g['parent_ix'])
+        for r in res:      # every rank computed the same, bit-exact plan
+            assert numpy.array_equal(r[1]['parent_ix'], g['parent_ix'])
     numpy.testing.assert_allclose(weight, g['weight'], rtol=tol, atol=1e-13)
     numpy.testing.assert_allclose(ot, g['ot'], rtol=tol)
     numpy.testing.assert_allclose(eloc, g['eloc'], rtol=tol, atol=tol)

@@ -216,3 +216,28 @@ def test_theta_travels_with_walkers():
     assert (eng.parent_ix.cpu().numpy()[:W] != 1).any()
     tha, thb, _ = orc.greens_function(ham, phi)
     assert relerr(e_reuse, orc.local_energy(ham, tha, thb)) < 1e-11
+
+
+@pytest.mark.parametrize('overlap', [True, False])
+def test_vanished_population_is_flagged_not_resurrected(golden, overlap):
+    """walkers/handler.py:236-241: the reference exits when the total weight drops below 1e-8.
+    The device paths raise a STICKY flag instead; the comb plan, the copies and the weight reset
+    become no-ops, so a dead population is never silently cloned back to weight 1."""
+    from pauxy_b200.systems import Generic
+    from pauxy_b200.qmc import AFQMC
+    g = golden('stress_comb')
+    nelec = tuple(int(x) for x in g['nelec'])
+    system = Generic(nelec=nelec, h1e=numpy.array([g['h1e'], g['h1e']]), chol=g['hs_pot'],
+                     ecore=float(g['ecore']))
+    opts = {'qmc': {'timestep': 0.02, 'steps': 5, 'blocks': 2, 'rng_seed': 3, 'num_walkers': 16},
+            'walkers': {'overlap_energy': overlap},
+            'estimates': {'mixed': {'energy_eval_freq': 1, 'verbose': False}}}
+    a = AFQMC(options=opts, system=system, verbose=0)
+    a.step(1)
+    a.psi.check_total_weight()            # healthy population: no complaint
+    a.engine.weight.zero_()
+    for step in (2, 3):                   # the flag survives later (healthy-looking) plans
+        a.psi.pop_control(a.comm, overlap_energy=overlap)
+        assert float(a.engine.weight.abs().max().item()) == 0.0
+    with pytest.raises(RuntimeError, match="total walker weight"):
+        a.psi.check_total_weight()
