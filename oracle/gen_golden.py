@@ -250,10 +250,10 @@ if __name__ == '__main__':
     if 'c2st' in which:
         case_shape('c2_stress', 24, 5, 120, 32, 10, 1002, 5, blocks=3, dt=0.02, scale=0.4, ramp=0.2)
     if 'c3st' in which:
-        case_shape('c3_stress', 60, 7, 300, 16, 10, 1003, 5, blocks=2, dt=0.02, scale=0.35, ramp=0.2)
+        case_shape('c3_stress', 60, 7, 300, 16, 10, 1003, 5, blocks=2, dt=0.02, scale=0.32, ramp=0.2)
     if 'c4st' in which:
         case_shape('c4_stress', 108, 21, 500, 32, 10, 1004, 5, blocks=2, dt=0.02, scale=0.25, ramp=0.2)
     if 'c5st' in which:
-        case_shape('c5_stress', 200, 40, 1000, 8, 4, 1005, 3, blocks=2, dt=0.02, scale=0.35, ramp=0.2)
+        case_shape('c5_stress', 200, 40, 1000, 8, 4, 1005, 3, blocks=2, dt=0.02, scale=0.32, ramp=0.2)
     if 'c5s' in which:
         case_shape('c5_shape', 200, 40, 1000, 4, 3, 1005, 2)
