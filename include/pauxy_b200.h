@@ -32,7 +32,7 @@ extern "C" {
 #define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
 #define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
 
-#define PXB_ABI_VERSION 7
+#define PXB_ABI_VERSION 8
 
 typedef struct pxb_context* pxb_handle;
 
@@ -86,7 +86,7 @@ enum pxb_field_id {
   PXB_F_DETR = 5,            /* f64  [W]    walker.detR                */
   PXB_F_LOG_DETR = 6,        /* f64  [W]    walker.log_detR            */
   PXB_F_ESTIMATES = 7,       /* c128 [10]   Mixed.estimates accumulators (mixed.py:460-469) */
-  PXB_F_COUNTERS = 8,        /* i64  [8]    nfb_trig, nhe_trig, n_inactive, n_comb_moves (-1: total weight < 1e-8) */
+  PXB_F_COUNTERS = 8,        /* i64  [8]    nfb_trig, nhe_trig, n_inactive, n_comb_moves, vanished (sticky: total weight < 1e-8 seen, handler.py:236-241) */
   PXB_F_PARENT_IX = 9,       /* i32  [Wtot] comb parent_ix of the last pop-control */
   PXB_F_XBAR = 10,           /* c128 [W,N]  force bias after clipping (debug/parity) */
   PXB_F_XSHIFTED = 11,       /* c128 [W,N]  x = xi - xbar (natural layout copy, debug/parity) */
@@ -183,6 +183,23 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed,
 /* Walkers.orthogonalise -> SingleDetWalker.reortho (walkers/handler.py:166-181,
  * walkers/single_det.py:215-255), phaseless branch. */
 int pxb_orthogonalise(pxb_handle h, void* stream);
+
+/* One whole pass of the driver loop body (qmc/afqmc.py:223-255) on ONE device as a single call:
+ * [pxb_orthogonalise] -> pxb_propagate -> [comb population control, its plan overlapped with
+ * pxb_local_energy] -> pxb_accumulate.  Same results as the separate calls; the launch sequence is
+ * captured as a CUDA graph the second time a (flags, dev_xi, state) variant is seen and replayed
+ * afterwards (small problems are bound by launch latency).  The per-step scalars travel through a
+ * device-side parameter block, not through kernel arguments.  comb_r: the comb's uniform draw
+ * (walkers/handler.py:275).  Not available with back propagation (nbp > 0) or several devices. */
+enum pxb_step_flags {
+  PXB_STEP_ORTHO = 1,  /* re-orthogonalise first (walkers/handler.py:166-181)            */
+  PXB_STEP_POP = 2,    /* comb population control after the propagation (handler.py:225-338) */
+  PXB_STEP_ENERGY = 4  /* local energy of every walker, accumulated with the other sums  */
+};
+int pxb_step(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t walker_offset,
+             double eshift, int64_t step, double comb_r, int flags, void* stream);
+/* enable (1) / disable (0) / query (-1) graph replay in pxb_step; *replays = graph launches so far */
+int pxb_step_graphs(pxb_handle h, int enable, long long* replays);
 
 /* greens_function + local_energy_generic_cholesky_opt for every walker
  * (walkers/single_det.py:295-321, estimators/generic.py:156-221) -> ELOC. */

@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libpauxy_b200.so')
 
 PXB_OK = 0
-ABI_VERSION = 7
+ABI_VERSION = 8
 EXCHANGE_MODES = {'auto': 0, 'cholesky': 1, 'eri': 2}
 ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_ERR_UNSUPPORTED'}
 
@@ -19,6 +19,7 @@ F_WEIGHT, F_UNSCALED_WEIGHT, F_OT, F_HYBRID_ENERGY, F_ELOC, F_DETR, F_LOG_DETR, 
     F_ESTIMATES, F_COUNTERS, F_PARENT_IX, F_XBAR, F_XSHIFTED, F_CMF_CFB, F_OVLP_NEW, \
     F_TOTAL_WEIGHT, F_PAIRS, F_PHASE, F_BP_RDM, F_BP_DENOM, F_THETA_SUM, F_COUNT = range(21)
 FLAG_FREE_PROJECTION, FLAG_NO_FORCE_BIAS = 1, 2
+STEP_ORTHO, STEP_POP, STEP_ENERGY = 1, 2, 4
 
 
 STAGES = ['greens', 'xgemm', 'field', 'vhs', 'one_body', 'taylor', 'weight', 'exchange', 'energy',
@@ -64,6 +65,9 @@ _PROTOS = {
     'pxb_propagate': (ctypes.c_int, [_vp, _vp, ctypes.c_uint64, ctypes.c_int64, ctypes.c_double,
                                      ctypes.c_int64, _vp]),
     'pxb_orthogonalise': (ctypes.c_int, [_vp, _vp]),
+    'pxb_step': (ctypes.c_int, [_vp, _vp, ctypes.c_uint64, ctypes.c_int64, ctypes.c_double,
+                                ctypes.c_int64, ctypes.c_double, ctypes.c_int, _vp]),
+    'pxb_step_graphs': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_longlong)]),
     'pxb_local_energy': (ctypes.c_int, [_vp, _vp]),
     'pxb_accumulate': (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     'pxb_zero_estimates': (ctypes.c_int, [_vp, _vp]),

@@ -32,7 +32,7 @@ enum ArenaId {
   A_LF, A_RF, A_BF, A_PSIT, A_H1ROT, A_VBAR,
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
   A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_OB, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
-  A_FC, A_PHI_OLD, A_PHI_BP, A_PHI_BP2, A_THETA_BP, A_BP_PART, A_PSI_NAT, A_INIT_NAT, A_BFT,
+  A_FC, A_PHI_OLD, A_PHI_BP, A_PHI_BP2, A_THETA_BP, A_BP_PART, A_PSI_NAT, A_INIT_NAT, A_BFT, A_STEP_PARAMS,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -54,7 +54,6 @@ struct pxb_context {
   // Theta / overlap / e1b (A_THETA, A_E1B) correspond to the current walkers; X to the current Theta
   bool theta_valid = false, x_valid = false;
   bool eloc_valid = false;  // ELOC holds the local energies of the current walkers (travels with them)
-  bool gemm_tma = true;  // TMA-fed persistent GEMM (PXB_GEMM=direct selects the L1/L2-streaming one)
   // optional per-stage timing with CUDA events on the launch stream (pxb_profile / pxb_stage_times)
   bool prof = false;
   struct Pending { int stage; cudaEvent_t a, b; };
@@ -79,6 +78,23 @@ struct pxb_context {
   int peer_rank = -1, peer_n = 0;
   unsigned char* peer_base[PXB_MAX_PEERS] = {nullptr};
   void* peer_map[PXB_MAX_PEERS] = {nullptr};  // what cudaIpcOpenMemHandle returned (to close)
+  // fused driver step (pxb_step): the launch sequence of one step, captured as a CUDA graph the
+  // second time a variant is seen and replayed afterwards; the scalars of the step are written to
+  // A_STEP_PARAMS by one setter launch in front of it
+  bool in_step = false;  // scalars already set by pxb_step: the entry points it calls leave them alone
+  bool graphs_enabled = true;
+  cudaStream_t side = nullptr;  // the comb plan runs here beside the local energy
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  struct StepGraph {
+    unsigned long long key;
+    const double* xi;
+    int seen;               // direct runs so far (the first one warms module loading / attributes)
+    cudaGraphExec_t exec;   // nullptr until captured
+    long long kernels;      // kernel launches one replay stands for
+    bool theta_valid, x_valid, eloc_valid;  // state after the sequence
+  };
+  std::vector<StepGraph> graphs;
+  long long graph_replays = 0;
   std::string err;
 
   template <class T>
@@ -311,10 +327,7 @@ int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
     g.KS = ns * d.KC;
     ++h->launches;
     // 16 x 8 tile blocks: 4 * WG/8 work units keep the 148 persistent CTAs balanced (XG is only ~63)
-    if (h->gemm_tma)
-      PXB_CUDA(h, (launch_gemm_tma<4, 4, 4, 2>(g, epi, 1, persist_sms(h), st)));
-    else
-      PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
+    PXB_CUDA(h, (launch_gemm_tma<4, 4, 4, 2>(g, epi, 1, persist_sms(h), st)));
   }
   return PXB_OK;
 }
@@ -335,10 +348,7 @@ int run_vhs_gemm(pxb_handle h, cudaStream_t st) {
   EpiVHS epi{h->ptr<double>(A_VF), d.KC, d.MT, d.sqrt_dt, vf_walker(d),
              h->vhs_sym ? h->ptr<int>(A_RTMAP) : nullptr};
   ++h->launches;
-  if (h->gemm_tma)
-    PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
-  else
-    PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
+  PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
   return PXB_OK;
 }
 
@@ -362,15 +372,9 @@ int run_one_body(pxb_handle h, const double* in, double* out, const int* active,
     EpiOF epi{out, active, d.ne, d.KC, ioff, ns};
     ++h->launches;
     if (d.MT % 7 == 0) {
-      if (h->gemm_tma)
-        PXB_CUDA(h, (launch_gemm_tma<7, 4, 2, 4>(g, epi, 1, h->sm_count, st)));
-      else
-        PXB_CUDA(h, (launch_gemm<7, 4, 2, 4>(g, epi, 1, st)));
+      PXB_CUDA(h, (launch_gemm_tma<7, 4, 2, 4>(g, epi, 1, h->sm_count, st)));
     } else {
-      if (h->gemm_tma)
-        PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
-      else
-        PXB_CUDA(h, (launch_gemm<4, 8, 4, 2>(g, epi, 1, st)));
+      PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
     }
   }
   return PXB_OK;
@@ -415,16 +419,20 @@ int run_taylor2(pxb_handle h, double* phi, const int* active, int ochunk, int nc
   a.nchunks = nchunks;
   a.NT = NT;
   a.dbg = 0;
+#ifdef PXB_EXPERIMENTS
   {
     const char* e = getenv("PXB_TAYLOR_DBG");
     if (e) a.dbg = atoi(e);
   }
+#endif
   // 4 column groups (16 consumer warps, 112 registers) unless the m-groups are too tall for that budget
   int NG = (NT >= 4 && (d.MT + 3) / 4 <= 4) ? 4 : 2;
+#ifdef PXB_EXPERIMENTS
   {
     const char* e = getenv("PXB_TAYLOR_GROUPS");
     if (e && atoi(e) == 2) NG = 2;
   }
+#endif
   // 4 m-groups and NG column groups, sizes differing by at most one, larger ones first
   const int base = d.MT / 4, rem = d.MT % 4;
   int msize[4];
@@ -457,10 +465,12 @@ int run_taylor2(pxb_handle h, double* phi, const int* active, int ochunk, int nc
   const size_t budget = (size_t)h->max_smem_optin;
   a.nbuf = 0;
   int nbuf_max = 2;
+#ifdef PXB_EXPERIMENTS
   {
     const char* e = getenv("PXB_TAYLOR_NBUF");
     if (e && atoi(e) == 1) nbuf_max = 1;
   }
+#endif
   for (int nbuf = nbuf_max; nbuf >= 1 && a.nbuf == 0; --nbuf)
     for (int nstage = 12; nstage >= 3; --nstage)
       if (taylor2_smem_bytes(d, NT, nbuf, nstage) <= budget) {
@@ -604,6 +614,13 @@ int ensure_x(pxb_handle h, cudaStream_t st) {
   return PXB_OK;
 }
 
+int set_step_params(pxb_handle h, const StepParams& v, int mask, cudaStream_t st) {
+  ++h->launches;
+  set_step_params_kernel<<<1, 1, 0, st>>>(h->ptr<StepParams>(A_STEP_PARAMS), v, mask);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
 }  // namespace
 
 // =============================================================================
@@ -664,9 +681,8 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   pxb_context* h = new (std::nothrow) pxb_context();
   if (!h) return PXB_ERR_ARG;
   h->cfg = *cfg;
+#ifdef PXB_EXPERIMENTS  // kernel-variant switches of development builds only (not in the product library)
   {
-    const char* g = getenv("PXB_GEMM");
-    if (g && strcmp(g, "direct") == 0) h->gemm_tma = false;
     const char* gr = getenv("PXB_GREENS");
     if (gr && strcmp(gr, "fused") == 0) h->greens_split = false;
     const char* v = getenv("PXB_VHS");
@@ -674,6 +690,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
     const char* t = getenv("PXB_TAYLOR");
     if (t && strcmp(t, "direct") == 0) h->taylor_tma = false;
   }
+#endif
   Dims& d = h->d;
   d.M = cfg->nbasis;
   d.na = cfg->nup;
@@ -793,6 +810,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_BFT, bp ? bf_size(d) * 8 : 0);
   add(A_PSI_NAT, (size_t)d.M * d.ne * 16);
   add(A_INIT_NAT, (size_t)d.M * d.ne * 16);
+  add(A_STEP_PARAMS, 256);
   add(A_FIELD0 + PXB_F_BP_RDM, bp ? (size_t)2 * d.M * d.M * 16 : 0);
   add(A_FIELD0 + PXB_F_BP_DENOM, 16);
   add(A_FIELD0 + PXB_F_THETA_SUM, (size_t)d.ne * d.M * 16);
@@ -810,6 +828,11 @@ int pxb_destroy(pxb_handle h) {
     for (auto e : h->evpool) cudaEventDestroy(e);
     for (int r = 0; r < PXB_MAX_PEERS; ++r)
       if (h->peer_map[r]) cudaIpcCloseMemHandle(h->peer_map[r]);
+    for (auto& g : h->graphs)
+      if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->side) cudaStreamDestroy(h->side);
   }
   delete h;
   return PXB_OK;
@@ -1007,6 +1030,10 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   int* active = h->ptr<int>(A_ACTIVE);
   long long* counters = h->field<long long>(PXB_F_COUNTERS);
   int rc;
+  if (!h->in_step) {
+    StepParams sp{rng_seed, (unsigned long long)step, walker_offset, eshift, 0.0};
+    if ((rc = set_step_params(h, sp, 1, st))) return rc;
+  }
   ++h->launches;
   active_kernel<<<(d.Wp + 255) / 256, 256, 0, st>>>(h->field<double>(PXB_F_WEIGHT), active, counters, d);
   PXB_CUDA(h, cudaGetLastError());
@@ -1030,9 +1057,7 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   f.cmfcfb = h->field<double2>(PXB_F_CMF_CFB);
   f.counters = counters;
   f.d = d;
-  f.seed = rng_seed;
-  f.step = (uint64_t)step;
-  f.walker_offset = walker_offset;
+  f.sp = h->ptr<StepParams>(A_STEP_PARAMS);
   {
     StageTimer timer__(h, PXB_STAGE_FIELD, st);
     ++h->launches;
@@ -1072,8 +1097,7 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   wa.total_weight = h->field<double>(PXB_F_TOTAL_WEIGHT);
   wa.counters = counters;
   wa.d = d;
-  wa.eshift = eshift;
-  wa.step = step;
+  wa.sp = h->ptr<StepParams>(A_STEP_PARAMS);
   {
     StageTimer timer__(h, PXB_STAGE_WEIGHT, st);
     ++h->launches;
@@ -1215,7 +1239,12 @@ int pxb_comb_plan(pxb_handle h, const double* gw, int64_t wtot, double r, void* 
   a.pairs = h->field<int>(PXB_F_PAIRS);
   a.counters = h->field<long long>(PXB_F_COUNTERS);
   a.Wtot = (int)wtot;
-  a.r = r;
+  a.sp = h->ptr<StepParams>(A_STEP_PARAMS);
+  if (!h->in_step) {
+    StepParams sp{0, 0, 0, 0.0, r};
+    int rc = set_step_params(h, sp, 2, S(stream));
+    if (rc) return rc;
+  }
   ++h->launches;
   comb_plan_kernel<<<1, 1024, 0, S(stream)>>>(a);
   PXB_CUDA(h, cudaGetLastError());
@@ -1422,6 +1451,126 @@ int pxb_comb_plan_host(const double* weights, int64_t n, double r, int32_t* pare
       if (iw >= n) return PXB_ERR_ARG;  // the reference raises IndexError here
     }
   }
+  return PXB_OK;
+}
+
+// ---- fused driver step ---------------------------------------------------------
+// One pass of the loop body of qmc/afqmc.py:223-255 on ONE device as a single call:
+//   [pxb_orthogonalise]  pxb_propagate  [comb: plan on a side stream || pxb_local_energy, then the
+//   copies and the weight reset]  pxb_accumulate
+// The sequence only depends on `flags` and on the field pointer, so it is captured as a CUDA graph
+// the second time a variant is seen and replayed from then on (c1/c2-sized problems are bound by
+// launch latency: ~24 launches of a few microseconds each).
+namespace {
+int step_sequence(pxb_handle h, const double* dev_xi, int flags, cudaStream_t st) {
+  int rc;
+  void* vst = reinterpret_cast<void*>(st);
+  if ((flags & PXB_STEP_ORTHO) && (rc = pxb_orthogonalise(h, vst))) return rc;
+  if ((rc = pxb_propagate(h, dev_xi, 0, 0, 0.0, 0, vst))) return rc;
+  const bool energy = (flags & PXB_STEP_ENERGY) != 0;
+  if (flags & PXB_STEP_POP) {
+    if (energy) {
+      // the plan needs only the weights: it runs beside the energy kernels
+      PXB_CUDA(h, cudaEventRecord(h->ev_fork, st));
+      PXB_CUDA(h, cudaStreamWaitEvent(h->side, h->ev_fork, 0));
+      if ((rc = pxb_pop_plan(h, nullptr, 0, 0.0, reinterpret_cast<void*>(h->side)))) return rc;
+      if ((rc = pxb_local_energy(h, vst))) return rc;
+      PXB_CUDA(h, cudaEventRecord(h->ev_join, h->side));
+      PXB_CUDA(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    } else {
+      if ((rc = pxb_pop_plan(h, nullptr, 0, 0.0, vst))) return rc;
+    }
+    if ((rc = pxb_pop_pull(h, vst))) return rc;
+    if ((rc = pxb_pop_control_finish(h, vst))) return rc;
+  } else if (energy) {
+    if ((rc = pxb_local_energy(h, vst))) return rc;
+  }
+  return pxb_accumulate(h, energy ? 1 : 0, vst);
+}
+}  // namespace
+
+int pxb_step(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t walker_offset, double eshift,
+             int64_t step, double comb_r, int flags, void* stream) {
+  PXB_REQUIRE_READY(h);
+  const Dims& d = h->d;
+  if (d.Wtot != d.W) return fail(h, PXB_ERR_ARG, "pxb_step is the single-device path");
+  if (h->nbp > 0) return fail(h, PXB_ERR_UNSUPPORTED, "pxb_step: not with back propagation (field history grows)");
+  if ((flags & PXB_STEP_POP) && d.W == 1) flags &= ~PXB_STEP_POP;  // handler.py:226-227
+  cudaStream_t st = S(stream);
+  if (!h->side) {
+    PXB_CUDA(h, cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+    PXB_CUDA(h, cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    PXB_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  }
+  int rc;
+  StepParams sp{rng_seed, (unsigned long long)step, walker_offset, eshift, comb_r};
+  if ((rc = set_step_params(h, sp, 3, st))) return rc;
+  // a replay is only valid from the state the variant was captured in
+  const unsigned long long key = (unsigned long long)(flags & 0xff) | (h->theta_valid ? 0x100ull : 0) |
+                                 (h->x_valid ? 0x200ull : 0) | (h->eloc_valid ? 0x400ull : 0) |
+                                 ((unsigned long long)h->reserved_sms << 16);
+  pxb_context::StepGraph* g = nullptr;
+  if (h->graphs_enabled && !h->prof) {
+    for (auto& c : h->graphs)
+      if (c.key == key && c.xi == dev_xi) g = &c;
+    if (!g) {
+      if (h->graphs.size() >= 16) h->graphs_enabled = false;  // something varies every step: stop caching
+      else {
+        h->graphs.push_back({key, dev_xi, 0, nullptr, 0, false, false, false});
+        g = &h->graphs.back();
+      }
+    }
+  }
+  if (g && g->exec) {
+    PXB_CUDA(h, cudaGraphLaunch(g->exec, st));
+    h->launches += g->kernels;
+    ++h->graph_replays;
+    h->theta_valid = g->theta_valid;
+    h->x_valid = g->x_valid;
+    h->eloc_valid = g->eloc_valid;
+    return PXB_OK;
+  }
+  h->in_step = true;
+  if (g && g->seen >= 1) {
+    const long long l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    PXB_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    rc = step_sequence(h, dev_xi, flags, st);
+    cudaError_t ce = cudaStreamEndCapture(st, &graph);
+    h->in_step = false;
+    if (rc == PXB_OK && ce == cudaSuccess && graph != nullptr &&
+        cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
+      g->kernels = h->launches - l0;
+      g->theta_valid = h->theta_valid;
+      g->x_valid = h->x_valid;
+      g->eloc_valid = h->eloc_valid;
+      cudaGraphDestroy(graph);
+      PXB_CUDA(h, cudaGraphLaunch(g->exec, st));
+      ++h->graph_replays;
+      return PXB_OK;
+    }
+    // capture failed: nothing was executed; drop graphs for this handle and run the step directly
+    if (graph) cudaGraphDestroy(graph);
+    cudaGetLastError();
+    g->exec = nullptr;
+    h->graphs_enabled = false;
+    h->launches = l0;
+    if (rc != PXB_OK && rc != PXB_ERR_CUDA) return rc;
+    h->theta_valid = (key & 0x100ull) != 0;
+    h->x_valid = (key & 0x200ull) != 0;
+    h->eloc_valid = (key & 0x400ull) != 0;
+    h->in_step = true;
+  }
+  rc = step_sequence(h, dev_xi, flags, st);
+  h->in_step = false;
+  if (g) ++g->seen;
+  return rc;
+}
+
+int pxb_step_graphs(pxb_handle h, int enable, long long* replays) {
+  if (!h) return PXB_ERR_ARG;
+  if (enable >= 0) h->graphs_enabled = enable != 0;
+  if (replays) *replays = h->graph_replays;
   return PXB_OK;
 }
 

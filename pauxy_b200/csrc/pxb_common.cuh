@@ -118,6 +118,22 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
       "r"(parity)
       : "memory");
 }
+// Consumer side of a TMA ring: a warp hands a stage back to the producer after its last read of it.
+// Product form: the warp's reads are ordered before lane 0's (release) arrive by __syncwarp().
+// -DPXB_RACECHECK_STRICT (a checker build, tools/gpu.sh sanitize): every lane arrives itself, which
+// is what compute-sanitizer's racecheck can follow (it does not carry the __syncwarp ordering over
+// to another lane's mbarrier arrive); used to show that the hazards it reports are of that kind.
+#ifdef PXB_RACECHECK_STRICT
+constexpr unsigned kReleaseArrivals = 32;
+__device__ __forceinline__ void ring_release(uint64_t* bar, int) { mbar_arrive(bar); }
+#else
+constexpr unsigned kReleaseArrivals = 1;
+__device__ __forceinline__ void ring_release(uint64_t* bar, int lane) {
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+#endif
+
 // 1-D bulk copy global -> shared, completion signalled on an mbarrier.
 // bytes must be a multiple of 16; both addresses 16-byte aligned.
 __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_src, unsigned bytes,

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
 #pragma unroll
     for (int s = 0; s < GT_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NCW);
+      mbar_init(&empty[s], NCW * kReleaseArrivals);
     }
     fence_barrier_init();
   }
@@ -194,8 +194,7 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
             for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      ring_release(&empty[s], lane);
     }
     // quadratic-form epilogue: lane (g,t) of tile (i,j) holds Y[a = 8(mt0+i)+g] of walker 4(nt0+j)+t
     // the diagonal block counts once, everything to its right twice (K symmetric): KF stores the

@@ -100,84 +100,6 @@ struct EpiOF {  // out OF buffer; n-tile nt = wg*nInner + il, orbital i = ioff +
   }
 };
 
-template <int WM, int WN, int CWM, int CWN, class Epi>
-__global__ void __launch_bounds__(CWM* CWN * 32)
-    gemm_frag_kernel(GemmArgs a, Epi epi) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wm = warp % CWM, wn = warp / CWM;
-  const int z = blockIdx.z;
-  const int mt0 = (blockIdx.x * CWM + wm) * WM;
-  const int nt0 = (blockIdx.y * CWN + wn) * WN;
-  if (mt0 >= a.MTiles || nt0 >= a.NTiles) return;
-
-  const double* Ap[WM];
-  const double* Bp[WN];
-  const int boff = b_lane_offset(lane);
-#pragma unroll
-  for (int i = 0; i < WM; ++i) {
-    int mt = min(mt0 + i, a.MTiles - 1);
-    Ap[i] = a.A + (size_t)z * a.strideAz + (size_t)mt * a.KS * 32 + lane;
-  }
-#pragma unroll
-  for (int j = 0; j < WN; ++j) {
-    int nt = min(nt0 + j, a.NTiles - 1);
-    Bp[j] = a.B + (size_t)z * a.strideBz + (size_t)(nt / a.ntInner) * a.strideBO +
-            (size_t)(nt % a.ntInner) * a.strideBI + boff;
-  }
-
-  double acc[WM][WN][2];
-#pragma unroll
-  for (int i = 0; i < WM; ++i)
-#pragma unroll
-    for (int j = 0; j < WN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-  double af[WM], bf[WN], an[WM], bn[WN];
-#pragma unroll
-  for (int i = 0; i < WM; ++i) af[i] = ldg_nc(Ap[i]);
-#pragma unroll
-  for (int j = 0; j < WN; ++j) bf[j] = ldg_nc(Bp[j]);
-
-  for (int ks = 0; ks < a.KS; ++ks) {
-    const int kn = (ks + 1 < a.KS) ? ks + 1 : ks;
-#pragma unroll
-    for (int i = 0; i < WM; ++i) an[i] = ldg_nc(Ap[i] + (size_t)kn * 32);
-#pragma unroll
-    for (int j = 0; j < WN; ++j) bn[j] = ldg_nc(Bp[j] + (size_t)kn * 32);
-#pragma unroll
-    for (int i = 0; i < WM; ++i)
-#pragma unroll
-      for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-#pragma unroll
-    for (int i = 0; i < WM; ++i) af[i] = an[i];
-#pragma unroll
-    for (int j = 0; j < WN; ++j) bf[j] = bn[j];
-  }
-
-  const int g = lane >> 2, t = lane & 3;
-  typename Epi::Row er[WM];
-  typename Epi::Col ec[WN];
-#pragma unroll
-  for (int i = 0; i < WM; ++i) er[i] = epi.row(min(mt0 + i, a.MTiles - 1), g);
-#pragma unroll
-  for (int j = 0; j < WN; ++j) ec[j] = epi.col(min(nt0 + j, a.NTiles - 1), z, t);
-#pragma unroll
-  for (int i = 0; i < WM; ++i) {
-#pragma unroll
-    for (int j = 0; j < WN; ++j) {
-      if (mt0 + i < a.MTiles && nt0 + j < a.NTiles) epi.store(er[i], ec[j], acc[i][j][0], acc[i][j][1]);
-    }
-  }
-}
-
-template <int WM, int WN, int CWM, int CWN, class Epi>
-inline cudaError_t launch_gemm(const GemmArgs& a, const Epi& epi, int batch, cudaStream_t st) {
-  dim3 grid((a.MTiles + WM * CWM - 1) / (WM * CWM), (a.NTiles + WN * CWN - 1) / (WN * CWN), batch);
-  // grid.y is limited to 65535: fold if needed by swapping roles is not required for
-  // the shapes of this path (NTiles/ (WN*CWN) <= 65535 up to ~4M walkers x orbitals)
-  gemm_frag_kernel<WM, WN, CWM, CWN, Epi><<<grid, CWM * CWN * 32, 0, st>>>(a, epi);
-  return cudaGetLastError();
-}
-
 // ----------------------------------------------------------------------------
 // TMA-fed version: persistent CTAs, one producer warp streaming both operands
 // into a shared-memory ring with 1-D bulk copies (cp.async.bulk -> SASS UBLKCP,
@@ -218,7 +140,7 @@ __global__ void __launch_bounds__(gemm_tma_threads<CWM * CWN>(), 1)
 #pragma unroll
     for (int s = 0; s < GT_STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], NCW);
+      mbar_init(&empty[s], NCW * kReleaseArrivals);
     }
     fence_barrier_init();
   }
@@ -313,8 +235,7 @@ __global__ void __launch_bounds__(gemm_tma_threads<CWM * CWN>(), 1)
             for (int j = 0; j < WN; ++j) dmma(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      ring_release(&empty[s], lane);
     }
     typename Epi::Row er[WM];
     typename Epi::Col ec[WN];

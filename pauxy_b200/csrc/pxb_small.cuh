@@ -228,6 +228,28 @@ __device__ __forceinline__ void philox_normal2(uint64_t seed, uint64_t step, uin
 }
 
 // ============================================================================
+// Per-step scalars.  They live in device memory (not in kernel arguments) so that the launch
+// sequence of a whole driver step can be captured once as a CUDA graph and replayed with new
+// values (pxb_step): one tiny setter launch in front of the graph instead of re-parametrising
+// its kernel nodes.
+// ============================================================================
+struct StepParams {
+  unsigned long long seed, step;  // Philox key / counter, driver step (weight cap needs step > 1)
+  long long walker_offset;        // global index of this device's first walker
+  double eshift;                  // energy shift of the block (continuous.py:202-214)
+  double comb_r;                  // the comb's uniform draw (handler.py:275)
+};
+__global__ void set_step_params_kernel(StepParams* dst, StepParams v, int mask) {
+  if (mask & 1) {
+    dst->seed = v.seed;
+    dst->step = v.step;
+    dst->walker_offset = v.walker_offset;
+    dst->eshift = v.eshift;
+  }
+  if (mask & 2) dst->comb_r = v.comb_r;
+}
+
+// ============================================================================
 // K2b: field shift (propagation/continuous.py:133-158, generic.py:152)
 //   xbar = -sqrt(dt) (i V - vbar), clip |xbar| > 1, x = xi - xbar,
 //   cmf = -sqrt(dt) x.vbar, cfb = xi.xbar - xbar.xbar/2.   One warp per walker.
@@ -243,12 +265,13 @@ struct FieldArgs {
   double2* cmfcfb;       // [Wp][2]
   long long* counters;
   Dims d;
-  uint64_t seed, step;
-  long long walker_offset;
+  const StepParams* sp;  // seed, step, walker_offset
 };
 
 __global__ void __launch_bounds__(256) field_kernel(FieldArgs a) {
   const Dims& d = a.d;
+  const uint64_t seed = a.sp->seed, step = a.sp->step;
+  const long long walker_offset = a.sp->walker_offset;
   const int lane = threadIdx.x & 31;
   const int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= d.Wp) return;
@@ -265,7 +288,7 @@ __global__ void __launch_bounds__(256) field_kernel(FieldArgs a) {
         if (n0 < d.N) z[0] = a.xi[(size_t)w * d.N + n0];
         if (n0 + 1 < d.N) z[1] = a.xi[(size_t)w * d.N + n0 + 1];
       } else {
-        philox_normal2(a.seed, a.step, (uint64_t)(a.walker_offset + w), (uint32_t)(n0 >> 1), z[0], z[1]);
+        philox_normal2(seed, step, (uint64_t)(walker_offset + w), (uint32_t)(n0 >> 1), z[0], z[1]);
       }
     }
 #pragma unroll
@@ -350,19 +373,20 @@ struct WeightArgs {
   const double* total_weight;
   long long* counters;
   Dims d;
-  double eshift;
-  long long step;
+  const StepParams* sp;  // eshift, step
 };
 
 __global__ void weight_kernel(WeightArgs a) {
   const Dims& d = a.d;
+  const double eshift = a.sp->eshift;
+  const long long step = (long long)a.sp->step;
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= d.W) return;
   double wt = a.weight[w];
   if (a.active[w] && (d.flags & FLAG_FREE_PROJECTION)) {
     // propagate_walker_free (continuous.py:194-200): the constant terms go into weight and phase
     const double2 cmf = a.cmfcfb[2 * w];
-    const double er = exp(cmf.x + d.dt * a.eshift);
+    const double er = exp(cmf.x + d.dt * eshift);
     double sn, cs;
     sincos(cmf.y, &sn, &cs);
     const double magn = hypot(er * cs, er * sn);
@@ -382,18 +406,18 @@ __global__ void weight_kernel(WeightArgs a) {
     const double lr = log(hypot(ratio.re, ratio.im)), li = atan2(ratio.im, ratio.re);
     double eh_r = -(lr + cfb.x + cmf.x) / d.dt;
     const double eh_i = -(li + cfb.y + cmf.y) / d.dt;
-    if (fabs(a.eshift) >= 1e-10) {
-      if (eh_r > a.eshift + d.ebound) {
-        eh_r = a.eshift + d.ebound;
+    if (fabs(eshift) >= 1e-10) {
+      if (eh_r > eshift + d.ebound) {
+        eh_r = eshift + d.ebound;
         atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 1), 1ull);
-      } else if (eh_r < a.eshift - d.ebound) {
-        eh_r = a.eshift - d.ebound;
+      } else if (eh_r < eshift - d.ebound) {
+        eh_r = eshift - d.ebound;
         atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 1), 1ull);
       }
     }
     const double2 eo = a.ehyb[w];
     // importance function exp(-dt (0.5 (Eh + Eh_old) - eshift))
-    const double ar = -d.dt * (0.5 * (eh_r + eo.x) - a.eshift);
+    const double ar = -d.dt * (0.5 * (eh_r + eo.x) - eshift);
     const double ai = -d.dt * (0.5 * (eh_i + eo.y));
     const double er = exp(ar);
     double sn, cs;
@@ -410,7 +434,7 @@ __global__ void weight_kernel(WeightArgs a) {
       a.ot[w] = on;
     }
   }
-  if (a.step > 1) {
+  if (step > 1) {
     const double cap = a.total_weight[0] * 0.10;
     if (fabs(wt) > cap) wt = cap;
   }
@@ -728,7 +752,7 @@ struct CombArgs {
   int* pairs;         // [1 + 2*Wtot]
   long long* counters;
   int Wtot;
-  double r;
+  const StepParams* sp;  // comb_r
 };
 
 // number of comb teeth (i + r) * spacing, i in [0, n), that lie below c -- evaluated with the
@@ -747,6 +771,7 @@ __global__ void __launch_bounds__(1024) comb_plan_kernel(CombArgs a) {
   __shared__ double s_total;
   __shared__ int s_warp[2][32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, n = a.Wtot;
+  const double r = a.sp->comb_r;
   double run = 0.0;
   for (int base = 0; base < n; base += 1024) {
     if (base + tid < n) chunk[tid] = a.gws[base + tid];
@@ -772,9 +797,9 @@ __global__ void __launch_bounds__(1024) comb_plan_kernel(CombArgs a) {
   const int i0 = min(tid * seg, n), i1 = min(i0 + seg, n);
   int nk = 0, nc = 0;
   {
-    int below = (i0 == 0) ? 0 : teeth_below(a.cprobs[i0 - 1], a.r, spacing, n);
+    int below = (i0 == 0) ? 0 : teeth_below(a.cprobs[i0 - 1], r, spacing, n);
     for (int i = i0; i < i1; ++i) {
-      const int upto = (i == n - 1) ? n : teeth_below(a.cprobs[i], a.r, spacing, n);
+      const int upto = (i == n - 1) ? n : teeth_below(a.cprobs[i], r, spacing, n);
       const int p = upto - below;
       below = upto;
       a.parent_ix[i] = p;

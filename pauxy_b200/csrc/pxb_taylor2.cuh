@@ -195,8 +195,7 @@ __device__ __forceinline__ void taylor2_orders(const Taylor2Args& a, double* Tbu
           }
         }
       }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[s]);
+      ring_release(&empty[s], lane);
     }
     // S_{n-1} = (n phi + VHS S_n) / n  -> the other iterate buffer (or global for n == 1).
     // The reference divides by n (Temp = VHS.dot(Temp) / n); multiplying by the correctly rounded
@@ -248,7 +247,7 @@ __global__ void __launch_bounds__(T2Cfg<NG>::threads, 1) taylor2_kernel(Taylor2A
   if (tid == 0) {
     for (int s = 0; s < a.nstage; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], T2_CONSUMERS);
+      mbar_init(&empty[s], T2_CONSUMERS * kReleaseArrivals);
     }
     fence_barrier_init();
   }

@@ -193,29 +193,58 @@ class Engine(object):
                 pf['ready'][i].record(pf['stream'])
         return pf['buf'][i]
 
+    def _xi_pointer(self, xi):
+        """Device pointer of the fields (None: device Philox) + the prefetch slot they sit in; the
+        launch stream is made to wait for a prefetched copy."""
+        if xi is None:
+            return None, None
+        if not torch.is_tensor(xi):
+            xi = self.stage_xi(xi)
+        assert xi.dtype == torch.float64 and tuple(xi.shape) == (self.W, self.N)
+        assert xi.is_contiguous()
+        ptr = xi.data_ptr()
+        slot = None
+        pf = getattr(self, '_pf', None)
+        if pf is not None:
+            for i in range(2):
+                if pf['buf'][i].data_ptr() == ptr:
+                    slot = i
+                    torch.cuda.current_stream(self.device).wait_event(pf['ready'][i])
+        return ptr, slot
+
+    def _xi_release(self, slot):
+        if slot is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(self.device))
+            self._pf['free'][slot] = ev
+
     def propagate(self, xi=None, eshift=0.0, step=1, seed=0, walker_offset=0):
         """xi: None (device Philox), numpy [W,N] or cuda float64 tensor [W,N]."""
         with torch.cuda.device(self.device):
-            ptr = None
-            slot = None
-            if xi is not None:
-                if not torch.is_tensor(xi):
-                    xi = self.stage_xi(xi)
-                assert xi.dtype == torch.float64 and tuple(xi.shape) == (self.W, self.N)
-                assert xi.is_contiguous()
-                ptr = xi.data_ptr()
-                pf = getattr(self, '_pf', None)
-                if pf is not None:
-                    for i in range(2):
-                        if pf['buf'][i].data_ptr() == ptr:
-                            slot = i
-                            torch.cuda.current_stream(self.device).wait_event(pf['ready'][i])
+            ptr, slot = self._xi_pointer(xi)
             self._check(self.lib.pxb_propagate(self._h, ptr, int(seed), int(walker_offset),
                                                float(eshift), int(step), self._stream()))
-            if slot is not None:
-                ev = torch.cuda.Event()
-                ev.record(torch.cuda.current_stream(self.device))
-                self._pf['free'][slot] = ev
+            self._xi_release(slot)
+
+    def step(self, xi=None, eshift=0.0, step=1, seed=0, walker_offset=0, comb_r=0.0,
+             ortho=False, pop=True, energy=True):
+        """One whole driver step on this device as ONE library call (pxb_step): [re-orthogonalise]
+        -> propagate -> [comb, plan overlapped with the local energy] -> accumulate; replayed from a
+        CUDA graph from the second occurrence of a variant on."""
+        flags = (L.STEP_ORTHO if ortho else 0) | (L.STEP_POP if pop else 0) | \
+            (L.STEP_ENERGY if energy else 0)
+        with torch.cuda.device(self.device):
+            ptr, slot = self._xi_pointer(xi)
+            self._check(self.lib.pxb_step(self._h, ptr, int(seed), int(walker_offset), float(eshift),
+                                          int(step), float(comb_r), flags, self._stream()))
+            self._xi_release(slot)
+
+    def step_graphs(self, enable=None):
+        """Enable / disable CUDA-graph replay in step(); returns the number of graph launches so far."""
+        n = ctypes.c_longlong()
+        self._check(self.lib.pxb_step_graphs(self._h, -1 if enable is None else int(bool(enable)),
+                                             ctypes.byref(n)))
+        return n.value
 
     def orthogonalise(self):
         with torch.cuda.device(self.device):

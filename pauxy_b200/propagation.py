@@ -107,20 +107,29 @@ class Continuous(object):
         """Hot loop 1 of AFQMC.run (pauxy/qmc/afqmc.py:231-236) for the whole
         device batch: propagate_walker_phaseless for every walker with
         |weight| > 1e-8, then the 10 % weight cap."""
-        eng = self.engine
+        xi = self.fields(psi, system, step, comm)
+        self.engine.propagate(xi, eshift=eshift, step=step, seed=self.rng_seed,
+                              walker_offset=psi.walker_offset)
+        self.fields_consumed(step)
+
+    def fields(self, psi, system, step, comm=None):
+        """The auxiliary fields of this step: a device tensor / host array [nwalkers, nfields], or
+        None when the device draws them itself (Philox)."""
         if self.field_source is not None:
             ahead = self._xi_ahead
-            xi = ahead[1] if (ahead is not None and ahead[0] == step) else \
-                eng.prefetch_xi(self.field_source(step))
-            eng.propagate(xi, eshift=eshift, step=step)
+            if ahead is not None and ahead[0] == step:
+                return ahead[1]
+            return self.engine.prefetch_xi(self.field_source(step))
+        if self.rng == 'host':
+            return psi.draw_fields(system.nfields, comm)
+        return None
+
+    def fields_consumed(self, step):
+        """Called once the step that reads fields(step) is enqueued: starts the host->device copy
+        of the next step's externally supplied fields."""
+        if self.field_source is not None:
             nxt = self.field_source(step + 1)
-            self._xi_ahead = (step + 1, eng.prefetch_xi(nxt)) if nxt is not None else None
-        elif self.rng == 'host':
-            xi = psi.draw_fields(system.nfields, comm)
-            eng.propagate(xi, eshift=eshift, step=step)
-        else:
-            eng.propagate(None, eshift=eshift, step=step, seed=self.rng_seed,
-                          walker_offset=psi.walker_offset)
+            self._xi_ahead = (step + 1, self.engine.prefetch_xi(nxt)) if nxt is not None else None
 
     def propagate_walker(self, walker, system, trial, eshift):
         raise NotImplementedError("pauxy_b200 propagates the device batch at once: "

@@ -127,6 +127,11 @@ class AFQMC(object):
         self.setup_timers()
         self.eshift = 0
         self.sync_timers = bool(options.get('sync_timers', False))
+        # one library call per step (Engine.step -> pxb_step, CUDA-graph replay) whenever the step
+        # is the plain single-device one; `fused_step: false` keeps the phase-by-phase calls
+        self.fused_step = bool(options.get('fused_step', True))
+        if not options.get('cuda_graphs', True):
+            self.engine.step_graphs(False)
         if verbose:
             self.estimators.estimators['mixed'].print_header()
 
@@ -162,6 +167,24 @@ class AFQMC(object):
         comm = comm if comm is not None else self.comm
         mixed = self.estimators.estimators['mixed']
         start_step = self._tick()
+        evaluate = step % mixed.energy_eval_freq == 0
+        if (self.fused_step and comm.size == 1 and self.engine.nbp == 0 and not mixed.calc_one_rdm
+                and self.psi.pcont_method == 'comb' and self.psi.overlap
+                and len(self.estimators.estimators) == 1 and (mixed.eval_energy or not evaluate)):
+            # orthogonalise + propagate + pop_control + estimators.update of the loop body below as
+            # ONE device call; RNG consumption order is unchanged (fields, then the comb's uniform)
+            prop, psi = self.propagators, self.psi
+            pop = step % self.qmc.npop_control == 0 and psi.ntot_walkers > 1
+            xi = prop.fields(psi, self.system, step, comm)
+            r = numpy.random.random() if pop else 0.0
+            self.engine.step(xi, eshift=self.eshift, step=step, seed=prop.rng_seed,
+                             walker_offset=psi.walker_offset, comb_r=r,
+                             ortho=(step % self.qmc.nstblz == 0), pop=pop, energy=evaluate)
+            prop.fields_consumed(step)
+            psi._phi_cache = None
+            self.tprop += self._tick() - start_step
+            self._end_of_step(step, comm, mixed, start_step)
+            return
         if step % self.qmc.nstblz == 0:
             start = self._tick()
             self.psi.orthogonalise(self.trial, self.propagators.free_projection)
@@ -179,6 +202,11 @@ class AFQMC(object):
         self.estimators.update(self.system, self.qmc, self.trial, self.psi, step,
                                self.propagators.free_projection)
         self.testim += self._tick() - start
+        self._end_of_step(step, comm, mixed, start_step)
+
+    def _end_of_step(self, step, comm, mixed, start_step):
+        """Block output, restart record, vanished-population poll and energy shift
+        (afqmc.py:243-254)."""
         self.estimators.print_step(comm, comm.size, step)
         if self.psi.write_restart and step % self.psi.write_freq == 0:
             self.psi.write_walkers(comm)

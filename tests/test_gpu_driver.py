@@ -33,11 +33,12 @@ def _options(g, walkers=None, propagator=None, back_propagated=None):
     return o
 
 
-def _run(g, h1e, hs, ecore, walkers=None, propagator=None, back_propagated=None):
+def _run(g, h1e, hs, ecore, walkers=None, propagator=None, back_propagated=None, top=None):
     nelec = tuple(int(x) for x in g['nelec'])
     system = Generic(nelec=nelec, h1e=numpy.array([h1e, h1e]), chol=hs, ecore=ecore)
-    afqmc = AFQMC(options=_options(g, walkers, propagator, back_propagated), system=system,
-                  verbose=0)
+    opts = _options(g, walkers, propagator, back_propagated)
+    opts.update(top or {})
+    afqmc = AFQMC(options=opts, system=system, verbose=0)
     hist = {k: [] for k in ('weight', 'unscaled_weight', 'ot', 'hybrid_energy', 'eloc',
                             'parent_ix', 'phase')}
 
@@ -73,6 +74,24 @@ def test_trace_matches_reference(golden, name):
     rows = afqmc.estimators.rows()
     _close(rows[:, :10], g['rows'][:, :10], atol=1e-10)
     _close(afqmc.psi.phi_host(), g['phi_final'], atol=1e-11)
+
+
+@pytest.mark.parametrize('top,replays', [({}, True), ({'cuda_graphs': False}, False),
+                                         ({'fused_step': False}, False)])
+def test_fused_step_and_graph_replay(golden, top, replays):
+    """The default driver step is ONE library call (pxb_step) replayed from a CUDA graph; with the
+    graphs off, or with the phase-by-phase calls of the reference's loop body, the trace is the same."""
+    g = golden('stress_comb')
+    afqmc, h = _run(g, g['h1e'], g['hs_pot'], float(g['ecore']), top=top)
+    assert (afqmc.engine.step_graphs() > 0) == replays
+    assert numpy.array_equal(h['parent_ix'], g['parent_ix'])
+    _close(h['weight'], g['weight'], atol=1e-13)
+    _close(h['ot'], g['ot'])
+    _close(h['hybrid_energy'], g['hybrid_energy'], rtol=RTOL, atol=EH_ATOL / float(g['dt']))
+    _close(h['eloc'], g['eloc'], atol=1e-10)
+    assert afqmc.propagators.nfb_trig == int(g['nfb_trig'])
+    assert afqmc.propagators.nhe_trig == int(g['nhe_trig'])
+    _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
 
 
 def test_sequential_pop_control_path(golden):
