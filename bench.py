@@ -207,7 +207,7 @@ def measure_fp64_peak(torch, dev):
 class Runner(object):
     """One AFQMC driver of the product on this rank + the timing loops around AFQMC.step."""
 
-    def __init__(self, torch, comm, dev, config, wpg, world, rng='philox', systems=None):
+    def __init__(self, torch, comm, dev, config, wpg, world, rng='philox', systems=None, top=None):
         from pauxy_b200.hamiltonians import CONFIGS, make_config_hamiltonian
         from pauxy_b200.systems import Generic
         from pauxy_b200.qmc import AFQMC
@@ -226,6 +226,7 @@ class Runner(object):
                         'pop_control_freq': 1},
                 'propagator': {'rng': rng},
                 'estimates': {'mixed': {'energy_eval_freq': 1, 'verbose': False}}}
+        opts.update(top or {})
         self.afqmc = AFQMC(comm=comm, options=opts, system=system, verbose=0, device=dev)
         self.eng = self.afqmc.engine
         self.stepno = 0
@@ -301,6 +302,9 @@ class Runner(object):
         prop._xi_ahead = None
 
 
+TOP_OPTIONS = {}
+
+
 def stage_table(runner, stage, nsteps, fl, peak, hbm_peak):
     """ms per step, calls per step and achieved TFLOP/s (GB/s) of every stage from the CUDA events
     recorded on the launch stream inside the timed region."""
@@ -336,11 +340,14 @@ def run_config(torch, comm, dev, config, wpg, world, steps, warmup, systems, pea
     from pauxy_b200.hamiltonians import CONFIGS
     cfg = CONFIGS[config]
     M, (na, nb) = cfg['nbasis'], cfg['nelec']
-    r = Runner(torch, comm, dev, config, wpg, world, rng='philox', systems=systems)
+    r = Runner(torch, comm, dev, config, wpg, world, rng='philox', systems=systems, top=TOP_OPTIONS)
     eng = r.eng
     N = r.N
     comm.warmup(dev)
-    for _ in range(max(warmup, 3)):
+    # at least one re-orthogonalisation and one block output before the clock starts: the first
+    # launch of a kernel loads its module lazily (0.1 - 2 ms, once per process)
+    nwarm = max(warmup, 3, cfg['stabilise_freq'] + 1, 11)
+    for _ in range(nwarm):
         r.step()
     out = {}
     launches0 = eng.launch_count()
@@ -367,14 +374,15 @@ def run_config(torch, comm, dev, config, wpg, world, steps, warmup, systems, pea
     # executed-form flops per walker-step: every stage once, one-body twice, QR every nst steps
     step_mflop = (fl['greens'] + fl['xgemm'] + fl['vhs'] + 2 * fl['one_body'] + fl['taylor'] +
                   fl['exchange'] + fl['energy'] + fl['qr'] / nst) * 1e-6
-    out.update({'config': config, 'walkers_per_gpu': wpg, 'walkers_total': wpg * world,
+    out.update({'config': config, 'warmup_done': nwarm, 'walkers_per_gpu': wpg, 'walkers_total': wpg * world,
                 'value': ws_total / (ms_total * 1e-3), 'ms_per_step': ms_total / steps,
                 'wall_ms_per_step': wall_total / steps, 'gpu_launches': int(launches),
                 'launches_per_step': launches / float(steps),
                 'whole_step_frac': step_mflop * 1e6 * wpg / (ms_total / steps * 1e-3) * 1e-12 / peak,
                 'mflop_per_walker_step_executed_form': step_mflop,
                 'exchange_form': exchange, 'vhs_symmetric': bool(eng.vhs_is_symmetric()),
-                'exp_nmax': r.afqmc.propagators.exp_nmax, 'fl': fl})
+                'exp_nmax': r.afqmc.propagators.exp_nmax, 'fl': fl,
+                'graph_replays': int(eng.step_graphs())})
     if detailed:
         out['stages'], _ = stage_table(r, stage, steps, fl, peak, hbm_peak)
         out['stage_raw'] = stage
@@ -480,6 +488,8 @@ def main():
     ap.add_argument('--no-other-configs', action='store_true')
     ap.add_argument('--no-parity-check', action='store_true')
     ap.add_argument('--no-parity-mode', action='store_true')
+    ap.add_argument('--no-graphs', action='store_true', help='pxb_step without CUDA-graph replay')
+    ap.add_argument('--no-fused', action='store_true', help='phase-by-phase calls instead of pxb_step')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -487,6 +497,10 @@ def main():
     import torch
     from pauxy_b200.hamiltonians import CONFIGS
     from pauxy_b200.comm import SingleComm, TorchComm
+    if args.no_graphs:
+        TOP_OPTIONS['cuda_graphs'] = False
+    if args.no_fused:
+        TOP_OPTIONS['fused_step'] = False
 
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
@@ -605,7 +619,7 @@ def main():
         pass
     line = {
         'metric': 'walker-steps/sec incl. local energy', 'value': value, 'unit': 'walker-steps/s',
-        'n_gpus': world, 'steps': args.steps, 'warmup': max(args.warmup, 3),
+        'n_gpus': world, 'steps': args.steps, 'warmup': main_res['warmup_done'],
         'ms_per_step': main_res['ms_per_step'], 'wall_ms_per_step': main_res['wall_ms_per_step'],
         'higher_is_better': True, 'scaling': 'strong' if strong_only else 'weak',
         'vs_baseline': None, 'dtype': 'f64 (complex128)', 'data': 'synthetic',
@@ -613,6 +627,7 @@ def main():
         'clocks': clocks,
         'e2e': main_res['e2e'],
         'gpu_launches': main_res['gpu_launches'],
+        'cuda_graph_replays': main_res['graph_replays'],
         'roofline': {'bound': 'tensor', 'kernel': kernel_names[dom],
                      'achieved': stages[dom]['tflops'], 'peak': peak, 'unit': 'TFLOP/s',
                      'frac': stages[dom]['tflops'] / peak, 'traffic': traffic,

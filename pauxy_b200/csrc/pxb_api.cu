@@ -84,7 +84,8 @@ struct pxb_context {
   bool in_step = false;  // scalars already set by pxb_step: the entry points it calls leave them alone
   bool graphs_enabled = true;
   cudaStream_t side = nullptr;  // the comb plan runs here beside the local energy
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t main = nullptr;  // carries the graph when the caller's stream is a default stream
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_in = nullptr, ev_out = nullptr;
   struct StepGraph {
     unsigned long long key;
     const double* xi;
@@ -832,7 +833,10 @@ int pxb_destroy(pxb_handle h) {
       if (g.exec) cudaGraphExecDestroy(g.exec);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->ev_in) cudaEventDestroy(h->ev_in);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     if (h->side) cudaStreamDestroy(h->side);
+    if (h->main) cudaStreamDestroy(h->main);
   }
   delete h;
   return PXB_OK;
@@ -1521,8 +1525,32 @@ int pxb_step(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t walk
       }
     }
   }
+  // The legacy default stream (and the per-thread one) cannot be captured: the graph then lives on
+  // an internal stream that is ordered after / before the caller's stream with two events.
+  const bool own = (st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread);
+  cudaStream_t gs = st;
+  if (g && own) {
+    if (!h->main) {
+      PXB_CUDA(h, cudaStreamCreateWithFlags(&h->main, cudaStreamNonBlocking));
+      PXB_CUDA(h, cudaEventCreateWithFlags(&h->ev_in, cudaEventDisableTiming));
+      PXB_CUDA(h, cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+    }
+    gs = h->main;
+  }
+  auto enter = [&]() -> cudaError_t {
+    if (gs == st) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(h->ev_in, st);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(gs, h->ev_in, 0);
+  };
+  auto leave = [&]() -> cudaError_t {
+    if (gs == st) return cudaSuccess;
+    cudaError_t e = cudaEventRecord(h->ev_out, gs);
+    return e != cudaSuccess ? e : cudaStreamWaitEvent(st, h->ev_out, 0);
+  };
   if (g && g->exec) {
-    PXB_CUDA(h, cudaGraphLaunch(g->exec, st));
+    PXB_CUDA(h, enter());
+    PXB_CUDA(h, cudaGraphLaunch(g->exec, gs));
+    PXB_CUDA(h, leave());
     h->launches += g->kernels;
     ++h->graph_replays;
     h->theta_valid = g->theta_valid;
@@ -1530,37 +1558,41 @@ int pxb_step(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t walk
     h->eloc_valid = g->eloc_valid;
     return PXB_OK;
   }
-  h->in_step = true;
   if (g && g->seen >= 1) {
     const long long l0 = h->launches;
     cudaGraph_t graph = nullptr;
-    PXB_CUDA(h, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-    rc = step_sequence(h, dev_xi, flags, st);
-    cudaError_t ce = cudaStreamEndCapture(st, &graph);
-    h->in_step = false;
-    if (rc == PXB_OK && ce == cudaSuccess && graph != nullptr &&
-        cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
-      g->kernels = h->launches - l0;
-      g->theta_valid = h->theta_valid;
-      g->x_valid = h->x_valid;
-      g->eloc_valid = h->eloc_valid;
-      cudaGraphDestroy(graph);
-      PXB_CUDA(h, cudaGraphLaunch(g->exec, st));
-      ++h->graph_replays;
-      return PXB_OK;
+    PXB_CUDA(h, enter());
+    if (cudaStreamBeginCapture(gs, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      h->in_step = true;
+      rc = step_sequence(h, dev_xi, flags, gs);
+      h->in_step = false;
+      cudaError_t ce = cudaStreamEndCapture(gs, &graph);
+      if (rc == PXB_OK && ce == cudaSuccess && graph != nullptr &&
+          cudaGraphInstantiate(&g->exec, graph, 0) == cudaSuccess) {
+        g->kernels = h->launches - l0;
+        g->theta_valid = h->theta_valid;
+        g->x_valid = h->x_valid;
+        g->eloc_valid = h->eloc_valid;
+        cudaGraphDestroy(graph);
+        PXB_CUDA(h, cudaGraphLaunch(g->exec, gs));
+        PXB_CUDA(h, leave());
+        ++h->graph_replays;
+        return PXB_OK;
+      }
+      if (graph) cudaGraphDestroy(graph);
+      if (rc != PXB_OK && rc != PXB_ERR_CUDA) return rc;
     }
-    // capture failed: nothing was executed; drop graphs for this handle and run the step directly
-    if (graph) cudaGraphDestroy(graph);
+    // capture unavailable or failed: nothing was executed; no graphs for this handle any more, the
+    // step runs as plain launches from the state it was entered in
     cudaGetLastError();
     g->exec = nullptr;
     h->graphs_enabled = false;
     h->launches = l0;
-    if (rc != PXB_OK && rc != PXB_ERR_CUDA) return rc;
     h->theta_valid = (key & 0x100ull) != 0;
     h->x_valid = (key & 0x200ull) != 0;
     h->eloc_valid = (key & 0x400ull) != 0;
-    h->in_step = true;
   }
+  h->in_step = true;
   rc = step_sequence(h, dev_xi, flags, st);
   h->in_step = false;
   if (g) ++g->seen;
