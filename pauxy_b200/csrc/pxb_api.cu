@@ -19,6 +19,7 @@
 #include "pxb_small.cuh"
 #include "pxb_taylor.cuh"
 #include "pxb_taylor2.cuh"
+#include "pxb_taylor3.cuh"
 
 using namespace pxb;
 
@@ -67,6 +68,7 @@ struct pxb_context {
   bool hs_near_sym = false;  // L symmetric in (p,q) to rounding (needed by the back propagation)
   int rtu = 0;           // row tiles kept in that case
   bool taylor_tma = true;  // persistent TMA-fed Taylor kernel (PXB_TAYLOR=direct selects the per-walker-CTA one)
+  bool taylor_3m = true;   // 3-product planar kernel where the shape allows (PXB_TAYLOR=4m: taylor2_kernel)
   bool exx_eri = false;  // exchange through the half-rotated ERI quadratic form (pxb_eri.cuh)
   bool kf_shared = false;  // both spins use the K of spin 0 (identical half-rotated Cholesky blocks)
   int eri_nslot = 0;
@@ -497,6 +499,91 @@ int run_taylor2(pxb_handle h, double* phi, const int* active, int ochunk, int nc
   return 1;
 }
 
+template <int WMX, int WNX>
+int launch_taylor3(pxb_handle h, const Taylor3Args& a, size_t smem, int grid, cudaStream_t st) {
+  auto kern = taylor3_kernel<WMX, WNX>;
+  PXB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ++h->launches;
+  kern<<<grid, T3_THREADS, smem, st>>>(a);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+// 3-product planar kernel (pxb_taylor3.cuh): shapes whose warp rectangle (ceil(MT/4) x ceil(NT8/2)
+// tile pairs x 3 accumulator sets) fits the 232-register consumer budget and whose two iterate
+// buffers leave room for a >= 3-deep ring.  Returns 1 if the shape is not covered.
+int run_taylor3(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
+  const Dims& d = h->d;
+  int nchunks = (d.ne + 47) / 48;
+  const int ochunk = round_up((d.ne + nchunks - 1) / nchunks, 8);
+  nchunks = (d.ne + ochunk - 1) / ochunk;
+  const int NT8 = ochunk / 8;
+  if (d.MT < 4 || d.MT > 16 || NT8 < 2 || NT8 > 6) return 1;
+  Taylor3Args a;
+  a.VF = h->ptr<double>(A_VF);
+  a.phi = phi;
+  a.active = active;
+  a.d = d;
+  a.ochunk = ochunk;
+  a.nchunks = nchunks;
+  a.NT8 = NT8;
+  a.S = NT8 * 64 + 4;
+  const int base = d.MT / 4, rem = d.MT % 4;
+  int msize[4];
+  a.m_off[0] = 0;
+  for (int g = 0; g < 4; ++g) {
+    msize[g] = base + (g < rem ? 1 : 0);
+    a.m_off[g + 1] = a.m_off[g] + msize[g];
+  }
+  const int nbase = NT8 / 2, nrem = NT8 % 2;
+  int nsize[2];
+  a.n_off[0] = 0;
+  for (int g = 0; g < 2; ++g) {
+    nsize[g] = nbase + (g < nrem ? 1 : 0);
+    a.n_off[g + 1] = a.n_off[g] + nsize[g];
+  }
+  // m-group permutation per column group: the largest remaining m-group goes to the least loaded
+  // sub-partition (column groups are in descending size)
+  int load[4] = {0, 0, 0, 0};
+  for (int g = 0; g < 2; ++g) {
+    int order[4] = {0, 1, 2, 3};
+    std::sort(order, order + 4, [&](int x, int y) { return load[x] != load[y] ? load[x] < load[y] : x < y; });
+    for (int k = 0; k < 4; ++k) {
+      a.mperm[g][order[k]] = k;
+      load[order[k]] += msize[k] * nsize[g];
+    }
+  }
+  const int wmx = base + (rem ? 1 : 0), wnx = nbase + (nrem ? 1 : 0);
+  if (wmx * wnx > 12) return 1;
+  // shared memory: iterate buffer + phi tile (+ a second phi tile, fetched one item ahead, when a
+  // >= 4-deep ring still fits beside it)
+  a.nstage = 0;
+  a.nbuf = 0;
+  a.dbg = 0;
+#ifdef PXB_EXPERIMENTS
+  {
+    const char* e3 = getenv("PXB_T3_DBG");
+    if (e3) a.dbg = atoi(e3);
+  }
+#endif
+  for (int nbuf = 3; nbuf >= 2 && a.nbuf == 0; --nbuf)
+    for (int nstage = 12; nstage >= (nbuf == 3 ? 4 : 3); --nstage)
+      if (taylor3_smem_bytes(d, NT8, nbuf, nstage) <= (size_t)h->max_smem_optin) {
+        a.nbuf = nbuf;
+        a.nstage = nstage;
+        break;
+      }
+  if (a.nbuf == 0) return 1;
+  const size_t smem = taylor3_smem_bytes(d, NT8, a.nbuf, a.nstage);
+  const int grid = std::min(d.W * nchunks, h->sm_count);
+#define PXB_T3(WM_, WN_) \
+  if (wmx == WM_ && wnx == WN_) return launch_taylor3<WM_, WN_>(h, a, smem, grid, st);
+  PXB_T3(1, 1) PXB_T3(1, 2) PXB_T3(1, 3) PXB_T3(2, 1) PXB_T3(2, 2) PXB_T3(2, 3)
+  PXB_T3(3, 1) PXB_T3(3, 2) PXB_T3(3, 3) PXB_T3(4, 1) PXB_T3(4, 2) PXB_T3(4, 3)
+#undef PXB_T3
+  return 1;
+}
+
 int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   StageTimer timer__(h, PXB_STAGE_TAYLOR, st);
   const Dims& d = h->d;
@@ -511,6 +598,10 @@ int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   nchunks = (d.ne + ochunk - 1) / ochunk;
   a.nchunks = nchunks;
   const int NT = ochunk / 4;
+  if (h->taylor_tma && h->taylor_3m) {
+    const int rc3 = run_taylor3(h, phi, active, st);
+    if (rc3 != 1) return rc3;
+  }
   if (h->taylor_tma) {
     const int rc2 = run_taylor2(h, phi, active, ochunk, nchunks, st);
     if (rc2 != 1) return rc2;
@@ -690,6 +781,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
     if (v && strcmp(v, "full") == 0) h->vhs_sym_allowed = false;
     const char* t = getenv("PXB_TAYLOR");
     if (t && strcmp(t, "direct") == 0) h->taylor_tma = false;
+    if (t && strcmp(t, "4m") == 0) h->taylor_3m = false;
   }
 #endif
   Dims& d = h->d;
