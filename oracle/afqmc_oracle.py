@@ -622,7 +622,9 @@ class OracleAFQMC(object):
             self.bp_update()
         self.print_step(step)
         if step < self.neqlb:
-            self.eshift = self.eshift_vec[0].real
+            # afqmc.py:251-252 get_shift(propagators.hybrid): hybrid energy, or the projected
+            # energy with the local-energy weight update (mixed.py:345-360)
+            self.eshift = self.eshift_vec[0 if getattr(self, 'hybrid', True) else 1].real
         else:
             self.eshift += (self.eshift_vec[0].real - self.eshift)
 

@@ -179,6 +179,90 @@ def case_shape(name, M, na, N, W, steps, seed_h, stab, blocks=1, dt=0.005, scale
     save(name, meta, tr, keep_xi=False, keep_phi=False)
 
 
+def _phmsd_inputs(nmo, nelec, ndet, seed=7, scale=1.0):
+    """Inputs of pauxy/propagation/tests/test_generic.py:52-92: random Hamiltonian, particle-hole
+    multi-determinant trial with random complex coefficients and a random complex initial walker."""
+    rh._install_paths()
+    from pauxy.utils.testing import get_random_phmsd
+    numpy.random.seed(seed)
+    h1e, chol, enuc, _ = generate_hamiltonian(nmo, nelec, cplx=False)
+    hs = scale * chol.reshape((-1, nmo * nmo)).T.copy()
+
+    class _S(object):
+        nbasis, nup, ndown = nmo, nelec[0], nelec[1]
+    wfn, init = get_random_phmsd(_S, ndet=ndet, init=True)
+    return h1e, hs, enuc, wfn, init
+
+
+def case_multi_det_walker(name, hybrid):
+    """The reference's own multi-determinant propagation tests (propagation/tests/test_generic.py:
+    52-70 hybrid=False -> local-energy weight update, :72-92 hybrid=True): one MultiDetWalker, ten
+    propagate_walker calls with eshift = trial.energy (complex), known final weights
+    0.68797524675701 / 0.7430443466368197."""
+    from unittest import mock
+    h1e, hs, enuc, wfn, init = _phmsd_inputs(10, (5, 5), 3)
+    from pauxy.systems.generic import Generic
+    from pauxy.trial_wavefunction.multi_slater import MultiSlater
+    from pauxy.propagation.continuous import Continuous
+    from pauxy.utils.misc import dotdict
+    from pauxy.walkers.multi_det import MultiDetWalker
+    system = Generic(nelec=(5, 5), h1e=numpy.array([h1e, h1e]), chol=hs, ecore=0)
+    trial = MultiSlater(system, wfn, init=init)
+    trial.calculate_energy(system)
+    prop = Continuous(system, trial, dotdict({'dt': 0.005, 'nstblz': 5}), options={'hybrid': hybrid})
+    walker = MultiDetWalker(system, trial)
+    tr = {k: [] for k in ('xi', 'weight', 'ot', 'hybrid_energy', 'eloc', 'ovlps')}
+    tr_init_ot = walker.ot
+    real_normal = numpy.random.normal
+
+    def rec(*a, **k):
+        v = real_normal(*a, **k)
+        tr['xi'].append(numpy.array(v, copy=True))
+        return v
+    numpy.random.normal = rec
+    try:
+        for i in range(10):
+            prop.propagate_walker(walker, system, trial, trial.energy)
+            tr['weight'].append(walker.weight)
+            tr['ot'].append(walker.ot)
+            tr['hybrid_energy'].append(walker.hybrid_energy)
+            tr['eloc'].append(walker.eloc)
+            tr['ovlps'].append(walker.ovlps.copy())
+    finally:
+        numpy.random.normal = real_normal
+    out = dict(h1e=h1e, hs_pot=hs, ecore=0.0, nelec=numpy.array((5, 5)), dt=0.005, hybrid=hybrid,
+               coeffs=numpy.array(wfn[0]), occa=numpy.array(wfn[1]), occb=numpy.array(wfn[2]),
+               init=init, trial_energy=numpy.array([trial.energy, trial.e1b, trial.e2b]),
+               init_ot=tr_init_ot, mf_shift=numpy.array(prop.propagator.mf_shift),
+               BH1=numpy.array(prop.propagator.BH1),
+               ref_test_golden_weight=0.7430443466368197 if hybrid else 0.68797524675701)
+    out.update({k: numpy.array(v) for k, v in tr.items()})
+    path = os.path.join(GOLD, name + '.npz')
+    numpy.savez_compressed(path, **out)
+    print(name, 'final weight %.16g' % walker.weight, 'golden', out['ref_test_golden_weight'])
+
+
+def case_multi_det_driver(name, hybrid=True):
+    """Full driver run (comb, re-orthogonalisation, block output) with a 3-determinant
+    particle-hole trial: walkers/handler.py:64-70 picks MultiDetWalker, estimators/mixed.py:211-221
+    evaluates local_energy_multi_det."""
+    h1e, hs, enuc, wfn, init = _phmsd_inputs(10, (5, 5), 3, scale=3.0)
+
+    def factory(system):
+        from pauxy.trial_wavefunction.multi_slater import MultiSlater
+        return MultiSlater(system, wfn, init=init)
+    opts = options(16, 0.01, 5, 4, 8, stab=4, popc=1)
+    opts['propagator'] = {'hybrid': hybrid}
+    a, tr = rh.run_reference_traced(h1e, hs, enuc, (5, 5), opts, trial_factory=factory)
+    meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array((5, 5)), dt=0.01,
+                nwalkers=16, steps=5, blocks=4, seed=8, stab=4, popc=1, hybrid=hybrid,
+                coeffs=numpy.array(wfn[0]), occa=numpy.array(wfn[1]), occb=numpy.array(wfn[2]),
+                init=init)
+    p = a.propagators.propagator
+    save(name, meta, tr, setup=dict(mf_shift=numpy.array(p.mf_shift), BH1=numpy.array(p.BH1),
+                                    mf_core=numpy.array(p.mf_core)))
+
+
 def case_local_energy():
     """pauxy/estimators/tests/test_generic.py:33-64 inputs and golden."""
     rh._install_paths()
@@ -211,6 +295,11 @@ def case_local_energy():
 if __name__ == '__main__':
     os.makedirs(GOLD, exist_ok=True)
     which = sys.argv[1:] or ['tg', 'c1', 'stress', 'pb', 'le', 'c2s', 'c3s', 'c4s', 'free', 'bp', 'rdm']
+    if 'md' in which:
+        case_multi_det_walker('md_hybrid', True)
+        case_multi_det_walker('md_local_energy', False)
+        case_multi_det_driver('md_driver', True)
+        case_multi_det_driver('md_driver_le', False)
     if 'free' in which:
         case_free('free_comb', True, True)
         case_free('free_pair_branch', True, False, pop='pair_branch',

@@ -35,7 +35,7 @@ def _install_paths():
     sys.dont_write_bytecode = True
 
 
-def build_reference_afqmc(h1e, hs_pot, ecore, nelec, options):
+def build_reference_afqmc(h1e, hs_pot, ecore, nelec, options, trial_factory=None):
     """Construct the reference AFQMC driver on a given Hamiltonian.
 
     Mirrors /root/reference/pauxy/qmc/tests/test_afqmc.py:211-217.
@@ -49,7 +49,10 @@ def build_reference_afqmc(h1e, hs_pot, ecore, nelec, options):
         system = Generic(nelec=nelec, h1e=numpy.array([h1e, h1e]),
                          chol=hs_pot, ecore=ecore)
     comm = MPI.COMM_WORLD
-    afqmc = AFQMC(comm=comm, system=system, options=options)
+    if trial_factory is not None:       # e.g. a multi-determinant MultiSlater built on `system`
+        afqmc = AFQMC(comm=comm, system=system, options=options, trial=trial_factory(system))
+    else:
+        afqmc = AFQMC(comm=comm, system=system, options=options)
     return afqmc, comm
 
 
@@ -78,13 +81,13 @@ def estimator_one_rdm(filename='estimates.0.h5'):
     return numpy.array([numpy.asarray(g[k]) for k in keys])
 
 
-def run_reference_traced(h1e, hs_pot, ecore, nelec, options, nsteps_total=None):
+def run_reference_traced(h1e, hs_pot, ecore, nelec, options, nsteps_total=None, trial_factory=None):
     """Re-run the loop body of AFQMC.run (/root/reference/pauxy/qmc/afqmc.py:
     200-255) calling the reference's own objects, recording per-step vectors.
 
     Returns (afqmc, trace dict of numpy arrays).
     """
-    afqmc, comm = build_reference_afqmc(h1e, hs_pot, ecore, nelec, options)
+    afqmc, comm = build_reference_afqmc(h1e, hs_pot, ecore, nelec, options, trial_factory)
     psi = afqmc.psi
     qmc = afqmc.qmc
     prop = afqmc.propagators
