@@ -32,7 +32,7 @@ extern "C" {
 #define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
 #define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
 
-#define PXB_ABI_VERSION 8
+#define PXB_ABI_VERSION 9
 
 typedef struct pxb_context* pxb_handle;
 
@@ -53,8 +53,10 @@ typedef struct {
   int32_t flags;         /* PXB_FLAG_* */
   int32_t nbp;           /* back propagation: field configurations kept per walker
                             (estimators/back_propagation.py:55 nmax = int(tau_bp/dt)); 0 = off */
-  int32_t reserved;
+  int32_t ndets;         /* determinants of the trial (walkers/multi_det.py); 0 or 1: single determinant.
+                            The per-determinant operands are supplied with pxb_set_trial_det. */
 } pxb_config;
+#define PXB_MAX_DETS 8
 
 /* propagator options of pauxy/propagation/continuous.py:14-33 */
 #define PXB_FLAG_FREE_PROJECTION 1 /* propagate_walker_free (continuous.py:175-200), the free-projection
@@ -62,6 +64,11 @@ typedef struct {
                                       Mixed.update (mixed.py:151-177); implies NO_FORCE_BIAS like the
                                       reference (continuous.py:30-33) */
 #define PXB_FLAG_NO_FORCE_BIAS 2   /* force_bias = False: xbar = 0 (continuous.py:136-138) */
+#define PXB_FLAG_LOCAL_ENERGY_WEIGHT 4 /* propagator.hybrid = false: update_weight_local_energy
+                                      (continuous.py:216-231,294-318) instead of the hybrid update.  The
+                                      reference supports it with MultiDetWalker only (its SingleDet +
+                                      Generic path raises TypeError); here it is available for any
+                                      number of determinants with the multi-determinant semantics. */
 
 /* Exchange energy of estimators/generic.py:198-214.  Both forms give the same number to
  * rounding (the ERI is rebuilt from the same Cholesky vectors):
@@ -100,7 +107,10 @@ enum pxb_field_id {
   PXB_F_BP_DENOM = 18,       /* c128 [1]    sum_w weight_w (back_propagation.py:200) */
   PXB_F_THETA_SUM = 19,      /* c128 [ne,M] sum_w weight_w Theta_w since the last pxb_zero_estimates: the mixed
                                 one-body density matrix is Re(conj(psi) THETA_SUM) (mixed.py:226-229) */
-  PXB_F_COUNT = 20
+  PXB_F_WALKER_ELOC = 20,    /* c128 [W]    walker.eloc of the local-energy weight update (walker.py:37) */
+  PXB_F_OVLP_DET = 21,       /* c128 [ndets, W(padded to 4, row stride a multiple of 256 bytes)] overlaps of
+                                the walkers with the single determinants of the trial (MultiDetWalker.ovlps) */
+  PXB_F_COUNT = 22
 };
 
 int pxb_abi_version(void);
@@ -157,6 +167,24 @@ int pxb_field(pxb_handle h, int field_id, size_t* offset_bytes, size_t* size_byt
 int pxb_set_hamiltonian(pxb_handle h, const double* dev_hs_pot, const void* dev_rchol,
                         const void* dev_bh1, const void* dev_h1rot, const void* dev_psi,
                         const void* dev_mf_shift, double ecore, void* stream);
+
+/* Multi-determinant trial (walkers/multi_det.py:27-300, propagation/generic.py:154-157,
+ * estimators/mixed.py:439-448; pxb_config.ndets > 1).  pxb_set_hamiltonian supplies determinant 0
+ * (and the determinant-independent arrays); this call supplies determinant `det` >= 1 -- its
+ * orbitals, half-rotated Cholesky vectors and half-rotated one-body integrals, same layouts as
+ * above -- and the CI coefficient of ANY determinant (det 0 included: pass NULL arrays to set the
+ * coefficient only; it defaults to 1).  The overlap is sum_i conj(c_i) <psi_i|phi>; force bias and
+ * local energy are the weighted averages over the determinants with w_i = conj(c_i) <psi_i|phi>.
+ * The orbitals must be real-valued like the single-determinant ones; the coefficients may be
+ * complex.  mf_shift / bh1 passed to pxb_set_hamiltonian are the multi-determinant ones
+ * (propagation/generic.py:82-86). */
+int pxb_set_trial_det(pxb_handle h, int det, double coeff_re, double coeff_im, const void* dev_rchol,
+                      const void* dev_h1rot, const void* dev_psi, void* stream);
+
+/* Imaginary part of the energy shift used by the following pxb_propagate / pxb_step calls (zero
+ * by default and in the driver; the reference's own propagation tests pass the complex trial
+ * energy, propagation/tests/test_generic.py:66-68). */
+int pxb_set_eshift_imag(pxb_handle h, double eshift_im);
 
 /* ---- walker state --------------------------------------------------------
  * phi: c128 [W, M, na+nb] device, the reference layout of walker.phi stacked

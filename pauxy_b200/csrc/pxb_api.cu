@@ -27,6 +27,7 @@ namespace {
 
 struct Region {
   size_t off = 0, bytes = 0;
+  size_t stride = 0;  // per-determinant regions: bytes between the copies of consecutive determinants
 };
 
 enum ArenaId {
@@ -34,6 +35,7 @@ enum ArenaId {
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
   A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_OB, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
   A_FC, A_PHI_OLD, A_PHI_BP, A_PHI_BP2, A_THETA_BP, A_BP_PART, A_PSI_NAT, A_INIT_NAT, A_BFT, A_STEP_PARAMS,
+  A_OVLP_DET, A_ELOC_DET, A_XC, A_COEFF, A_ELOC_MIX,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -70,7 +72,8 @@ struct pxb_context {
   bool taylor_tma = true;  // persistent TMA-fed Taylor kernel (PXB_TAYLOR=direct selects the per-walker-CTA one)
   bool taylor_3m = true;   // 3-product planar kernel where the shape allows (PXB_TAYLOR=4m: taylor2_kernel)
   bool exx_eri = false;  // exchange through the half-rotated ERI quadratic form (pxb_eri.cuh)
-  bool kf_shared = false;  // both spins use the K of spin 0 (identical half-rotated Cholesky blocks)
+  bool kf_shared[PXB_MAX_DETS] = {false};  // both spins use the K of spin 0 (identical half-rotated Cholesky blocks)
+  bool ham_base_set = false;
   int eri_nslot = 0;
   // back propagation: stored field configurations per walker (walkers/stack.py:5-127)
   int nbp = 0;      // capacity (steps), 0: back propagation off
@@ -83,6 +86,7 @@ struct pxb_context {
   // fused driver step (pxb_step): the launch sequence of one step, captured as a CUDA graph the
   // second time a variant is seen and replayed afterwards; the scalars of the step are written to
   // A_STEP_PARAMS by one setter launch in front of it
+  double eshift_im = 0.0;  // pxb_set_eshift_imag
   bool in_step = false;  // scalars already set by pxb_step: the entry points it calls leave them alone
   bool graphs_enabled = true;
   cudaStream_t side = nullptr;  // the comb plan runs here beside the local energy
@@ -100,8 +104,17 @@ struct pxb_context {
   long long graph_replays = 0;
   std::string err;
 
+  // multi-determinant trial (walkers/multi_det.py): the per-determinant operands and intermediates
+  // (psi, half-rotated Cholesky / ERI / one-body integrals, Theta, X, exchange, e1b, overlaps, local
+  // energies) exist once per determinant; `det` selects the copy the stage launchers work on
+  int ndets = 1, det = 0;
+  unsigned dets_set = 0;  // bit i: pxb_set_hamiltonian / pxb_set_trial_det has supplied determinant i
   template <class T>
   T* ptr(int id) const {
+    return reinterpret_cast<T*>(arena + reg[id].off + (size_t)det * reg[id].stride);
+  }
+  template <class T>
+  T* ptr0(int id) const {  // determinant 0 / base of a per-determinant region
     return reinterpret_cast<T*>(arena + reg[id].off);
   }
   template <class T>
@@ -188,6 +201,7 @@ CopyArgs copy_args(pxb_handle h) {
   c.detR = h->field<double>(PXB_F_DETR);
   c.log_detR = h->field<double>(PXB_F_LOG_DETR);
   c.phase = h->field<double2>(PXB_F_PHASE);
+  c.weloc = h->field<double2>(PXB_F_WALKER_ELOC);
   c.X = h->ptr<double2>(A_X);
   c.phi_old = h->nbp > 0 ? h->ptr<double>(A_PHI_OLD) : nullptr;
   c.fc = h->nbp > 0 ? h->ptr<double>(A_FC) : nullptr;
@@ -640,7 +654,7 @@ int run_exchange_eri(pxb_handle h, cudaStream_t st) {
   const Dims& d = h->d;
   EriArgs a;
   a.KF[0] = h->ptr<double>(A_KF0);
-  a.KF[1] = h->kf_shared ? h->ptr<double>(A_KF0) : h->ptr<double>(A_KF1);
+  a.KF[1] = h->kf_shared[h->det] ? h->ptr<double>(A_KF0) : h->ptr<double>(A_KF1);
   a.theta = h->ptr<double>(A_THETA);
   a.part = h->ptr<double2>(A_EPART);
   a.d = d;
@@ -688,21 +702,89 @@ int run_exchange(pxb_handle h, cudaStream_t st) {
   return PXB_OK;
 }
 
+// Green's function stage for every determinant of the trial: Theta_i, e1b_i and the determinant
+// overlaps; ovlp_out receives the trial overlap sum_i conj(c_i) <psi_i|phi> (multi_det.py:198-231)
+int run_greens_all(pxb_handle h, const double* phi, double2* ovlp_out, cudaStream_t st) {
+  if (h->ndets == 1) return run_greens(h, phi, true, ovlp_out, true, st);
+  int rc = PXB_OK;
+  for (int i = 0; i < h->ndets && rc == PXB_OK; ++i) {
+    h->det = i;
+    rc = run_greens(h, phi, true, h->ptr<double2>(A_OVLP_DET), true, st);
+  }
+  h->det = 0;
+  if (rc) return rc;
+  const Dims& d = h->d;
+  ++h->launches;
+  md_overlap_kernel<<<(d.Wp + 255) / 256, 256, 0, st>>>(h->ptr0<double2>(A_COEFF), h->ptr0<double2>(A_OVLP_DET),
+                                                        h->reg[A_OVLP_DET].stride / 16, h->ndets, ovlp_out, d.Wp);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
 // Theta, overlap and e1b of the CURRENT walkers (recomputed only when stale)
 int ensure_theta(pxb_handle h, cudaStream_t st) {
   if (h->theta_valid) return PXB_OK;
-  int rc = run_greens(h, h->phi(), true, h->ptr<double2>(A_OVLP_OLD), true, st);
+  int rc = run_greens_all(h, h->phi(), h->ptr0<double2>(A_OVLP_OLD), st);
   if (rc) return rc;
   h->theta_valid = true;
   h->x_valid = false;
   return PXB_OK;
 }
 
+// X_i = R_i^T Theta_i for every determinant; with several, also the weighted average that the
+// force bias uses (propagation/generic.py:154-157) as a combined X for field_kernel
 int ensure_x(pxb_handle h, cudaStream_t st) {
   if (h->x_valid) return PXB_OK;
-  int rc = run_force_bias_gemm(h, st);
+  int rc = PXB_OK;
+  for (int i = 0; i < h->ndets && rc == PXB_OK; ++i) {
+    h->det = i;
+    rc = run_force_bias_gemm(h, st);
+  }
+  h->det = 0;
   if (rc) return rc;
+  if (h->ndets > 1) {
+    const Dims& d = h->d;
+    ++h->launches;
+    md_x_kernel<<<dim3((d.Np + 255) / 256, d.Wp), 256, 0, st>>>(
+        h->ptr0<double2>(A_COEFF), h->ptr0<double2>(A_OVLP_DET), h->reg[A_OVLP_DET].stride / 16,
+        h->ptr0<double2>(A_X), h->reg[A_X].stride / 16, h->ndets, h->ptr0<double2>(A_XC), d);
+    PXB_CUDA(h, cudaGetLastError());
+  }
   h->x_valid = true;
+  return PXB_OK;
+}
+
+// exchange + energy assembly of every determinant into eloc_det (or straight into the walker
+// field for a single determinant when to_field is set)
+int run_det_energies(pxb_handle h, bool to_field, cudaStream_t st) {
+  const Dims& d = h->d;
+  int rc = PXB_OK;
+  for (int i = 0; i < h->ndets && rc == PXB_OK; ++i) {
+    h->det = i;
+    if ((rc = run_exchange(h, st))) break;
+    EnergyArgs e;
+    e.X = h->ptr<double2>(A_X);
+    e.exx = h->ptr<double2>(A_EXX);
+    e.e1b = h->ptr<double2>(A_E1B);
+    e.eloc = (to_field && h->ndets == 1) ? h->field<double2>(PXB_F_ELOC) : h->ptr<double2>(A_ELOC_DET);
+    e.d = d;
+    StageTimer timer__(h, PXB_STAGE_ENERGY, st);
+    ++h->launches;
+    energy_kernel<<<(d.W + 7) / 8, 256, 0, st>>>(e);
+    if (cudaGetLastError() != cudaSuccess) rc = fail(h, PXB_ERR_CUDA, "energy_kernel launch failed");
+  }
+  h->det = 0;
+  return rc;
+}
+
+// sum_i w_i E_i / sum_i w_i with the CURRENT determinant overlaps (estimators/mixed.py:439-448)
+int run_md_energy(pxb_handle h, double2* out, int only_total, cudaStream_t st) {
+  const Dims& d = h->d;
+  ++h->launches;
+  md_energy_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(h->ptr0<double2>(A_COEFF), h->ptr0<double2>(A_OVLP_DET),
+                                                      h->reg[A_OVLP_DET].stride / 16, h->ptr0<double2>(A_ELOC_DET),
+                                                      h->reg[A_ELOC_DET].stride / 16, h->ndets, out, only_total, d.W);
+  PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
 
@@ -773,6 +855,11 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   pxb_context* h = new (std::nothrow) pxb_context();
   if (!h) return PXB_ERR_ARG;
   h->cfg = *cfg;
+  h->ndets = cfg->ndets > 1 ? cfg->ndets : 1;
+  if (h->ndets > PXB_MAX_DETS || (h->ndets > 1 && cfg->nbp > 0)) {
+    delete h;
+    return PXB_ERR_ARG;  // at most PXB_MAX_DETS determinants; no back propagation with several
+  }
 #ifdef PXB_EXPERIMENTS  // kernel-variant switches of development builds only (not in the product library)
   {
     const char* gr = getenv("PXB_GREENS");
@@ -804,6 +891,10 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   d.RT = ((d.M + 1) / 2) * d.KC;
   d.exp_order = cfg->exp_order;
   d.flags = cfg->flags;
+  if ((d.flags & FLAG_LOCAL_ENERGY_WEIGHT) && (d.flags & FLAG_FREE_PROJECTION)) {
+    delete h;
+    return PXB_ERR_ARG;
+  }
   if (d.flags & FLAG_FREE_PROJECTION) d.flags |= FLAG_NO_FORCE_BIAS;  // continuous.py:30-33
   d.dt = cfg->dt;
   d.sqrt_dt = sqrt(cfg->dt);
@@ -821,7 +912,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   }
 
   {
-    const size_t kbytes = (eri_kf_doubles(d, 0) + eri_kf_doubles(d, 1)) * 8;
+    const size_t kbytes = (eri_kf_doubles(d, 0) + eri_kf_doubles(d, 1)) * 8 * (size_t)h->ndets;
     if (cfg->exchange_mode == PXB_EXCHANGE_ERI)
       h->exx_eri = true;
     else if (cfg->exchange_mode == PXB_EXCHANGE_CHOLESKY)
@@ -841,36 +932,44 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
     h->reg[id].bytes = bytes;
     off += (bytes + 255) / 256 * 256;
   };
+  // one copy per determinant of the trial
+  const int D = h->ndets;
+  auto addd = [&](int id, size_t bytes) {
+    h->reg[id].off = off;
+    h->reg[id].bytes = bytes;
+    h->reg[id].stride = (bytes + 255) / 256 * 256;
+    off += h->reg[id].stride * (size_t)D;
+  };
   const size_t W = d.Wp, Wt = (size_t)d.Wtot;
   add(A_LF, lf_size(d) * 8);
-  add(A_RF, rf_size(d) * 8);
+  addd(A_RF, rf_size(d) * 8);
   add(A_BF, bf_size(d) * 8);
-  add(A_PSIT, (size_t)d.ne * d.Mp * 8);
-  add(A_H1ROT, (size_t)d.ne * d.Mp * 16);
+  addd(A_PSIT, (size_t)d.ne * d.Mp * 8);
+  addd(A_H1ROT, (size_t)d.ne * d.Mp * 16);
   add(A_VBAR, (size_t)d.Np * 16);
   add(A_PHI_A, of_size(d) * 8);
   add(A_PHI_B, of_size(d) * 8);
-  add(A_THETA, of_size(d) * 8);
-  add(A_X, (size_t)2 * W * d.Np * 16);
+  addd(A_THETA, of_size(d) * 8);
+  addd(A_X, (size_t)2 * W * d.Np * 16);
   add(A_XF, xf_size(d) * 8);
   add(A_VF, (size_t)W * vf_walker(d) * 8);
-  add(A_EXX, 2 * W * 16);
-  add(A_KF0, h->exx_eri ? eri_kf_doubles(d, 0) * 8 : 0);
-  add(A_KF1, h->exx_eri ? eri_kf_doubles(d, 1) * 8 : 0);
+  addd(A_EXX, 2 * W * 16);
+  addd(A_KF0, h->exx_eri ? eri_kf_doubles(d, 0) * 8 : 0);
+  addd(A_KF1, h->exx_eri ? eri_kf_doubles(d, 1) * 8 : 0);
   add(A_RTMAP, (size_t)d.RT * 4);
   {
     const size_t nmax = d.na > d.nb ? d.na : d.nb;
     add(A_OB, W * 2 * nmax * (nmax | 1) * 16);
   }
   add(A_EPART, h->exx_eri ? (size_t)2 * h->eri_nslot * W * 16 : 0);
-  add(A_E1B, W * 16);
+  addd(A_E1B, W * 16);
   add(A_OVLP_OLD, W * 16);
   add(A_ACTIVE, W * 4);
   add(A_GW, Wt * 8);
   add(A_GWS, Wt * 8);
   add(A_CPROBS, Wt * 8);
   add(A_FLAG, 256);
-  add(A_PF, (size_t)(((d.na + 7) >> 3) + ((d.nb + 7) >> 3)) * d.KC * 32 * 8);
+  addd(A_PF, (size_t)(((d.na + 7) >> 3) + ((d.nb + 7) >> 3)) * d.KC * 32 * 8);
   add(A_SLOG, W * 8 * 8);
   add(A_E1BP, W * 2 * 16);
   add(A_QRLD, W * 2 * 8);
@@ -901,12 +1000,21 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_THETA_BP, bp ? of_size(d) * 8 : 0);
   add(A_BP_PART, bp ? (size_t)h->bp_chunks * 2 * d.M * d.M * 16 : 0);
   add(A_BFT, bp ? bf_size(d) * 8 : 0);
-  add(A_PSI_NAT, (size_t)d.M * d.ne * 16);
+  addd(A_PSI_NAT, (size_t)d.M * d.ne * 16);
   add(A_INIT_NAT, (size_t)d.M * d.ne * 16);
   add(A_STEP_PARAMS, 256);
+  addd(A_OVLP_DET, W * 16);
+  addd(A_ELOC_DET, W * 3 * 16);
+  add(A_XC, D > 1 ? (size_t)2 * W * d.Np * 16 : 0);
+  add(A_COEFF, (size_t)PXB_MAX_DETS * 16);
+  add(A_ELOC_MIX, W * 16);
+  add(A_FIELD0 + PXB_F_WALKER_ELOC, W * 16);
+  add(A_FIELD0 + PXB_F_OVLP_DET, 0);  // alias of A_OVLP_DET, fixed up below
   add(A_FIELD0 + PXB_F_BP_RDM, bp ? (size_t)2 * d.M * d.M * 16 : 0);
   add(A_FIELD0 + PXB_F_BP_DENOM, 16);
   add(A_FIELD0 + PXB_F_THETA_SUM, (size_t)d.ne * d.M * 16);
+  h->reg[A_FIELD0 + PXB_F_OVLP_DET] = h->reg[A_OVLP_DET];
+  h->reg[A_FIELD0 + PXB_F_OVLP_DET].bytes = h->reg[A_OVLP_DET].stride * (size_t)D;
   h->arena_bytes = off;
   *out = h;
   return PXB_OK;
@@ -953,6 +1061,8 @@ int pxb_bind_arena(pxb_handle h, void* dev_arena, size_t bytes, void* stream) {
     h->peer_base[0] = h->arena;
   }
   h->ham_set = false;
+  h->ham_base_set = false;
+  h->dets_set = 0;
   h->phi_cur = 0;
   h->theta_valid = h->x_valid = h->eloc_valid = false;
   return PXB_OK;
@@ -965,6 +1075,72 @@ int pxb_field(pxb_handle h, int field_id, size_t* offset_bytes, size_t* size_byt
   return PXB_OK;
 }
 
+// trial-dependent operands of determinant `det`: half-rotated Cholesky vectors (RF), psi as overlap
+// GEMM fragments (PF), half-rotated one-body integrals, half-rotated ERI (K) when the exchange uses it
+static int set_trial_det_impl(pxb_handle h, int det, const void* rchol, const void* h1rot, const void* psi,
+                              const void* mf_shift, cudaStream_t st) {
+  const Dims& d = h->d;
+  int* flag = h->ptr0<int>(A_FLAG);
+  PXB_CUDA(h, cudaMemsetAsync(flag, 0, 4, st));
+  const int det_saved = h->det;
+  h->det = det;
+  struct Restore {
+    pxb_handle h;
+    int det;
+    ~Restore() { h->det = det; }
+  } restore{h, det_saved};
+  ++h->launches;
+  pack_rf_kernel<<<grid_for(rf_size(d)), 256, 0, st>>>(static_cast<const double2*>(rchol),
+                                                       h->ptr<double>(A_RF), d, flag);
+  ++h->launches;
+  pack_small_kernel<<<grid_for((size_t)d.ne * d.Mp), 256, 0, st>>>(
+      static_cast<const double2*>(psi), static_cast<const double2*>(h1rot),
+      static_cast<const double2*>(mf_shift), h->ptr<double>(A_PSIT), h->ptr<double2>(A_H1ROT),
+      h->ptr0<double2>(A_VBAR), d, flag);
+  ++h->launches;
+  pack_pf_kernel<<<grid_for((size_t)d.ne * d.Mp), 256, 0, st>>>(static_cast<const double2*>(psi),
+                                                                h->ptr<double>(A_PF), d);
+  PXB_CUDA(h, cudaGetLastError());
+  if (h->exx_eri) {
+    // identical spin blocks of R (RHF-type determinant): one K serves both spins
+    const bool cmp = d.na == d.nb && d.nb > 0;
+    if (cmp) {
+      ++h->launches;
+      rf_spin_compare_kernel<<<grid_for(rf_spin_base(d, 1)), 256, 0, st>>>(h->ptr<double>(A_RF), rf_spin_base(d, 1),
+                                                                         rf_spin_base(d, 1), flag);
+    }
+    int f2 = 0;
+    PXB_CUDA(h, cudaMemcpyAsync(&f2, flag, 4, cudaMemcpyDeviceToHost, st));
+    PXB_CUDA(h, cudaStreamSynchronize(st));
+    h->kf_shared[det] = cmp && (f2 & 8) == 0;
+    for (int s = 0; s < (h->kf_shared[det] ? 1 : 2); ++s) {
+      const int ns = s ? d.nb : d.na;
+      if (ns == 0) continue;
+      double* KF = h->ptr<double>(s ? A_KF1 : A_KF0);
+      PXB_CUDA(h, cudaMemsetAsync(KF, 0, eri_kf_doubles(d, s) * 8, st));
+      const int tiles = (d.M + 31) / 32;
+      ++h->launches;
+      eri_build_kernel<<<dim3(tiles * tiles, ns, ns), 1024, 0, st>>>(static_cast<const double2*>(rchol), KF, d, s);
+      PXB_CUDA(h, cudaGetLastError());
+    }
+  }
+  int hflag = 0;
+  PXB_CUDA(h, cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
+  PXB_CUDA(h, cudaStreamSynchronize(st));
+  hflag &= 5;  // bit 0: rchol, bit 2: psi (bit 1 is bh1, bit 3 the spin-block comparison of the ERI setup)
+  if (hflag != 0) {
+    char buf[160];
+    snprintf(buf, sizeof buf,
+             "complex-valued trial orbitals are not supported in this version (determinant %d: rchol:%d psi:%d)",
+             det, hflag & 1, (hflag >> 2) & 1);
+    return fail(h, PXB_ERR_UNSUPPORTED, buf);
+  }
+  PXB_CUDA(h, cudaMemcpyAsync(h->ptr<void>(A_PSI_NAT), psi, (size_t)d.M * d.ne * 16, cudaMemcpyDeviceToDevice, st));
+  h->dets_set |= 1u << det;
+  h->theta_valid = h->x_valid = h->eloc_valid = false;
+  return PXB_OK;
+}
+
 int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, const void* bh1,
                         const void* h1rot, const void* psi, const void* mf_shift, double ecore,
                         void* stream) {
@@ -973,13 +1149,10 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
   if (!hs_pot || !rchol || !bh1 || !h1rot || !psi || !mf_shift) return fail(h, PXB_ERR_ARG, "null pointer");
   const Dims& d = h->d;
   cudaStream_t st = S(stream);
-  int* flag = h->ptr<int>(A_FLAG);
+  int* flag = h->ptr0<int>(A_FLAG);
   PXB_CUDA(h, cudaMemsetAsync(flag, 0, 4, st));
   ++h->launches;
   hs_symmetry_kernel<<<grid_for((size_t)d.M * d.M * d.N), 256, 0, st>>>(hs_pot, d, flag);
-  ++h->launches;
-  pack_rf_kernel<<<grid_for(rf_size(d)), 256, 0, st>>>(static_cast<const double2*>(rchol),
-                                                       h->ptr<double>(A_RF), d, flag);
   ++h->launches;
   pack_bf_kernel<<<grid_for(bf_size(d)), 256, 0, st>>>(static_cast<const double2*>(bh1), h->ptr<double>(A_BF),
                                                        d, flag, 0);
@@ -988,14 +1161,6 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
     pack_bf_kernel<<<grid_for(bf_size(d)), 256, 0, st>>>(static_cast<const double2*>(bh1), h->ptr<double>(A_BFT),
                                                          d, flag, 1);
   }
-  ++h->launches;
-  pack_small_kernel<<<grid_for((size_t)d.ne * d.Mp), 256, 0, st>>>(
-      static_cast<const double2*>(psi), static_cast<const double2*>(h1rot),
-      static_cast<const double2*>(mf_shift), h->ptr<double>(A_PSIT), h->ptr<double2>(A_H1ROT),
-      h->ptr<double2>(A_VBAR), d, flag);
-  ++h->launches;
-  pack_pf_kernel<<<grid_for((size_t)d.ne * d.Mp), 256, 0, st>>>(static_cast<const double2*>(psi),
-                                                                h->ptr<double>(A_PF), d);
   PXB_CUDA(h, cudaGetLastError());
   {
     // symmetric Cholesky matrices (real orbitals): keep the row tiles (p pair, q chunk) that touch
@@ -1003,6 +1168,7 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
     int f1 = 0;
     PXB_CUDA(h, cudaMemcpyAsync(&f1, flag, 4, cudaMemcpyDeviceToHost, st));
     PXB_CUDA(h, cudaStreamSynchronize(st));
+    if (f1 & 2) return fail(h, PXB_ERR_UNSUPPORTED, "complex-valued one-body propagator is not supported in this version");
     h->vhs_sym = h->vhs_sym_allowed && (f1 & 16) == 0;
     h->hs_near_sym = (f1 & 32) == 0;
     const int* map = nullptr;
@@ -1022,44 +1188,45 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
     pack_lf_kernel<<<grid_for((size_t)nrt * d.NKC * 32), 256, 0, st>>>(hs_pot, h->ptr<double>(A_LF), d, map, nrt);
     PXB_CUDA(h, cudaGetLastError());
   }
-  if (h->exx_eri) {
-    // identical spin blocks of R (RHF-type trial): one K serves both spins
-    const bool cmp = d.na == d.nb && d.nb > 0;
-    if (cmp) {
-      ++h->launches;
-      rf_spin_compare_kernel<<<grid_for(rf_spin_base(d, 1)), 256, 0, st>>>(h->ptr<double>(A_RF), rf_spin_base(d, 1),
-                                                                         rf_spin_base(d, 1), flag);
-    }
-    int f2 = 0;
-    PXB_CUDA(h, cudaMemcpyAsync(&f2, flag, 4, cudaMemcpyDeviceToHost, st));
+  h->dets_set = 0;
+  int rc = set_trial_det_impl(h, 0, rchol, h1rot, psi, mf_shift, st);
+  if (rc) return rc;
+  {  // CI coefficients default to 1
+    std::vector<double> ones(2 * PXB_MAX_DETS, 0.0);
+    for (int i = 0; i < PXB_MAX_DETS; ++i) ones[2 * i] = 1.0;
+    PXB_CUDA(h, cudaMemcpyAsync(h->ptr0<void>(A_COEFF), ones.data(), ones.size() * 8, cudaMemcpyHostToDevice, st));
     PXB_CUDA(h, cudaStreamSynchronize(st));
-    h->kf_shared = cmp && (f2 & 8) == 0;
-    for (int s = 0; s < (h->kf_shared ? 1 : 2); ++s) {
-      const int ns = s ? d.nb : d.na;
-      if (ns == 0) continue;
-      double* KF = h->ptr<double>(s ? A_KF1 : A_KF0);
-      PXB_CUDA(h, cudaMemsetAsync(KF, 0, eri_kf_doubles(d, s) * 8, st));
-      const int tiles = (d.M + 31) / 32;
-      ++h->launches;
-      eri_build_kernel<<<dim3(tiles * tiles, ns, ns), 1024, 0, st>>>(static_cast<const double2*>(rchol), KF, d, s);
-      PXB_CUDA(h, cudaGetLastError());
-    }
   }
-  int hflag = 0;
-  PXB_CUDA(h, cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
-  PXB_CUDA(h, cudaStreamSynchronize(st));
-  hflag &= 7;  // bit 3 is the spin-block comparison of the ERI setup
-  if (hflag != 0) {
-    char buf[160];
-    snprintf(buf, sizeof buf,
-             "complex-valued input not supported in this version (rchol:%d bh1:%d psi:%d)", hflag & 1,
-             (hflag >> 1) & 1, (hflag >> 2) & 1);
-    return fail(h, PXB_ERR_UNSUPPORTED, buf);
-  }
-  PXB_CUDA(h, cudaMemcpyAsync(h->ptr<void>(A_PSI_NAT), psi, (size_t)d.M * d.ne * 16, cudaMemcpyDeviceToDevice, st));
   h->d.ecore = ecore;
-  h->ham_set = true;
+  h->ham_set = h->dets_set == (1u << h->ndets) - 1u;
+  h->ham_base_set = true;
   h->theta_valid = h->x_valid = h->eloc_valid = false;
+  return PXB_OK;
+}
+
+int pxb_set_trial_det(pxb_handle h, int det, double coeff_re, double coeff_im, const void* rchol,
+                      const void* h1rot, const void* psi, void* stream) {
+  if (!h) return PXB_ERR_ARG;
+  if (!h->arena) return fail(h, PXB_ERR_STATE, "arena not bound");
+  if (!h->ham_base_set) return fail(h, PXB_ERR_STATE, "pxb_set_hamiltonian has to come first");
+  if (det < 0 || det >= h->ndets) return fail(h, PXB_ERR_ARG, "pxb_set_trial_det: determinant index out of range");
+  cudaStream_t st = S(stream);
+  if (rchol || h1rot || psi) {
+    if (!rchol || !h1rot || !psi) return fail(h, PXB_ERR_ARG, "pxb_set_trial_det: rchol, h1rot and psi go together");
+    int rc = set_trial_det_impl(h, det, rchol, h1rot, psi, nullptr, st);
+    if (rc) return rc;
+  }
+  const double c[2] = {coeff_re, coeff_im};
+  PXB_CUDA(h, cudaMemcpyAsync(h->ptr0<double>(A_COEFF) + 2 * det, c, 16, cudaMemcpyHostToDevice, st));
+  PXB_CUDA(h, cudaStreamSynchronize(st));
+  h->ham_set = h->dets_set == (1u << h->ndets) - 1u;
+  h->theta_valid = h->x_valid = h->eloc_valid = false;
+  return PXB_OK;
+}
+
+int pxb_set_eshift_imag(pxb_handle h, double eshift_im) {
+  if (!h) return PXB_ERR_ARG;
+  h->eshift_im = eshift_im;
   return PXB_OK;
 }
 
@@ -1100,7 +1267,7 @@ int pxb_init_walkers(pxb_handle h, const void* dev_init_phi, double total_walker
       h->field<double>(PXB_F_WEIGHT), h->field<double>(PXB_F_UNSCALED_WEIGHT), h->field<double2>(PXB_F_OT),
       h->ptr<double2>(A_OVLP_OLD), h->field<double2>(PXB_F_HYBRID_ENERGY), h->field<double>(PXB_F_DETR),
       h->field<double>(PXB_F_LOG_DETR), h->field<double>(PXB_F_TOTAL_WEIGHT),
-      h->field<double2>(PXB_F_PHASE), total_walkers, d);
+      h->field<double2>(PXB_F_PHASE), h->field<double2>(PXB_F_WALKER_ELOC), total_walkers, d);
   PXB_CUDA(h, cudaGetLastError());
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ESTIMATES), 0, 160, st));
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_COUNTERS), 0, 64, st));
@@ -1127,7 +1294,7 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   long long* counters = h->field<long long>(PXB_F_COUNTERS);
   int rc;
   if (!h->in_step) {
-    StepParams sp{rng_seed, (unsigned long long)step, walker_offset, eshift, 0.0};
+    StepParams sp{rng_seed, (unsigned long long)step, walker_offset, eshift, h->eshift_im, 0.0};
     if ((rc = set_step_params(h, sp, 1, st))) return rc;
   }
   ++h->launches;
@@ -1142,8 +1309,12 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   if ((rc = ensure_theta(h, st))) return rc;
   // (c1) force bias GEMM X_s = R_s^T Theta_s (shared with the Coulomb term of the estimator)
   if ((rc = ensure_x(h, st))) return rc;
+  const bool le_mode = (d.flags & FLAG_LOCAL_ENERGY_WEIGHT) != 0;
+  // local-energy weight update: walker.local_energy of continuous.py:296 uses the Green's functions
+  // of the walker BEFORE the step (left by greens_function at the top of it)
+  if (le_mode && (rc = run_det_energies(h, false, st))) return rc;
   FieldArgs f;
-  f.X = h->ptr<double2>(A_X);
+  f.X = h->ndets > 1 ? h->ptr0<double2>(A_XC) : h->ptr0<double2>(A_X);
   f.xi = dev_xi;
   f.vbar = h->ptr<double2>(A_VBAR);
   f.active = active;
@@ -1178,22 +1349,44 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   // (e) Green's function of the propagated walkers: its determinant is the new overlap
   //     (single_det.py:170-199) and its Theta serves the estimator and the next step
   h->theta_valid = h->x_valid = h->eloc_valid = false;
-  if ((rc = run_greens(h, h->phi(), true, h->field<double2>(PXB_F_OVLP_NEW), true, st))) return rc;
+  if ((rc = run_greens_all(h, h->phi(), h->field<double2>(PXB_F_OVLP_NEW), st))) return rc;
   h->theta_valid = true;
   // (f) weights
+  if (le_mode) {
+    // eloc = sum_i w_i(new) E_i(old) / sum_i w_i(new): calc_overlap refreshed the determinant
+    // weights, the Green's functions are still those of the start of the step (continuous.py:296)
+    if ((rc = run_md_energy(h, h->ptr0<double2>(A_ELOC_MIX), 1, st))) return rc;
+    WeightLeArgs wl;
+    wl.weight = h->field<double>(PXB_F_WEIGHT);
+    wl.ot = h->field<double2>(PXB_F_OT);
+    wl.walker_eloc = h->field<double2>(PXB_F_WALKER_ELOC);
+    wl.eloc_mix = h->ptr0<double2>(A_ELOC_MIX);
+    wl.ovlp_new = h->field<double2>(PXB_F_OVLP_NEW);
+    wl.ovlp_old = ot_stale ? h->ptr0<double2>(A_OVLP_OLD) : h->field<double2>(PXB_F_OT);
+    wl.active = active;
+    wl.total_weight = h->field<double>(PXB_F_TOTAL_WEIGHT);
+    wl.counters = counters;
+    wl.d = d;
+    wl.sp = h->ptr0<StepParams>(A_STEP_PARAMS);
+    StageTimer timer__(h, PXB_STAGE_WEIGHT, st);
+    ++h->launches;
+    weight_le_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(wl);
+    PXB_CUDA(h, cudaGetLastError());
+    return PXB_OK;
+  }
   WeightArgs wa;
   wa.weight = h->field<double>(PXB_F_WEIGHT);
   wa.phase = h->field<double2>(PXB_F_PHASE);
   wa.ot = h->field<double2>(PXB_F_OT);
   wa.ehyb = h->field<double2>(PXB_F_HYBRID_ENERGY);
   wa.ovlp_new = h->field<double2>(PXB_F_OVLP_NEW);
-  wa.ovlp_old = ot_stale ? h->ptr<double2>(A_OVLP_OLD) : h->field<double2>(PXB_F_OT);
+  wa.ovlp_old = ot_stale ? h->ptr0<double2>(A_OVLP_OLD) : h->field<double2>(PXB_F_OT);
   wa.cmfcfb = h->field<double2>(PXB_F_CMF_CFB);
   wa.active = active;
   wa.total_weight = h->field<double>(PXB_F_TOTAL_WEIGHT);
   wa.counters = counters;
   wa.d = d;
-  wa.sp = h->ptr<StepParams>(A_STEP_PARAMS);
+  wa.sp = h->ptr0<StepParams>(A_STEP_PARAMS);
   {
     StageTimer timer__(h, PXB_STAGE_WEIGHT, st);
     ++h->launches;
@@ -1242,19 +1435,8 @@ int pxb_local_energy(pxb_handle h, void* stream) {
   if (h->theta_valid && h->x_valid && h->eloc_valid) return PXB_OK;
   if ((rc = ensure_theta(h, st))) return rc;
   if ((rc = ensure_x(h, st))) return rc;
-  if ((rc = run_exchange(h, st))) return rc;
-  EnergyArgs e;
-  e.X = h->ptr<double2>(A_X);
-  e.exx = h->ptr<double2>(A_EXX);
-  e.e1b = h->ptr<double2>(A_E1B);
-  e.eloc = h->field<double2>(PXB_F_ELOC);
-  e.d = d;
-  {
-    StageTimer timer__(h, PXB_STAGE_ENERGY, st);
-    ++h->launches;
-    energy_kernel<<<(d.W + 7) / 8, 256, 0, st>>>(e);
-  }
-  PXB_CUDA(h, cudaGetLastError());
+  if ((rc = run_det_energies(h, true, st))) return rc;
+  if (h->ndets > 1 && (rc = run_md_energy(h, h->field<double2>(PXB_F_ELOC), 0, st))) return rc;
   h->eloc_valid = true;
   return PXB_OK;
 }
@@ -1284,6 +1466,7 @@ int pxb_accumulate(pxb_handle h, int with_energy, void* stream) {
 int pxb_accumulate_theta(pxb_handle h, void* stream) {
   PXB_REQUIRE_READY(h);
   const Dims& d = h->d;
+  if (h->ndets > 1) return fail(h, PXB_ERR_UNSUPPORTED, "mixed one-body density matrix: single-determinant trials only");
   int rc = ensure_theta(h, S(stream));
   if (rc) return rc;
   StageTimer timer__(h, PXB_STAGE_ACCUMULATE, S(stream));
@@ -1337,7 +1520,7 @@ int pxb_comb_plan(pxb_handle h, const double* gw, int64_t wtot, double r, void* 
   a.Wtot = (int)wtot;
   a.sp = h->ptr<StepParams>(A_STEP_PARAMS);
   if (!h->in_step) {
-    StepParams sp{0, 0, 0, 0.0, r};
+    StepParams sp{0, 0, 0, 0.0, 0.0, r};
     int rc = set_step_params(h, sp, 2, S(stream));
     if (rc) return rc;
   }
@@ -1373,6 +1556,7 @@ int pxb_pop_control_comb(pxb_handle h, double r, void* stream) {
   ++h->launches;
   copy_pairs_kernel<<<std::min(d.W, 4 * h->sm_count), 256, 0, st>>>(copy_args(h), h->field<int>(PXB_F_PAIRS), 0);
   PXB_CUDA(h, cudaGetLastError());
+  if (h->ndets > 1) h->theta_valid = h->x_valid = false;  // only determinant 0's Theta / X travel
   return pxb_set_weights(h, 1.0, stream);
 }
 
@@ -1463,6 +1647,7 @@ int pxb_pop_pull(pxb_handle h, void* stream) {
   ++h->launches;
   pull_pairs_kernel<<<4 * h->sm_count, 256, 0, st>>>(copy_args(h), p, h->field<int>(PXB_F_PAIRS));
   PXB_CUDA(h, cudaGetLastError());
+  if (h->ndets > 1) h->theta_valid = h->x_valid = false;  // only determinant 0's Theta / X travel
   return PXB_OK;  // Theta, e1b, X and ELOC travel with the walkers: their validity is unchanged
 }
 
@@ -1502,6 +1687,7 @@ int pxb_copy_walkers(pxb_handle h, const int32_t* src, const int32_t* dst, int n
   ++h->launches;
   copy_list_kernel<<<std::min(n, 4 * h->sm_count), 256, 0, S(stream)>>>(copy_args(h), src, dst, n);
   PXB_CUDA(h, cudaGetLastError());
+  if (h->ndets > 1) h->theta_valid = h->x_valid = false;
   return PXB_OK;
 }
 
@@ -1521,6 +1707,7 @@ int pxb_unpack_walkers(pxb_handle h, const int32_t* slots, int n, const double* 
   pack_kernel<<<std::min(n, 4 * h->sm_count), 256, 0, S(stream)>>>(copy_args(h), slots, n,
                                                                   const_cast<double*>(buf), 1);
   PXB_CUDA(h, cudaGetLastError());
+  if (h->ndets > 1) h->theta_valid = h->x_valid = false;
   return PXB_OK;
 }
 
@@ -1599,7 +1786,7 @@ int pxb_step(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t walk
     PXB_CUDA(h, cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   }
   int rc;
-  StepParams sp{rng_seed, (unsigned long long)step, walker_offset, eshift, comb_r};
+  StepParams sp{rng_seed, (unsigned long long)step, walker_offset, eshift, h->eshift_im, comb_r};
   if ((rc = set_step_params(h, sp, 3, st))) return rc;
   // a replay is only valid from the state the variant was captured in
   const unsigned long long key = (unsigned long long)(flags & 0xff) | (h->theta_valid ? 0x100ull : 0) |

@@ -39,6 +39,10 @@ struct Dims {
 };
 constexpr int FLAG_FREE_PROJECTION = 1;  // == PXB_FLAG_FREE_PROJECTION
 constexpr int FLAG_NO_FORCE_BIAS = 2;    // == PXB_FLAG_NO_FORCE_BIAS
+constexpr int FLAG_LOCAL_ENERGY_WEIGHT = 4;  // == PXB_FLAG_LOCAL_ENERGY_WEIGHT
+#ifndef PXB_MAX_DETS
+#define PXB_MAX_DETS 8  // == include/pauxy_b200.h
+#endif
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 

@@ -117,7 +117,8 @@ __global__ void pack_small_kernel(const double2* __restrict__ psi, const double2
     psiT[(size_t)p * d.ne + j] = v;
     h1r[idx] = h;
   }
-  for (int n = tid; n < d.Np; n += nth) vbar[n] = n < d.N ? mf[n] : make_double2(0.0, 0.0);
+  if (mf != nullptr)
+    for (int n = tid; n < d.Np; n += nth) vbar[n] = n < d.N ? mf[n] : make_double2(0.0, 0.0);
 }
 
 // psi as DMMA B-fragments for the overlap GEMM: PF[s][jt][pc][lane=(g,t)] = psi[4pc+t][ioff_s + 8jt+g]
@@ -237,6 +238,8 @@ struct StepParams {
   unsigned long long seed, step;  // Philox key / counter, driver step (weight cap needs step > 1)
   long long walker_offset;        // global index of this device's first walker
   double eshift;                  // energy shift of the block (continuous.py:202-214)
+  double eshift_im;               // its imaginary part (zero in the driver; the reference's own
+                                  // propagation tests pass a complex trial energy)
   double comb_r;                  // the comb's uniform draw (handler.py:275)
 };
 __global__ void set_step_params_kernel(StepParams* dst, StepParams v, int mask) {
@@ -245,6 +248,7 @@ __global__ void set_step_params_kernel(StepParams* dst, StepParams v, int mask) 
     dst->step = v.step;
     dst->walker_offset = v.walker_offset;
     dst->eshift = v.eshift;
+    dst->eshift_im = v.eshift_im;
   }
   if (mask & 2) dst->comb_r = v.comb_r;
 }
@@ -378,7 +382,7 @@ struct WeightArgs {
 
 __global__ void weight_kernel(WeightArgs a) {
   const Dims& d = a.d;
-  const double eshift = a.sp->eshift;
+  const double eshift = a.sp->eshift, eshift_im = a.sp->eshift_im;
   const long long step = (long long)a.sp->step;
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= d.W) return;
@@ -388,7 +392,7 @@ __global__ void weight_kernel(WeightArgs a) {
     const double2 cmf = a.cmfcfb[2 * w];
     const double er = exp(cmf.x + d.dt * eshift);
     double sn, cs;
-    sincos(cmf.y, &sn, &cs);
+    sincos(cmf.y + d.dt * eshift_im, &sn, &cs);
     const double magn = hypot(er * cs, er * sn);
     const double dtheta = atan2(er * sn, er * cs);
     wt = wt * magn;
@@ -406,7 +410,7 @@ __global__ void weight_kernel(WeightArgs a) {
     const double lr = log(hypot(ratio.re, ratio.im)), li = atan2(ratio.im, ratio.re);
     double eh_r = -(lr + cfb.x + cmf.x) / d.dt;
     const double eh_i = -(li + cfb.y + cmf.y) / d.dt;
-    if (fabs(eshift) >= 1e-10) {
+    if (hypot(eshift, eshift_im) >= 1e-10) {
       if (eh_r > eshift + d.ebound) {
         eh_r = eshift + d.ebound;
         atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 1), 1ull);
@@ -418,7 +422,7 @@ __global__ void weight_kernel(WeightArgs a) {
     const double2 eo = a.ehyb[w];
     // importance function exp(-dt (0.5 (Eh + Eh_old) - eshift))
     const double ar = -d.dt * (0.5 * (eh_r + eo.x) - eshift);
-    const double ai = -d.dt * (0.5 * (eh_i + eo.y));
+    const double ai = -d.dt * (0.5 * (eh_i + eo.y) - eshift_im);
     const double er = exp(ar);
     double sn, cs;
     sincos(ai, &sn, &cs);
@@ -433,6 +437,142 @@ __global__ void weight_kernel(WeightArgs a) {
       wt = 0.0;
       a.ot[w] = on;
     }
+  }
+  if (step > 1) {
+    const double cap = a.total_weight[0] * 0.10;
+    if (fabs(wt) > cap) wt = cap;
+  }
+  a.weight[w] = wt;
+}
+
+// ============================================================================
+// Multi-determinant trials (walkers/multi_det.py): the per-determinant stages are
+// the single-determinant kernels run once per determinant; these kernels contract over the
+// determinant index with the weights w_i = conj(c_i) <psi_i|phi>.
+// ============================================================================
+// ovlp[w] = sum_i conj(c_i) ovlp_det[i][w]   (multi_det.py:141-166, :198-231)
+__global__ void md_overlap_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ ovlp_det,
+                                  size_t det_stride, int ndets, double2* __restrict__ out, int Wp) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= Wp) return;
+  double re = 0.0, im = 0.0;
+  for (int i = 0; i < ndets; ++i) {
+    const double2 c = coeffs[i], o = ovlp_det[(size_t)i * det_stride + w];
+    re += c.x * o.x + c.y * o.y;   // conj(c) * o
+    im += c.x * o.y - c.y * o.x;
+  }
+  out[w] = make_double2(re, im);
+}
+
+// Force bias of propagation/generic.py:154-157: V[n] = sum_i w_i (X_i_up + X_i_dn)[n] / sum_i w_i,
+// written as the "up" half of a combined X (the "down" half is zero) so that field_kernel is unchanged
+__global__ void __launch_bounds__(256) md_x_kernel(const double2* __restrict__ coeffs,
+                                                   const double2* __restrict__ ovlp_det, size_t ovlp_stride,
+                                                   const double2* __restrict__ X, size_t x_stride, int ndets,
+                                                   double2* __restrict__ XC, Dims d) {
+  const int w = blockIdx.y;
+  if (w >= d.Wp) return;
+  double wr[8], wi[8];   // ndets <= PXB_MAX_DETS
+  double sr = 0.0, si = 0.0;
+  for (int i = 0; i < ndets; ++i) {
+    const double2 c = coeffs[i], o = ovlp_det[(size_t)i * ovlp_stride + w];
+    wr[i] = c.x * o.x + c.y * o.y;
+    wi[i] = c.x * o.y - c.y * o.x;
+    sr += wr[i];
+    si += wi[i];
+  }
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < d.Np; n += gridDim.x * blockDim.x) {
+    double nr = 0.0, ni = 0.0;
+    for (int i = 0; i < ndets; ++i) {
+      const double2* Xi = X + (size_t)i * x_stride;
+      const double2 a = Xi[(size_t)w * d.Np + n], b = Xi[((size_t)d.Wp + w) * d.Np + n];
+      const double vr = a.x + b.x, vi = a.y + b.y;
+      nr += wr[i] * vr - wi[i] * vi;
+      ni += wr[i] * vi + wi[i] * vr;
+    }
+    const cplx q = cdiv({nr, ni}, {sr, si});
+    XC[(size_t)w * d.Np + n] = make_double2(q.re, q.im);
+    XC[((size_t)d.Wp + w) * d.Np + n] = make_double2(0.0, 0.0);
+  }
+}
+
+// local_energy_multi_det (estimators/mixed.py:439-448): E[w][k] = sum_i w_i E_i[w][k] / sum_i w_i.
+// only_total != 0: just the total energy into out[w] (the local-energy weight update)
+__global__ void md_energy_kernel(const double2* __restrict__ coeffs, const double2* __restrict__ ovlp_det,
+                                 size_t ovlp_stride, const double2* __restrict__ eloc_det, size_t eloc_stride,
+                                 int ndets, double2* __restrict__ out, int only_total, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  double sr = 0.0, si = 0.0, er[3] = {0, 0, 0}, ei[3] = {0, 0, 0};
+  for (int i = 0; i < ndets; ++i) {
+    double wr = 1.0, wi = 0.0;
+    if (ndets > 1) {
+      const double2 c = coeffs[i], o = ovlp_det[(size_t)i * ovlp_stride + w];
+      wr = c.x * o.x + c.y * o.y;
+      wi = c.x * o.y - c.y * o.x;
+    }
+    sr += wr;
+    si += wi;
+    for (int k = 0; k < (only_total ? 1 : 3); ++k) {
+      const double2 e = eloc_det[(size_t)i * eloc_stride + 3 * (size_t)w + k];
+      er[k] += wr * e.x - wi * e.y;
+      ei[k] += wr * e.y + wi * e.x;
+    }
+  }
+  for (int k = 0; k < (only_total ? 1 : 3); ++k) {
+    const cplx q = cdiv({er[k], ei[k]}, {sr, si});
+    out[(only_total ? (size_t)w : 3 * (size_t)w + k)] = make_double2(q.re, q.im);
+  }
+}
+
+// Local-energy weight update (propagation/continuous.py:216-231,294-318; row A8' of SURVEY.md):
+//   eloc = walker.local_energy (Green's functions of the walker BEFORE the step, determinant
+//   weights AFTER it), real part bounded to eshift +- sqrt(2/dt) once eshift != 0,
+//   weight *= exp(-dt/2 Re(eloc_b + walker.eloc - eshift)) max(0, cos(arg(ot_new / ot_old)))
+struct WeightLeArgs {
+  double* weight;
+  double2* ot;
+  double2* walker_eloc;        // walker.eloc (walkers/walker.py:37), travels with the walker
+  const double2* eloc_mix;     // [Wp] eloc of this step
+  const double2* ovlp_new;
+  const double2* ovlp_old;
+  const int* active;
+  const double* total_weight;
+  long long* counters;
+  Dims d;
+  const StepParams* sp;
+};
+
+__global__ void weight_le_kernel(WeightLeArgs a) {
+  const Dims& d = a.d;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= d.W) return;
+  const double eshift = a.sp->eshift, eshift_im = a.sp->eshift_im;
+  const long long step = (long long)a.sp->step;
+  double wt = a.weight[w];
+  if (a.active[w]) {
+    const double2 oo = a.ovlp_old[w], on = a.ovlp_new[w];
+    const cplx ratio = cdiv({on.x, on.y}, {oo.x, oo.y});
+    const double2 el = a.eloc_mix[w], eold = a.walker_eloc[w];
+    double re_b = el.x;
+    if (hypot(eshift, eshift_im) >= 1e-10) {
+      if (el.x > eshift + d.ebound) {
+        re_b = eshift + d.ebound;
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 1), 1ull);
+      } else if (el.x < eshift - d.ebound) {
+        re_b = eshift - d.ebound;
+        atomicAdd(reinterpret_cast<unsigned long long*>(a.counters + 1), 1ull);
+      }
+    }
+    const double magn = exp(-0.5 * d.dt * (re_b + eold.x - eshift));
+    a.walker_eloc[w] = el;
+    if (!isinf(magn)) {
+      const double dtheta = atan2(ratio.im, ratio.re);
+      wt = wt * (magn * fmax(0.0, cos(dtheta)));
+    } else {
+      wt = 0.0;
+    }
+    a.ot[w] = on;
   }
   if (step > 1) {
     const double cap = a.total_weight[0] * 0.10;
@@ -863,6 +1003,7 @@ struct CopyArgs {
   double* detR;
   double* log_detR;
   double2* phase;
+  double2* weloc;   // walker.eloc of the local-energy weight update
   double2* X;       // [2][Wp][Np] X_s = R_s^T Theta_s travels with the walker like Theta does
   double* phi_old;  // back propagation only (else nullptr): walker.phi_old, OF layout
   double* fc;       // back propagation only: field history, rows = nbp * NKC per walker group
@@ -871,7 +1012,7 @@ struct CopyArgs {
 };
 
 __device__ __host__ __forceinline__ size_t payload_doubles(const Dims& d, bool bp, int fc_rows) {
-  return (size_t)(bp ? 3 : 2) * d.ne * d.KC * 8 + (bp ? (size_t)fc_rows * 8 : 0) + (size_t)4 * d.Np + 18;
+  return (size_t)(bp ? 3 : 2) * d.ne * d.KC * 8 + (bp ? (size_t)fc_rows * 8 : 0) + (size_t)4 * d.Np + 20;
 }
 
 // X rows of walker src (array sX) -> walker dst (array dX)
@@ -928,6 +1069,7 @@ __global__ void __launch_bounds__(256) copy_pairs_kernel(CopyArgs a, const int* 
       a.ot[dst] = a.ot[src];
       a.ehyb[dst] = a.ehyb[src];
       a.phase[dst] = a.phase[src];
+      a.weloc[dst] = a.weloc[src];
       a.detR[dst] = a.detR[src];
       a.log_detR[dst] = a.log_detR[src];
       for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)dst + k] = a.eloc[3 * (size_t)src + k];
@@ -955,6 +1097,7 @@ __global__ void __launch_bounds__(256) copy_list_kernel(CopyArgs a, const int* s
       a.ot[dst] = a.ot[src];
       a.ehyb[dst] = a.ehyb[src];
       a.phase[dst] = a.phase[src];
+      a.weloc[dst] = a.weloc[src];
       a.detR[dst] = a.detR[src];
       a.log_detR[dst] = a.log_detR[src];
       for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)dst + k] = a.eloc[3 * (size_t)src + k];
@@ -1008,6 +1151,7 @@ __global__ void __launch_bounds__(256) pull_pairs_kernel(CopyArgs a, PeerArgs p,
       a.ot[dst] = rebase(a.ot, lb, pb)[src];
       a.ehyb[dst] = rebase(a.ehyb, lb, pb)[src];
       a.phase[dst] = rebase(a.phase, lb, pb)[src];
+      a.weloc[dst] = rebase(a.weloc, lb, pb)[src];
       a.detR[dst] = rebase(a.detR, lb, pb)[src];
       a.log_detR[dst] = rebase(a.log_detR, lb, pb)[src];
       const double2* se = rebase(a.eloc, lb, pb);
@@ -1045,7 +1189,7 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
       pack_rows(a.fc, b + (size_t)3 * n8 * 8, a.fc_rows, w, unpack);
     }
     {
-      double2* xb = reinterpret_cast<double2*>(b + pd - 18 - (size_t)4 * d.Np);
+      double2* xb = reinterpret_cast<double2*>(b + pd - 20 - (size_t)4 * d.Np);
       for (int idx = threadIdx.x; idx < 2 * d.Np; idx += blockDim.x) {
         const int sp = idx / d.Np, n = idx - sp * d.Np;
         double2* gx = a.X + ((size_t)sp * d.Wp + w) * d.Np + n;
@@ -1056,7 +1200,7 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
       }
     }
     if (threadIdx.x == 0) {
-      double* s = b + pd - 18;
+      double* s = b + pd - 20;
       if (unpack) {
         a.weight[w] = s[0];
         a.unscaled[w] = s[1];
@@ -1067,6 +1211,7 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
         for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)w + k] = make_double2(s[8 + 2 * k], s[9 + 2 * k]);
         a.e1b[w] = make_double2(s[14], s[15]);
         a.phase[w] = make_double2(s[16], s[17]);
+        a.weloc[w] = make_double2(s[18], s[19]);
       } else {
         s[0] = a.weight[w];
         s[1] = a.unscaled[w];
@@ -1084,6 +1229,8 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
         s[15] = a.e1b[w].y;
         s[16] = a.phase[w].x;
         s[17] = a.phase[w].y;
+        s[18] = a.weloc[w].x;
+        s[19] = a.weloc[w].y;
       }
     }
   }
@@ -1098,7 +1245,7 @@ __global__ void fill_kernel(double* p, double v, int n, const long long* skip_fl
 
 __global__ void init_scalars_kernel(double* weight, double* unscaled, double2* ot, const double2* ovlp,
                                     double2* ehyb, double* detR, double* log_detR, double* total_weight,
-                                    double2* phase, double total, Dims d) {
+                                    double2* phase, double2* weloc, double total, Dims d) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w == 0) total_weight[0] = total;
   if (w >= d.Wp) return;
@@ -1108,6 +1255,7 @@ __global__ void init_scalars_kernel(double* weight, double* unscaled, double2* o
   ot[w] = ovlp[w];
   ehyb[w] = make_double2(0.0, 0.0);
   phase[w] = make_double2(1.0, 0.0);
+  weloc[w] = make_double2(0.0, 0.0);
   detR[w] = 1.0;
   log_detR[w] = 0.0;
 }
