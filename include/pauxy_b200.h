@@ -70,6 +70,11 @@ typedef struct {
                                       Generic path raises TypeError); here it is available for any
                                       number of determinants with the multi-determinant semantics. */
 
+#define PXB_FLAG_COMPLEX_ONE_BODY 8 /* propagator.BH1 has an imaginary part (complex mean-field shift, e.g.
+                                      a multi-determinant trial with complex CI coefficients): the
+                                      one-body step runs as [Re BH1 | Im BH1] [phi ; i phi] on the real
+                                      GEMM kernel; without the flag a complex BH1 is PXB_ERR_UNSUPPORTED */
+
 /* Exchange energy of estimators/generic.py:198-214.  Both forms give the same number to
  * rounding (the ERI is rebuilt from the same Cholesky vectors):
  *   CHOLESKY  T[x] = R[x] Theta^T per Cholesky vector, fused trace   4 N ns^2 M flop / walker / spin

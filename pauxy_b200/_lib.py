@@ -10,15 +10,17 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libpauxy_b200.so')
 
 PXB_OK = 0
-ABI_VERSION = 8
+ABI_VERSION = 9
 EXCHANGE_MODES = {'auto': 0, 'cholesky': 1, 'eri': 2}
 ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_ERR_UNSUPPORTED'}
 
 # enum pxb_field_id
 F_WEIGHT, F_UNSCALED_WEIGHT, F_OT, F_HYBRID_ENERGY, F_ELOC, F_DETR, F_LOG_DETR, \
     F_ESTIMATES, F_COUNTERS, F_PARENT_IX, F_XBAR, F_XSHIFTED, F_CMF_CFB, F_OVLP_NEW, \
-    F_TOTAL_WEIGHT, F_PAIRS, F_PHASE, F_BP_RDM, F_BP_DENOM, F_THETA_SUM, F_COUNT = range(21)
-FLAG_FREE_PROJECTION, FLAG_NO_FORCE_BIAS = 1, 2
+    F_TOTAL_WEIGHT, F_PAIRS, F_PHASE, F_BP_RDM, F_BP_DENOM, F_THETA_SUM, F_WALKER_ELOC, F_OVLP_DET, \
+    F_COUNT = range(23)
+FLAG_FREE_PROJECTION, FLAG_NO_FORCE_BIAS, FLAG_LOCAL_ENERGY_WEIGHT, FLAG_COMPLEX_ONE_BODY = 1, 2, 4, 8
+MAX_DETS = 8
 STEP_ORTHO, STEP_POP, STEP_ENERGY = 1, 2, 4
 
 
@@ -32,7 +34,7 @@ class PxbConfig(ctypes.Structure):
                 ('exp_order', ctypes.c_int32), ('device', ctypes.c_int32),
                 ('total_walkers', ctypes.c_int32), ('dt', ctypes.c_double),
                 ('exchange_mode', ctypes.c_int32), ('flags', ctypes.c_int32), ('nbp', ctypes.c_int32),
-                ('reserved', ctypes.c_int32)]
+                ('ndets', ctypes.c_int32)]
 
 
 class PxbError(RuntimeError):
@@ -59,6 +61,8 @@ _PROTOS = {
     'pxb_field': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.POINTER(ctypes.c_size_t),
                                  ctypes.POINTER(ctypes.c_size_t)]),
     'pxb_set_hamiltonian': (ctypes.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, _vp]),
+    'pxb_set_trial_det': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.c_double, _vp, _vp, _vp, _vp]),
+    'pxb_set_eshift_imag': (ctypes.c_int, [_vp, ctypes.c_double]),
     'pxb_set_phi': (ctypes.c_int, [_vp, _vp, _vp]),
     'pxb_get_phi': (ctypes.c_int, [_vp, _vp, _vp]),
     'pxb_init_walkers': (ctypes.c_int, [_vp, _vp, ctypes.c_double, _vp]),

@@ -35,7 +35,7 @@ enum ArenaId {
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
   A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_OB, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
   A_FC, A_PHI_OLD, A_PHI_BP, A_PHI_BP2, A_THETA_BP, A_BP_PART, A_PSI_NAT, A_INIT_NAT, A_BFT, A_STEP_PARAMS,
-  A_OVLP_DET, A_ELOC_DET, A_XC, A_COEFF, A_ELOC_MIX,
+  A_OVLP_DET, A_ELOC_DET, A_XC, A_COEFF, A_ELOC_MIX, A_BF2, A_PHI_STACK,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -373,19 +373,29 @@ int run_one_body(pxb_handle h, const double* in, double* out, const int* active,
                  bool transposed = false) {
   StageTimer timer__(h, PXB_STAGE_ONE_BODY, st);
   const Dims& d = h->d;
+  // complex BH1: [Re BH1 | Im BH1] [phi ; i phi] -- the same real GEMM over a doubled k range
+  const bool cplx = (d.flags & FLAG_COMPLEX_ONE_BODY) != 0;
+  const int kc = cplx ? 2 * d.KC : d.KC;
+  if (cplx) {
+    if (transposed) return fail(h, PXB_ERR_UNSUPPORTED, "back propagation with a complex one-body propagator");
+    ++h->launches;
+    phi_stack_kernel<<<grid_for((size_t)d.WG * d.ne * d.KC * 16), 256, 0, st>>>(in, h->ptr<double>(A_PHI_STACK), d);
+    PXB_CUDA(h, cudaGetLastError());
+    in = h->ptr<double>(A_PHI_STACK);
+  }
   for (int s = 0; s < 2; ++s) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     if (ns == 0) continue;
     GemmArgs g;
-    g.A = h->ptr<double>(transposed ? A_BFT : A_BF) + (size_t)s * d.MT * d.KC * 32;
-    g.B = in + (size_t)ioff * d.KC * 32;
+    g.A = (cplx ? h->ptr<double>(A_BF2) : h->ptr<double>(transposed ? A_BFT : A_BF)) + (size_t)s * d.MT * kc * 32;
+    g.B = in + (size_t)ioff * kc * 32;
     g.strideAz = g.strideBz = 0;
-    g.strideBO = (size_t)d.ne * d.KC * 32;
-    g.strideBI = (size_t)d.KC * 32;
+    g.strideBO = (size_t)d.ne * kc * 32;
+    g.strideBI = (size_t)kc * 32;
     g.ntInner = ns;
     g.MTiles = d.MT;
     g.NTiles = d.WG * ns;
-    g.KS = d.KC;
+    g.KS = kc;
     EpiOF epi{out, active, d.ne, d.KC, ioff, ns};
     ++h->launches;
     if (d.MT % 7 == 0) {
@@ -891,7 +901,8 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   d.RT = ((d.M + 1) / 2) * d.KC;
   d.exp_order = cfg->exp_order;
   d.flags = cfg->flags;
-  if ((d.flags & FLAG_LOCAL_ENERGY_WEIGHT) && (d.flags & FLAG_FREE_PROJECTION)) {
+  if (((d.flags & FLAG_LOCAL_ENERGY_WEIGHT) && (d.flags & FLAG_FREE_PROJECTION)) ||
+      ((d.flags & FLAG_COMPLEX_ONE_BODY) && cfg->nbp > 0)) {
     delete h;
     return PXB_ERR_ARG;
   }
@@ -1008,6 +1019,11 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_XC, D > 1 ? (size_t)2 * W * d.Np * 16 : 0);
   add(A_COEFF, (size_t)PXB_MAX_DETS * 16);
   add(A_ELOC_MIX, W * 16);
+  {
+    const bool cob = (d.flags & FLAG_COMPLEX_ONE_BODY) != 0;
+    add(A_BF2, cob ? 2 * bf_size(d) * 8 : 0);
+    add(A_PHI_STACK, cob ? 2 * of_size(d) * 8 : 0);
+  }
   add(A_FIELD0 + PXB_F_WALKER_ELOC, W * 16);
   add(A_FIELD0 + PXB_F_OVLP_DET, 0);  // alias of A_OVLP_DET, fixed up below
   add(A_FIELD0 + PXB_F_BP_RDM, bp ? (size_t)2 * d.M * d.M * 16 : 0);
@@ -1168,7 +1184,15 @@ int pxb_set_hamiltonian(pxb_handle h, const double* hs_pot, const void* rchol, c
     int f1 = 0;
     PXB_CUDA(h, cudaMemcpyAsync(&f1, flag, 4, cudaMemcpyDeviceToHost, st));
     PXB_CUDA(h, cudaStreamSynchronize(st));
-    if (f1 & 2) return fail(h, PXB_ERR_UNSUPPORTED, "complex-valued one-body propagator is not supported in this version");
+    if ((f1 & 2) && !(d.flags & FLAG_COMPLEX_ONE_BODY))
+      return fail(h, PXB_ERR_UNSUPPORTED,
+                  "complex-valued one-body propagator: create the handle with PXB_FLAG_COMPLEX_ONE_BODY");
+    if (d.flags & FLAG_COMPLEX_ONE_BODY) {
+      ++h->launches;
+      pack_bf2_kernel<<<grid_for(2 * bf_size(d)), 256, 0, st>>>(static_cast<const double2*>(bh1),
+                                                               h->ptr<double>(A_BF2), d);
+      PXB_CUDA(h, cudaGetLastError());
+    }
     h->vhs_sym = h->vhs_sym_allowed && (f1 & 16) == 0;
     h->hs_near_sym = (f1 & 32) == 0;
     const int* map = nullptr;

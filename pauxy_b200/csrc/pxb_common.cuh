@@ -40,6 +40,7 @@ struct Dims {
 constexpr int FLAG_FREE_PROJECTION = 1;  // == PXB_FLAG_FREE_PROJECTION
 constexpr int FLAG_NO_FORCE_BIAS = 2;    // == PXB_FLAG_NO_FORCE_BIAS
 constexpr int FLAG_LOCAL_ENERGY_WEIGHT = 4;  // == PXB_FLAG_LOCAL_ENERGY_WEIGHT
+constexpr int FLAG_COMPLEX_ONE_BODY = 8;     // == PXB_FLAG_COMPLEX_ONE_BODY
 #ifndef PXB_MAX_DETS
 #define PXB_MAX_DETS 8  // == include/pauxy_b200.h
 #endif

@@ -98,6 +98,45 @@ __global__ void pack_bf_kernel(const double2* __restrict__ bh1, double* __restri
   }
 }
 
+// Complex one-body propagator (multi-determinant trials with complex CI coefficients make the
+// mean-field shift, hence BH1, genuinely complex): BH1 phi = [Re BH1 | Im BH1] [phi ; i phi], i.e.
+// the REAL fragment-major GEMM with the k range doubled.  BF2[s][mt][kc'][g][t]: kc' < KC the real
+// part of BH1[s][8mt+g][4kc'+t], kc' >= KC the imaginary part.
+__global__ void pack_bf2_kernel(const double2* __restrict__ bh1, double* __restrict__ BF2, Dims d) {
+  const size_t total = 2 * bf_size(d);
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int tt = idx & 3, g = (idx >> 2) & 7;
+    size_t r = idx >> 5;
+    const int kc2 = r % (2 * d.KC);
+    r /= 2 * d.KC;
+    const int mt = r % d.MT, s = r / d.MT;
+    const int kc = kc2 < d.KC ? kc2 : kc2 - d.KC;
+    const int p = 8 * mt + g, q = 4 * kc + tt;
+    double v = 0.0;
+    if (p < d.M && q < d.M) {
+      const double2 z = bh1[((size_t)s * d.M + p) * d.M + q];
+      v = kc2 < d.KC ? z.x : z.y;
+    }
+    BF2[idx] = v;
+  }
+}
+// [phi ; i phi] stacked along k per (walker group, orbital): out[(wg, i)][kc'][wl][t][c]
+__global__ void phi_stack_kernel(const double* __restrict__ in, double* __restrict__ out, Dims d) {
+  const size_t total = (size_t)d.WG * d.ne * d.KC * 16;  // complex elements
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = idx & 15;
+    size_t r = idx >> 4;
+    const int kc = r % d.KC;
+    const size_t col = r / d.KC;  // (wg, orbital)
+    const double2 v = *reinterpret_cast<const double2*>(in + (col * d.KC + kc) * 32 + e * 2);
+    double* o = out + (col * 2 * d.KC + kc) * 32 + e * 2;
+    *reinterpret_cast<double2*>(o) = v;
+    *reinterpret_cast<double2*>(o + (size_t)d.KC * 32) = make_double2(-v.y, v.x);
+  }
+}
+
 // psiT[p][j] (real, [Mp][ne]), h1rot [ne][Mp] complex, vbar [Np] complex
 __global__ void pack_small_kernel(const double2* __restrict__ psi, const double2* __restrict__ h1rot,
                                   const double2* __restrict__ mf, double* __restrict__ psiT,

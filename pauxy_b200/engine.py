@@ -25,7 +25,7 @@ class Engine(object):
 
     def __init__(self, nbasis, nup, ndown, nchol, nwalkers, dt, exp_order=6, device=None,
                  total_walkers=None, exchange='auto', free_projection=False, force_bias=True,
-                 nbp=0):
+                 nbp=0, ndets=1, local_energy_weight=False, complex_one_body=False):
         if not torch.cuda.is_available():
             raise RuntimeError("pauxy_b200.Engine needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -41,7 +41,14 @@ class Engine(object):
         cfg = L.PxbConfig(nbasis, nup, ndown, nchol, nwalkers, exp_order,
                           self.device.index or 0, self.Wtot, dt, L.EXCHANGE_MODES[exchange],
                           (L.FLAG_FREE_PROJECTION if free_projection else 0) |
-                          (0 if force_bias else L.FLAG_NO_FORCE_BIAS), int(nbp or 0), 0)
+                          (0 if force_bias else L.FLAG_NO_FORCE_BIAS) |
+                          (L.FLAG_LOCAL_ENERGY_WEIGHT if local_energy_weight else 0) |
+                          (L.FLAG_COMPLEX_ONE_BODY if complex_one_body else 0), int(nbp or 0),
+                          int(ndets))
+        if ndets > L.MAX_DETS:
+            raise L.PxbError(-4, "at most %d determinants in the trial" % L.MAX_DETS)
+        self.ndets = int(ndets)
+        self._eshift_im = 0.0
         self.nbp = int(nbp or 0)
         self._h = ctypes.c_void_p()
         rc = self.lib.pxb_create(ctypes.byref(self._h), ctypes.byref(cfg))
@@ -101,6 +108,10 @@ class Engine(object):
             self.bp_rdm = self._view(L.F_BP_RDM, c128, (2, self.M, self.M))
         self.bp_denom = self._view(L.F_BP_DENOM, c128)
         self.theta_sum = self._view(L.F_THETA_SUM, c128, (self.ne, self.M))
+        self.walker_eloc = self._view(L.F_WALKER_ELOC, c128)[:W]
+        # overlaps with the single determinants of the trial, [ndets, W] (MultiDetWalker.ovlps)
+        od = self._view(L.F_OVLP_DET, c128)
+        self.ovlp_det = od.view(self.ndets, od.numel() // self.ndets)[:, :W]
 
     def _dev(self, a, dtype):
         t = torch.as_tensor(numpy.ascontiguousarray(a, dtype=dtype))
@@ -134,6 +145,32 @@ class Engine(object):
             self._check(self.lib.pxb_set_hamiltonian(self._h, *[x.data_ptr() for x in t],
                                                      float(numpy.real(ecore)), self._stream()))
         del t
+
+    def set_trial_det(self, det, coeff, rchol=None, h1rot=None, psi=None):
+        """Determinant `det` of a multi-determinant trial: its CI coefficient and (det >= 1, or to
+        replace determinant 0) its half-rotated Cholesky vectors, one-body integrals and orbitals."""
+        M, ne, N = self.M, self.ne, self.N
+        c = complex(coeff)
+        with torch.cuda.device(self.device):
+            if rchol is None:
+                self._check(self.lib.pxb_set_trial_det(self._h, int(det), c.real, c.imag, None, None,
+                                                       None, self._stream()))
+                return
+            assert rchol.shape == (ne * M, N) and h1rot.shape == (ne, M) and psi.shape == (M, ne)
+            t = [self._dev(rchol, numpy.complex128), self._dev(h1rot, numpy.complex128),
+                 self._dev(psi, numpy.complex128)]
+            self._check(self.lib.pxb_set_trial_det(self._h, int(det), c.real, c.imag,
+                                                   *[x.data_ptr() for x in t], self._stream()))
+        del t
+
+    def _set_eshift(self, eshift):
+        """Real part of the (possibly complex) energy shift; its imaginary part goes through
+        pxb_set_eshift_imag when it changes."""
+        e = complex(eshift)
+        if e.imag != self._eshift_im:
+            self._check(self.lib.pxb_set_eshift_imag(self._h, e.imag))
+            self._eshift_im = e.imag
+        return e.real
 
     def init_walkers(self, init_phi, total_walkers=None):
         tw = float(self.Wtot if total_walkers is None else total_walkers)
@@ -223,7 +260,7 @@ class Engine(object):
         with torch.cuda.device(self.device):
             ptr, slot = self._xi_pointer(xi)
             self._check(self.lib.pxb_propagate(self._h, ptr, int(seed), int(walker_offset),
-                                               float(eshift), int(step), self._stream()))
+                                               self._set_eshift(eshift), int(step), self._stream()))
             self._xi_release(slot)
 
     def step(self, xi=None, eshift=0.0, step=1, seed=0, walker_offset=0, comb_r=0.0,
@@ -235,7 +272,7 @@ class Engine(object):
             (L.STEP_ENERGY if energy else 0)
         with torch.cuda.device(self.device):
             ptr, slot = self._xi_pointer(xi)
-            self._check(self.lib.pxb_step(self._h, ptr, int(seed), int(walker_offset), float(eshift),
+            self._check(self.lib.pxb_step(self._h, ptr, int(seed), int(walker_offset), self._set_eshift(eshift),
                                           int(step), float(comb_r), flags, self._stream()))
             self._xi_release(slot)
 

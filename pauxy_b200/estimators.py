@@ -44,6 +44,8 @@ class Mixed(object):
             # the reference then accumulates the Green's function left behind by the propagator
             # (of the walker BEFORE the step); only the per-step evaluation is mirrored
             raise NotImplementedError("pauxy_b200: mixed one_rdm needs energy_eval_freq = 1")
+        if self.calc_one_rdm and trial.ndets > 1:
+            raise NotImplementedError("pauxy_b200: mixed one_rdm needs a single-determinant trial")
         self.psi_trial = numpy.array(trial.psi)
         self.nup = system.nup
         self.one_rdm = []

@@ -22,8 +22,6 @@ class GenericContinuous(object):
         if not options.get('optimised', True):
             raise NotImplementedError("pauxy_b200: only the optimised (half-rotated) force bias "
                                       "and VHS construction exist on the device")
-        if trial.ndets != 1:
-            raise NotImplementedError("pauxy_b200: multi-determinant trials are not on the hot path")
         self.dt = qmc.dt
         self.sqrt_dt = qmc.dt ** 0.5
         self.isqrt_dt = 1j * self.sqrt_dt
@@ -34,6 +32,11 @@ class GenericContinuous(object):
         self.ebound = (2.0 / self.dt) ** 0.5
 
     def construct_mean_field_shift(self, system, trial):
+        if trial.ndets > 1:
+            # propagation/generic.py:82-86: one-body expectation values of the trial itself
+            nb = system.nbasis
+            return 1j * numpy.array([trial.contract_one_body(system.hs_pot[:, n].reshape(nb, nb))
+                                     for n in range(system.nfields)])
         return 1j * numpy.dot(system.hs_pot.T, (trial.G[0] + trial.G[1]).ravel())
 
     def construct_one_body_propagator(self, system, dt):
@@ -54,10 +57,11 @@ class Continuous(object):
         self.force_bias = options.get('force_bias', True)
         if self.free_projection:
             self.force_bias = False     # continuous.py:30-33
-        if not self.hybrid:
-            raise NotImplementedError(
-                "pauxy_b200: the local-energy weight update crashes in the reference for "
-                "SingleDet + Generic (SURVEY.md row A8'), there is no oracle for it")
+        # hybrid = False: update_weight_local_energy (continuous.py:294-318).  The reference supports it
+        # with MultiDetWalker only (its SingleDet + Generic path raises TypeError, SURVEY.md row A8');
+        # here a single determinant runs through the same (multi-determinant) semantics.
+        if not self.hybrid and self.free_projection:
+            raise ValueError("propagator.hybrid = false has no meaning under free projection")
         if options.get('stochastic_ri', False):
             raise NotImplementedError("pauxy_b200: stochastic RI is out of scope")
         self.exp_nmax = options.get('expansion_order', 6)

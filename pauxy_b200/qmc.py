@@ -112,11 +112,19 @@ class AFQMC(object):
                              total_walkers=self.qmc.ntot_walkers,
                              exchange=est_opts.get('mixed', {}).get('exchange', 'auto'),
                              free_projection=self.propagators.free_projection,
-                             force_bias=self.propagators.force_bias, nbp=nbp)
+                             force_bias=self.propagators.force_bias, nbp=nbp,
+                             ndets=self.trial.ndets,
+                             local_energy_weight=not self.propagators.hybrid,
+                             complex_one_body=bool(numpy.abs(numpy.imag(
+                                 self.propagators.propagator.BH1)).max() > 0.0))
         p = self.propagators.propagator
-        self.engine.set_hamiltonian(s.hs_pot, self.trial._rchol, p.BH1,
-                                    self.trial.half_rotated_h1(s), self.trial.psi, p.mf_shift,
-                                    s.ecore)
+        t = self.trial
+        self.engine.set_hamiltonian(s.hs_pot, t.rchol(0), p.BH1, t.half_rotated_h1(s, 0), t.det(0),
+                                    p.mf_shift, s.ecore)
+        if t.ndets > 1:     # walkers/multi_det.py: one set of rotated operands per determinant
+            self.engine.set_trial_det(0, t.coeffs[0])
+            for i in range(1, t.ndets):
+                self.engine.set_trial_det(i, t.coeffs[i], t.rchol(i), t.half_rotated_h1(s, i), t.det(i))
         self.propagators.bind(self.engine)
         self.estimators = Estimators(est_opts, self.root, self.qmc, self.system, self.trial,
                                      self.propagators.BT_BP, verbose, engine=self.engine)
@@ -170,7 +178,8 @@ class AFQMC(object):
         evaluate = step % mixed.energy_eval_freq == 0
         if (self.fused_step and comm.size == 1 and self.engine.nbp == 0 and not mixed.calc_one_rdm
                 and self.psi.pcont_method == 'comb' and self.psi.overlap
-                and len(self.estimators.estimators) == 1 and (mixed.eval_energy or not evaluate)):
+                and len(self.estimators.estimators) == 1 and (mixed.eval_energy or not evaluate)
+                and self.propagators.hybrid):
             # orthogonalise + propagate + pop_control + estimators.update of the loop body below as
             # ONE device call; RNG consumption order is unchanged (fields, then the comb's uniform)
             prop, psi = self.propagators, self.psi

@@ -112,6 +112,45 @@ class SingleDetWalker(object):
         self._h._phi_cache = None
 
 
+class MultiDetWalker(SingleDetWalker):
+    """View of walker `index` for a multi-determinant trial (pauxy/walkers/multi_det.py:8-300): the
+    overlaps with the single determinants and their weights conj(c_i) <psi_i|phi> are device
+    fields; the walker's overlap `ot` is their sum."""
+
+    def __init__(self, handler, index, trial):
+        SingleDetWalker.__init__(self, handler, index)
+        self.ndets = trial.ndets
+        self._coeffs = numpy.array(trial.coeffs)
+
+    @property
+    def ovlps(self):
+        return self._h.engine.ovlp_det[:, self._i].cpu().numpy()
+
+    @property
+    def weights(self):
+        return self._coeffs.conj() * self.ovlps
+
+    eloc = property(lambda s: s._scalar('walker_eloc'))
+
+    def greens_function(self, trial):
+        """Host-side per-determinant Green's functions Gi [ndets, 2, M, M] for inspection
+        (multi_det.py:198-231); returns the total overlap."""
+        phi = self.phi
+        nup = self.nup
+        M = phi.shape[0]
+        self.Gi = numpy.zeros((self.ndets, 2, M, M), dtype=numpy.complex128)
+        tot = 0.0
+        for ix in range(self.ndets):
+            det = trial.psi[ix]
+            ovlp = 1.0
+            for s, sl in enumerate((slice(0, nup), slice(nup, nup + self.ndown))):
+                O = numpy.dot(phi[:, sl].T, det[:, sl].conj())
+                ovlp = ovlp * scipy.linalg.det(O)
+                self.Gi[ix, s] = numpy.dot(det[:, sl].conj(), numpy.dot(scipy.linalg.inv(O), phi[:, sl].T))
+            tot += trial.coeffs[ix].conj() * ovlp
+        return tot
+
+
 class Walkers(object):
     """Container of the walkers owned by this rank (device batch)."""
 
@@ -136,7 +175,7 @@ class Walkers(object):
         self.use_log_shift = walker_opts.get('use_log_shift', False)
         if self.use_log_shift:
             raise NotImplementedError("pauxy_b200: use_log_shift is not built")
-        self.walker_type = 'SD'
+        self.walker_type = 'SD' if trial.ndets == 1 else 'MSD'
         self.pcont_method = get_input_value(walker_opts, 'population_control', default='comb')
         self.min_weight = walker_opts.get('min_weight', 0.1)
         self.max_weight = walker_opts.get('max_weight', 4.0)
@@ -151,7 +190,10 @@ class Walkers(object):
         engine.init_walkers(trial.init, qmc.ntot_walkers)
         if self.peer_copy and comm is not None and comm.size > 1:
             engine.attach_peers(comm)
-        self.walkers = [SingleDetWalker(self, i) for i in range(self.nwalkers)]
+        if trial.ndets == 1:
+            self.walkers = [SingleDetWalker(self, i) for i in range(self.nwalkers)]
+        else:               # handler.py:64-70
+            self.walkers = [MultiDetWalker(self, i, trial) for i in range(self.nwalkers)]
         if self.read_file is not None:
             self.read_walkers(comm)
         self.buff_size = engine.payload_doubles()

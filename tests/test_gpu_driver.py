@@ -33,12 +33,14 @@ def _options(g, walkers=None, propagator=None, back_propagated=None):
     return o
 
 
-def _run(g, h1e, hs, ecore, walkers=None, propagator=None, back_propagated=None, top=None):
+def _run(g, h1e, hs, ecore, walkers=None, propagator=None, back_propagated=None, top=None,
+         trial_factory=None):
     nelec = tuple(int(x) for x in g['nelec'])
     system = Generic(nelec=nelec, h1e=numpy.array([h1e, h1e]), chol=hs, ecore=ecore)
     opts = _options(g, walkers, propagator, back_propagated)
     opts.update(top or {})
-    afqmc = AFQMC(options=opts, system=system, verbose=0)
+    trial = trial_factory(system) if trial_factory is not None else None
+    afqmc = AFQMC(options=opts, system=system, trial=trial, verbose=0)
     hist = {k: [] for k in ('weight', 'unscaled_weight', 'ot', 'hybrid_energy', 'eloc',
                             'parent_ix', 'phase')}
 
@@ -255,3 +257,68 @@ def test_shape_fixture_matches_reference(golden, name):
     assert afqmc.propagators.nhe_trig == int(g['nhe_trig'])
     _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
     _close(afqmc.psi.phi_host()[:2], g['phi_final_head'], atol=1e-11)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-determinant trials and the local-energy weight update (row A8')
+# ---------------------------------------------------------------------------------------------
+def _md_trial(g):
+    from pauxy_b200.trial import MultiSlater
+
+    def factory(system):
+        return MultiSlater(system, (g['coeffs'], g['occa'], g['occb']), init=g['init'])
+    return factory
+
+
+@pytest.mark.parametrize('name', ['md_hybrid', 'md_local_energy'])
+def test_multi_det_walker_reference_tests(golden, name):
+    """The reference's own multi-determinant propagation tests on the device
+    (pauxy/propagation/tests/test_generic.py:52-70 local-energy weight update, :72-92 hybrid): one
+    walker, ten propagation steps at the complex eshift = trial.energy; known final weights
+    0.68797524675701 / 0.7430443466368197."""
+    import torch
+    g = golden(name)
+    nelec = tuple(int(x) for x in g['nelec'])
+    system = Generic(nelec=nelec, h1e=numpy.array([g['h1e'], g['h1e']]), chol=g['hs_pot'], ecore=0.0)
+    trial = _md_trial(g)(system)
+    opts = {'qmc': {'timestep': 0.005, 'steps': 10, 'blocks': 1, 'rng_seed': 7, 'num_walkers': 1,
+                    'stabilise_freq': 5},
+            'propagator': {'hybrid': bool(g['hybrid'])},
+            'estimates': {'mixed': {'energy_eval_freq': 1, 'verbose': False}}}
+    afqmc = AFQMC(options=opts, system=system, trial=trial, verbose=0)
+    eng = afqmc.engine
+    assert abs(trial.energy - g['trial_energy'][0]) < 1e-12 * abs(trial.energy)
+    assert abs(eng.ot[0].item() - g['init_ot']) <= 1e-11 * abs(g['init_ot'])
+    for s in range(10):
+        eng.propagate(g['xi'][s][None, :].copy(), eshift=complex(g['trial_energy'][0]), step=1)
+        w, ot = eng.weight[0].item(), eng.ot[0].item()
+        assert w == pytest.approx(float(g['weight'][s]), rel=1e-10)
+        assert abs(ot - g['ot'][s]) <= 1e-10 * abs(g['ot'][s])
+        numpy.testing.assert_allclose(eng.ovlp_det[:, 0].cpu().numpy(), g['ovlps'][s], rtol=1e-10)
+        if bool(g['hybrid']):
+            assert abs(eng.hybrid_energy[0].item() - g['hybrid_energy'][s]) <= 1e-9 * abs(g['hybrid_energy'][s])
+        else:
+            assert abs(eng.walker_eloc[0].item() - g['eloc'][s]) <= 1e-10 * abs(g['eloc'][s])
+    assert eng.weight[0].item() == pytest.approx(float(g['ref_test_golden_weight']), rel=1e-9)
+
+
+@pytest.mark.parametrize('name', ['md_driver', 'md_driver_le'])
+def test_multi_det_driver(golden, name):
+    """Whole driver loop with a 3-determinant particle-hole trial (MultiDetWalker population, comb,
+    re-orthogonalisation, local_energy_multi_det in the mixed estimator) against traces of the
+    reference; md_driver_le uses the local-energy weight update (propagator.hybrid = false)."""
+    g = golden(name)
+    afqmc, h = _run(g, g['h1e'], g['hs_pot'], float(g['ecore']),
+                    propagator={'hybrid': bool(g['hybrid'])}, trial_factory=_md_trial(g))
+    assert afqmc.psi.walker_type == 'MSD'
+    assert numpy.array_equal(h['parent_ix'], g['parent_ix'])
+    _close(h['weight'], g['weight'], atol=1e-13)
+    _close(h['unscaled_weight'], g['unscaled_weight'], atol=1e-13)
+    _close(h['ot'], g['ot'])
+    _close(h['eloc'], g['eloc'], atol=1e-10)
+    if bool(g['hybrid']):
+        _close(h['hybrid_energy'], g['hybrid_energy'], rtol=RTOL, atol=EH_ATOL / float(g['dt']))
+    assert afqmc.propagators.nfb_trig == int(g['nfb_trig'])
+    assert afqmc.propagators.nhe_trig == int(g['nhe_trig'])
+    _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
+    _close(afqmc.psi.phi_host(), g['phi_final'], atol=1e-11)

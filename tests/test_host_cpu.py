@@ -109,9 +109,12 @@ def test_unsupported_modes_fail_loudly():
     class Q(object):
         dt = 0.01
         nstblz = 10
-    for opts in ({'hybrid': False}, {'optimised': False}):
+    for opts in ({'optimised': False}, {'stochastic_ri': True}):
         with pytest.raises(NotImplementedError):
             Continuous(system, trial, Q(), options=opts)
+    with pytest.raises(ValueError):     # the local-energy weight update has no free-projection form
+        Continuous(system, trial, Q(), options={'hybrid': False, 'free_projection': True})
+    assert Continuous(system, trial, Q(), options={'hybrid': False}).hybrid is False
     # continuous.py:30-33: free projection switches the force bias off
     assert Continuous(system, trial, Q(), options={'free_projection': True}).force_bias is False
 
@@ -289,3 +292,41 @@ def test_mixed_print_step_block_arithmetic():
     with pytest.raises(NotImplementedError):
         Mixed({'energy_eval_freq': 5, 'one_rdm': True}, system, True, None, _Qmc(), trial, complex,
               engine=eng)
+
+
+def test_multi_det_trial_setup_matches_reference(golden):
+    """Host setup for a particle-hole multi-determinant trial: orbitals, variational energy by the
+    Slater-Condon rules (multi_slater.py:153-176, estimators/mixed.py:537-572), mean-field shift
+    through contract_one_body (propagation/generic.py:82-86, multi_slater.py:235-259) and the
+    one-body propagator, against arrays recorded from the reference."""
+    from pauxy_b200.systems import Generic
+    from pauxy_b200.trial import MultiSlater
+    from pauxy_b200.propagation import GenericContinuous
+    g = golden('md_hybrid')
+    nelec = tuple(int(x) for x in g['nelec'])
+    system = Generic(nelec=nelec, h1e=numpy.array([g['h1e'], g['h1e']]), chol=g['hs_pot'], ecore=0.0)
+    trial = MultiSlater(system, (g['coeffs'], g['occa'], g['occb']), init=g['init'])
+    assert trial.ndets == 3 and trial.psi.shape == (3, 10, 10)
+    trial.half_rotate(system)
+    trial.calculate_energy(system)
+    numpy.testing.assert_allclose([trial.energy, trial.e1b, trial.e2b], g['trial_energy'], rtol=1e-12)
+
+    class Q(object):
+        dt = 0.005
+        nstblz = 5
+    prop = GenericContinuous(system, trial, Q())
+    numpy.testing.assert_allclose(prop.mf_shift, g['mf_shift'], rtol=1e-12, atol=1e-14)
+    numpy.testing.assert_allclose(prop.BH1, g['BH1'], rtol=1e-12, atol=1e-14)
+    # non-orthogonal expansion (random real orbitals): the host classes against the oracle's
+    # restatement of mixed.py:511-535 / multi_slater.py:244-258
+    from oracle import multi_det_oracle as mdo
+    rs = numpy.random.RandomState(5)
+    psi = rs.rand(3, 10, 10)
+    coeffs = rs.rand(3) + 1j * rs.rand(3)
+    trial2 = MultiSlater(system, (coeffs, psi))
+    trial2.half_rotate(system)
+    trial2.calculate_energy(system)
+    ham = mdo.MultiDetHamiltonian(g['h1e'], g['hs_pot'], 0.0, nelec, 0.005, coeffs, psi).setup_multi_det()
+    numpy.testing.assert_allclose([trial2.energy, trial2.e1b, trial2.e2b], ham.trial_energy(), rtol=1e-10)
+    prop2 = GenericContinuous(system, trial2, Q())
+    numpy.testing.assert_allclose(prop2.mf_shift, ham.mf_shift, rtol=1e-10, atol=1e-13)
