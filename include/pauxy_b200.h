@@ -115,7 +115,10 @@ enum pxb_field_id {
   PXB_F_WALKER_ELOC = 20,    /* c128 [W]    walker.eloc of the local-energy weight update (walker.py:37) */
   PXB_F_OVLP_DET = 21,       /* c128 [ndets, W(padded to 4, row stride a multiple of 256 bytes)] overlaps of
                                 the walkers with the single determinants of the trial (MultiDetWalker.ovlps) */
-  PXB_F_COUNT = 22
+  PXB_F_LOG_SHIFTS = 22,     /* walkers.use_log_shift: f64 log_shift, detR_shift, log_detR_shift, i64 shift
+                                counter, ... ; at byte 64: f64 [3] population sums |ot|, |detR|, |log_detR| of
+                                this device (all-reduce them between pxb_log_shift_sums and _update) */
+  PXB_F_COUNT = 23
 };
 
 int pxb_abi_version(void);
@@ -250,6 +253,14 @@ int pxb_accumulate_theta(pxb_handle h, void* stream);
  * rescale, comb selection with the caller's uniform r (numpy.random.random()
  * in the reference, handler.py:276), walker copies, weights reset to 1.
  * Entirely on the device, no host synchronisation. */
+/* walkers.use_log_shift (walkers/handler.py:228,456-475): running population averages that rescale
+ * the stored overlaps and detR factors.  pop_control does: pxb_log_shift_sums -> all-reduce of the
+ * three sums over the devices (the caller's collective) -> pxb_log_shift_update.  The walk itself
+ * (weights, energies, selection) is unaffected: every ratio the propagation uses is shift-free. */
+int pxb_log_shift_enable(pxb_handle h, int enable, void* stream);
+int pxb_log_shift_sums(pxb_handle h, void* stream);
+int pxb_log_shift_update(pxb_handle h, void* stream);
+
 int pxb_pop_control_comb(pxb_handle h, double r, void* stream);
 
 /* Multi-device pieces.  dev_global_abs_weights: f64 [Wtot] = |weight| of all
@@ -346,6 +357,10 @@ int pxb_pop_control_finish(pxb_handle h, void* stream);
 int pxb_bp_steps(pxb_handle h);
 int pxb_back_propagate(pxb_handle h, int nsteps, int nstblz, int init_walker, void* stream);
 int pxb_bp_reset(pxb_handle h, void* stream);
+/* estimator weights of the following pxb_back_propagate calls (back_propagation.py:75-80,187-196):
+ * 0 BP-PhL (walker.weight), 1 restore_weights = "partial" (times the product of the phase factors
+ * I/|I| of the stored steps), 2 "full" (also divided by the product of the cosine factors). */
+int pxb_bp_restore_weights(pxb_handle h, int mode);
 int pxb_bp_zero(pxb_handle h, void* stream);
 int pxb_get_phi_bp(pxb_handle h, int which, void* dev_out, void* stream);
 

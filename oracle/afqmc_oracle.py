@@ -367,8 +367,13 @@ class OracleAFQMC(object):
                  npop_control=1, energy_eval_freq=1, exp_order=6,
                  pop_control='comb', min_weight=0.1, max_weight=4.0,
                  verbose_step0=False, free_projection=False, force_bias=True,
-                 nbp=0, nsplit=1, init_walker=False, one_rdm=False):
+                 nbp=0, nsplit=1, init_walker=False, one_rdm=False, use_log_shift=False,
+                 restore_weights=None):
         self.ham = ham
+        # walkers/handler.py:45-46,456-475, walkers/walker.py:49-52
+        self.use_log_shift = use_log_shift
+        self.log_shift = self.detR_shift = self.log_detR_shift = 0.0
+        self.shift_counter = 1
         W = nwalkers
         self.W = W
         self.nsteps, self.nblocks, self.nstblz = nsteps, nblocks, nstblz
@@ -411,6 +416,10 @@ class OracleAFQMC(object):
         self.phi_old = self.phi.copy()
         self.configs = numpy.zeros((W, max(nbp, 1), ham.nchol), dtype=numpy.complex128)
         self.cfg_step = numpy.zeros(W, dtype=int)
+        # FieldConfig.weight_fac / cos_fac as running products (walkers/stack.py:51-71,118-121)
+        self.restore_weights = restore_weights
+        self.bp_ph = numpy.ones(W, dtype=numpy.complex128)
+        self.bp_cos = numpy.ones(W)
         self.bp_estimates = numpy.zeros(1 + 2 * ham.nbasis * ham.nbasis, dtype=numpy.complex128)
         self.bp_out = []          # (buff_ix, denominator, one_rdm [2, M, M]) per print
         self.estimator_update(0)
@@ -456,8 +465,17 @@ class OracleAFQMC(object):
                     ham, float(self.weight[iw]), complex(ovlp_old[k]), complex(ovlp_new[k]),
                     complex(self.hybrid_energy[iw]), complex(cfb[k]), complex(cmf[k]),
                     self.eshift)
+                if self.nbp:
+                    # continuous.py:273-289: wfac = (I / |I|, cosine_fac) or (0, 0), stored with the fields
+                    imp = cmath.exp(-ham.dt * (0.5 * (eh + complex(self.hybrid_energy[iw])) - self.eshift))
+                    magn = abs(imp)
+                    if not math.isinf(magn):
+                        cf = max(0, math.cos((-ham.dt * eh - complex(cfb[k])).imag))
+                        self.bp_ph[iw] *= (imp / magn) if magn > 1e-16 else 0.0
+                        self.bp_cos[iw] *= cf if magn > 1e-16 else 0.0
                 self.weight[iw] = w
-                self.ot[iw] = ot
+                # calc_overlap reports exp(logdet - log_shift) (single_det.py:192)
+                self.ot[iw] = ot * math.exp(-self.log_shift)
                 self.hybrid_energy[iw] = eh
                 self.nhe_trig += trig
         if self.step > 1:
@@ -469,6 +487,13 @@ class OracleAFQMC(object):
         """walkers/handler.py:225-254; `rand()` returns numpy.random.random()."""
         if self.W == 1:
             return
+        if self.use_log_shift:
+            # Walkers.update_log_ovlp (walkers/handler.py:456-475)
+            n, nm1 = self.shift_counter, self.shift_counter - 1
+            self.log_shift = (self.log_shift * nm1 + math.log(sum(abs(o) for o in self.ot) / self.W)) / n
+            self.detR_shift = (self.detR_shift * nm1 + math.log(sum(abs(x) for x in self.detR) / self.W)) / n
+            self.log_detR_shift = (self.log_detR_shift * nm1 + sum(abs(x) for x in self.log_detR) / self.W) / n
+            self.shift_counter += 1
         weights = numpy.abs(self.weight)
         total_weight = sum(weights)
         scale = total_weight / self.W
@@ -505,6 +530,8 @@ class OracleAFQMC(object):
             self.phi_old[k] = self.phi_old[c]
             self.configs[k] = self.configs[c]
             self.cfg_step[k] = self.cfg_step[c]
+            self.bp_ph[k] = self.bp_ph[c]
+            self.bp_cos[k] = self.bp_cos[c]
 
     # -- estimators -----------------------------------------------------------
     def estimator_update(self, step):
@@ -586,12 +613,18 @@ class OracleAFQMC(object):
             if ham.ne > na:
                 G[1] = gab(phi_bp[:, na:], self.phi_old[iw][:, na:]).T
             w = self.weight[iw]
+            if self.restore_weights == 'full':          # back_propagation.py:187-196
+                w = w * (self.bp_ph[iw] / self.bp_cos[iw])
+            elif self.restore_weights is not None:
+                w = w * self.bp_ph[iw]
             self.bp_estimates[0] += w
             self.bp_estimates[1:] += w * G.flatten()
             if buff_ix == self.bp_splits[-1]:
                 # FieldConfig.reset (walkers/stack.py:122-125), nprop_tot == nbp
                 if self.cfg_step[iw] % self.nbp == 0:
                     self.cfg_step[iw] = 0
+                    self.bp_ph[iw] = 1.0
+                    self.bp_cos[iw] = 1.0
         if buff_ix == self.bp_splits[-1]:
             self.phi_old = self.phi.copy()          # copy_historic_wfn (handler.py:200-203)
         self.bp_out.append((buff_ix, self.bp_estimates[0],
@@ -606,6 +639,7 @@ class OracleAFQMC(object):
         step = self.step
         if step % self.nstblz == 0:
             self.phi, detR, logdet = reortho(self.ham, self.phi)
+            detR = numpy.exp(logdet - self.detR_shift)      # single_det.py:250
             self.detR = detR
             self.log_detR = self.log_detR + numpy.log(detR)
             self.ot = self.ot / detR

@@ -113,7 +113,8 @@ def case_free(name, free, force_bias, pop='comb', walkers=None):
     save(name, meta, tr, setup=rh.reference_setup_arrays(a))
 
 
-def case_bp(name, nmo, nelec, nwalkers, tau_bp, nsplit, stab, scale, dt=0.005, steps=10, blocks=3):
+def case_bp(name, nmo, nelec, nwalkers, tau_bp, nsplit, stab, scale, dt=0.005, steps=10, blocks=3,
+            restore_weights=None):
     """Back propagation (estimators/back_propagation.py:127-225, propagation/generic.py:253-290,
     walkers/stack.py:5-127).  'bp_ref' is the reference's own driver test
     (qmc/tests/test_afqmc.py:232-278); 'bp_stress' re-orthogonalises inside the back
@@ -122,13 +123,16 @@ def case_bp(name, nmo, nelec, nwalkers, tau_bp, nsplit, stab, scale, dt=0.005, s
     h1e, chol, enuc, _ = generate_hamiltonian(nmo, nelec, cplx=False)
     hs = scale * chol.reshape((-1, nmo * nmo)).T.copy()
     opts = options(nwalkers, dt, steps, blocks, 8, stab=stab, popc=1)
-    opts['estimator'] = {'back_propagated': {'tau_bp': tau_bp, 'one_rdm': True, 'nsplit': nsplit},
+    bpo = {'tau_bp': tau_bp, 'one_rdm': True, 'nsplit': nsplit}
+    if restore_weights is not None:
+        bpo['restore_weights'] = restore_weights     # back_propagation.py:75-80,187-196
+    opts['estimator'] = {'back_propagated': bpo,
                          'mixed': {'energy_eval_freq': 1, 'verbose': False}}
     opts.pop('estimates', None)
     a, tr = rh.run_reference_traced(h1e, hs, enuc, nelec, opts)
     meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array(nelec), dt=dt,
                 nwalkers=nwalkers, steps=steps, blocks=blocks, seed=8, stab=stab, popc=1,
-                tau_bp=tau_bp, nsplit=nsplit)
+                tau_bp=tau_bp, nsplit=nsplit, restore_weights=str(restore_weights))
     extra = {k: tr[k] for k in ('bp_buff_ix', 'bp_denominator', 'bp_one_rdm', 'phi_old_final')}
     print(name, 'bp prints', len(tr['bp_buff_ix']), 'buff_ix', tr['bp_buff_ix'][:6])
     save(name, meta, tr, setup=rh.reference_setup_arrays(a), extra=extra)
@@ -311,6 +315,11 @@ if __name__ == '__main__':
     if 'bp' in which:
         case_bp('bp_ref', 11, (3, 3), 10, 0.025, 1, 10, 1.0, blocks=10)
         case_bp('bp_stress', 12, (4, 4), 16, 0.12, 2, 2, 6.0, dt=0.02, steps=5, blocks=4)
+    if 'bpw' in which:
+        case_bp('bp_restore_full', 12, (4, 4), 16, 0.06, 2, 2, 3.0, dt=0.01, steps=5, blocks=4,
+                restore_weights='full')
+        case_bp('bp_restore_partial', 12, (4, 4), 16, 0.06, 2, 2, 3.0, dt=0.01, steps=5, blocks=4,
+                restore_weights='partial')
     if 'tg' in which:
         case_test_generic()
     if 'c1' in which:
@@ -323,6 +332,8 @@ if __name__ == '__main__':
                     walkers={'population_control': 'pair_branch',
                              'min_weight': 0.9, 'max_weight': 1.1},
                     scale_chol=3.0, dt=0.01, nwalkers=64, keep_xi=False)
+    if 'logshift' in which:
+        case_stress('stress_logshift', 'comb', walkers={'use_log_shift': True})
     if 'pb' in which:
         case_stress('stress_pair_branch', 'pair_branch',
                     walkers={'population_control': 'pair_branch',

@@ -18,7 +18,7 @@ ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_E
 F_WEIGHT, F_UNSCALED_WEIGHT, F_OT, F_HYBRID_ENERGY, F_ELOC, F_DETR, F_LOG_DETR, \
     F_ESTIMATES, F_COUNTERS, F_PARENT_IX, F_XBAR, F_XSHIFTED, F_CMF_CFB, F_OVLP_NEW, \
     F_TOTAL_WEIGHT, F_PAIRS, F_PHASE, F_BP_RDM, F_BP_DENOM, F_THETA_SUM, F_WALKER_ELOC, F_OVLP_DET, \
-    F_COUNT = range(23)
+    F_LOG_SHIFTS, F_COUNT = range(24)
 FLAG_FREE_PROJECTION, FLAG_NO_FORCE_BIAS, FLAG_LOCAL_ENERGY_WEIGHT, FLAG_COMPLEX_ONE_BODY = 1, 2, 4, 8
 MAX_DETS = 8
 STEP_ORTHO, STEP_POP, STEP_ENERGY = 1, 2, 4
@@ -76,6 +76,9 @@ _PROTOS = {
     'pxb_accumulate': (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
     'pxb_zero_estimates': (ctypes.c_int, [_vp, _vp]),
     'pxb_accumulate_theta': (ctypes.c_int, [_vp, _vp]),
+    'pxb_log_shift_enable': (ctypes.c_int, [_vp, ctypes.c_int, _vp]),
+    'pxb_log_shift_sums': (ctypes.c_int, [_vp, _vp]),
+    'pxb_log_shift_update': (ctypes.c_int, [_vp, _vp]),
     'pxb_pop_control_comb': (ctypes.c_int, [_vp, ctypes.c_double, _vp]),
     'pxb_pop_rescale': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, _vp]),
     'pxb_comb_plan': (ctypes.c_int, [_vp, _vp, ctypes.c_int64, ctypes.c_double, _vp]),
@@ -94,6 +97,7 @@ _PROTOS = {
     'pxb_bp_steps': (ctypes.c_int, [_vp]),
     'pxb_back_propagate': (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
     'pxb_bp_reset': (ctypes.c_int, [_vp, _vp]),
+    'pxb_bp_restore_weights': (ctypes.c_int, [_vp, ctypes.c_int]),
     'pxb_bp_zero': (ctypes.c_int, [_vp, _vp]),
     'pxb_get_phi_bp': (ctypes.c_int, [_vp, ctypes.c_int, _vp, _vp]),
     'pxb_comb_plan_host': (ctypes.c_int, [_vp, ctypes.c_int64, ctypes.c_double, _vp]),

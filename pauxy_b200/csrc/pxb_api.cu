@@ -35,7 +35,7 @@ enum ArenaId {
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
   A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_OB, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
   A_FC, A_PHI_OLD, A_PHI_BP, A_PHI_BP2, A_THETA_BP, A_BP_PART, A_PSI_NAT, A_INIT_NAT, A_BFT, A_STEP_PARAMS,
-  A_OVLP_DET, A_ELOC_DET, A_XC, A_COEFF, A_ELOC_MIX, A_BF2, A_PHI_STACK,
+  A_OVLP_DET, A_ELOC_DET, A_XC, A_COEFF, A_ELOC_MIX, A_BF2, A_PHI_STACK, A_OT_TRUE, A_BPFAC, A_BPW,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -79,6 +79,7 @@ struct pxb_context {
   int nbp = 0;      // capacity (steps), 0: back propagation off
   int bp_step = 0;  // configurations stored since the last pxb_bp_reset
   int bp_chunks = 0;
+  int bp_restore = 0;  // estimator weights: 0 BP-PhL, 1 restore_weights = 'partial', 2 'full'
   // peer-memory population control: arena bases of all ranks mapped through CUDA IPC
   int peer_rank = -1, peer_n = 0;
   unsigned char* peer_base[PXB_MAX_PEERS] = {nullptr};
@@ -87,6 +88,7 @@ struct pxb_context {
   // second time a variant is seen and replayed afterwards; the scalars of the step are written to
   // A_STEP_PARAMS by one setter launch in front of it
   double eshift_im = 0.0;  // pxb_set_eshift_imag
+  bool log_shift_on = false;  // walkers.use_log_shift
   bool in_step = false;  // scalars already set by pxb_step: the entry points it calls leave them alone
   bool graphs_enabled = true;
   cudaStream_t side = nullptr;  // the comb plan runs here beside the local energy
@@ -202,6 +204,8 @@ CopyArgs copy_args(pxb_handle h) {
   c.log_detR = h->field<double>(PXB_F_LOG_DETR);
   c.phase = h->field<double2>(PXB_F_PHASE);
   c.weloc = h->field<double2>(PXB_F_WALKER_ELOC);
+  c.ottrue = h->ptr0<double2>(A_OT_TRUE);
+  c.bpfac = h->ptr0<double2>(A_BPFAC);
   c.X = h->ptr<double2>(A_X);
   c.phi_old = h->nbp > 0 ? h->ptr<double>(A_PHI_OLD) : nullptr;
   c.fc = h->nbp > 0 ? h->ptr<double>(A_FC) : nullptr;
@@ -1019,6 +1023,10 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_XC, D > 1 ? (size_t)2 * W * d.Np * 16 : 0);
   add(A_COEFF, (size_t)PXB_MAX_DETS * 16);
   add(A_ELOC_MIX, W * 16);
+  add(A_OT_TRUE, W * 16);
+  add(A_BPFAC, W * 32);
+  add(A_BPW, W * 16);
+  add(A_FIELD0 + PXB_F_LOG_SHIFTS, 256);   // LogShifts, then the three population sums at +64 bytes
   {
     const bool cob = (d.flags & FLAG_COMPLEX_ONE_BODY) != 0;
     add(A_BF2, cob ? 2 * bf_size(d) * 8 : 0);
@@ -1291,7 +1299,17 @@ int pxb_init_walkers(pxb_handle h, const void* dev_init_phi, double total_walker
       h->field<double>(PXB_F_WEIGHT), h->field<double>(PXB_F_UNSCALED_WEIGHT), h->field<double2>(PXB_F_OT),
       h->ptr<double2>(A_OVLP_OLD), h->field<double2>(PXB_F_HYBRID_ENERGY), h->field<double>(PXB_F_DETR),
       h->field<double>(PXB_F_LOG_DETR), h->field<double>(PXB_F_TOTAL_WEIGHT),
-      h->field<double2>(PXB_F_PHASE), h->field<double2>(PXB_F_WALKER_ELOC), total_walkers, d);
+      h->field<double2>(PXB_F_PHASE), h->field<double2>(PXB_F_WALKER_ELOC), h->ptr0<double2>(A_OT_TRUE),
+      total_walkers, d);
+  PXB_CUDA(h, cudaGetLastError());
+  ++h->launches;
+  bpfac_reset_kernel<<<(d.Wp + 255) / 256, 256, 0, st>>>(h->ptr0<double2>(A_BPFAC), d.Wp);
+  PXB_CUDA(h, cudaGetLastError());
+  {  // handler.py:46 shift_counter = 1, all shifts zero; `enabled` is kept
+    LogShifts ls{0.0, 0.0, 0.0, 1, h->log_shift_on ? 1 : 0, 0};
+    PXB_CUDA(h, cudaMemcpyAsync(h->field<void>(PXB_F_LOG_SHIFTS), &ls, sizeof ls, cudaMemcpyHostToDevice, st));
+    PXB_CUDA(h, cudaStreamSynchronize(st));
+  }
   PXB_CUDA(h, cudaGetLastError());
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ESTIMATES), 0, 160, st));
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_COUNTERS), 0, 64, st));
@@ -1384,9 +1402,12 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
     wl.weight = h->field<double>(PXB_F_WEIGHT);
     wl.ot = h->field<double2>(PXB_F_OT);
     wl.walker_eloc = h->field<double2>(PXB_F_WALKER_ELOC);
+    wl.ot_true = h->ptr0<double2>(A_OT_TRUE);
+    wl.shifts = h->field<LogShifts>(PXB_F_LOG_SHIFTS);
     wl.eloc_mix = h->ptr0<double2>(A_ELOC_MIX);
     wl.ovlp_new = h->field<double2>(PXB_F_OVLP_NEW);
-    wl.ovlp_old = ot_stale ? h->ptr0<double2>(A_OVLP_OLD) : h->field<double2>(PXB_F_OT);
+    wl.ovlp_old = ot_stale ? h->ptr0<double2>(A_OVLP_OLD)
+                           : (h->log_shift_on ? h->ptr0<double2>(A_OT_TRUE) : h->field<double2>(PXB_F_OT));
     wl.active = active;
     wl.total_weight = h->field<double>(PXB_F_TOTAL_WEIGHT);
     wl.counters = counters;
@@ -1404,7 +1425,11 @@ int pxb_propagate(pxb_handle h, const double* dev_xi, uint64_t rng_seed, int64_t
   wa.ot = h->field<double2>(PXB_F_OT);
   wa.ehyb = h->field<double2>(PXB_F_HYBRID_ENERGY);
   wa.ovlp_new = h->field<double2>(PXB_F_OVLP_NEW);
-  wa.ovlp_old = ot_stale ? h->ptr0<double2>(A_OVLP_OLD) : h->field<double2>(PXB_F_OT);
+  wa.ovlp_old = ot_stale ? h->ptr0<double2>(A_OVLP_OLD)
+                         : (h->log_shift_on ? h->ptr0<double2>(A_OT_TRUE) : h->field<double2>(PXB_F_OT));
+  wa.ot_true = h->ptr0<double2>(A_OT_TRUE);
+  wa.shifts = h->field<LogShifts>(PXB_F_LOG_SHIFTS);
+  wa.bpfac = (h->nbp > 0 && !(d.flags & FLAG_FREE_PROJECTION)) ? h->ptr0<double2>(A_BPFAC) : nullptr;
   wa.cmfcfb = h->field<double2>(PXB_F_CMF_CFB);
   wa.active = active;
   wa.total_weight = h->field<double>(PXB_F_TOTAL_WEIGHT);
@@ -1438,12 +1463,10 @@ int pxb_orthogonalise(pxb_handle h, void* stream) {
   qr_kernel<<<2 * d.Wp, GR_THREADS, smem, st>>>(a);
   PXB_CUDA(h, cudaGetLastError());
   ++h->launches;
-  qr_combine_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(a.logdet, h->field<double2>(PXB_F_OT),
-                                                       h->field<double>(PXB_F_DETR),
-                                                       h->field<double>(PXB_F_LOG_DETR),
-                                                       (d.flags & FLAG_FREE_PROJECTION)
-                                                           ? h->field<double>(PXB_F_WEIGHT) : nullptr,
-                                                       d.W);
+  qr_combine_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(
+      a.logdet, h->field<double2>(PXB_F_OT), h->ptr0<double2>(A_OT_TRUE), h->field<double>(PXB_F_DETR),
+      h->field<double>(PXB_F_LOG_DETR), (d.flags & FLAG_FREE_PROJECTION) ? h->field<double>(PXB_F_WEIGHT) : nullptr,
+      h->log_shift_on ? &h->field<LogShifts>(PXB_F_LOG_SHIFTS)->detR_shift : nullptr, d.W);
   PXB_CUDA(h, cudaGetLastError());
   // Theta = O^-1 phi^T is invariant under phi -> phi R^-1: it stays valid (to rounding)
   return PXB_OK;
@@ -1505,6 +1528,35 @@ int pxb_zero_estimates(pxb_handle h, void* stream) {
   PXB_REQUIRE_READY(h);
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_THETA_SUM), 0, (size_t)h->d.ne * h->d.M * 16, S(stream)));
   PXB_CUDA(h, cudaMemsetAsync(h->field<void>(PXB_F_ESTIMATES), 0, 160, S(stream)));
+  return PXB_OK;
+}
+
+// walkers.use_log_shift (walkers/handler.py:228,456-475)
+int pxb_log_shift_enable(pxb_handle h, int enable, void* stream) {
+  PXB_REQUIRE_READY(h);
+  h->log_shift_on = enable != 0;
+  const int e = enable ? 1 : 0;
+  PXB_CUDA(h, cudaMemcpyAsync(&h->field<LogShifts>(PXB_F_LOG_SHIFTS)->enabled, &e, 4, cudaMemcpyHostToDevice, S(stream)));
+  PXB_CUDA(h, cudaStreamSynchronize(S(stream)));
+  return PXB_OK;
+}
+
+int pxb_log_shift_sums(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  ++h->launches;
+  shift_sums_kernel<<<1, 1024, 0, S(stream)>>>(h->field<double2>(PXB_F_OT), h->field<double>(PXB_F_DETR),
+                                               h->field<double>(PXB_F_LOG_DETR),
+                                               h->field<double>(PXB_F_LOG_SHIFTS) + 8, h->d.W);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+int pxb_log_shift_update(pxb_handle h, void* stream) {
+  PXB_REQUIRE_READY(h);
+  ++h->launches;
+  shift_update_kernel<<<1, 1, 0, S(stream)>>>(h->field<LogShifts>(PXB_F_LOG_SHIFTS),
+                                             h->field<double>(PXB_F_LOG_SHIFTS) + 8, (double)h->d.Wtot);
+  PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
 
@@ -1976,7 +2028,11 @@ int pxb_back_propagate(pxb_handle h, int nsteps, int nstblz, int init_walker, vo
   BpRdmArgs a;
   a.phi_bp = phi_bp;
   a.theta = thbp;
-  a.weight = h->field<double>(PXB_F_WEIGHT);
+  ++h->launches;
+  bp_weight_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(h->field<double>(PXB_F_WEIGHT), h->ptr0<double2>(A_BPFAC),
+                                                     h->ptr0<double2>(A_BPW), h->bp_restore, d.W);
+  PXB_CUDA(h, cudaGetLastError());
+  a.weight = h->ptr0<double2>(A_BPW);
   a.part = h->ptr<double2>(A_BP_PART);
   a.d = d;
   a.nchunks = h->bp_chunks;
@@ -1998,7 +2054,16 @@ int pxb_bp_reset(pxb_handle h, void* stream) {
   // copy_historic_wfn (walkers/handler.py:200-203) + FieldConfig.reset (walkers/stack.py:122-125)
   PXB_CUDA(h, cudaMemcpyAsync(h->ptr<void>(A_PHI_OLD), h->phi(), of_size(h->d) * 8, cudaMemcpyDeviceToDevice,
                               S(stream)));
+  ++h->launches;
+  bpfac_reset_kernel<<<(h->d.Wp + 255) / 256, 256, 0, S(stream)>>>(h->ptr0<double2>(A_BPFAC), h->d.Wp);
+  PXB_CUDA(h, cudaGetLastError());
   h->bp_step = 0;
+  return PXB_OK;
+}
+
+int pxb_bp_restore_weights(pxb_handle h, int mode) {
+  if (!h || mode < 0 || mode > 2) return PXB_ERR_ARG;
+  h->bp_restore = mode;
   return PXB_OK;
 }
 

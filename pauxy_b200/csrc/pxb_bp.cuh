@@ -65,7 +65,7 @@ constexpr int BPR_T = 64, BPR_K = 8;
 struct BpRdmArgs {
   const double* phi_bp;   // OF
   const double* theta;    // OF, Theta_bp = (phi_old^T conj(phi_bp))^-1 phi_old^T
-  const double* weight;   // [W]
+  const double2* weight;  // [W] complex estimator weights (bp_weight_kernel)
   double2* part;          // [nchunks][2][M][M]
   Dims d;
   int nchunks, wchunk, tiles;
@@ -101,11 +101,11 @@ __global__ void __launch_bounds__(256) bp_rdm_kernel(BpRdmArgs a) {
       double2 va = make_double2(0.0, 0.0), vt = va;
       if (k < ktot) {
         const int w = w0 + (int)(k / ns), i = ioff + (int)(k % ns);
-        const double wt = a.weight[w];
-        if (wt != 0.0) {
+        const double2 wt = a.weight[w];
+        if (wt.x != 0.0 || wt.y != 0.0) {
           if (p0 + c < d.M) {
             const double2 x = *reinterpret_cast<const double2*>(a.phi_bp + of_index(d, w, i, p0 + c, 0));
-            va = make_double2(wt * x.x, -wt * x.y);  // weight * conj(phi_bp)
+            va = make_double2(wt.x * x.x + wt.y * x.y, wt.y * x.x - wt.x * x.y);  // weight * conj(phi_bp)
           }
           if (q0 + c < d.M) vt = *reinterpret_cast<const double2*>(a.theta + of_index(d, w, i, q0 + c, 0));
         }
@@ -144,10 +144,27 @@ __global__ void __launch_bounds__(256) bp_rdm_kernel(BpRdmArgs a) {
   }
 }
 
+// Estimator weight of back_propagation.py:187-196: BP-PhL walker.weight (mode 0), BP-PRes
+// weight * prod(I/|I|) (mode 1, restore_weights = "partial"), BP-Pres weight * prod(I/|I|) /
+// prod(cosine_fac) (mode 2, "full")
+__global__ void bp_weight_kernel(const double* __restrict__ weight, const double2* __restrict__ bpfac,
+                                 double2* __restrict__ out, int mode, int W) {
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= W) return;
+  double2 f = make_double2(1.0, 0.0);
+  if (mode >= 1) f = bpfac[2 * w];
+  if (mode == 2) {
+    const double c = bpfac[2 * w + 1].x;
+    f = make_double2(f.x / c, f.y / c);
+  }
+  const double wt = weight[w];
+  out[w] = make_double2(wt * f.x, wt * f.y);
+}
+
 // rdm[s][p][q] += sum_chunk part (fixed order); denom += sum_w weight (fixed tree), thread 0 of CTA 0
 __global__ void __launch_bounds__(256) bp_reduce_kernel(const double2* __restrict__ part, double2* __restrict__ rdm,
                                                         double2* __restrict__ denom,
-                                                        const double* __restrict__ weight, Dims d, int nchunks) {
+                                                        const double2* __restrict__ weight, Dims d, int nchunks) {
   const size_t n = (size_t)2 * d.M * d.M;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n;
        idx += (size_t)gridDim.x * blockDim.x) {
@@ -161,16 +178,25 @@ __global__ void __launch_bounds__(256) bp_reduce_kernel(const double2* __restric
     rdm[idx].y += im;
   }
   if (blockIdx.x == 0) {
-    __shared__ double red[256];
-    double s = 0.0;
-    for (int w = threadIdx.x; w < d.W; w += 256) s += weight[w];
-    red[threadIdx.x] = s;
+    __shared__ double2 red[256];
+    double sr = 0.0, si = 0.0;
+    for (int w = threadIdx.x; w < d.W; w += 256) {
+      sr += weight[w].x;
+      si += weight[w].y;
+    }
+    red[threadIdx.x] = make_double2(sr, si);
     __syncthreads();
     for (int m = 128; m > 0; m >>= 1) {
-      if (threadIdx.x < m) red[threadIdx.x] += red[threadIdx.x + m];
+      if (threadIdx.x < m) {
+        red[threadIdx.x].x += red[threadIdx.x + m].x;
+        red[threadIdx.x].y += red[threadIdx.x + m].y;
+      }
       __syncthreads();
     }
-    if (threadIdx.x == 0) denom[0].x += red[0];
+    if (threadIdx.x == 0) {
+      denom[0].x += red[0].x;
+      denom[0].y += red[0].y;
+    }
   }
 }
 

@@ -338,17 +338,24 @@ inline size_t qr_smem_bytes(const Dims& d) {
   return sizeof(cplx) * (size_t)nmax * greens_ld(d) + sizeof(double) * (GR_THREADS / 32) + 32;
 }
 
-// detR = exp(log_det - detR_shift[=0]); log_detR += log(detR); ot = ot / detR (single_det.py:245-254)
+// detR = exp(log_det - detR_shift); log_detR += log(detR); ot = ot / detR (single_det.py:245-254).
+// detR_shift != 0 only with walkers.use_log_shift; ot_true then follows the un-shifted determinant.
 __global__ void qr_combine_kernel(const double* __restrict__ logdet, double2* __restrict__ ot,
-                                  double* __restrict__ detR, double* __restrict__ log_detR,
-                                  double* __restrict__ weight_free, int n) {
+                                  double2* __restrict__ ot_true, double* __restrict__ detR,
+                                  double* __restrict__ log_detR, double* __restrict__ weight_free,
+                                  const double* __restrict__ detR_shift, int n) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= n) return;
-  const double dr = exp(logdet[2 * w] + logdet[2 * w + 1]);
+  const double ld = logdet[2 * w] + logdet[2 * w + 1];
+  const double shift = detR_shift != nullptr ? *detR_shift : 0.0;
+  const double dr = exp(ld - shift);
   detR[w] = dr;
   log_detR[w] += log(dr);
   const double2 o = ot[w];
   ot[w] = make_double2(o.x / dr, o.y / dr);
+  const double dt = shift != 0.0 ? exp(ld) : dr;
+  const double2 q = ot_true[w];
+  ot_true[w] = make_double2(q.x / dt, q.y / dt);
   // free projection (handler.py:178-181): polar(detR) with detR real and positive -> the
   // magnitude goes into the weight, the phase factor is exactly 1
   if (weight_free != nullptr) weight_free[w] *= dr;

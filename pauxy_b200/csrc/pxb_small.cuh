@@ -401,6 +401,57 @@ __global__ void active_kernel(const double* __restrict__ weight, int* __restrict
 }
 
 // ============================================================================
+// walkers.use_log_shift (walkers/handler.py:228,456-475): running averages of log(mean |ot|),
+// log(mean |detR|) and mean |log_detR| over the whole population; determinants are reported as
+// exp(logdet - log_shift) (single_det.py:159,192,320) and detR as exp(log_det - detR_shift)
+// (single_det.py:250).  Every ratio the propagation uses is shift-free, so the walk itself does
+// not change: the shifts only rescale the stored ot / detR / log_detR (and the Overlap column).
+// ============================================================================
+struct LogShifts {
+  double log_shift, detR_shift, log_detR_shift;
+  long long counter;  // handler.shift_counter (starts at 1)
+  int enabled, pad;
+};
+// sums[0..2] = sum_w |ot|, sum_w |detR|, sum_w |log_detR| over this device's walkers (fixed order)
+__global__ void __launch_bounds__(1024) shift_sums_kernel(const double2* __restrict__ ot, const double* __restrict__ detR,
+                                                          const double* __restrict__ log_detR,
+                                                          double* __restrict__ sums, int W) {
+  __shared__ double red[3][32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double v[3] = {0.0, 0.0, 0.0};
+  for (int w = tid; w < W; w += 1024) {
+    const double2 o = ot[w];
+    v[0] += hypot(o.x, o.y);
+    v[1] += fabs(detR[w]);
+    v[2] += fabs(log_detR[w]);
+  }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v[k] += __shfl_xor_sync(0xffffffffu, v[k], m);
+    if (lane == 0) red[k][warp] = v[k];
+  }
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      double x = red[k][lane];
+#pragma unroll
+      for (int m = 16; m > 0; m >>= 1) x += __shfl_xor_sync(0xffffffffu, x, m);
+      if (lane == 0) sums[k] = x;
+    }
+  }
+}
+// handler.py:465-475 from the (all-reduced) sums
+__global__ void shift_update_kernel(LogShifts* s, const double* __restrict__ sums, double ntot) {
+  const double n = (double)s->counter, nm1 = (double)(s->counter - 1);
+  s->log_shift = (s->log_shift * nm1 + log(sums[0] / ntot)) / n;
+  s->detR_shift = (s->detR_shift * nm1 + log(sums[1] / ntot)) / n;
+  s->log_detR_shift = (s->log_detR_shift * nm1 + sums[2] / ntot) / n;
+  s->counter += 1;
+}
+
+// ============================================================================
 // K6: hybrid weight update + cap (propagation/continuous.py:202-214,264-292,
 //     qmc/afqmc.py:235-236)
 // ============================================================================
@@ -411,6 +462,10 @@ struct WeightArgs {
   double2* ehyb;
   const double2* ovlp_new;
   const double2* ovlp_old;  // walker.ot, or the overlap recomputed at the top of the step when ot was stale
+  double2* ot_true;         // use_log_shift: the un-shifted overlap (ovlp_old of the next step)
+  const LogShifts* shifts;
+  double2* bpfac;           // back propagation: [W][2] running products of the phase factors I/|I| and of the
+                            // cosine factors since the last reset (walkers/stack.py:51-71,118-121), or null
   const double2* cmfcfb;
   const int* active;
   const double* total_weight;
@@ -426,6 +481,8 @@ __global__ void weight_kernel(WeightArgs a) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w >= d.W) return;
   double wt = a.weight[w];
+  // reported overlap: exp(-log_shift) times the determinant (single_det.py:192)
+  const double osc = a.shifts->enabled ? exp(-a.shifts->log_shift) : 1.0;
   if (a.active[w] && (d.flags & FLAG_FREE_PROJECTION)) {
     // propagate_walker_free (continuous.py:194-200): the constant terms go into weight and phase
     const double2 cmf = a.cmfcfb[2 * w];
@@ -438,7 +495,8 @@ __global__ void weight_kernel(WeightArgs a) {
     sincos(dtheta, &sn, &cs);
     const double2 ph = a.phase[w];
     a.phase[w] = make_double2(ph.x * cs - ph.y * sn, ph.x * sn + ph.y * cs);
-    a.ot[w] = a.ovlp_new[w];
+    a.ot[w] = make_double2(a.ovlp_new[w].x * osc, a.ovlp_new[w].y * osc);
+    a.ot_true[w] = a.ovlp_new[w];
   } else if (a.active[w]) {
     // ovlp_old == walker.ot: the overlap of the walker before this step (single_det.py:321 equals
     // the stored ot up to rounding; after a re-orthogonalisation ot was divided by detR)
@@ -471,11 +529,19 @@ __global__ void weight_kernel(WeightArgs a) {
       const double dtheta = -d.dt * eh_i - cfb.y;
       const double cf = fmax(0.0, cos(dtheta));
       wt = wt * (magn * cf);
-      a.ot[w] = on;
+      if (a.bpfac != nullptr) {
+        // FieldConfig.update(xmxbar, wfac) with wfac = (I / |I|, cosine_fac), or (0, 0) when
+        // |I| <= 1e-16 (continuous.py:284-289)
+        const bool ok = magn > 1e-16;
+        const double2 ph = a.bpfac[2 * w];
+        a.bpfac[2 * w] = ok ? make_double2(ph.x * cs - ph.y * sn, ph.x * sn + ph.y * cs) : make_double2(0.0, 0.0);
+        a.bpfac[2 * w + 1].x *= ok ? cf : 0.0;
+      }
     } else {
       wt = 0.0;
-      a.ot[w] = on;
     }
+    a.ot[w] = make_double2(on.x * osc, on.y * osc);
+    a.ot_true[w] = on;
   }
   if (step > 1) {
     const double cap = a.total_weight[0] * 0.10;
@@ -572,6 +638,8 @@ struct WeightLeArgs {
   double* weight;
   double2* ot;
   double2* walker_eloc;        // walker.eloc (walkers/walker.py:37), travels with the walker
+  double2* ot_true;
+  const LogShifts* shifts;
   const double2* eloc_mix;     // [Wp] eloc of this step
   const double2* ovlp_new;
   const double2* ovlp_old;
@@ -611,7 +679,9 @@ __global__ void weight_le_kernel(WeightLeArgs a) {
     } else {
       wt = 0.0;
     }
-    a.ot[w] = on;
+    const double osc = a.shifts->enabled ? exp(-a.shifts->log_shift) : 1.0;
+    a.ot[w] = make_double2(on.x * osc, on.y * osc);
+    a.ot_true[w] = on;
   }
   if (step > 1) {
     const double cap = a.total_weight[0] * 0.10;
@@ -1043,6 +1113,8 @@ struct CopyArgs {
   double* log_detR;
   double2* phase;
   double2* weloc;   // walker.eloc of the local-energy weight update
+  double2* ottrue;  // un-shifted overlap (use_log_shift)
+  double2* bpfac;   // [W][2] back-propagation weight-factor products
   double2* X;       // [2][Wp][Np] X_s = R_s^T Theta_s travels with the walker like Theta does
   double* phi_old;  // back propagation only (else nullptr): walker.phi_old, OF layout
   double* fc;       // back propagation only: field history, rows = nbp * NKC per walker group
@@ -1051,7 +1123,7 @@ struct CopyArgs {
 };
 
 __device__ __host__ __forceinline__ size_t payload_doubles(const Dims& d, bool bp, int fc_rows) {
-  return (size_t)(bp ? 3 : 2) * d.ne * d.KC * 8 + (bp ? (size_t)fc_rows * 8 : 0) + (size_t)4 * d.Np + 20;
+  return (size_t)(bp ? 3 : 2) * d.ne * d.KC * 8 + (bp ? (size_t)fc_rows * 8 : 0) + (size_t)4 * d.Np + 26;
 }
 
 // X rows of walker src (array sX) -> walker dst (array dX)
@@ -1109,6 +1181,9 @@ __global__ void __launch_bounds__(256) copy_pairs_kernel(CopyArgs a, const int* 
       a.ehyb[dst] = a.ehyb[src];
       a.phase[dst] = a.phase[src];
       a.weloc[dst] = a.weloc[src];
+      a.ottrue[dst] = a.ottrue[src];
+      a.bpfac[2 * dst] = a.bpfac[2 * src];
+      a.bpfac[2 * dst + 1] = a.bpfac[2 * src + 1];
       a.detR[dst] = a.detR[src];
       a.log_detR[dst] = a.log_detR[src];
       for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)dst + k] = a.eloc[3 * (size_t)src + k];
@@ -1137,6 +1212,9 @@ __global__ void __launch_bounds__(256) copy_list_kernel(CopyArgs a, const int* s
       a.ehyb[dst] = a.ehyb[src];
       a.phase[dst] = a.phase[src];
       a.weloc[dst] = a.weloc[src];
+      a.ottrue[dst] = a.ottrue[src];
+      a.bpfac[2 * dst] = a.bpfac[2 * src];
+      a.bpfac[2 * dst + 1] = a.bpfac[2 * src + 1];
       a.detR[dst] = a.detR[src];
       a.log_detR[dst] = a.log_detR[src];
       for (int k = 0; k < 3; ++k) a.eloc[3 * (size_t)dst + k] = a.eloc[3 * (size_t)src + k];
@@ -1191,6 +1269,9 @@ __global__ void __launch_bounds__(256) pull_pairs_kernel(CopyArgs a, PeerArgs p,
       a.ehyb[dst] = rebase(a.ehyb, lb, pb)[src];
       a.phase[dst] = rebase(a.phase, lb, pb)[src];
       a.weloc[dst] = rebase(a.weloc, lb, pb)[src];
+      a.ottrue[dst] = rebase(a.ottrue, lb, pb)[src];
+      a.bpfac[2 * dst] = rebase(a.bpfac, lb, pb)[2 * src];
+      a.bpfac[2 * dst + 1] = rebase(a.bpfac, lb, pb)[2 * src + 1];
       a.detR[dst] = rebase(a.detR, lb, pb)[src];
       a.log_detR[dst] = rebase(a.log_detR, lb, pb)[src];
       const double2* se = rebase(a.eloc, lb, pb);
@@ -1228,7 +1309,7 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
       pack_rows(a.fc, b + (size_t)3 * n8 * 8, a.fc_rows, w, unpack);
     }
     {
-      double2* xb = reinterpret_cast<double2*>(b + pd - 20 - (size_t)4 * d.Np);
+      double2* xb = reinterpret_cast<double2*>(b + pd - 26 - (size_t)4 * d.Np);
       for (int idx = threadIdx.x; idx < 2 * d.Np; idx += blockDim.x) {
         const int sp = idx / d.Np, n = idx - sp * d.Np;
         double2* gx = a.X + ((size_t)sp * d.Wp + w) * d.Np + n;
@@ -1239,7 +1320,7 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
       }
     }
     if (threadIdx.x == 0) {
-      double* s = b + pd - 20;
+      double* s = b + pd - 26;
       if (unpack) {
         a.weight[w] = s[0];
         a.unscaled[w] = s[1];
@@ -1251,6 +1332,9 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
         a.e1b[w] = make_double2(s[14], s[15]);
         a.phase[w] = make_double2(s[16], s[17]);
         a.weloc[w] = make_double2(s[18], s[19]);
+        a.ottrue[w] = make_double2(s[20], s[21]);
+        a.bpfac[2 * w] = make_double2(s[22], s[23]);
+        a.bpfac[2 * w + 1] = make_double2(s[24], s[25]);
       } else {
         s[0] = a.weight[w];
         s[1] = a.unscaled[w];
@@ -1270,12 +1354,27 @@ __global__ void __launch_bounds__(256) pack_kernel(CopyArgs a, const int* slots,
         s[17] = a.phase[w].y;
         s[18] = a.weloc[w].x;
         s[19] = a.weloc[w].y;
+        s[20] = a.ottrue[w].x;
+        s[21] = a.ottrue[w].y;
+        s[22] = a.bpfac[2 * w].x;
+        s[23] = a.bpfac[2 * w].y;
+        s[24] = a.bpfac[2 * w + 1].x;
+        s[25] = a.bpfac[2 * w + 1].y;
       }
     }
   }
 }
 
 // skip_flag (optional): nothing is written when *skip_flag != 0 (vanished population)
+// bpfac[w] = (1, 1): FieldConfig.reset (walkers/stack.py:122-127)
+__global__ void bpfac_reset_kernel(double2* bpfac, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    bpfac[2 * i] = make_double2(1.0, 0.0);
+    bpfac[2 * i + 1] = make_double2(1.0, 0.0);
+  }
+}
+
 __global__ void fill_kernel(double* p, double v, int n, const long long* skip_flag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (skip_flag != nullptr && *skip_flag != 0) return;
@@ -1284,7 +1383,7 @@ __global__ void fill_kernel(double* p, double v, int n, const long long* skip_fl
 
 __global__ void init_scalars_kernel(double* weight, double* unscaled, double2* ot, const double2* ovlp,
                                     double2* ehyb, double* detR, double* log_detR, double* total_weight,
-                                    double2* phase, double2* weloc, double total, Dims d) {
+                                    double2* phase, double2* weloc, double2* ottrue, double total, Dims d) {
   const int w = blockIdx.x * blockDim.x + threadIdx.x;
   if (w == 0) total_weight[0] = total;
   if (w >= d.Wp) return;
@@ -1292,6 +1391,7 @@ __global__ void init_scalars_kernel(double* weight, double* unscaled, double2* o
   weight[w] = real ? 1.0 : 0.0;
   unscaled[w] = real ? 1.0 : 0.0;
   ot[w] = ovlp[w];
+  ottrue[w] = ovlp[w];
   ehyb[w] = make_double2(0.0, 0.0);
   phase[w] = make_double2(1.0, 0.0);
   weloc[w] = make_double2(0.0, 0.0);

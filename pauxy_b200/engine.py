@@ -109,6 +109,9 @@ class Engine(object):
         self.bp_denom = self._view(L.F_BP_DENOM, c128)
         self.theta_sum = self._view(L.F_THETA_SUM, c128, (self.ne, self.M))
         self.walker_eloc = self._view(L.F_WALKER_ELOC, c128)[:W]
+        ls = self._view(L.F_LOG_SHIFTS, f64)
+        self.log_shifts = ls[:3]          # log_shift, detR_shift, log_detR_shift
+        self.shift_sums = ls[8:11]        # population sums of |ot|, |detR|, |log_detR| (this device)
         # overlaps with the single determinants of the trial, [ndets, W] (MultiDetWalker.ovlps)
         od = self._view(L.F_OVLP_DET, c128)
         self.ovlp_det = od.view(self.ndets, od.numel() // self.ndets)[:, :W]
@@ -304,6 +307,18 @@ class Engine(object):
             self._check(self.lib.pxb_zero_estimates(self._h, self._stream()))
 
     # ----------------------------------------------------- population control
+    def log_shift_enable(self, on=True):
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_log_shift_enable(self._h, 1 if on else 0, self._stream()))
+
+    def update_log_shifts(self, comm=None):
+        """Walkers.update_log_ovlp (walkers/handler.py:456-475): device sums, all-reduce, running average."""
+        with torch.cuda.device(self.device):
+            self._check(self.lib.pxb_log_shift_sums(self._h, self._stream()))
+            if comm is not None and comm.size > 1:
+                comm.allreduce_sum_(self.shift_sums)
+            self._check(self.lib.pxb_log_shift_update(self._h, self._stream()))
+
     def pop_control_comb(self, r):
         with torch.cuda.device(self.device):
             self._check(self.lib.pxb_pop_control_comb(self._h, float(r), self._stream()))
@@ -413,6 +428,9 @@ class Engine(object):
         with torch.cuda.device(self.device):
             self._check(self.lib.pxb_back_propagate(self._h, int(nsteps), int(nstblz),
                                                     1 if init_walker else 0, self._stream()))
+
+    def bp_restore_weights(self, mode):
+        self._check(self.lib.pxb_bp_restore_weights(self._h, {None: 0, 'partial': 1, 'full': 2}[mode]))
 
     def bp_reset(self):
         with torch.cuda.device(self.device):

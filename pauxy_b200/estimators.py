@@ -149,19 +149,27 @@ class BackPropagation(object):
         self.nreg = len(self.header)
         self.accumulated = False
         self.eval_energy = bp.get('evaluate_energy', False)
-        for key, off in (('two_rdm', None), ('evaluate_ekt', False), ('restore_weights', None),
-                         ('evaluate_energy', False)):
+        self.restore_weights = bp.get('restore_weights', None)
+        if self.restore_weights not in (None, 'full', 'partial'):
+            self.restore_weights = 'partial'      # back_propagation.py:190-195: anything but "full"
+        for key, off in (('two_rdm', None), ('evaluate_ekt', False), ('evaluate_energy', False)):
             if bp.get(key, off) not in (off,):
                 raise NotImplementedError("pauxy_b200: back_propagated option %r is not built "
                                           "(one_rdm with BP-PhL weights is)" % key)
         if self.nmax < 1:
             raise ValueError("back_propagated: tau_bp < timestep")
+        if self.nmax % self.nsplit != 0:
+            # the reference's FieldConfig.reset only rewinds when step % nprop_tot == 0 (stack.py:122-125),
+            # which never happens then: the history would overflow
+            raise ValueError("back_propagated: int(tau_bp / timestep) must be a multiple of nsplit")
         if trial.ndets != 1:
             raise NotImplementedError("pauxy_b200: back propagation needs a single-determinant trial")
         self.nstblz = qmc.nstblz
         self.BT2 = BT2
         self.dt = qmc.dt
         self.engine = engine
+        if engine is not None and self.restore_weights is not None:
+            engine.bp_restore_weights(self.restore_weights)
         self.G = numpy.zeros((2, system.nbasis, system.nbasis), dtype=numpy.complex128)
         self.buff_ix = 0
         # what the reference pushes to estimates.h5 under back_propagated/ (in memory here)

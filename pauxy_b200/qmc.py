@@ -177,7 +177,7 @@ class AFQMC(object):
         start_step = self._tick()
         evaluate = step % mixed.energy_eval_freq == 0
         if (self.fused_step and comm.size == 1 and self.engine.nbp == 0 and not mixed.calc_one_rdm
-                and self.psi.pcont_method == 'comb' and self.psi.overlap
+                and self.psi.pcont_method == 'comb' and self.psi.overlap and not self.psi.use_log_shift
                 and len(self.estimators.estimators) == 1 and (mixed.eval_energy or not evaluate)
                 and self.propagators.hybrid):
             # orthogonalise + propagate + pop_control + estimators.update of the loop body below as

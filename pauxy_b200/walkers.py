@@ -173,8 +173,6 @@ class Walkers(object):
         self.read_file = walker_opts.get('read_file', None)
         self.write_restart = self.write_freq > 0
         self.use_log_shift = walker_opts.get('use_log_shift', False)
-        if self.use_log_shift:
-            raise NotImplementedError("pauxy_b200: use_log_shift is not built")
         self.walker_type = 'SD' if trial.ndets == 1 else 'MSD'
         self.pcont_method = get_input_value(walker_opts, 'population_control', default='comb')
         self.min_weight = walker_opts.get('min_weight', 0.1)
@@ -188,6 +186,8 @@ class Walkers(object):
         self.target_weight = qmc.ntot_walkers
         self.nw = qmc.nwalkers
         engine.init_walkers(trial.init, qmc.ntot_walkers)
+        if self.use_log_shift:
+            engine.log_shift_enable(True)
         if self.peer_copy and comm is not None and comm.size > 1:
             engine.attach_peers(comm)
         if trial.ndets == 1:
@@ -241,6 +241,8 @@ class Walkers(object):
         same numbers."""
         if self.ntot_walkers == 1:
             return
+        if self.use_log_shift:
+            self.engine.update_log_shifts(comm)      # handler.py:228-229
         if self.pcont_method == "comb":
             self.comb(comm, overlap_energy)
         elif self.pcont_method == "pair_branch":

@@ -96,6 +96,18 @@ def test_fused_step_and_graph_replay(golden, top, replays):
     _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
 
 
+def test_log_shift(golden):
+    """walkers.use_log_shift (walkers/handler.py:228,456-475) against a trace of the reference."""
+    g = golden('stress_logshift')
+    afqmc, h = _run(g, g['h1e'], g['hs_pot'], float(g['ecore']), walkers={'use_log_shift': True})
+    assert numpy.array_equal(h['parent_ix'], g['parent_ix'])
+    _close(h['weight'], g['weight'], atol=1e-13)
+    _close(h['ot'], g['ot'])
+    _close(h['eloc'], g['eloc'], atol=1e-10)
+    _close(afqmc.engine.detR.cpu().numpy(), g['detR'][-1], rtol=1e-10)
+    _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
+
+
 def test_sequential_pop_control_path(golden):
     """walkers.overlap_energy=False: comb first, energy afterwards on the copied walkers (the
     reference's literal order); must give the same trace as the overlapped default."""
@@ -200,7 +212,7 @@ def test_free_projection_and_no_force_bias(golden, name):
     _close(afqmc.psi.phi_host(), g['phi_final'], atol=1e-11)
 
 
-@pytest.mark.parametrize('name', ['bp_ref', 'bp_stress'])
+@pytest.mark.parametrize('name', ['bp_ref', 'bp_stress', 'bp_restore_full', 'bp_restore_partial'])
 def test_back_propagation(golden, name):
     """Back-propagated one-body density matrices (estimators/back_propagation.py:127-225,
     propagation/generic.py:180-213,253-290, walkers/stack.py:5-127) against traces of the
@@ -208,12 +220,13 @@ def test_back_propagation(golden, name):
     bp_stress re-orthogonalises inside the back propagation, splits it in two and moves field
     histories between walkers in the comb."""
     g = golden(name)
-    afqmc, h = _run(g, g['h1e'], g['hs_pot'], float(g['ecore']),
-                    back_propagated={'tau_bp': float(g['tau_bp']), 'nsplit': int(g['nsplit']),
-                                     'one_rdm': True})
+    bpo = {'tau_bp': float(g['tau_bp']), 'nsplit': int(g['nsplit']), 'one_rdm': True}
+    if 'restore_weights' in g and str(g['restore_weights']) != 'None':
+        bpo['restore_weights'] = str(g['restore_weights'])     # back_propagation.py:75-80,187-196
+    afqmc, h = _run(g, g['h1e'], g['hs_pot'], float(g['ecore']), back_propagated=bpo)
     assert numpy.array_equal(h['parent_ix'], g['parent_ix'])
     _close(h['weight'], g['weight'], atol=1e-13)
-    _close(h['ot'], g['ot'], rtol=1e-10 if name == 'bp_ref' else 2e-9)   # stress walk amplifies rounding
+    _close(h['ot'], g['ot'], rtol=2e-9 if name == 'bp_stress' else 1e-10)   # stress walk amplifies rounding
     bp = afqmc.estimators.estimators['back_prop']
     ix = list(g['bp_buff_ix'])
     got_den = numpy.zeros(len(ix), dtype=numpy.complex128)
@@ -225,7 +238,7 @@ def test_back_propagation(golden, name):
         got_rdm[n] = bp.output['one_rdm'][b][k]
         seen[b] = k + 1
     assert all(len(bp.output['denominator'][b]) == seen[b] for b in seen)
-    _close(got_den, g['bp_denominator'], rtol=1e-12)
+    _close(got_den, g['bp_denominator'], rtol=1e-12 if 'restore' not in name else 1e-10)
     _close(got_rdm, g['bp_one_rdm'], rtol=1e-9, atol=1e-9)
     _close(afqmc.engine.get_phi_bp(historic=True).cpu().numpy(), g['phi_old_final'], atol=1e-9)
     if name == 'bp_ref':

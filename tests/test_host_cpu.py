@@ -252,10 +252,18 @@ def test_back_propagation_estimator_schedule():
     assert bp.output['denominator'][6] == [2.0 + 0j, 2.0 + 0j]
     assert float(bp.output['one_rdm'][3][0].real.max()) == 3.0
     numpy.testing.assert_allclose(bp.one_rdm()[0], numpy.full((2, 4, 4), 3.0))
-    for bad in ({'restore_weights': 'full'}, {'evaluate_energy': True}, {'two_rdm': True}):
+    for bad in ({'evaluate_energy': True}, {'two_rdm': True}):
         with pytest.raises(NotImplementedError):
             BackPropagation(dict(tau_bp=0.06, **bad), True, None, _Qmc(), system, trial, complex,
                             prop.BH1, engine=eng)
+    # restore_weights selects the estimator weights on the device (back_propagation.py:187-196)
+    eng.bp_restore_weights = lambda mode: eng.calls.append(('bp_restore_weights', mode))
+    bpw = BackPropagation(dict(tau_bp=0.06, restore_weights='full'), True, None, _Qmc(), system, trial,
+                          complex, prop.BH1, engine=eng)
+    assert bpw.restore_weights == 'full' and ('bp_restore_weights', 'full') in eng.calls
+    with pytest.raises(ValueError):     # nmax = 6 steps cannot be split in 4
+        BackPropagation(dict(tau_bp=0.06, nsplit=4), True, None, _Qmc(), system, trial, complex,
+                        prop.BH1, engine=eng)
 
 
 def test_mixed_print_step_block_arithmetic():
