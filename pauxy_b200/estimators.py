@@ -260,6 +260,13 @@ class Estimators(object):
         container: 'basic/headers', 'basic/energies/%09d', 'back_propagated/denominator_<ix>/%09d',
         'back_propagated/one_rdm_<ix>/%09d', 'metadata'."""
         import json
+        from . import io
+        if filename is not None and str(filename).endswith(('.h5', '.hdf5')) and io.have_h5py():
+            bp = self.estimators.get('back_prop')
+            io.write_estimates(filename, self.estimators['mixed'].header[1:],
+                               [row[1:] for row in self.estimators['mixed'].rows], metadata,
+                               bp.output if bp is not None else None)
+            return filename
         filename = filename or (self.basename + '.0.npz')
         out = {'basic/headers': numpy.array(self.estimators['mixed'].header[1:]).astype('S')}
         for n, row in enumerate(self.estimators['mixed'].rows):

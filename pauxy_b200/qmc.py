@@ -72,8 +72,14 @@ class AFQMC(object):
         self._init_time = time.time()
         self.run_time = time.asctime()
         if system is None:
-            raise NotImplementedError("pauxy_b200: pass system=Generic(...); integral files need "
-                                      "HDF5 (SURVEY.md section 8f.2)")
+            # afqmc.py:120-126 get_system: a QMCPACK-format integral file (needs h5py, pauxy_b200/io.py)
+            sys_opts = get_input_value(options, 'system', default={}, alias=['model'])
+            integrals = sys_opts.get('integrals', None)
+            if integrals is None:
+                raise ValueError("pauxy_b200: pass system=Generic(...) or options['system']['integrals']")
+            from . import io
+            nelec = (sys_opts['nup'], sys_opts['ndown']) if 'nup' in sys_opts else None
+            system = io.system_from_file(integrals, nelec)
         self.system = system
         qmc_opt = get_input_value(options, 'qmc', default={}, alias=['qmc_options'])
         self.qmc = QMCOpts(qmc_opt, self.system, verbose=self.verbosity > 1)

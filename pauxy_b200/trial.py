@@ -199,8 +199,15 @@ def get_trial_wavefunction(system, options=None, comm=None, scomm=None, verbose=
         raise NotImplementedError("pauxy_b200: only the MultiSlater single-determinant trial "
                                   "is on the hot path (got %r)" % name)
     if options.get('filename') is not None:
-        raise NotImplementedError("pauxy_b200: wavefunction files need HDF5 (SURVEY.md 8f.2); "
-                                  "pass trial=MultiSlater(system, (coeffs, psi)) instead")
+        # trial_wavefunction/utils.py:26-58: QMCPACK-format wavefunction file (needs h5py)
+        from . import io
+        wfn, psi0 = io.read_qmcpack_wfn(options['filename'], nelec=system.nelec)
+        ndets = options.get('ndets', None)
+        if ndets is not None:
+            wfn = tuple(w[:ndets] for w in wfn)
+        trial = MultiSlater(system, wfn, init=psi0, options=options, verbose=verbose)
+        trial.half_rotate(system, scomm)
+        return trial
     na, nb = system.nup, system.ndown
     wfn = numpy.zeros((1, system.nbasis, na + nb), dtype=numpy.complex128)
     I = numpy.identity(system.nbasis, dtype=numpy.complex128)

@@ -376,16 +376,34 @@ class Walkers(object):
                             eng.phase.cpu().numpy(), eng.ot.cpu().numpy()], axis=1)
         return numpy.concatenate([head, phi], axis=1)
 
+    def _use_h5(self, base):
+        from . import io
+        return str(base).endswith(('.h5', '.hdf5')) and io.have_h5py()
+
     def write_walkers(self, comm=None):
-        numpy.save(self._restart_name(self.write_file), self.get_write_buffers())
+        """handler.py:443-454.  HDF5 ('walker_%d' datasets, all ranks into one file) where h5py is
+        installed and the name ends in .h5; otherwise one .npy per rank with the same records."""
+        buffers = self.get_write_buffers()
+        if self._use_h5(self.write_file):
+            from . import io
+            for r in range(1 if comm is None else comm.size):    # ranks take turns appending
+                if r == self.rank:
+                    io.write_walkers_h5(self.write_file, buffers, self.walker_offset, create=(r == 0))
+                if comm is not None:
+                    comm.barrier()
+            return
+        numpy.save(self._restart_name(self.write_file), buffers)
 
     def read_walkers(self, comm=None):
         """set_walker_from_buffer for every walker (handler.py:437-442, :477-485)."""
         eng = self.engine
-        buff = numpy.load(self._restart_name(self.read_file))
+        if self._use_h5(self.read_file):
+            from . import io
+            buff = io.read_walkers_h5(self.read_file, self.walker_offset, self.nwalkers)
+        else:
+            buff = numpy.load(self._restart_name(self.read_file))
         if buff.shape != (self.nwalkers, 3 + eng.M * eng.ne):
-            raise ValueError("restart file %s does not match this walker population"
-                             % self._restart_name(self.read_file))
+            raise ValueError("restart file %s does not match this walker population" % self.read_file)
         eng.set_phi(numpy.ascontiguousarray(buff[:, 3:].reshape(self.nwalkers, eng.M, eng.ne)))
         eng.weight.copy_(torch.as_tensor(numpy.ascontiguousarray(buff[:, 0].real)))
         eng.phase.copy_(torch.as_tensor(numpy.ascontiguousarray(buff[:, 1])))

@@ -338,3 +338,60 @@ def test_multi_det_trial_setup_matches_reference(golden):
     numpy.testing.assert_allclose([trial2.energy, trial2.e1b, trial2.e2b], ham.trial_energy(), rtol=1e-10)
     prop2 = GenericContinuous(system, trial2, Q())
     numpy.testing.assert_allclose(prop2.mf_shift, ham.mf_shift, rtol=1e-10, atol=1e-13)
+
+
+def test_hdf5_formats_round_trip(golden, tmp_path, monkeypatch):
+    """pauxy_b200/io.py writes and reads the reference's HDF5 layouts (QMCPACK Hamiltonians and
+    wavefunctions, estimator output, walker restart).  h5py is not in the image: the round trips run
+    against the in-memory stand-in the reference harness uses (oracle/stubs/h5py), which checks the
+    dataset names, shapes and the complex [..., 2] storage, not the HDF5 library itself."""
+    import os
+    import sys
+    stubs = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', 'stubs')
+    monkeypatch.syspath_prepend(stubs)
+    sys.modules.pop('h5py', None)
+    from pauxy_b200 import io
+    assert io.have_h5py()
+    g = golden('md_hybrid')
+    M = g['h1e'].shape[0]
+    # dense Hamiltonian, real and complex storage
+    for real in (True, False):
+        fn = str(tmp_path / ('ham_%d.h5' % real))
+        io.write_qmcpack_dense(g['h1e'], g['hs_pot'], (5, 5), M, enuc=0.25, filename=fn, real_chol=real)
+        h, chol, enuc, nmo, na, nb = io.read_qmcpack_hamiltonian(fn)
+        assert (nmo, na, nb, enuc) == (M, 5, 5, 0.25)
+        numpy.testing.assert_array_equal(numpy.real(h), g['h1e'])
+        numpy.testing.assert_array_equal(numpy.real(chol), g['hs_pot'])
+        system = io.system_from_file(fn)
+        assert system.nbasis == M and system.nelec == (5, 5) and not numpy.iscomplexobj(system.chol_vecs)
+    # particle-hole and non-orthogonal wavefunctions
+    fn = str(tmp_path / 'phmsd.h5')
+    io.write_qmcpack_wfn(fn, (g['coeffs'], g['occa'], g['occb']), 'uhf', (5, 5), M,
+                         init=(g['init'][:, :5], g['init'][:, 5:]))
+    (c, oa, ob), psi0 = io.read_qmcpack_wfn(fn, nelec=(5, 5))
+    numpy.testing.assert_array_equal(c, g['coeffs'])
+    numpy.testing.assert_array_equal(oa, g['occa'])
+    numpy.testing.assert_array_equal(ob, g['occb'])
+    numpy.testing.assert_array_equal(psi0, g['init'])
+    rs = numpy.random.RandomState(3)
+    psi = rs.rand(2, M, 10) + 1j * rs.rand(2, M, 10)
+    fn = str(tmp_path / 'nomsd.h5')
+    io.write_qmcpack_wfn(fn, (numpy.array([0.6, 0.8j]), psi), 'uhf', (5, 5), M)
+    (c, p2), psi0 = io.read_qmcpack_wfn(fn)
+    numpy.testing.assert_array_equal(p2, psi)
+    numpy.testing.assert_array_equal(psi0, psi[0])
+    # estimator rows and walker records
+    fn = str(tmp_path / 'estimates.0.h5')
+    rows = [numpy.arange(10) + 0.5j, numpy.arange(10) * 2.0]
+    io.write_estimates(fn, ['WeightFactor', 'Weight'], rows, {'qmc': {'dt': 0.01}},
+                       {'one_rdm': {6: [numpy.ones((2, 3, 3))]}})
+    import h5py
+    with h5py.File(fn, 'r') as fh5:
+        numpy.testing.assert_array_equal(fh5['basic/energies/000000001'][:], rows[1])
+        assert fh5['back_propagated/one_rdm_6/000000000'].shape == (2, 3, 3)
+    fn = str(tmp_path / 'restart.h5')
+    buf = rs.rand(4, 7) + 0j
+    io.write_walkers_h5(fn, buf[:2], 0, create=True)
+    io.write_walkers_h5(fn, buf[2:], 2, create=False)
+    numpy.testing.assert_array_equal(io.read_walkers_h5(fn, 1, 3), buf[1:])
+    sys.modules.pop('h5py', None)
