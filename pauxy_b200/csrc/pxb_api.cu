@@ -527,19 +527,20 @@ int run_taylor2(pxb_handle h, double* phi, const int* active, int ochunk, int nc
   return 1;
 }
 
-template <int WMX, int WNX>
+template <int WMX, int WNX, int NG>
 int launch_taylor3(pxb_handle h, const Taylor3Args& a, size_t smem, int grid, cudaStream_t st) {
-  auto kern = taylor3_kernel<WMX, WNX>;
+  auto kern = taylor3_kernel<WMX, WNX, NG>;
   PXB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->launches;
-  kern<<<grid, T3_THREADS, smem, st>>>(a);
+  kern<<<grid, T3Cfg<NG>::threads, smem, st>>>(a);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
 
-// 3-product planar kernel (pxb_taylor3.cuh): shapes whose warp rectangle (ceil(MT/4) x ceil(NT8/2)
-// tile pairs x 3 accumulator sets) fits the 232-register consumer budget and whose two iterate
-// buffers leave room for a >= 3-deep ring.  Returns 1 if the shape is not covered.
+// 3-product planar kernel (pxb_taylor3.cuh): shapes whose warp rectangle (ceil(MT/4) x ceil(NT8/NG)
+// tile pairs x 3 accumulator sets) fits the consumer register budget (NG = 3: 160 registers, up to
+// 4 x 2; NG = 2: 232 registers, up to 4 x 3) and whose tile buffers leave room for a >= 3-deep ring.
+// Returns 1 if the shape is not covered.
 int run_taylor3(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   const Dims& d = h->d;
   int nchunks = (d.ne + 47) / 48;
@@ -557,32 +558,43 @@ int run_taylor3(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   a.NT8 = NT8;
   a.S = NT8 * 64 + 4;
   const int base = d.MT / 4, rem = d.MT % 4;
+  const int wmx = base + (rem ? 1 : 0);
+  // three column groups (12 consumer warps) when the columns split evenly and the rectangle fits
+  // 160 registers, else two (8 warps at 232 registers)
+  int NG = (NT8 % 3 == 0 && wmx * (NT8 / 3) <= 8) ? 3 : 2;
+#ifdef PXB_EXPERIMENTS
+  {
+    const char* e = getenv("PXB_TAYLOR_GROUPS");
+    if (e && atoi(e) == 2) NG = 2;
+  }
+#endif
   int msize[4];
   a.m_off[0] = 0;
   for (int g = 0; g < 4; ++g) {
     msize[g] = base + (g < rem ? 1 : 0);
     a.m_off[g + 1] = a.m_off[g] + msize[g];
   }
-  const int nbase = NT8 / 2, nrem = NT8 % 2;
-  int nsize[2];
+  const int nbase = NT8 / NG, nrem = NT8 % NG;
+  int nsize[3] = {0, 0, 0};
   a.n_off[0] = 0;
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < NG; ++g) {
     nsize[g] = nbase + (g < nrem ? 1 : 0);
     a.n_off[g + 1] = a.n_off[g] + nsize[g];
   }
+  for (int g = NG; g < 3; ++g) a.n_off[g + 1] = a.n_off[NG];
   // m-group permutation per column group: the largest remaining m-group goes to the least loaded
   // sub-partition (column groups are in descending size)
   int load[4] = {0, 0, 0, 0};
-  for (int g = 0; g < 2; ++g) {
+  for (int g = 0; g < 3; ++g) {
     int order[4] = {0, 1, 2, 3};
     std::sort(order, order + 4, [&](int x, int y) { return load[x] != load[y] ? load[x] < load[y] : x < y; });
     for (int k = 0; k < 4; ++k) {
       a.mperm[g][order[k]] = k;
-      load[order[k]] += msize[k] * nsize[g];
+      if (g < NG) load[order[k]] += msize[k] * nsize[g];
     }
   }
-  const int wmx = base + (rem ? 1 : 0), wnx = nbase + (nrem ? 1 : 0);
-  if (wmx * wnx > 12) return 1;
+  const int wnx = nbase + (nrem ? 1 : 0);
+  if (wmx * wnx > (NG == 3 ? 8 : 12)) return 1;
   // shared memory: iterate buffer + phi tile (+ a second phi tile, fetched one item ahead, when a
   // >= 4-deep ring still fits beside it)
   a.nstage = 0;
@@ -604,10 +616,12 @@ int run_taylor3(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   if (a.nbuf == 0) return 1;
   const size_t smem = taylor3_smem_bytes(d, NT8, a.nbuf, a.nstage);
   const int grid = std::min(d.W * nchunks, h->sm_count);
-#define PXB_T3(WM_, WN_) \
-  if (wmx == WM_ && wnx == WN_) return launch_taylor3<WM_, WN_>(h, a, smem, grid, st);
-  PXB_T3(1, 1) PXB_T3(1, 2) PXB_T3(1, 3) PXB_T3(2, 1) PXB_T3(2, 2) PXB_T3(2, 3)
-  PXB_T3(3, 1) PXB_T3(3, 2) PXB_T3(3, 3) PXB_T3(4, 1) PXB_T3(4, 2) PXB_T3(4, 3)
+#define PXB_T3(WM_, WN_, NG_) \
+  if (wmx == WM_ && wnx == WN_ && NG == NG_) return launch_taylor3<WM_, WN_, NG_>(h, a, smem, grid, st);
+  PXB_T3(1, 1, 3) PXB_T3(1, 2, 3) PXB_T3(2, 1, 3) PXB_T3(2, 2, 3) PXB_T3(3, 1, 3) PXB_T3(3, 2, 3)
+  PXB_T3(4, 1, 3) PXB_T3(4, 2, 3)
+  PXB_T3(1, 1, 2) PXB_T3(1, 2, 2) PXB_T3(1, 3, 2) PXB_T3(2, 1, 2) PXB_T3(2, 2, 2) PXB_T3(2, 3, 2)
+  PXB_T3(3, 1, 2) PXB_T3(3, 2, 2) PXB_T3(3, 3, 2) PXB_T3(4, 1, 2) PXB_T3(4, 2, 2) PXB_T3(4, 3, 2)
 #undef PXB_T3
   return 1;
 }

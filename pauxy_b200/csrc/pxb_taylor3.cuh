@@ -36,18 +36,30 @@ struct Taylor3Args {
   int nstage;           // ring depth
   int nbuf;             // tile buffers: iterate + 1 phi tile (2) or iterate + 2 alternating phi tiles (3)
   int m_off[5];         // m-group boundaries (4 groups)
-  int n_off[3];         // column-group boundaries (2 groups)
-  int mperm[2][4];      // m-group of the warp of column group g on sub-partition s
+  int n_off[4];         // column-group boundaries (NG = 2 or 3 groups)
+  int mperm[3][4];      // m-group of the warp of column group g on sub-partition s
   int dbg;              // timing experiments (PXB_EXPERIMENTS builds): 1 no epilogue / barriers, 2 no ring hand-shake, 4 no phi reload
 };
 
-constexpr int T3_CONSUMERS = 8;
+// NG column groups of 4 consumer warps (one per SM sub-partition) + the producer warpgroup.
+//   NG = 2:  8 consumer warps at 232 registers, warp rectangles up to 4 x 3 tile pairs
+//   NG = 3: 12 consumer warps at 160 registers, up to 4 x 2: three warps per sub-partition cover
+//           each other's epilogues better and nothing spills, at the price of an uneven split of
+//           14 m-tiles x 3 groups over 4 sub-partitions (11 : 10)
+template <int NG>
+struct T3Cfg {
+  static constexpr int consumers = 4 * NG;
+  static constexpr int threads = (consumers + 4) * 32;
+  static constexpr int regs_producer = NG == 2 ? 40 : 24;
+  static constexpr int regs_consumer = NG == 2 ? 232 : 160;
+  static_assert(consumers * (regs_consumer - (65536 / threads) / 8 * 8) <= 4 * ((65536 / threads) / 8 * 8 - regs_producer),
+                "setmaxnreg.inc would block: more registers requested than the producer warpgroup releases");
+};
 constexpr int T3_MIN_STAGES2 = 3;  // fewest ring stages accepted with two iterate buffers
-constexpr int T3_THREADS = (T3_CONSUMERS + 4) * 32;
 
 inline size_t taylor3_smem_bytes(const Dims& d, int NT8, int nbuf, int nstage) {
   const size_t S = (size_t)NT8 * 64 + 4;
-  return ((size_t)nbuf * d.KC * S + (size_t)nstage * d.MT * T2_KS * 64) * sizeof(double) + 2 * (size_t)nstage * 8 + 128;
+  return ((size_t)nbuf * d.KC * S + (size_t)nstage * d.MT * T2_KS * 64) * sizeof(double) + 2 * (size_t)nstage * 8 + 6 * 8 + 128;
 }
 
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
@@ -160,7 +172,8 @@ __device__ __forceinline__ void t3_kstep(double (&P1)[WM][WN][2], double (&P2)[W
 template <int WM, int WN>
 __device__ __forceinline__ void taylor3_orders(const Taylor3Args& a, uint32_t phib, uint32_t itb, uint32_t ring,
                                                uint32_t full, uint32_t empty, unsigned& rs, unsigned& rph,
-                                               int m0, int n0, double* gphi, int no, int lane, int ng) {
+                                               int m0, int n0, double* gphi, int no, int lane, int ng, uint32_t gbar,
+                                               unsigned& gph) {
   const Dims& d = a.d;
   const int g = lane >> 2, t = lane & 3;
   const int Sb = a.S * 8;                        // bytes per kc row of a tile buffer
@@ -205,7 +218,34 @@ __device__ __forceinline__ void taylor3_orders(const Taylor3Args& a, uint32_t ph
     // reference divides by n; multiplying by the correctly rounded reciprocal differs by at most
     // one ulp per element.
     const double rn = 1.0 / (double)n;
-    if (n > 1 && n < d.exp_order) bar_sync_group(ng);  // in place: the group has finished reading S_n
+    // The group's two rendez-vous per order are split into "arrive" and "wait" (mbarriers, one
+    // arrival per warp): a warp announces that it has finished READING S_n, does the epilogue
+    // arithmetic (phi comes from the read-only phi tile), and only then waits for the others
+    // before it overwrites its part of the iterate in place.
+    const bool inplace = n > 1 && n < d.exp_order;
+    if (inplace) {
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar) : "memory");
+    }
+#pragma unroll
+    for (int i = 0; i < WM; ++i) {
+#pragma unroll
+      for (int j = 0; j < WN; ++j) {
+        const uint32_t so = st_off + (uint32_t)(2 * i) * Sb + j * 512;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          // (values of padding rows are computed from in-range shared memory and never stored)
+          const double re = (P1[i][j][e] - P2[i][j][e]) * rn + lds_f64(phib + so + e * 32);
+          const double im = ((P3[i][j][e] - P1[i][j][e]) - P2[i][j][e]) * rn + lds_f64(phib + so + e * 32 + 256);
+          P1[i][j][e] = re;
+          P3[i][j][e] = im;
+        }
+      }
+    }
+    if (inplace) {
+      mbar_wait_u32(gbar, gph & 1u);
+      gph ^= 1u;
+    }
 #pragma unroll
     for (int i = 0; i < WM; ++i) {
       const int kc2 = 2 * (m0 + i) + (g >> 2);
@@ -215,26 +255,31 @@ __device__ __forceinline__ void taylor3_orders(const Taylor3Args& a, uint32_t ph
           const uint32_t so = st_off + (uint32_t)(2 * i) * Sb + j * 512;
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
-            const double re = (P1[i][j][e] - P2[i][j][e]) * rn + lds_f64(phib + so + e * 32);
-            const double im = ((P3[i][j][e] - P1[i][j][e]) - P2[i][j][e]) * rn + lds_f64(phib + so + e * 32 + 256);
             if (n > 1) {
-              sts_f64(itb + so + e * 32, re);
-              sts_f64(itb + so + e * 32 + 256, im);
+              sts_f64(itb + so + e * 32, P1[i][j][e]);
+              sts_f64(itb + so + e * 32 + 256, P3[i][j][e]);
             } else {
               const int ol = 8 * (n0 + j) + 2 * t + e;
-              if (ol < no) *reinterpret_cast<double2*>(gphi + ((size_t)ol * d.KC + kc2) * 32) = make_double2(re, im);
+              if (ol < no)
+                *reinterpret_cast<double2*>(gphi + ((size_t)ol * d.KC + kc2) * 32) = make_double2(P1[i][j][e], P3[i][j][e]);
             }
           }
         }
       }
     }
-    if (n > 1) bar_sync_group(ng);  // S_{n-1} complete
+    if (n > 1) {  // S_{n-1} complete
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar + 8) : "memory");
+      mbar_wait_u32(gbar + 8, (gph >> 1) & 1u);
+      gph ^= 2u;
+    }
   }
 }
 
-// WMX = ceil(MT / 4), WNX = ceil(NT8 / 2): the largest warp rectangle; smaller groups use WMX-1 / WNX-1
-template <int WMX, int WNX>
-__global__ void __launch_bounds__(T3_THREADS, 1) taylor3_kernel(Taylor3Args a) {
+// WMX = ceil(MT / 4), WNX = ceil(NT8 / NG): the largest warp rectangle; smaller groups use WMX-1 / WNX-1
+template <int WMX, int WNX, int NG>
+__global__ void __launch_bounds__(T3Cfg<NG>::threads, 1) taylor3_kernel(Taylor3Args a) {
+  constexpr int T3_CONSUMERS = T3Cfg<NG>::consumers;
   extern __shared__ __align__(128) double t3_smem[];
   const Dims& d = a.d;
   const size_t tsz = (size_t)d.KC * a.S;
@@ -243,12 +288,14 @@ __global__ void __launch_bounds__(T3_THREADS, 1) taylor3_kernel(Taylor3Args a) {
   const int stage_doubles = d.MT * T2_KS * 64;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)a.nstage * stage_doubles);
   uint64_t* empty = full + a.nstage;
+  uint64_t* group_bar = empty + a.nstage;  // per column group: "finished reading", "iterate complete"
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     for (int s = 0; s < a.nstage; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], T3_CONSUMERS * kReleaseArrivals);
     }
+    for (int g2 = 0; g2 < 2 * NG; ++g2) mbar_init(&group_bar[g2], 4);
     fence_barrier_init();
   }
   __syncthreads();
@@ -256,7 +303,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) taylor3_kernel(Taylor3Args a) {
   const int nks = (d.KC + T2_KS - 1) / T2_KS;
 
   if (warp >= T3_CONSUMERS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T2Cfg<2>::regs_producer));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG>::regs_producer));
     if (warp != T3_CONSUMERS || (a.dbg & 2)) return;
     // ---------------- producer: lane mt streams m-tile mt of the walker's VHS ----------------
     unsigned s = 0, ph = 0;
@@ -285,11 +332,13 @@ __global__ void __launch_bounds__(T3_THREADS, 1) taylor3_kernel(Taylor3Args a) {
   }
 
   // ---------------- consumers ----------------
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T2Cfg<2>::regs_consumer));
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG>::regs_consumer));
   const int ng = warp >> 2, mg = a.mperm[ng][warp & 3];
   const int m0 = a.m_off[mg], wm = a.m_off[mg + 1] - m0;
   const int n0 = a.n_off[ng], wn = a.n_off[ng + 1] - n0;
   unsigned rs = 0, rph = 0;
+  unsigned gph = 0;  // phases of this group's two barriers
+  const uint32_t gbar = smem_u32(group_bar + 2 * ng);
   const int gtid = tid & 127;  // thread index inside the column group
   auto next_active = [&](int item) {
     while (item < nitems && a.active != nullptr && a.active[item / a.nchunks] == 0) item += gridDim.x;
@@ -324,7 +373,7 @@ __global__ void __launch_bounds__(T3_THREADS, 1) taylor3_kernel(Taylor3Args a) {
     const uint32_t phib = smem_u32(Tbuf + (size_t)pcur * tsz), itb = smem_u32(Tbuf);
 #define PXB_T3_CASE(WM_, WN_)                                                                                  \
   taylor3_orders<WM_, WN_>(a, phib, itb, smem_u32(ring), smem_u32(full), smem_u32(empty), rs, rph, m0, n0, gphi, no, \
-                           lane, ng)
+                           lane, ng, gbar, gph)
     if (wm == WMX && wn == WNX) PXB_T3_CASE(WMX, WNX);
     else if (WNX > 1 && wm == WMX && wn == WNX - 1) PXB_T3_CASE(WMX, (WNX > 1 ? WNX - 1 : 1));
     else if (WMX > 1 && wm == WMX - 1 && wn == WNX) PXB_T3_CASE((WMX > 1 ? WMX - 1 : 1), WNX);

@@ -46,8 +46,8 @@ for T in ${TASKS//,/ }; do
     cfgs) for c in c1 c2 c3 c5; do echo "-- $c"; run_bench 1 gpurun_out/bench_${TAG}_$c --config $c --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline --no-other-configs $EXTRA; done ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NLAUNCH:-400} --csv --log-file gpurun_out/launches_$TAG.csv \
                 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs $EXTRA > gpurun_out/bench_ncu_$TAG.log 2>&1; wc -l gpurun_out/launches_$TAG.csv ;;
-    ncu) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${KREGEX:-exx_eri_kernel|taylor2_kernel|gemm_tma_kernel|theta_kernel}" \
-           -c ${NCU_COUNT:-12} -f -o gpurun_out/prof_$TAG python tools/profile_stages.py ${PROF_ARGS:-c4 2368 1} > gpurun_out/ncu_$TAG.log 2>&1; tail -2 gpurun_out/ncu_$TAG.log ;;
+    ncu) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${KREGEX:-exx_eri_kernel|taylor3_kernel|taylor2_kernel|gemm_tma_kernel|theta_kernel|qr_kernel}" \
+           -c ${NCU_COUNT:-24} -f -o gpurun_out/prof_$TAG python tools/profile_stages.py ${PROF_ARGS:-c4 2368 1} > gpurun_out/ncu_$TAG.log 2>&1; tail -2 gpurun_out/ncu_$TAG.log ;;
     sanitize) for tool in memcheck racecheck; do
                 timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_case.py > gpurun_out/sanitizer_${tool}_$TAG.log 2>&1
                 echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_case" gpurun_out/sanitizer_${tool}_$TAG.log | tail -4
