@@ -234,14 +234,17 @@ int launch_greens2(pxb_handle h, const double* phi, cudaStream_t st) {
   const Dims& d = h->d;
   const int nmax = d.na > d.nb ? d.na : d.nb;
   const int nld = nmax | 1, nsq = nmax * nld;
-  // 1. O_s = phi_s^T psi_s for all walkers
-  for (int s = 0; s < 2; ++s) {
+  // 1. O_s = phi_s^T psi_s for all walkers; both spins in one launch (batch index = spin) when
+  //    they have the same number of orbitals
+  const bool both = d.na == d.nb && d.nb > 0;
+  for (int s = 0; s < (both ? 1 : 2); ++s) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     if (ns == 0) continue;
     GemmArgs g;
     g.A = h->ptr<double>(A_PF) + (s ? (size_t)((d.na + 7) >> 3) * d.KC * 32 : 0);
     g.B = phi + (size_t)ioff * d.KC * 32;
-    g.strideAz = g.strideBz = 0;
+    g.strideAz = (size_t)((d.na + 7) >> 3) * d.KC * 32;
+    g.strideBz = (size_t)d.na * d.KC * 32;
     g.strideBO = (size_t)d.ne * d.KC * 32;
     g.strideBI = (size_t)d.KC * 32;
     g.ntInner = ns;
@@ -250,7 +253,7 @@ int launch_greens2(pxb_handle h, const double* phi, cudaStream_t st) {
     g.KS = d.KC;
     EpiO epi{h->ptr<double2>(A_OB), ns, s, nld, nsq};
     ++h->launches;
-    PXB_CUDA(h, (launch_gemm_tma<NMT, 4, 1, 6>(g, epi, 1, h->sm_count, st)));
+    PXB_CUDA(h, (launch_gemm_tma<NMT, 4, 1, 6>(g, epi, both ? 2 : 1, h->sm_count, st)));
   }
   return launch_theta<NMT>(h, phi, h->ptr<double>(A_THETA), st);
 }
@@ -329,7 +332,8 @@ int run_greens(pxb_handle h, const double* phi, bool want_theta, double2* ovlp_o
 int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
   StageTimer timer__(h, PXB_STAGE_XGEMM, st);
   const Dims& d = h->d;
-  for (int s = 0; s < 2; ++s) {
+  const bool both = d.na == d.nb && d.nb > 0;   // one launch, batch index = spin
+  for (int s = 0; s < (both ? 1 : 2); ++s) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     EpiX epi{h->ptr<double>(A_X) + (size_t)s * d.Wp * d.Np * 2, d.Wp, d.Np};
     if (ns == 0) {
@@ -339,7 +343,8 @@ int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
     GemmArgs g;
     g.A = h->ptr<double>(A_RF) + rf_spin_base(d, s);
     g.B = h->ptr<double>(A_THETA) + (size_t)ioff * d.KC * 32;
-    g.strideAz = g.strideBz = 0;
+    g.strideAz = rf_spin_base(d, 1);
+    g.strideBz = (size_t)d.na * d.KC * 32;
     g.strideBO = (size_t)d.ne * d.KC * 32;
     g.strideBI = 0;
     g.ntInner = 1;
@@ -348,7 +353,7 @@ int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
     g.KS = ns * d.KC;
     ++h->launches;
     // 16 x 8 tile blocks: 4 * WG/8 work units keep the 148 persistent CTAs balanced (XG is only ~63)
-    PXB_CUDA(h, (launch_gemm_tma<4, 4, 4, 2>(g, epi, 1, persist_sms(h), st)));
+    PXB_CUDA(h, (launch_gemm_tma<4, 4, 4, 2>(g, epi, both ? 2 : 1, persist_sms(h), st)));
   }
   return PXB_OK;
 }
@@ -387,13 +392,15 @@ int run_one_body(pxb_handle h, const double* in, double* out, const int* active,
     PXB_CUDA(h, cudaGetLastError());
     in = h->ptr<double>(A_PHI_STACK);
   }
-  for (int s = 0; s < 2; ++s) {
+  const bool both = d.na == d.nb && d.nb > 0;   // one launch, batch index = spin
+  for (int s = 0; s < (both ? 1 : 2); ++s) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     if (ns == 0) continue;
     GemmArgs g;
     g.A = (cplx ? h->ptr<double>(A_BF2) : h->ptr<double>(transposed ? A_BFT : A_BF)) + (size_t)s * d.MT * kc * 32;
     g.B = in + (size_t)ioff * kc * 32;
-    g.strideAz = g.strideBz = 0;
+    g.strideAz = (size_t)d.MT * kc * 32;
+    g.strideBz = (size_t)d.na * kc * 32;
     g.strideBO = (size_t)d.ne * kc * 32;
     g.strideBI = (size_t)kc * 32;
     g.ntInner = ns;
@@ -403,9 +410,9 @@ int run_one_body(pxb_handle h, const double* in, double* out, const int* active,
     EpiOF epi{out, active, d.ne, d.KC, ioff, ns};
     ++h->launches;
     if (d.MT % 7 == 0) {
-      PXB_CUDA(h, (launch_gemm_tma<7, 4, 2, 4>(g, epi, 1, h->sm_count, st)));
+      PXB_CUDA(h, (launch_gemm_tma<7, 4, 2, 4>(g, epi, both ? 2 : 1, h->sm_count, st)));
     } else {
-      PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
+      PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, both ? 2 : 1, h->sm_count, st)));
     }
   }
   return PXB_OK;

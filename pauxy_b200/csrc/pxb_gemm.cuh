@@ -92,7 +92,7 @@ struct EpiOF {  // out OF buffer; n-tile nt = wg*nInner + il, orbital i = ioff +
   __device__ __forceinline__ Col col(int nt, int z, int t) const {
     const int wg = nt / nInner, il = nt - wg * nInner;
     if (active != nullptr && active[wg * 4 + t] == 0) return {nullptr};
-    return {out + ((size_t)wg * ne + ioff + il) * KC * 32 + t * 8};
+    return {out + ((size_t)wg * ne + ioff + z * nInner + il) * KC * 32 + t * 8};  // z: spin of a spin-batched launch
   }
   __device__ __forceinline__ void store(const Row& r, const Col& c, double c0, double c1) const {
     if (r.off < 0 || c.base == nullptr) return;

@@ -29,7 +29,7 @@ struct EpiO {  // O[(w, spin)][i][j] complex, row-major with leading dimension n
   }
   __device__ __forceinline__ Col col(int nt, int z, int t) const {
     const int wg = nt / ns, i = nt - wg * ns;
-    return {OB + ((size_t)(4 * wg + t) * 2 + spin) * nsq + (size_t)i * nld};
+    return {OB + ((size_t)(4 * wg + t) * 2 + spin + z) * nsq + (size_t)i * nld};  // z: spin of a spin-batched launch
   }
   __device__ __forceinline__ void store(const Row& r, const Col& c, double c0, double c1) const {
     if (r.j >= 0) c.base[r.j] = make_double2(c0, c1);
