@@ -697,13 +697,16 @@ int run_exchange_eri(pxb_handle h, cudaStream_t st) {
   const int nrb = std::max(eri_rowblocks(d, 0), eri_rowblocks(d, 1));
   const int nwb = (d.WG + EQ_TN - 1) / EQ_TN;
   const int nitems = nrb * 2 * nwb;
+  // work counter of the dynamic item scheduler: lives behind the partial sums, zero from the arena
+  // memset and put back to zero by the reduce kernel that follows every exchange launch
+  int* counter = reinterpret_cast<int*>(a.part + (size_t)2 * a.nslot * d.Wp);
   const size_t smem = eri_smem_bytes();
   PXB_CUDA(h, cudaFuncSetAttribute(exx_eri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->launches;
-  exx_eri_kernel<<<std::min(nitems, persist_sms(h)), gemm_tma_threads<EQ_CWM * EQ_CWN>(), smem, st>>>(a, nitems, nwb);
+  exx_eri_kernel<<<std::min(nitems, persist_sms(h)), gemm_tma_threads<EQ_CWM * EQ_CWN>(), smem, st>>>(a, nitems, 2 * nrb, counter);
   PXB_CUDA(h, cudaGetLastError());
   ++h->launches;
-  exx_eri_reduce_kernel<<<(2 * d.Wp + 255) / 256, 256, 0, st>>>(a.part, h->ptr<double2>(A_EXX), d, a.nslot);
+  exx_eri_reduce_kernel<<<(2 * d.Wp + 255) / 256, 256, 0, st>>>(a.part, h->ptr<double2>(A_EXX), d, a.nslot, counter);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -997,7 +1000,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
     const size_t nmax = d.na > d.nb ? d.na : d.nb;
     add(A_OB, W * 2 * nmax * (nmax | 1) * 16);
   }
-  add(A_EPART, h->exx_eri ? (size_t)2 * h->eri_nslot * W * 16 : 0);
+  add(A_EPART, h->exx_eri ? (size_t)2 * h->eri_nslot * W * 16 + 16 : 0);  // + the item counter of exx_eri_kernel
   addd(A_E1B, W * 16);
   add(A_OVLP_OLD, W * 16);
   add(A_ACTIVE, W * 4);

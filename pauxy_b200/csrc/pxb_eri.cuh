@@ -46,18 +46,25 @@ __host__ __device__ inline int eri_rowblocks(const Dims& d, int s) {
 __host__ __device__ inline size_t eri_kf_doubles(const Dims& d, int s) {
   return (size_t)eri_mtiles(d, s) * (size_t)((s ? d.nb : d.na) * d.KC) * 32;
 }
-inline size_t eri_smem_bytes() { return gemm_tma_smem_bytes<EQ_WM, EQ_WN, EQ_CWM, EQ_CWN>(); }
+inline size_t eri_smem_bytes() { return gemm_tma_smem_bytes<EQ_WM, EQ_WN, EQ_CWM, EQ_CWN>() + 2 * 4 * 8 + 4 * 4 + 16; }
 
-// item -> (row block, spin, walker block); longest k-ranges (row block 0) first
+// item -> (walker block, row block, spin), walker block OUTERMOST and, inside it, the longest
+// k-ranges (row block 0) first.  The CTAs take items from a global counter (dynamic scheduling),
+// so the ~148 items in flight belong to ~4 consecutive walker blocks: their Theta (4.6 MB per
+// block at c4) is read from DRAM once and then served by L2 to all the row blocks, while K (41-82 MB
+// at c4) stays L2-resident because every row block of it is being streamed all the time.  (With the
+// row block outermost each walker block's Theta came back from DRAM once per row block: 8.4 x the
+// algorithmic traffic.)  Items differ in length by a factor of 25; handing them out dynamically,
+// longest first within a walker block, keeps the CTAs level to within one short item.
 struct EriItem {
   int rb, s, nb;
   int mt0, nt0, ks0, nkstage, MT, KS;
   bool valid;
 };
-__device__ __forceinline__ EriItem eri_item(const Dims& d, int item, int nwb) {
+__device__ __forceinline__ EriItem eri_item(const Dims& d, int item, int nrb2) {
   EriItem it;
-  it.nb = item % nwb;
-  const int r = item / nwb;
+  it.nb = item / nrb2;          // walker block
+  const int r = item - it.nb * nrb2;
   it.s = r & 1;
   it.rb = r >> 1;
   it.MT = eri_mtiles(d, it.s);
@@ -70,8 +77,10 @@ __device__ __forceinline__ EriItem eri_item(const Dims& d, int item, int nwb) {
   return it;
 }
 
+constexpr int EQ_QD = 4;  // depth of the producer -> consumer item queue
+
 static_assert(EQ_CWM * EQ_CWN == 8, "register rebalancing below assumes two consumer warpgroups");
-__global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_eri_kernel(EriArgs a, int nitems, int nwb) {
+__global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_eri_kernel(EriArgs a, int nitems, int nrb2, int* __restrict__ counter) {
   constexpr int TM = EQ_TM, TN = EQ_TN, NCW = EQ_CWM * EQ_CWN, WM = EQ_WM, WN = EQ_WN;
   constexpr int A_STAGE = TM * GT_KS * 32, B_STAGE = TN * GT_KS * 32;
   extern __shared__ __align__(128) double eq_smem[];
@@ -79,6 +88,9 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
   double* Bs = eq_smem + GT_STAGES * A_STAGE;
   uint64_t* full = reinterpret_cast<uint64_t*>(Bs + GT_STAGES * B_STAGE);
   uint64_t* empty = full + GT_STAGES;
+  uint64_t* qfull = empty + GT_STAGES;   // item queue: the producer announces the items it draws
+  uint64_t* qempty = qfull + EQ_QD;
+  volatile int* qitem = reinterpret_cast<volatile int*>(qempty + EQ_QD);
   const Dims& d = a.d;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
@@ -86,6 +98,11 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
     for (int s = 0; s < GT_STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], NCW * kReleaseArrivals);
+    }
+#pragma unroll
+    for (int q = 0; q < EQ_QD; ++q) {
+      mbar_init(&qfull[q], 1);
+      mbar_init(&qempty[q], NCW);
     }
     fence_barrier_init();
   }
@@ -96,10 +113,31 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
     if (warp != NCW) return;
     // ---------------- producer: lane L streams row L of the stage (A rows, then B rows) -----------
     static_assert(TM + TN <= 32, "one producer lane per tile row");
-    unsigned itc = 0;
-    for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-      const EriItem it = eri_item(d, item, nwb);
-      if (!it.valid) continue;
+    unsigned itc = 0, qc = 0;
+    for (;;) {
+      // next item from the global counter (invalid combinations of an uneven spin pair are skipped
+      // here, so consumers only ever see real items); -1 ends the kernel
+      int item = -1;
+      for (;;) {
+        if (lane == 0) item = atomicAdd(counter, 1);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= nitems) {
+          item = -1;
+          break;
+        }
+        if (eri_item(d, item, nrb2).valid) break;
+      }
+      {
+        const unsigned q = qc % EQ_QD, qph = (qc / EQ_QD) & 1u;
+        mbar_wait(&qempty[q], qph ^ 1u);
+        if (lane == 0) {
+          qitem[q] = item;
+          mbar_arrive(&qfull[q]);   // release: the slot's content is visible to whoever sees the phase flip
+        }
+        ++qc;
+      }
+      if (item < 0) break;
+      const EriItem it = eri_item(d, item, nrb2);
       const int ioff = it.s ? d.na : 0;
       const int rows_m = min(TM, it.MT - it.mt0), rows_n = min(TN, d.WG - it.nt0);
       const double* src = nullptr;
@@ -133,10 +171,19 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
   const int wm = warp % EQ_CWM, wn = warp / EQ_CWM;
   const int g = lane >> 2, t = lane & 3;
   const int boff = b_lane_offset(lane);
-  unsigned itc = 0;
-  for (int item = blockIdx.x; item < nitems; item += gridDim.x) {
-    const EriItem it = eri_item(d, item, nwb);
-    if (!it.valid) continue;
+  unsigned itc = 0, qc = 0;
+  for (;;) {
+    int item;
+    {
+      const unsigned q = qc % EQ_QD, qph = (qc / EQ_QD) & 1u;
+      mbar_wait(&qfull[q], qph);
+      item = qitem[q];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&qempty[q]);
+      ++qc;
+    }
+    if (item < 0) break;
+    const EriItem it = eri_item(d, item, nrb2);
     double acc[WM][WN][2];
 #pragma unroll
     for (int i = 0; i < WM; ++i)
@@ -227,8 +274,9 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
 
 // exx[s][w] = sum over the slots of spin s, fixed order (deterministic)
 __global__ void exx_eri_reduce_kernel(const double2* __restrict__ part, double2* __restrict__ exx, Dims d,
-                                      int nslot) {
+                                      int nslot, int* __restrict__ counter) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx == 0) *counter = 0;  // re-arm the item scheduler of exx_eri_kernel for its next launch
   if (idx >= 2 * d.Wp) return;
   const int s = idx / d.Wp, w = idx % d.Wp;
   const int ns = eri_rowblocks(d, s) * EQ_CWM;

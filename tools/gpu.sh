@@ -9,6 +9,7 @@
 #   cfgs       bench.py for c1, c2, c3, c5 (one GPU)
 #   launches   ncu launch list of a short bench.py run
 #   ncu        ncu --set full of the hot kernels on tools/profile_stages.py (KREGEX, PROF_ARGS override)
+#   traffic    DRAM bytes of the exchange / Taylor kernels at full c4 and c5 sizes (ncu, 5 metrics) -> gpurun_out/traffic_TAG.csv
 #   sanitize   compute-sanitizer memcheck + racecheck over the c1 smoke (and a 2-GPU comb step if 2 GPUs)
 #   ab         A/B bench of an environment variant: AB="VAR=value"
 TASKS=${1:-tests,bench}
@@ -48,6 +49,11 @@ for T in ${TASKS//,/ }; do
                 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs $EXTRA > gpurun_out/bench_ncu_$TAG.log 2>&1; wc -l gpurun_out/launches_$TAG.csv ;;
     ncu) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${KREGEX:-exx_eri_kernel|taylor3_kernel|taylor2_kernel|gemm_tma_kernel|theta_kernel|qr_kernel}" \
            -c ${NCU_COUNT:-24} -f -o gpurun_out/prof_$TAG python tools/profile_stages.py ${PROF_ARGS:-c4 2368 1} > gpurun_out/ncu_$TAG.log 2>&1; tail -2 gpurun_out/ncu_$TAG.log ;;
+    traffic) for cfg in "c4 8192" "c5 2048"; do set -- $cfg
+               timeout 900 ncu --clock-control none -k regex:"${KREGEX:-exx_eri_kernel|taylor3_kernel|taylor2_kernel}" -c 4 --csv \
+                 --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,lts__t_bytes.sum \
+                 --log-file gpurun_out/traffic_${TAG}_$1.csv python tools/profile_stages.py $1 $2 1 > gpurun_out/traffic_${TAG}_$1.log 2>&1
+               tail -5 gpurun_out/traffic_${TAG}_$1.csv | cut -c1-300; done ;;
     sanitize) for tool in memcheck racecheck; do
                 timeout 1500 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_case.py > gpurun_out/sanitizer_${tool}_$TAG.log 2>&1
                 echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitize_case" gpurun_out/sanitizer_${tool}_$TAG.log | tail -4
