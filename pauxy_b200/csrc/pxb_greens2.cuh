@@ -12,6 +12,7 @@
 //          straight from the OF layout in global memory (a fragment = four 64-byte segments), the
 //          rotated partner (i B) by a lane shuffle; Theta stored back in OF layout, e1b fused.
 #pragma once
+#include <type_traits>
 #include "pxb_common.cuh"
 #include "pxb_gemm.cuh"
 #include "pxb_greens.cuh"
@@ -51,12 +52,124 @@ constexpr int TH_WARPS = 4;
 
 inline size_t theta_smem_per_warp(int nmax) {
   const int nld = nmax | 1;
-  return ((size_t)nmax * nld * sizeof(cplx) + (size_t)nmax * sizeof(cplx) + (size_t)nmax * sizeof(int) + 15) / 16 * 16;
+  const int nc = (nmax + 7) / 8 * 8;
+  // inverse [nmax][nld], colk [nmax] + 3 elements of slack (the A fragments of the last k-step read up
+  // to 3 entries past a row), the pivot-row exchange buffer [2][nc] of the register path, piv [nc]
+  // and its pivots with their reciprocals [2][nc]
+  return ((size_t)nmax * nld * sizeof(cplx) + (size_t)(nmax + 3) * sizeof(cplx) + (size_t)4 * nc * sizeof(cplx) +
+          (size_t)nc * sizeof(int) + 15) / 16 * 16;
+}
+
+// Register-resident Gauss-Jordan inversion of the ns x ns matrix in A (ns <= NC <= 32), result back
+// in A, with LAPACK's pivot choice (zgetrf: first row of largest |re| + |im| in the column).
+//   - lane i owns row i of the matrix, zero-padded to NC columns: 2 NC doubles in registers; rows are never moved, every lane tracks the position its row has in the pivoted
+//     order instead (pos), so ties are resolved exactly as with physical interchanges;
+//   - each step works on column slot 0 and writes the updated row shifted down by one slot
+//     (new[j-1] = old[j] - f p[j], new[NC-1] = the column of the inverse): the active column has a
+//     static register index although the step loop is not unrolled; after the ns steps the column
+//     of the inverse that pivot step j produced sits in slot j + NC - ns;
+//   - pivot rows stay unscaled (their column-of-the-inverse entry is 1); a row is linear in its own
+//     scale, so each lane multiplies its row by the reciprocal of its pivot once at the end;
+//   - pivot search: two 32-bit REDUX.MAX over the bit pattern of the (non-negative) magnitudes and a
+//     REDUX.MIN over the positions of the tied rows; the pivot row travels through a
+//     double-buffered row in shared memory (one predicated STS + one broadcast LDS per element).
+// sign, logdet: each lane takes log / phase of the pivot it supplied; warp tree reduction.
+template <int NC>
+__device__ __forceinline__ void gj_invert_regs(cplx* A, int lda, int ns, cplx* prow, int* piv, int lane, cplx& sign,
+                                               double& logdet) {
+  constexpr unsigned FULL = 0xffffffffu;
+  double2 r[NC];
+#pragma unroll
+  for (int j = 0; j < NC; ++j) {
+    r[j] = make_double2(0.0, 0.0);
+    if (lane < ns && j < ns) r[j] = *reinterpret_cast<const double2*>(A + (size_t)lane * lda + j);
+  }
+  unsigned pos = lane < ns ? (unsigned)lane : 0xffu;
+  bool done = lane >= ns;
+  double2* pvk = reinterpret_cast<double2*>(prow) + 2 * NC;  // pivot of step k and its reciprocal: [k], [NC + k]
+  bool odd = false;
+  __syncwarp();
+#pragma unroll 1
+  for (int k = 0; k < ns; ++k) {
+    const double v = fabs(r[0].x) + fabs(r[0].y);
+    const unsigned vh = (unsigned)__double2hiint(v), vl = (unsigned)__double2loint(v);
+    const unsigned kh = done ? 0u : vh + 1u;
+    const unsigned mh = __reduce_max_sync(FULL, kh);
+    const bool top = !done && kh == mh;
+    const unsigned ml = __reduce_max_sync(FULL, top ? vl : 0u);
+    const bool tie = top && vl == ml;
+    const unsigned mp = __reduce_min_sync(FULL, tie ? pos : 0xffu);
+    const bool is_piv = tie && pos == mp;
+    if (mp != (unsigned)k) {  // interchange of positions k and mp (warp-uniform)
+      odd = !odd;
+      if (pos == (unsigned)k) pos = mp;
+    }
+    double2* pb = reinterpret_cast<double2*>(prow) + (k & 1) * NC;
+    if (is_piv) {
+      pos = (unsigned)k;
+      if (true) piv[k] = lane;
+#pragma unroll
+      for (int j = 0; j < NC; ++j) pb[j] = r[j];
+    }
+    __syncwarp();
+    const double2 pv = pb[0];
+    // 1 / pv with one division: pv is scaled by the power of two that brings its larger component
+    // into [1, 2) (built from the exponent bits, exact), so that a^2 + b^2 lies in [1, 8)
+    const int eh = max(__double2hiint(pv.x) & 0x7ff00000, __double2hiint(pv.y) & 0x7ff00000);
+    const double sc = __hiloint2double(0x7fe00000 - eh, 0);
+    const double pa = pv.x * sc, pbi = pv.y * sc;
+    const double inv = sc / (pa * pa + pbi * pbi);
+    const double2 rp = make_double2(pa * inv, -pbi * inv);
+    double2 f = make_double2(r[0].x * rp.x - r[0].y * rp.y, r[0].x * rp.y + r[0].y * rp.x);
+    if (is_piv) {
+      f = make_double2(0.0, 0.0);
+      pvk[k] = pv;
+      pvk[NC + k] = rp;
+      done = true;
+    }
+#pragma unroll
+    for (int j = 1; j < NC; ++j) {
+      const double2 p = pb[j];
+      r[j - 1].x = r[j].x - (f.x * p.x - f.y * p.y);
+      r[j - 1].y = r[j].y - (f.x * p.y + f.y * p.x);
+    }
+    r[NC - 1] = is_piv ? make_double2(1.0, 0.0) : make_double2(-f.x, -f.y);
+  }
+  __syncwarp();  // piv[] complete; every lane is past its reads of A
+  // the row of lane i was the pivot row of step pos
+  const double2 mypv = lane < ns ? pvk[pos] : make_double2(1.0, 0.0);
+  const double2 myrp = lane < ns ? pvk[NC + pos] : make_double2(1.0, 0.0);
+  // row `pos` of the inverse; after ns steps the column of pivot step j sits in slot j + NC - ns
+  if (lane < ns) {
+    cplx* arow = A + (size_t)pos * lda;
+    const int* pj = piv - (NC - ns);
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      if (j >= NC - ns) {
+        const double2 x = r[j];
+        arow[pj[j]] = {x.x * myrp.x - x.y * myrp.y, x.x * myrp.y + x.y * myrp.x};
+      }
+    }
+  }
+  // det = (-1)^interchanges prod pivots
+  const double au = hypot(mypv.x, mypv.y);
+  double ld = log(au);
+  cplx sg = {mypv.x / au, mypv.y / au};
+#pragma unroll
+  for (int m = 16; m > 0; m >>= 1) {
+    ld += __shfl_xor_sync(FULL, ld, m);
+    const cplx o = {__shfl_xor_sync(FULL, sg.re, m), __shfl_xor_sync(FULL, sg.im, m)};
+    sg = cmul(sg, o);
+  }
+  sign = odd ? cplx{-sg.re, -sg.im} : sg;
+  logdet = ld;
+  __syncwarp();
 }
 
 // NMT: 8-row tiles over the occupied orbitals of one spin (ceil(ns/8) <= NMT)
 template <int NMT>
-__global__ void __launch_bounds__(TH_WARPS * 32, NMT <= 3 ? 7 : 1) theta_kernel(ThetaArgs a, int smem_per_warp) {
+__global__ void __launch_bounds__(TH_WARPS * 32, NMT == 1 ? 6 : NMT == 2 ? 4 : NMT == 3 ? 3 : NMT == 4 ? 2 : 1)
+    theta_kernel(ThetaArgs a, int smem_per_warp) {
   extern __shared__ __align__(16) unsigned char th_raw[];
   const Dims& d = a.d;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -77,8 +190,9 @@ __global__ void __launch_bounds__(TH_WARPS * 32, NMT <= 3 ? 7 : 1) theta_kernel(
   const int nmax = max(d.na, d.nb);
   const int lda = a.nld;
   cplx* A = reinterpret_cast<cplx*>(th_raw + (size_t)warp * smem_per_warp);  // [ns][lda]
-  cplx* colk = A + (size_t)nmax * lda;                                        // [ns]
-  int* piv = reinterpret_cast<int*>(colk + nmax);                             // [ns]
+  cplx* colk = A + (size_t)nmax * lda;                                        // [ns] + 3 (slack, zero)
+  cplx* prow = colk + nmax + 3;                                               // [2][nc], register path
+  int* piv = reinterpret_cast<int*>(prow + 4 * ((nmax + 7) / 8 * 8));         // [nc], behind the pivots [2][nc]
   const int g = lane >> 2, t = lane & 3;
   const int wg = w >> 2, wl = w & 3;
 
@@ -89,13 +203,17 @@ __global__ void __launch_bounds__(TH_WARPS * 32, NMT <= 3 ? 7 : 1) theta_kernel(
       const double2 v = src[idx];
       A[idx] = {v.x, v.y};
     }
+    if (lane < nmax + 3) colk[lane < 3 ? nmax + lane : lane - 3] = {0.0, 0.0};
   }
   __syncwarp();
 
-  // 2. in-place Gauss-Jordan inversion with partial pivoting; lanes own columns j = lane, lane + 32
+  // 2. Gauss-Jordan inversion with partial pivoting: in registers up to 32 orbitals per spin, else
+  //    in place in shared memory with lanes owning columns j = lane, lane + 32
   cplx sign = {1.0, 0.0};
   double logdet = 0.0;
-  for (int k = 0; k < ns; ++k) {
+  constexpr bool GJ_REGS = NMT <= 4;
+  if constexpr (GJ_REGS) gj_invert_regs<8 * NMT>(A, lda, ns, prow, piv, lane, sign, logdet);
+  for (int k = 0; k < (GJ_REGS ? 0 : ns); ++k) {
     double bv = -1.0;
     int bi = k;
     for (int i = k + lane; i < ns; i += 32) {
@@ -179,7 +297,7 @@ __global__ void __launch_bounds__(TH_WARPS * 32, NMT <= 3 ? 7 : 1) theta_kernel(
     __syncwarp();
   }
   // undo the row interchanges as column interchanges, last first
-  for (int k = ns - 1; k >= 0; --k) {
+  for (int k = (GJ_REGS ? 0 : ns) - 1; k >= 0; --k) {
     const int p = piv[k];
     if (p != k) {
       for (int i = lane; i < ns; i += 32) {
@@ -197,91 +315,102 @@ __global__ void __launch_bounds__(TH_WARPS * 32, NMT <= 3 ? 7 : 1) theta_kernel(
   }
   __syncwarp();
 
-  // 3. Theta[a][p] = sum_i Oinv[a][i] phi[p][i]; two basis chunks (n-tiles) per iteration
+  // 3. Theta[a][p] = sum_i Oinv[a][i] phi[p][i], one basis chunk (n-tile of 4 basis functions) per
+  //    iteration.  Everything that does not depend on the chunk is hoisted: A fragments are read
+  //    from the row-major inverse with one base address per m-tile plus immediates (rows >= ns of the
+  //    last m-tile are clamped to row ns - 1: a row of A only reaches the same row of C, and those
+  //    rows are never stored; columns >= ns read the start of the next row or of colk, finite
+  //    numbers, and meet B entries that are forced to zero); B / Theta / h1rot are addressed with
+  //    pointers that advance by one chunk; only the LAST k-step can hold padding (4 (KS-1) + t >= ns).
+  //    The B fragments of the next chunk and the h1rot entries of this one are requested before the
+  //    DMMAs of the current chunk (16 warps per SM: latency has to be hidden inside the warp).
   const int KS = (ns + 3) >> 2;
-  const int nmt = (ns + 7) >> 3;
-  const double* phis = a.phi + ((size_t)wg * d.ne + ioff) * d.KC * 32 + wl * 8 + g;
-  const unsigned smask = (g & 1) ? 0u : 0x80000000u;  // (i B)^: (re, im) -> (-im, re)
-  double er = 0.0, ei = 0.0;
-  // B fragments of one iteration (two basis chunks x all k-steps) are loaded together: one
-  // global-load latency per iteration instead of one per k-step.  For the larger shapes, where few
-  // warps fit on an SM, they are also loaded one iteration ahead (costs 4 NMT more registers).
   constexpr int KSM = 2 * NMT;  // >= ceil(ns / 4)
-  constexpr bool AHEAD = NMT >= 4;
-  const double* bptr[KSM];
+  const unsigned rowB = (unsigned)d.KC * 32u;
+  const unsigned smask = (g & 1) ? 0u : 0x80000000u;  // (i B)^: (re, im) -> (-im, re)
+  const bool last_pad = 4 * (KS - 1) + t >= ns;       // this lane's entry of the last k-step is padding
+  const double* bp = a.phi + ((size_t)wg * d.ne + ioff + t) * rowB + wl * 8 + g;  // k-step 0, chunk 0
+  const double* bl = a.phi + ((size_t)wg * d.ne + ioff + min(4 * (KS - 1) + t, ns - 1)) * rowB + wl * 8 + g;
+  const unsigned brow4 = 4u * rowB;
+  const double2* Am[NMT];  // rows >= ns are clamped to the last row (their C rows are not stored)
 #pragma unroll
-  for (int ks = 0; ks < KSM; ++ks) {
-    const int i = min(4 * ks + t, ns - 1);  // clamped: the matching A entries are zero
-    bptr[ks] = phis + (size_t)i * d.KC * 32;
+  for (int m = 0; m < NMT; ++m) Am[m] = reinterpret_cast<const double2*>(A + (size_t)min(8 * m + g, ns - 1) * lda + t);
+  const int klast = 4 * (KS - 1);
+  // up to 32 orbitals the A fragments stay in registers for all chunks (the shared-memory data path
+  // is what bounds this kernel: 6 NMT^2 LDS.128 per chunk otherwise)
+  constexpr bool AREG = NMT <= 4;
+  double2 af[AREG ? NMT : 1][AREG ? KSM : 1];
+  if constexpr (AREG) {
+#pragma unroll
+    for (int ks = 0; ks < KSM; ++ks)
+#pragma unroll
+      for (int m = 0; m < NMT; ++m)
+        af[m][ks] = ks == KSM - 1 ? Am[m][klast] : ks < KS - 1 ? Am[m][4 * ks] : make_double2(0.0, 0.0);
   }
-  double bn[KSM][2];
-  auto load_b = [&](int pc0) {
-    const bool one = pc0 < d.KC, two = pc0 + 1 < d.KC;
+  double* tp = a.theta + ((size_t)wg * d.ne + ioff + g) * rowB + wl * 8 + t * 2;
+  const double2* hp = a.h1rot + (size_t)(ioff + g) * d.Mp + t;
+  const unsigned trow8 = 8u * rowB, hrow8 = 8u * (unsigned)d.Mp;
+  bool rowok[NMT];
 #pragma unroll
-    for (int ks = 0; ks < KSM; ++ks) {
-      bn[ks][0] = (one && ks < KS) ? ldg_nc(bptr[ks] + (size_t)pc0 * 32) : 0.0;
-      bn[ks][1] = (two && ks < KS) ? ldg_nc(bptr[ks] + (size_t)pc0 * 32 + 32) : 0.0;
-    }
+  for (int m = 0; m < NMT; ++m) rowok[m] = 8 * m + g < ns;
+  double er = 0.0, ei = 0.0;
+  double bn[KSM];
+  // KFULL: every k-step slot is in use (KS == KSM, e.g. 21 orbitals in 6 k-steps): no guards
+  auto chunks = [&](auto kfull_tag) {
+  constexpr bool KFULL = decltype(kfull_tag)::value;
+  auto load_b = [&]() {  // slot KSM - 1 holds k-step KS - 1, whatever KS is
+#pragma unroll
+    for (int ks = 0; ks < KSM - 1; ++ks)
+      if (KFULL || ks < KS - 1) bn[ks] = ldg_nc(bp + ks * brow4);
+    bn[KSM - 1] = last_pad ? 0.0 : ldg_nc(bl);
+    bp += 32;
+    bl += 32;
   };
-  if (AHEAD) load_b(0);
-  for (int pc0 = 0; pc0 < d.KC; pc0 += 2) {
-    if (!AHEAD) load_b(pc0);
-    double b[KSM][2];
+  load_b();
+  const int pz0 = d.M - t;  // entries with 4 pc >= pz0 are basis padding
+  for (int pc = 0; pc < d.KC; ++pc) {
+    double b[KSM];
+#pragma unroll
+    for (int ks = 0; ks < KSM; ++ks) b[ks] = bn[ks];
+    if (pc + 1 < d.KC) load_b();
+    double2 hq[NMT];
+#pragma unroll
+    for (int m = 0; m < NMT; ++m) hq[m] = rowok[m] ? hp[m * hrow8] : make_double2(0.0, 0.0);
+    hp += 4;
+    double acc[NMT][2];
+#pragma unroll
+    for (int m = 0; m < NMT; ++m) acc[m][0] = acc[m][1] = 0.0;
 #pragma unroll
     for (int ks = 0; ks < KSM; ++ks) {
-      b[ks][0] = bn[ks][0];
-      b[ks][1] = bn[ks][1];
-    }
-    if (AHEAD) load_b(pc0 + 2);
-    double acc[NMT][2][2];
+      const bool lastk = ks == KSM - 1;
+      if (KFULL || lastk || ks < KS - 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, b[ks], 4);  // the other component of the same element
+        const double bq = __hiloint2double(__double2hiint(o) ^ (int)smask, __double2loint(o));
 #pragma unroll
-    for (int m = 0; m < NMT; ++m)
-#pragma unroll
-      for (int q = 0; q < 2; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
-#pragma unroll
-    for (int ks = 0; ks < KSM; ++ks) {
-      if (ks < KS) {
-        double bq[2];
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const double o = __shfl_xor_sync(0xffffffffu, b[ks][q], 4);
-          bq[q] = __hiloint2double(__double2hiint(o) ^ (int)smask, __double2loint(o));
-        }
-        const bool iv = 4 * ks + t < ns;
-#pragma unroll
-        for (int m = 0; m < NMT; ++m) {
-          if (m < nmt) {
-            const int ar = 8 * m + g;
-            const cplx av = (iv && ar < ns) ? A[(size_t)ar * lda + 4 * ks + t] : cplx{0.0, 0.0};
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-              dmma(acc[m][q][0], acc[m][q][1], av.re, b[ks][q]);
-              dmma(acc[m][q][0], acc[m][q][1], av.im, bq[q]);
-            }
-          }
+        for (int m = 0; m < NMT; ++m) {  // m-tiles beyond ceil(ns / 8) (uneven spins) compute on clamped rows
+          double2 av;
+          if constexpr (AREG) av = af[m][ks];
+          else av = lastk ? Am[m][klast] : Am[m][4 * ks];
+          dmma(acc[m][0], acc[m][1], av.x, b[ks]);
+          dmma(acc[m][0], acc[m][1], av.y, bq);
         }
       }
     }
+    const bool pz = 4 * pc >= pz0;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      const int pc = pc0 + q;
-      if (pc >= d.KC) continue;
-      const int p = 4 * pc + t;
-#pragma unroll
-      for (int m = 0; m < NMT; ++m) {
-        const int ar = 8 * m + g;
-        if (m < nmt && ar < ns) {
-          double vr = acc[m][q][0], vi = acc[m][q][1];
-          if (p >= d.M) vr = vi = 0.0;
-          *reinterpret_cast<double2*>(a.theta + (((size_t)wg * d.ne + ioff + ar) * d.KC + pc) * 32 + wl * 8 + t * 2) =
-              make_double2(vr, vi);
-          const double2 h = a.h1rot[(size_t)(ioff + ar) * d.Mp + p];
-          er += h.x * vr - h.y * vi;
-          ei += h.x * vi + h.y * vr;
-        }
+    for (int m = 0; m < NMT; ++m) {
+      if (rowok[m]) {
+        const double vr = pz ? 0.0 : acc[m][0], vi = pz ? 0.0 : acc[m][1];
+        *reinterpret_cast<double2*>(tp + m * trow8) = make_double2(vr, vi);
+        er += hq[m].x * vr - hq[m].y * vi;
+        ei += hq[m].x * vi + hq[m].y * vr;
       }
     }
+    tp += 32;
   }
+  };
+  if (KS == KSM) chunks(std::true_type{});
+  else chunks(std::false_type{});
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) {
     er += __shfl_xor_sync(0xffffffffu, er, m);
