@@ -8,8 +8,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB = os.path.join(CSRC, 'libpauxy_b200.so')
 SOURCES = ['pxb_api.cu']
-HEADERS = ['pxb_common.cuh', 'pxb_gemm.cuh', 'pxb_exchange.cuh', 'pxb_eri.cuh', 'pxb_greens.cuh', 'pxb_greens2.cuh', 'pxb_taylor.cuh', 'pxb_taylor2.cuh', 'pxb_taylor3.cuh', 'pxb_bp.cuh',
-           'pxb_small.cuh', os.path.join('..', '..', 'include', 'pauxy_b200.h')]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith('.cuh')) + [os.path.join('..', '..', 'include', 'pauxy_b200.h')]
 # --split-compile=0: the optimisation phase of the single translation unit runs on every host core
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3',
               '-std=c++17', '-Xcompiler', '-fPIC', '-shared', '--split-compile=0']

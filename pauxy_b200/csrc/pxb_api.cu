@@ -16,6 +16,7 @@
 #include "pxb_gemm.cuh"
 #include "pxb_greens.cuh"
 #include "pxb_greens2.cuh"
+#include "pxb_qr.cuh"
 #include "pxb_small.cuh"
 #include "pxb_taylor.cuh"
 #include "pxb_taylor2.cuh"
@@ -33,7 +34,7 @@ struct Region {
 enum ArenaId {
   A_LF, A_RF, A_BF, A_PSIT, A_H1ROT, A_VBAR,
   A_PHI_A, A_PHI_B, A_THETA, A_X, A_XF, A_VF,
-  A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_OB, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD,
+  A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_OB, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD, A_QRMASK,
   A_FC, A_PHI_OLD, A_PHI_BP, A_PHI_BP2, A_THETA_BP, A_BP_PART, A_PSI_NAT, A_INIT_NAT, A_BFT, A_STEP_PARAMS,
   A_OVLP_DET, A_ELOC_DET, A_XC, A_COEFF, A_ELOC_MIX, A_BF2, A_PHI_STACK, A_OT_TRUE, A_BPFAC, A_BPW,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
@@ -67,6 +68,7 @@ struct pxb_context {
   bool greens_split = true;  // batched overlap GEMM + warp-per-walker inverse/Theta (PXB_GREENS=fused: one CTA per walker)
   bool vhs_sym = false;  // L symmetric in (p,q): the VHS GEMM computes the upper triangle only
   bool vhs_sym_allowed = true;
+  bool qr_cholesky = true;  // CholeskyQR2 where the shape allows it (PXB_QR=mgs in experiment builds: Gram-Schmidt only)
   bool hs_near_sym = false;  // L symmetric in (p,q) to rounding (needed by the back propagation)
   int rtu = 0;           // row tiles kept in that case
   bool taylor_tma = true;  // persistent TMA-fed Taylor kernel (PXB_TAYLOR=direct selects the per-walker-CTA one)
@@ -280,6 +282,54 @@ int launch_theta(pxb_handle h, const double* phi, double* theta_out, cudaStream_
   PXB_CUDA(h, cudaFuncSetAttribute(theta_kernel<NMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->launches;
   theta_kernel<NMT><<<(2 * d.Wp + TH_WARPS - 1) / TH_WARPS, TH_WARPS * 32, smem, st>>>(a, (int)spw);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+// phi = Q R in place (R_ii > 0), log det R per (walker, spin) -> A_QRLD.  Up to 32 orbitals per spin:
+// CholeskyQR2 on DMMA (pxb_qr.cuh), then the Gram-Schmidt kernel for the items it marked; else
+// Gram-Schmidt for everything.
+template <int NMT>
+static int launch_cholqr(pxb_handle h, double* phi, cudaStream_t st) {
+  const Dims& d = h->d;
+  const int nmax = d.na > d.nb ? d.na : d.nb;
+  CholQrArgs a;
+  a.phi = phi;
+  a.logdet = h->ptr<double>(A_QRLD);
+  a.need_mgs = h->ptr<int>(A_QRMASK);
+  a.d = d;
+  a.lda = nmax | 1;
+  const size_t spw = cholqr_smem_per_warp(nmax);
+  const size_t smem = spw * TH_WARPS;
+  if (smem > (size_t)h->max_smem_optin) return 1;
+  PXB_CUDA(h, cudaFuncSetAttribute(cholqr_kernel<NMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ++h->launches;
+  cholqr_kernel<NMT><<<(2 * d.Wp + TH_WARPS - 1) / TH_WARPS, TH_WARPS * 32, smem, st>>>(a, (int)spw);
+  PXB_CUDA(h, cudaGetLastError());
+  return PXB_OK;
+}
+
+static int run_qr(pxb_handle h, double* phi, cudaStream_t st) {
+  const Dims& d = h->d;
+  const int nmt = ((d.na > d.nb ? d.na : d.nb) + 7) >> 3;
+  int rc = 1;
+  if (h->qr_cholesky) {
+    if (nmt <= 1) rc = launch_cholqr<1>(h, phi, st);
+    else if (nmt <= 2) rc = launch_cholqr<2>(h, phi, st);
+    else if (nmt <= 3) rc = launch_cholqr<3>(h, phi, st);
+    else if (nmt <= 4) rc = launch_cholqr<4>(h, phi, st);
+  }
+  if (rc < 0) return rc;
+  QrArgs a;
+  a.phi = phi;
+  a.logdet = h->ptr<double>(A_QRLD);
+  a.d = d;
+  a.mask = rc == PXB_OK ? h->ptr<int>(A_QRMASK) : nullptr;
+  const size_t smem = qr_smem_bytes(d);
+  if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "qr: problem too large for shared memory");
+  PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  ++h->launches;
+  qr_kernel<<<2 * d.Wp, GR_THREADS, smem, st>>>(a);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -907,6 +957,8 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
     const char* t = getenv("PXB_TAYLOR");
     if (t && strcmp(t, "direct") == 0) h->taylor_tma = false;
     if (t && strcmp(t, "4m") == 0) h->taylor_3m = false;
+    const char* q = getenv("PXB_QR");
+    if (q && strcmp(q, "mgs") == 0) h->qr_cholesky = false;
   }
 #endif
   Dims& d = h->d;
@@ -1012,6 +1064,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_SLOG, W * 8 * 8);
   add(A_E1BP, W * 2 * 16);
   add(A_QRLD, W * 2 * 8);
+  add(A_QRMASK, W * 2 * 4);
   add(A_FIELD0 + PXB_F_WEIGHT, W * 8);
   add(A_FIELD0 + PXB_F_UNSCALED_WEIGHT, W * 8);
   add(A_FIELD0 + PXB_F_OT, W * 16);
@@ -1474,21 +1527,14 @@ int pxb_orthogonalise(pxb_handle h, void* stream) {
   const Dims& d = h->d;
   cudaStream_t st = S(stream);
   StageTimer timer__(h, PXB_STAGE_QR, st);
-  QrArgs a;
-  a.phi = h->phi();
-  a.logdet = h->ptr<double>(A_QRLD);
-  a.d = d;
-  const size_t smem = qr_smem_bytes(d);
-  if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "qr: problem too large for shared memory");
-  PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                   (int)cudaSharedmemCarveoutMaxShared));
-  ++h->launches;
-  qr_kernel<<<2 * d.Wp, GR_THREADS, smem, st>>>(a);
-  PXB_CUDA(h, cudaGetLastError());
+  {
+    const int rc = run_qr(h, h->phi(), st);
+    if (rc) return rc;
+  }
+  double* qrld = h->ptr<double>(A_QRLD);
   ++h->launches;
   qr_combine_kernel<<<(d.W + 255) / 256, 256, 0, st>>>(
-      a.logdet, h->field<double2>(PXB_F_OT), h->ptr0<double2>(A_OT_TRUE), h->field<double>(PXB_F_DETR),
+      qrld, h->field<double2>(PXB_F_OT), h->ptr0<double2>(A_OT_TRUE), h->field<double>(PXB_F_DETR),
       h->field<double>(PXB_F_LOG_DETR), (d.flags & FLAG_FREE_PROJECTION) ? h->field<double>(PXB_F_WEIGHT) : nullptr,
       h->log_shift_on ? &h->field<LogShifts>(PXB_F_LOG_SHIFTS)->detR_shift : nullptr, d.W);
   PXB_CUDA(h, cudaGetLastError());
@@ -2017,16 +2063,7 @@ int pxb_back_propagate(pxb_handle h, int nsteps, int nstblz, int init_walker, vo
     if ((rc = run_taylor(h, work, nullptr, st))) return rc;
     if ((rc = run_one_body(h, work, phi_bp, nullptr, st, true))) return rc;
     if (i != 0 && i % nstblz == 0) {
-      QrArgs q;
-      q.phi = phi_bp;
-      q.logdet = h->ptr<double>(A_QRLD);
-      q.d = d;
-      const size_t smem = qr_smem_bytes(d);
-      if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "qr: problem too large for shared memory");
-      PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      ++h->launches;
-      qr_kernel<<<2 * d.Wp, GR_THREADS, smem, st>>>(q);
-      PXB_CUDA(h, cudaGetLastError());
+      if ((rc = run_qr(h, phi_bp, st))) return rc;
     }
   }
   // G_s = gab(phi_bp_s, phi_old_s)^T = conj(phi_bp_s) (phi_old_s^T conj(phi_bp_s))^-1 phi_old_s^T

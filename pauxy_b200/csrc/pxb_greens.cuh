@@ -257,11 +257,13 @@ struct QrArgs {
   double* phi;      // OF, in place
   double* logdet;   // [Wp][2] sum_k log R_kk of this spin
   Dims d;
+  const int* mask = nullptr;  // when set: only the (walker, spin) items it marks, and logdet is ADDED to
 };
 
 __global__ void __launch_bounds__(GR_THREADS) qr_kernel(QrArgs a) {
   extern __shared__ __align__(16) unsigned char qs_raw[];
   const Dims& d = a.d;
+  if (a.mask != nullptr && a.mask[blockIdx.x] == 0) return;  // CholeskyQR2 (pxb_qr.cuh) has done this one
   const int w = blockIdx.x >> 1, s = blockIdx.x & 1;
   const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -330,7 +332,7 @@ __global__ void __launch_bounds__(GR_THREADS) qr_kernel(QrArgs a) {
     *reinterpret_cast<double2*>(a.phi + (((size_t)wg * d.ne + ioff + i) * d.KC + (p >> 2)) * 32 + wl * 8 +
                                 (p & 3) * 2) = make_double2(v.re, v.im);
   }
-  if (tid == 0) a.logdet[(size_t)w * 2 + s] = logdet;
+  if (tid == 0) a.logdet[(size_t)w * 2 + s] = (a.mask != nullptr ? a.logdet[(size_t)w * 2 + s] : 0.0) + logdet;
 }
 
 inline size_t qr_smem_bytes(const Dims& d) {

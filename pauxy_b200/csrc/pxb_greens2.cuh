@@ -166,6 +166,117 @@ __device__ __forceinline__ void gj_invert_regs(cplx* A, int lda, int ns, cplx* p
   __syncwarp();
 }
 
+// out[a][p] = sum_i A[a][i] in[p][i] for one (walker, spin) by one warp on DMMA: A is an ns x ns complex
+// matrix, row-major with leading dimension lda in shared memory (readable up to 3 elements past each
+// row), `in` / `out` point at the walker's slot of the first orbital row of the spin in the OF layout
+// (base + wl * 8).  in == out is allowed: a chunk is read completely before it is stored.
+// E1B: also er + i ei += sum_{a,p} h1rot[a][p] out[a][p] (this lane's share; h1rot at the spin's first row).
+// NC: read `in` through the non-coherent path (only when nothing in this kernel writes it).
+// LOWER: A is lower triangular (zero tiles are skipped; needs every k-step slot in use, KS == 2 NMT).
+template <int NMT, bool E1B, bool NC, bool LOWER = false>
+__device__ __forceinline__ void warp_apply_left(const cplx* A, int lda, int ns, const Dims& d, const double* in,
+                                                double* out, const double2* h1rot, int lane, double& er, double& ei) {
+  const int g = lane >> 2, t = lane & 3;
+  // one basis chunk (n-tile of 4 basis functions) per
+  //    iteration.  Everything that does not depend on the chunk is hoisted: A fragments are read
+  //    from the row-major inverse with one base address per m-tile plus immediates (rows >= ns of the
+  //    last m-tile are clamped to row ns - 1: a row of A only reaches the same row of C, and those
+  //    rows are never stored; columns >= ns read the start of the next row or of colk, finite
+  //    numbers, and meet B entries that are forced to zero); B / Theta / h1rot are addressed with
+  //    pointers that advance by one chunk; only the LAST k-step can hold padding (4 (KS-1) + t >= ns).
+  //    The B fragments of the next chunk and the h1rot entries of this one are requested before the
+  //    DMMAs of the current chunk (16 warps per SM: latency has to be hidden inside the warp).
+  const int KS = (ns + 3) >> 2;
+  constexpr int KSM = 2 * NMT;  // >= ceil(ns / 4)
+  const unsigned rowB = (unsigned)d.KC * 32u;
+  const unsigned smask = (g & 1) ? 0u : 0x80000000u;  // (i B)^: (re, im) -> (-im, re)
+  const bool last_pad = 4 * (KS - 1) + t >= ns;       // this lane's entry of the last k-step is padding
+  const double* bp = in + (size_t)t * rowB + g;  // k-step 0, chunk 0
+  const double* bl = in + (size_t)min(4 * (KS - 1) + t, ns - 1) * rowB + g;
+  const unsigned brow4 = 4u * rowB;
+  const double2* Am[NMT];  // rows >= ns are clamped to the last row (their C rows are not stored)
+#pragma unroll
+  for (int m = 0; m < NMT; ++m) Am[m] = reinterpret_cast<const double2*>(A + (size_t)min(8 * m + g, ns - 1) * lda + t);
+  const int klast = 4 * (KS - 1);
+  // up to 32 orbitals the A fragments stay in registers for all chunks (the shared-memory data path
+  // is what bounds this kernel: 6 NMT^2 LDS.128 per chunk otherwise)
+  constexpr bool AREG = NMT <= 4;
+  double2 af[AREG ? NMT : 1][AREG ? KSM : 1];
+  if constexpr (AREG) {
+#pragma unroll
+    for (int ks = 0; ks < KSM; ++ks)
+#pragma unroll
+      for (int m = 0; m < NMT; ++m)
+        af[m][ks] = ks == KSM - 1 ? Am[m][klast] : ks < KS - 1 ? Am[m][4 * ks] : make_double2(0.0, 0.0);
+  }
+  double* tp = out + (size_t)g * rowB + t * 2;
+  const double2* hp = E1B ? h1rot + (size_t)g * d.Mp + t : nullptr;
+  const unsigned trow8 = 8u * rowB, hrow8 = 8u * (unsigned)d.Mp;
+  bool rowok[NMT];
+#pragma unroll
+  for (int m = 0; m < NMT; ++m) rowok[m] = 8 * m + g < ns;
+  double bn[KSM];
+  // KFULL: every k-step slot is in use (KS == KSM, e.g. 21 orbitals in 6 k-steps): no guards
+  auto chunks = [&](auto kfull_tag) {
+  constexpr bool KFULL = decltype(kfull_tag)::value;
+  auto load_b = [&]() {  // slot KSM - 1 holds k-step KS - 1, whatever KS is
+#pragma unroll
+    for (int ks = 0; ks < KSM - 1; ++ks)
+      if (KFULL || ks < KS - 1) bn[ks] = NC ? ldg_nc(bp + ks * brow4) : bp[ks * brow4];
+    bn[KSM - 1] = last_pad ? 0.0 : NC ? ldg_nc(bl) : *bl;
+    bp += 32;
+    bl += 32;
+  };
+  load_b();
+  const int pz0 = d.M - t;  // entries with 4 pc >= pz0 are basis padding
+  for (int pc = 0; pc < d.KC; ++pc) {
+    double b[KSM];
+#pragma unroll
+    for (int ks = 0; ks < KSM; ++ks) b[ks] = bn[ks];
+    if (pc + 1 < d.KC) load_b();
+    double2 hq[NMT];
+#pragma unroll
+    for (int m = 0; m < NMT; ++m) hq[m] = E1B && rowok[m] ? hp[m * hrow8] : make_double2(0.0, 0.0);
+    if (E1B) hp += 4;
+    double acc[NMT][2];
+#pragma unroll
+    for (int m = 0; m < NMT; ++m) acc[m][0] = acc[m][1] = 0.0;
+#pragma unroll
+    for (int ks = 0; ks < KSM; ++ks) {
+      const bool lastk = ks == KSM - 1;
+      if (KFULL || lastk || ks < KS - 1) {
+        const double o = __shfl_xor_sync(0xffffffffu, b[ks], 4);  // the other component of the same element
+        const double bq = __hiloint2double(__double2hiint(o) ^ (int)smask, __double2loint(o));
+#pragma unroll
+        for (int m = 0; m < NMT; ++m) {  // m-tiles beyond ceil(ns / 8) (uneven spins) compute on clamped rows
+          if (LOWER && KFULL && 4 * ks > 8 * m + 7) continue;  // A[8m..8m+7][4ks..] = 0
+          double2 av;
+          if constexpr (AREG) av = af[m][ks];
+          else av = lastk ? Am[m][klast] : Am[m][4 * ks];
+          dmma(acc[m][0], acc[m][1], av.x, b[ks]);
+          dmma(acc[m][0], acc[m][1], av.y, bq);
+        }
+      }
+    }
+    const bool pz = 4 * pc >= pz0;
+#pragma unroll
+    for (int m = 0; m < NMT; ++m) {
+      if (rowok[m]) {
+        const double vr = pz ? 0.0 : acc[m][0], vi = pz ? 0.0 : acc[m][1];
+        *reinterpret_cast<double2*>(tp + m * trow8) = make_double2(vr, vi);
+        if (E1B) {
+          er += hq[m].x * vr - hq[m].y * vi;
+          ei += hq[m].x * vi + hq[m].y * vr;
+        }
+      }
+    }
+    tp += 32;
+  }
+  };
+  if (KS == KSM) chunks(std::true_type{});
+  else chunks(std::false_type{});
+}
+
 // NMT: 8-row tiles over the occupied orbitals of one spin (ceil(ns/8) <= NMT)
 template <int NMT>
 __global__ void __launch_bounds__(TH_WARPS * 32, NMT == 1 ? 6 : NMT == 2 ? 4 : NMT == 3 ? 3 : NMT == 4 ? 2 : 1)
@@ -315,102 +426,12 @@ __global__ void __launch_bounds__(TH_WARPS * 32, NMT == 1 ? 6 : NMT == 2 ? 4 : N
   }
   __syncwarp();
 
-  // 3. Theta[a][p] = sum_i Oinv[a][i] phi[p][i], one basis chunk (n-tile of 4 basis functions) per
-  //    iteration.  Everything that does not depend on the chunk is hoisted: A fragments are read
-  //    from the row-major inverse with one base address per m-tile plus immediates (rows >= ns of the
-  //    last m-tile are clamped to row ns - 1: a row of A only reaches the same row of C, and those
-  //    rows are never stored; columns >= ns read the start of the next row or of colk, finite
-  //    numbers, and meet B entries that are forced to zero); B / Theta / h1rot are addressed with
-  //    pointers that advance by one chunk; only the LAST k-step can hold padding (4 (KS-1) + t >= ns).
-  //    The B fragments of the next chunk and the h1rot entries of this one are requested before the
-  //    DMMAs of the current chunk (16 warps per SM: latency has to be hidden inside the warp).
-  const int KS = (ns + 3) >> 2;
-  constexpr int KSM = 2 * NMT;  // >= ceil(ns / 4)
-  const unsigned rowB = (unsigned)d.KC * 32u;
-  const unsigned smask = (g & 1) ? 0u : 0x80000000u;  // (i B)^: (re, im) -> (-im, re)
-  const bool last_pad = 4 * (KS - 1) + t >= ns;       // this lane's entry of the last k-step is padding
-  const double* bp = a.phi + ((size_t)wg * d.ne + ioff + t) * rowB + wl * 8 + g;  // k-step 0, chunk 0
-  const double* bl = a.phi + ((size_t)wg * d.ne + ioff + min(4 * (KS - 1) + t, ns - 1)) * rowB + wl * 8 + g;
-  const unsigned brow4 = 4u * rowB;
-  const double2* Am[NMT];  // rows >= ns are clamped to the last row (their C rows are not stored)
-#pragma unroll
-  for (int m = 0; m < NMT; ++m) Am[m] = reinterpret_cast<const double2*>(A + (size_t)min(8 * m + g, ns - 1) * lda + t);
-  const int klast = 4 * (KS - 1);
-  // up to 32 orbitals the A fragments stay in registers for all chunks (the shared-memory data path
-  // is what bounds this kernel: 6 NMT^2 LDS.128 per chunk otherwise)
-  constexpr bool AREG = NMT <= 4;
-  double2 af[AREG ? NMT : 1][AREG ? KSM : 1];
-  if constexpr (AREG) {
-#pragma unroll
-    for (int ks = 0; ks < KSM; ++ks)
-#pragma unroll
-      for (int m = 0; m < NMT; ++m)
-        af[m][ks] = ks == KSM - 1 ? Am[m][klast] : ks < KS - 1 ? Am[m][4 * ks] : make_double2(0.0, 0.0);
-  }
-  double* tp = a.theta + ((size_t)wg * d.ne + ioff + g) * rowB + wl * 8 + t * 2;
-  const double2* hp = a.h1rot + (size_t)(ioff + g) * d.Mp + t;
-  const unsigned trow8 = 8u * rowB, hrow8 = 8u * (unsigned)d.Mp;
-  bool rowok[NMT];
-#pragma unroll
-  for (int m = 0; m < NMT; ++m) rowok[m] = 8 * m + g < ns;
+  // 3. Theta = Oinv phi^T (DMMA), e1b fused
   double er = 0.0, ei = 0.0;
-  double bn[KSM];
-  // KFULL: every k-step slot is in use (KS == KSM, e.g. 21 orbitals in 6 k-steps): no guards
-  auto chunks = [&](auto kfull_tag) {
-  constexpr bool KFULL = decltype(kfull_tag)::value;
-  auto load_b = [&]() {  // slot KSM - 1 holds k-step KS - 1, whatever KS is
-#pragma unroll
-    for (int ks = 0; ks < KSM - 1; ++ks)
-      if (KFULL || ks < KS - 1) bn[ks] = ldg_nc(bp + ks * brow4);
-    bn[KSM - 1] = last_pad ? 0.0 : ldg_nc(bl);
-    bp += 32;
-    bl += 32;
-  };
-  load_b();
-  const int pz0 = d.M - t;  // entries with 4 pc >= pz0 are basis padding
-  for (int pc = 0; pc < d.KC; ++pc) {
-    double b[KSM];
-#pragma unroll
-    for (int ks = 0; ks < KSM; ++ks) b[ks] = bn[ks];
-    if (pc + 1 < d.KC) load_b();
-    double2 hq[NMT];
-#pragma unroll
-    for (int m = 0; m < NMT; ++m) hq[m] = rowok[m] ? hp[m * hrow8] : make_double2(0.0, 0.0);
-    hp += 4;
-    double acc[NMT][2];
-#pragma unroll
-    for (int m = 0; m < NMT; ++m) acc[m][0] = acc[m][1] = 0.0;
-#pragma unroll
-    for (int ks = 0; ks < KSM; ++ks) {
-      const bool lastk = ks == KSM - 1;
-      if (KFULL || lastk || ks < KS - 1) {
-        const double o = __shfl_xor_sync(0xffffffffu, b[ks], 4);  // the other component of the same element
-        const double bq = __hiloint2double(__double2hiint(o) ^ (int)smask, __double2loint(o));
-#pragma unroll
-        for (int m = 0; m < NMT; ++m) {  // m-tiles beyond ceil(ns / 8) (uneven spins) compute on clamped rows
-          double2 av;
-          if constexpr (AREG) av = af[m][ks];
-          else av = lastk ? Am[m][klast] : Am[m][4 * ks];
-          dmma(acc[m][0], acc[m][1], av.x, b[ks]);
-          dmma(acc[m][0], acc[m][1], av.y, bq);
-        }
-      }
-    }
-    const bool pz = 4 * pc >= pz0;
-#pragma unroll
-    for (int m = 0; m < NMT; ++m) {
-      if (rowok[m]) {
-        const double vr = pz ? 0.0 : acc[m][0], vi = pz ? 0.0 : acc[m][1];
-        *reinterpret_cast<double2*>(tp + m * trow8) = make_double2(vr, vi);
-        er += hq[m].x * vr - hq[m].y * vi;
-        ei += hq[m].x * vi + hq[m].y * vr;
-      }
-    }
-    tp += 32;
+  {
+    const size_t wbase = ((size_t)wg * d.ne + ioff) * d.KC * 32 + wl * 8;
+    warp_apply_left<NMT, true, true>(A, lda, ns, d, a.phi + wbase, a.theta + wbase, a.h1rot + (size_t)ioff * d.Mp, lane, er, ei);
   }
-  };
-  if (KS == KSM) chunks(std::true_type{});
-  else chunks(std::false_type{});
 #pragma unroll
   for (int m = 16; m > 0; m >>= 1) {
     er += __shfl_xor_sync(0xffffffffu, er, m);

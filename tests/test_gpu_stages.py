@@ -213,3 +213,35 @@ def test_reortho(setup):
     assert relerr(orc.calc_overlap(ham, q) * detR, ot0) < 1e-11
     eng.local_energy()
     assert relerr(eng.eloc.cpu().numpy(), e_before) < 1e-10
+
+
+def test_reortho_ill_conditioned_walkers_fall_back(setup):
+    """CholeskyQR2 (csrc/pxb_qr.cuh) hands (walker, spin) blocks whose first Cholesky pivots fall
+    below 1e-10 of the diagonal to the Gram-Schmidt kernel.  Walkers with two nearly parallel
+    orbitals (cond ~ 1e7) next to healthy ones: every walker still comes out as the reference's
+    QR with a positive diagonal (walkers/single_det.py:215-255), the ill-conditioned ones to the
+    accuracy Gram-Schmidt has there (u cond)."""
+    eng, phi, ham, W = setup['eng'], setup['phi'], setup['ham'], setup['W']
+    import torch
+    na = ham.nup
+    bad = phi.copy()
+    ill = list(range(0, W, 3))
+    for w in ill:
+        bad[w, :, 1] = bad[w, :, 0] * (1.0 + 0.3j) + 1e-7 * bad[w, :, 1]             # spin up
+        bad[w, :, na + 1] = bad[w, :, na] * (0.5 - 0.2j) + 1e-7 * bad[w, :, na + 1]  # spin down
+    eng.init_walkers(ham.psi)
+    eng.set_phi(bad)
+    ot0 = orc.calc_overlap(ham, bad)
+    eng.ot.copy_(torch.as_tensor(ot0))
+    eng.orthogonalise()
+    q = eng.get_phi().cpu().numpy()
+    ref, detR, logdet = orc.reortho(ham, bad)
+    good = [w for w in range(W) if w not in ill]
+    assert relerr(q[good], ref[good]) < 1e-10
+    assert relerr(eng.detR.cpu().numpy()[good], detR[good]) < 1e-11
+    assert relerr(q[ill], ref[ill]) < 1e-6
+    assert relerr(eng.detR.cpu().numpy()[ill], detR[ill]) < 1e-8
+    for w in ill:
+        for sl in (slice(0, na), slice(na, None)):
+            g = q[w][:, sl].conj().T @ q[w][:, sl]
+            assert numpy.abs(g - numpy.eye(g.shape[0])).max() < 1e-7
