@@ -753,7 +753,12 @@ int run_exchange_eri(pxb_handle h, cudaStream_t st) {
   const size_t smem = eri_smem_bytes();
   PXB_CUDA(h, cudaFuncSetAttribute(exx_eri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->launches;
-  exx_eri_kernel<<<std::min(nitems, persist_sms(h)), gemm_tma_threads<EQ_CWM * EQ_CWN>(), smem, st>>>(a, nitems, 2 * nrb, counter);
+  // walker blocks per super-block: Theta of a super-block <= 64 MB, super-blocks of equal size
+  const size_t theta_wb = (size_t)EQ_TN * d.ne * d.KC * 32 * 8;
+  const int sbmax = (int)std::max<size_t>(1, ((size_t)64 << 20) / theta_wb);
+  const int nsb = (nwb + sbmax - 1) / sbmax;
+  const int SB = (nwb + nsb - 1) / nsb;
+  exx_eri_kernel<<<std::min(nitems, persist_sms(h)), gemm_tma_threads<EQ_CWM * EQ_CWN>(), smem, st>>>(a, nitems, 2 * nrb, SB, counter);
   PXB_CUDA(h, cudaGetLastError());
   ++h->launches;
   exx_eri_reduce_kernel<<<(2 * d.Wp + 255) / 256, 256, 0, st>>>(a.part, h->ptr<double2>(A_EXX), d, a.nslot, counter);

@@ -48,23 +48,28 @@ __host__ __device__ inline size_t eri_kf_doubles(const Dims& d, int s) {
 }
 inline size_t eri_smem_bytes() { return gemm_tma_smem_bytes<EQ_WM, EQ_WN, EQ_CWM, EQ_CWN>() + 2 * 4 * 8 + 4 * 4 + 16; }
 
-// item -> (walker block, row block, spin), walker block OUTERMOST and, inside it, the longest
-// k-ranges (row block 0) first.  The CTAs take items from a global counter (dynamic scheduling),
-// so the ~148 items in flight belong to ~4 consecutive walker blocks: their Theta (4.6 MB per
-// block at c4) is read from DRAM once and then served by L2 to all the row blocks, while K (41-82 MB
-// at c4) stays L2-resident because every row block of it is being streamed all the time.  (With the
-// row block outermost each walker block's Theta came back from DRAM once per row block: 8.4 x the
-// algorithmic traffic.)  Items differ in length by a factor of 25; handing them out dynamically,
-// longest first within a walker block, keeps the CTAs level to within one short item.
+// item -> (walker super-block, row block, spin, walker block inside the super-block).  A super-block
+// is a run of SB consecutive walker blocks whose Theta (4.6 MB per block at c4) fits in L2 next to K
+// (41-82 MB at c4): its Theta is read from DRAM once and then served by L2 to all the row blocks,
+// while K stays L2-resident because every row block of it is streamed all the time.  (With the row
+// block outermost over ALL walkers each walker block's Theta came back from DRAM once per row block:
+// 8.4 x the algorithmic traffic.)  Inside a super-block the items are ordered longest k-range first
+// (row block 0 first; lengths differ by a factor of 25) and handed out from a global counter, so the
+// CTAs finish level to within one short item also when there are only a few items per CTA
+// (1024 walkers per GPU: 576 items on 148 CTAs).
 struct EriItem {
   int rb, s, nb;
   int mt0, nt0, ks0, nkstage, MT, KS;
   bool valid;
 };
-__device__ __forceinline__ EriItem eri_item(const Dims& d, int item, int nrb2) {
+__device__ __forceinline__ EriItem eri_item(const Dims& d, int item, int nrb2, int SB) {
   EriItem it;
-  it.nb = item / nrb2;          // walker block
-  const int r = item - it.nb * nrb2;
+  const int nwb = (d.WG + EQ_TN - 1) / EQ_TN;
+  const int sb = item / (nrb2 * SB);             // all super-blocks but the last hold SB walker blocks
+  const int rem = item - sb * nrb2 * SB;
+  const int nin = min(SB, nwb - sb * SB);
+  const int r = rem / nin;
+  it.nb = sb * SB + (rem - r * nin);             // walker block
   it.s = r & 1;
   it.rb = r >> 1;
   it.MT = eri_mtiles(d, it.s);
@@ -80,7 +85,7 @@ __device__ __forceinline__ EriItem eri_item(const Dims& d, int item, int nrb2) {
 constexpr int EQ_QD = 4;  // depth of the producer -> consumer item queue
 
 static_assert(EQ_CWM * EQ_CWN == 8, "register rebalancing below assumes two consumer warpgroups");
-__global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_eri_kernel(EriArgs a, int nitems, int nrb2, int* __restrict__ counter) {
+__global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_eri_kernel(EriArgs a, int nitems, int nrb2, int SB, int* __restrict__ counter) {
   constexpr int TM = EQ_TM, TN = EQ_TN, NCW = EQ_CWM * EQ_CWN, WM = EQ_WM, WN = EQ_WN;
   constexpr int A_STAGE = TM * GT_KS * 32, B_STAGE = TN * GT_KS * 32;
   extern __shared__ __align__(128) double eq_smem[];
@@ -125,7 +130,7 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
           item = -1;
           break;
         }
-        if (eri_item(d, item, nrb2).valid) break;
+        if (eri_item(d, item, nrb2, SB).valid) break;
       }
       {
         const unsigned q = qc % EQ_QD, qph = (qc / EQ_QD) & 1u;
@@ -137,7 +142,7 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
         ++qc;
       }
       if (item < 0) break;
-      const EriItem it = eri_item(d, item, nrb2);
+      const EriItem it = eri_item(d, item, nrb2, SB);
       const int ioff = it.s ? d.na : 0;
       const int rows_m = min(TM, it.MT - it.mt0), rows_n = min(TN, d.WG - it.nt0);
       const double* src = nullptr;
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
       ++qc;
     }
     if (item < 0) break;
-    const EriItem it = eri_item(d, item, nrb2);
+    const EriItem it = eri_item(d, item, nrb2, SB);
     double acc[WM][WN][2];
 #pragma unroll
     for (int i = 0; i < WM; ++i)
