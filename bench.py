@@ -599,7 +599,12 @@ def main():
     exchange = main_res['exchange_form']
     tensor_stages = [k for k in stages if k in ('xgemm', 'vhs', 'one_body', 'taylor', 'exchange')]
     dom = max(tensor_stages, key=lambda k: stages[k]['ms_per_step'])
-    kernel_names = {'taylor': 'taylor2_kernel (exp(VHS) phi: persistent, TMA-fed DMMA, Horner)',
+    # which Taylor kernel the dispatch in csrc/pxb_api.cu (run_taylor3) picks for this shape
+    nch = (na + nb + 47) // 48
+    nt8 = (-(-(na + nb) // nch) + 7) // 8
+    t3 = 4 <= (M + 7) // 8 <= 16 and 2 <= nt8 <= 6
+    kernel_names = {'taylor': ('taylor3_kernel (exp(VHS) phi: persistent, TMA-fed DMMA, 3-product complex Horner)'
+                               if t3 else 'taylor2_kernel (exp(VHS) phi: persistent, TMA-fed DMMA, Horner)'),
                     'vhs': 'gemm_tma_kernel<EpiVHS> (VHS = i sqrt(dt) L x)',
                     'exchange': ('exx_eri_kernel (Theta.K.Theta, symmetric half-rotated ERI)'
                                  if exchange == 'eri' else 'exchange_kernel (fused T = R Theta^T + trace)'),

@@ -47,8 +47,11 @@ for T in ${TASKS//,/ }; do
     cfgs) for c in c1 c2 c3 c5; do echo "-- $c"; run_bench 1 gpurun_out/bench_${TAG}_$c --config $c --steps ${STEPS:-10} --warmup 3 --no-cpu-baseline --no-other-configs $EXTRA; done ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c ${NLAUNCH:-400} --csv --log-file gpurun_out/launches_$TAG.csv \
                 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-other-configs $EXTRA > gpurun_out/bench_ncu_$TAG.log 2>&1; wc -l gpurun_out/launches_$TAG.csv ;;
-    ncu) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${KREGEX:-exx_eri_kernel|taylor3_kernel|taylor2_kernel|gemm_tma_kernel|theta_kernel|qr_kernel}" \
-           -c ${NCU_COUNT:-24} -f -o gpurun_out/prof_$TAG python tools/profile_stages.py ${PROF_ARGS:-c4 2368 1} > gpurun_out/ncu_$TAG.log 2>&1; tail -2 gpurun_out/ncu_$TAG.log ;;
+    ncu) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:"${KREGEX:-exx_eri_kernel|taylor3_kernel|taylor2_kernel|gemm_tma_kernel|theta_kernel|cholqr_kernel|qr_kernel}" \
+           -c ${NCU_COUNT:-24} -f -o gpurun_out/prof_$TAG python tools/profile_stages.py ${PROF_ARGS:-c4 2368 1} > gpurun_out/ncu_$TAG.log 2>&1; tail -2 gpurun_out/ncu_$TAG.log
+         python tools/ncu_summary.py gpurun_out/prof_$TAG.ncu-rep > gpurun_out/ncu_full_$TAG.txt 2>/dev/null; wc -l gpurun_out/ncu_full_$TAG.txt
+         # gpurun brings back at most 64 MiB: keep the report itself only when asked to (KEEP_REP=1, few kernels)
+         [ "${KEEP_REP:-0}" = "1" ] || rm -f gpurun_out/prof_$TAG.ncu-rep ;;
     traffic) for cfg in "c4 8192" "c5 2048"; do set -- $cfg
                timeout 900 ncu --clock-control none -k regex:"${KREGEX:-exx_eri_kernel|taylor3_kernel|taylor2_kernel}" -c 4 --csv \
                  --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sector_hit_rate.pct,lts__t_bytes.sum \
