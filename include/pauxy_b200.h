@@ -32,7 +32,7 @@ extern "C" {
 #define PXB_ERR_STATE -3        /* call order (arena / hamiltonian not set) */
 #define PXB_ERR_UNSUPPORTED -4  /* e.g. complex-valued Cholesky / trial */
 
-#define PXB_ABI_VERSION 9
+#define PXB_ABI_VERSION 10
 
 typedef struct pxb_context* pxb_handle;
 
@@ -70,6 +70,11 @@ typedef struct {
                                       Generic path raises TypeError); here it is available for any
                                       number of determinants with the multi-determinant semantics. */
 
+#define PXB_FLAG_COMPLEX_CHOLESKY 16 /* complex-valued Cholesky vectors (system.hs_pot, trial._rchol) and / or trial
+                                       orbitals: every GEMM against them runs as the real GEMM
+                                       [Re A | Im A] [B ; i B] over a doubled k range, the exchange as two
+                                       quadratic forms (Re K, Im K).  ERI form of the exchange only; no back
+                                       propagation. */
 #define PXB_FLAG_COMPLEX_ONE_BODY 8 /* propagator.BH1 has an imaginary part (complex mean-field shift, e.g.
                                       a multi-determinant trial with complex CI coefficients): the
                                       one-body step runs as [Re BH1 | Im BH1] [phi ; i phi] on the real
@@ -170,8 +175,11 @@ int pxb_field(pxb_handle h, int field_id, size_t* offset_bytes, size_t* size_byt
  *                               e1b = sum h1rot * Theta == sum H1*G (estimators/generic.py:178)
  *   psi      c128 [M, na+nb]    trial.psi                (walkers/handler.py:57-61)
  *   mf_shift c128 [N]           propagator.mf_shift      (propagation/generic.py:66-80)
- * rchol, bh1 and psi must be real-valued (imag == 0) in this version:
- * PXB_ERR_UNSUPPORTED otherwise (checked on the device, synchronous call). */
+ * Without PXB_FLAG_COMPLEX_CHOLESKY rchol and psi must be real-valued (imag == 0) and hs_pot is an
+ * array of doubles; PXB_ERR_UNSUPPORTED otherwise (checked on the device, synchronous call).  With
+ * the flag (systems/generic.py:126 "complex integrals", generate_hamiltonian(cplx=True)) hs_pot is
+ * complex128 [M*M, N] (interleaved re, im: pass the pointer as const double*), rchol and psi may be
+ * complex.  A complex bh1 needs PXB_FLAG_COMPLEX_ONE_BODY in both cases. */
 int pxb_set_hamiltonian(pxb_handle h, const double* dev_hs_pot, const void* dev_rchol,
                         const void* dev_bh1, const void* dev_h1rot, const void* dev_psi,
                         const void* dev_mf_shift, double ecore, void* stream);

@@ -168,6 +168,22 @@ def case_stress(name, pop, walkers=None, scale_chol=6.0, dt=0.02, nwalkers=16, k
     save(name, meta, tr, setup=rh.reference_setup_arrays(a), keep_xi=keep_xi)
 
 
+def case_complex(name, nmo, nelec, nwalkers, scale_chol=1.0, dt=0.005, steps=5, blocks=3, stab=3):
+    """Complex integrals (the reference's generate_hamiltonian(cplx=True, sym=4),
+    systems/tests/test_generic.py:30): complex h1e (made Hermitian), complex Cholesky vectors, hence
+    complex half-rotated vectors, mean-field shift and one-body propagator.  The unmodified
+    reference driver runs it through the same code path as a real Hamiltonian."""
+    numpy.random.seed(7)
+    h1e, chol, enuc, _ = generate_hamiltonian(nmo, nelec, cplx=True, sym=4)
+    h1e = 0.5 * (h1e + h1e.conj().T)
+    hs = scale_chol * chol.reshape((-1, nmo * nmo)).T.copy()
+    opts = options(nwalkers, dt, steps, blocks, 8, stab=stab, popc=1)
+    a, tr = rh.run_reference_traced(h1e, hs, enuc, nelec, opts)
+    meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array(nelec), dt=dt, nwalkers=nwalkers,
+                steps=steps, blocks=blocks, seed=8, stab=stab, popc=1)
+    save(name, meta, tr, setup=rh.reference_setup_arrays(a))
+
+
 def case_shape(name, M, na, N, W, steps, seed_h, stab, blocks=1, dt=0.005, scale=0.02, ramp=0.05):
     """BASELINE c2..c5 shapes at reduced walker count; inputs regenerate from seeds, fields from
     the global legacy stream.  The `*_shape` fixtures use the benchmark's benign Hamiltonian
@@ -339,6 +355,9 @@ if __name__ == '__main__':
                     walkers={'population_control': 'pair_branch',
                              'min_weight': 0.9, 'max_weight': 1.1},
                     scale_chol=3.0, dt=0.01)
+    if 'cplx' in which:
+        case_complex('cplx_driver', 10, (3, 3), 12)
+        case_complex('cplx_stress', 10, (4, 2), 16, scale_chol=4.0, dt=0.02, steps=5, blocks=4, stab=3)
     if 'le' in which:
         case_local_energy()
     if 'c2s' in which:

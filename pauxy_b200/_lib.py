@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'csrc', 'libpauxy_b200.so')
 
 PXB_OK = 0
-ABI_VERSION = 9
+ABI_VERSION = 10
 EXCHANGE_MODES = {'auto': 0, 'cholesky': 1, 'eri': 2}
 ERRORS = {-1: 'PXB_ERR_ARG', -2: 'PXB_ERR_CUDA', -3: 'PXB_ERR_STATE', -4: 'PXB_ERR_UNSUPPORTED'}
 
@@ -20,6 +20,7 @@ F_WEIGHT, F_UNSCALED_WEIGHT, F_OT, F_HYBRID_ENERGY, F_ELOC, F_DETR, F_LOG_DETR, 
     F_TOTAL_WEIGHT, F_PAIRS, F_PHASE, F_BP_RDM, F_BP_DENOM, F_THETA_SUM, F_WALKER_ELOC, F_OVLP_DET, \
     F_LOG_SHIFTS, F_COUNT = range(24)
 FLAG_FREE_PROJECTION, FLAG_NO_FORCE_BIAS, FLAG_LOCAL_ENERGY_WEIGHT, FLAG_COMPLEX_ONE_BODY = 1, 2, 4, 8
+FLAG_COMPLEX_CHOLESKY = 16
 MAX_DETS = 8
 STEP_ORTHO, STEP_POP, STEP_ENERGY = 1, 2, 4
 

@@ -37,6 +37,7 @@ enum ArenaId {
   A_EXX, A_KF0, A_KF1, A_EPART, A_RTMAP, A_OB, A_E1B, A_OVLP_OLD, A_ACTIVE, A_GW, A_GWS, A_CPROBS, A_FLAG, A_PF, A_SLOG, A_E1BP, A_QRLD, A_QRMASK,
   A_FC, A_PHI_OLD, A_PHI_BP, A_PHI_BP2, A_THETA_BP, A_BP_PART, A_PSI_NAT, A_INIT_NAT, A_BFT, A_STEP_PARAMS,
   A_OVLP_DET, A_ELOC_DET, A_XC, A_COEFF, A_ELOC_MIX, A_BF2, A_PHI_STACK, A_OT_TRUE, A_BPFAC, A_BPW,
+  A_THETA_STACK, A_XF2, A_KF0I, A_KF1I, A_EPART2,
   A_FIELD0,  // public fields follow: A_FIELD0 + pxb_field_id
   A_COUNT = A_FIELD0 + PXB_F_COUNT
 };
@@ -239,20 +240,31 @@ int launch_greens2(pxb_handle h, const double* phi, cudaStream_t st) {
   // 1. O_s = phi_s^T psi_s for all walkers; both spins in one launch (batch index = spin) when
   //    they have the same number of orbitals
   const bool both = d.na == d.nb && d.nb > 0;
+  // complex orbitals: conj(psi)^T phi = [Re psi^T | -Im psi^T] [phi ; i phi] over a doubled k range
+  const int km = kmul(d);
+  const size_t kc = (size_t)km * d.KC;
+  const double* pin = phi;
+  if (km == 2) {
+    ++h->launches;
+    stack_rows_kernel<<<grid_for((size_t)d.WG * d.ne * d.KC * 16), 256, 0, st>>>(phi, h->ptr0<double>(A_PHI_STACK),
+                                                                              (size_t)d.WG * d.ne, d.KC);
+    PXB_CUDA(h, cudaGetLastError());
+    pin = h->ptr0<double>(A_PHI_STACK);
+  }
   for (int s = 0; s < (both ? 1 : 2); ++s) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     if (ns == 0) continue;
     GemmArgs g;
-    g.A = h->ptr<double>(A_PF) + (s ? (size_t)((d.na + 7) >> 3) * d.KC * 32 : 0);
-    g.B = phi + (size_t)ioff * d.KC * 32;
-    g.strideAz = (size_t)((d.na + 7) >> 3) * d.KC * 32;
-    g.strideBz = (size_t)d.na * d.KC * 32;
-    g.strideBO = (size_t)d.ne * d.KC * 32;
-    g.strideBI = (size_t)d.KC * 32;
+    g.A = h->ptr<double>(A_PF) + (s ? (size_t)((d.na + 7) >> 3) * kc * 32 : 0);
+    g.B = pin + (size_t)ioff * kc * 32;
+    g.strideAz = (size_t)((d.na + 7) >> 3) * kc * 32;
+    g.strideBz = (size_t)d.na * kc * 32;
+    g.strideBO = (size_t)d.ne * kc * 32;
+    g.strideBI = kc * 32;
     g.ntInner = ns;
     g.MTiles = (ns + 7) >> 3;
     g.NTiles = d.WG * ns;
-    g.KS = d.KC;
+    g.KS = (int)kc;
     EpiO epi{h->ptr<double2>(A_OB), ns, s, nld, nsq};
     ++h->launches;
     PXB_CUDA(h, (launch_gemm_tma<NMT, 4, 1, 6>(g, epi, both ? 2 : 1, h->sm_count, st)));
@@ -362,6 +374,8 @@ int run_greens(pxb_handle h, const double* phi, bool want_theta, double2* ovlp_o
   }
   if (rc != 1) {
     if (rc) return rc;
+  } else if (kmul(d) == 2) {
+    return fail(h, PXB_ERR_UNSUPPORTED, "complex trial orbitals: shape outside the split Green's function path");
   } else if (nmt <= 1) rc = launch_greens<1>(h, a, smem, st);
   else if (nmt <= 2) rc = launch_greens<2>(h, a, smem, st);
   else if (nmt <= 3) rc = launch_greens<3>(h, a, smem, st);
@@ -383,6 +397,17 @@ int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
   StageTimer timer__(h, PXB_STAGE_XGEMM, st);
   const Dims& d = h->d;
   const bool both = d.na == d.nb && d.nb > 0;   // one launch, batch index = spin
+  // complex Cholesky vectors: [Re R | Im R]^T [Theta ; i Theta], k range doubled per orbital row
+  const int km = kmul(d);
+  const size_t kc = (size_t)km * d.KC;
+  const double* tin = h->ptr<double>(A_THETA);
+  if (km == 2) {
+    ++h->launches;
+    stack_rows_kernel<<<grid_for((size_t)d.WG * d.ne * d.KC * 16), 256, 0, st>>>(tin, h->ptr0<double>(A_THETA_STACK),
+                                                                              (size_t)d.WG * d.ne, d.KC);
+    PXB_CUDA(h, cudaGetLastError());
+    tin = h->ptr0<double>(A_THETA_STACK);
+  }
   for (int s = 0; s < (both ? 1 : 2); ++s) {
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     EpiX epi{h->ptr<double>(A_X) + (size_t)s * d.Wp * d.Np * 2, d.Wp, d.Np};
@@ -392,15 +417,15 @@ int run_force_bias_gemm(pxb_handle h, cudaStream_t st) {
     }
     GemmArgs g;
     g.A = h->ptr<double>(A_RF) + rf_spin_base(d, s);
-    g.B = h->ptr<double>(A_THETA) + (size_t)ioff * d.KC * 32;
+    g.B = tin + (size_t)ioff * kc * 32;
     g.strideAz = rf_spin_base(d, 1);
-    g.strideBz = (size_t)d.na * d.KC * 32;
-    g.strideBO = (size_t)d.ne * d.KC * 32;
+    g.strideBz = (size_t)d.na * kc * 32;
+    g.strideBO = (size_t)d.ne * kc * 32;
     g.strideBI = 0;
     g.ntInner = 1;
     g.MTiles = d.XG;
     g.NTiles = d.WG;
-    g.KS = ns * d.KC;
+    g.KS = ns * (int)kc;
     ++h->launches;
     // 16 x 8 tile blocks: 4 * WG/8 work units keep the 148 persistent CTAs balanced (XG is only ~63)
     PXB_CUDA(h, (launch_gemm_tma<4, 4, 4, 2>(g, epi, both ? 2 : 1, persist_sms(h), st)));
@@ -412,15 +437,25 @@ int run_vhs_gemm(pxb_handle h, cudaStream_t st) {
   StageTimer timer__(h, PXB_STAGE_VHS, st);
   const Dims& d = h->d;
   GemmArgs g;
+  // complex Cholesky vectors: [Re L | Im L] [x ; i x] over a doubled k range
+  const int km = kmul(d);
+  const double* xin = h->ptr<double>(A_XF);
+  if (km == 2) {
+    ++h->launches;
+    stack_rows_kernel<<<grid_for((size_t)d.WG * d.NKC * 16), 256, 0, st>>>(xin, h->ptr<double>(A_XF2), (size_t)d.WG,
+                                                                        d.NKC);
+    PXB_CUDA(h, cudaGetLastError());
+    xin = h->ptr<double>(A_XF2);
+  }
   g.A = h->ptr<double>(A_LF);
-  g.B = h->ptr<double>(A_XF);
+  g.B = xin;
   g.strideAz = g.strideBz = 0;
-  g.strideBO = (size_t)d.NKC * 32;
+  g.strideBO = (size_t)km * d.NKC * 32;
   g.strideBI = 0;
   g.ntInner = 1;
   g.MTiles = h->vhs_sym ? h->rtu : d.RT;
   g.NTiles = d.WG;
-  g.KS = d.NKC;
+  g.KS = km * d.NKC;
   EpiVHS epi{h->ptr<double>(A_VF), d.KC, d.MT, d.sqrt_dt, vf_walker(d),
              h->vhs_sym ? h->ptr<int>(A_RTMAP) : nullptr};
   ++h->launches;
@@ -738,10 +773,7 @@ int run_taylor(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
 int run_exchange_eri(pxb_handle h, cudaStream_t st) {
   const Dims& d = h->d;
   EriArgs a;
-  a.KF[0] = h->ptr<double>(A_KF0);
-  a.KF[1] = h->kf_shared[h->det] ? h->ptr<double>(A_KF0) : h->ptr<double>(A_KF1);
   a.theta = h->ptr<double>(A_THETA);
-  a.part = h->ptr<double2>(A_EPART);
   a.d = d;
   a.nslot = h->eri_nslot;
   const int nrb = std::max(eri_rowblocks(d, 0), eri_rowblocks(d, 1));
@@ -749,19 +781,29 @@ int run_exchange_eri(pxb_handle h, cudaStream_t st) {
   const int nitems = nrb * 2 * nwb;
   // work counter of the dynamic item scheduler: lives behind the partial sums, zero from the arena
   // memset and put back to zero by the reduce kernel that follows every exchange launch
-  int* counter = reinterpret_cast<int*>(a.part + (size_t)2 * a.nslot * d.Wp);
+  double2* part_r = h->ptr<double2>(A_EPART);
+  int* counter = reinterpret_cast<int*>(part_r + (size_t)2 * a.nslot * d.Wp);
   const size_t smem = eri_smem_bytes();
   PXB_CUDA(h, cudaFuncSetAttribute(exx_eri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  ++h->launches;
   // walker blocks per super-block: Theta of a super-block <= 64 MB, super-blocks of equal size
   const size_t theta_wb = (size_t)EQ_TN * d.ne * d.KC * 32 * 8;
   const int sbmax = (int)std::max<size_t>(1, ((size_t)64 << 20) / theta_wb);
   const int nsb = (nwb + sbmax - 1) / sbmax;
   const int SB = (nwb + nsb - 1) / nsb;
-  exx_eri_kernel<<<std::min(nitems, persist_sms(h)), gemm_tma_threads<EQ_CWM * EQ_CWN>(), smem, st>>>(a, nitems, 2 * nrb, SB, counter);
-  PXB_CUDA(h, cudaGetLastError());
+  // complex Cholesky vectors: K = Kr + i Ki, two passes of the same real quadratic form
+  const bool cc = kmul(d) == 2;
+  for (int pass = 0; pass < (cc ? 2 : 1); ++pass) {
+    a.KF[0] = h->ptr<double>(pass ? A_KF0I : A_KF0);
+    a.KF[1] = h->kf_shared[h->det] ? a.KF[0] : h->ptr<double>(pass ? A_KF1I : A_KF1);
+    a.part = pass ? h->ptr<double2>(A_EPART2) : part_r;
+    if (pass) PXB_CUDA(h, cudaMemsetAsync(counter, 0, 4, st));
+    ++h->launches;
+    exx_eri_kernel<<<std::min(nitems, persist_sms(h)), gemm_tma_threads<EQ_CWM * EQ_CWN>(), smem, st>>>(a, nitems, 2 * nrb, SB, counter);
+    PXB_CUDA(h, cudaGetLastError());
+  }
   ++h->launches;
-  exx_eri_reduce_kernel<<<(2 * d.Wp + 255) / 256, 256, 0, st>>>(a.part, h->ptr<double2>(A_EXX), d, a.nslot, counter);
+  exx_eri_reduce_kernel<<<(2 * d.Wp + 255) / 256, 256, 0, st>>>(part_r, cc ? h->ptr<double2>(A_EPART2) : nullptr,
+                                                              h->ptr<double2>(A_EXX), d, a.nslot, counter);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -770,6 +812,8 @@ int run_exchange(pxb_handle h, cudaStream_t st) {
   StageTimer timer__(h, PXB_STAGE_EXCHANGE, st);
   const Dims& d = h->d;
   if (h->exx_eri) return run_exchange_eri(h, st);
+  if (kmul(d) == 2)
+    return fail(h, PXB_ERR_UNSUPPORTED, "complex Cholesky vectors need the ERI form of the exchange (exchange_mode)");
   ExArgs a;
   a.RF = h->ptr<double>(A_RF);
   a.theta = h->ptr<double>(A_THETA);
@@ -987,7 +1031,8 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   d.exp_order = cfg->exp_order;
   d.flags = cfg->flags;
   if (((d.flags & FLAG_LOCAL_ENERGY_WEIGHT) && (d.flags & FLAG_FREE_PROJECTION)) ||
-      ((d.flags & FLAG_COMPLEX_ONE_BODY) && cfg->nbp > 0)) {
+      ((d.flags & (FLAG_COMPLEX_ONE_BODY | FLAG_COMPLEX_CHOLESKY)) && cfg->nbp > 0) ||
+      ((d.flags & FLAG_COMPLEX_CHOLESKY) && cfg->exchange_mode == PXB_EXCHANGE_CHOLESKY)) {
     delete h;
     return PXB_ERR_ARG;
   }
@@ -1008,13 +1053,13 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   }
 
   {
-    const size_t kbytes = (eri_kf_doubles(d, 0) + eri_kf_doubles(d, 1)) * 8 * (size_t)h->ndets;
+    const size_t kbytes = (eri_kf_doubles(d, 0) + eri_kf_doubles(d, 1)) * 8 * (size_t)h->ndets * kmul(d);
     if (cfg->exchange_mode == PXB_EXCHANGE_ERI)
       h->exx_eri = true;
     else if (cfg->exchange_mode == PXB_EXCHANGE_CHOLESKY)
       h->exx_eri = false;
     else if (cfg->exchange_mode == PXB_EXCHANGE_AUTO)
-      h->exx_eri = kbytes <= ((size_t)16 << 30);
+      h->exx_eri = kmul(d) == 2 || kbytes <= ((size_t)16 << 30);
     else {
       delete h;
       return PXB_ERR_ARG;
@@ -1058,6 +1103,14 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
     add(A_OB, W * 2 * nmax * (nmax | 1) * 16);
   }
   add(A_EPART, h->exx_eri ? (size_t)2 * h->eri_nslot * W * 16 + 16 : 0);  // + the item counter of exx_eri_kernel
+  {  // complex Cholesky vectors: stacked copies of Theta and of the fields, imaginary part of K
+    const bool cc = kmul(d) == 2;
+    add(A_THETA_STACK, cc ? 2 * of_size(d) * 8 : 0);
+    add(A_XF2, cc ? 2 * xf_size(d) * 8 : 0);
+    addd(A_KF0I, cc && h->exx_eri ? eri_kf_doubles(d, 0) * 8 : 0);
+    addd(A_KF1I, cc && h->exx_eri ? eri_kf_doubles(d, 1) * 8 : 0);
+    add(A_EPART2, cc && h->exx_eri ? (size_t)2 * h->eri_nslot * W * 16 : 0);
+  }
   addd(A_E1B, W * 16);
   add(A_OVLP_OLD, W * 16);
   add(A_ACTIVE, W * 4);
@@ -1065,7 +1118,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   add(A_GWS, Wt * 8);
   add(A_CPROBS, Wt * 8);
   add(A_FLAG, 256);
-  addd(A_PF, (size_t)(((d.na + 7) >> 3) + ((d.nb + 7) >> 3)) * d.KC * 32 * 8);
+  addd(A_PF, (size_t)(((d.na + 7) >> 3) + ((d.nb + 7) >> 3)) * d.KC * 32 * 8 * kmul(d));
   add(A_SLOG, W * 8 * 8);
   add(A_E1BP, W * 2 * 16);
   add(A_QRLD, W * 2 * 8);
@@ -1112,7 +1165,7 @@ int pxb_create(pxb_handle* out, const pxb_config* cfg) {
   {
     const bool cob = (d.flags & FLAG_COMPLEX_ONE_BODY) != 0;
     add(A_BF2, cob ? 2 * bf_size(d) * 8 : 0);
-    add(A_PHI_STACK, cob ? 2 * of_size(d) * 8 : 0);
+    add(A_PHI_STACK, (cob || kmul(d) == 2) ? 2 * of_size(d) * 8 : 0);
   }
   add(A_FIELD0 + PXB_F_WALKER_ELOC, W * 16);
   add(A_FIELD0 + PXB_F_OVLP_DET, 0);  // alias of A_OVLP_DET, fixed up below
@@ -1219,25 +1272,31 @@ static int set_trial_det_impl(pxb_handle h, int det, const void* rchol, const vo
     PXB_CUDA(h, cudaMemcpyAsync(&f2, flag, 4, cudaMemcpyDeviceToHost, st));
     PXB_CUDA(h, cudaStreamSynchronize(st));
     h->kf_shared[det] = cmp && (f2 & 8) == 0;
+    const bool cc = kmul(d) == 2;
     for (int s = 0; s < (h->kf_shared[det] ? 1 : 2); ++s) {
       const int ns = s ? d.nb : d.na;
       if (ns == 0) continue;
-      double* KF = h->ptr<double>(s ? A_KF1 : A_KF0);
-      PXB_CUDA(h, cudaMemsetAsync(KF, 0, eri_kf_doubles(d, s) * 8, st));
-      const int tiles = (d.M + 31) / 32;
-      ++h->launches;
-      eri_build_kernel<<<dim3(tiles * tiles, ns, ns), 1024, 0, st>>>(static_cast<const double2*>(rchol), KF, d, s);
-      PXB_CUDA(h, cudaGetLastError());
+      for (int part = cc ? 1 : 0; part <= (cc ? 2 : 0); ++part) {
+        double* KF = part == 2 ? h->ptr<double>(s ? A_KF1I : A_KF0I) : h->ptr<double>(s ? A_KF1 : A_KF0);
+        PXB_CUDA(h, cudaMemsetAsync(KF, 0, eri_kf_doubles(d, s) * 8, st));
+        const int tiles = (d.M + 31) / 32;
+        ++h->launches;
+        eri_build_kernel<<<dim3(tiles * tiles, ns, ns), 1024, 0, st>>>(static_cast<const double2*>(rchol), KF, d, s,
+                                                                       part);
+        PXB_CUDA(h, cudaGetLastError());
+      }
     }
   }
   int hflag = 0;
   PXB_CUDA(h, cudaMemcpyAsync(&hflag, flag, 4, cudaMemcpyDeviceToHost, st));
   PXB_CUDA(h, cudaStreamSynchronize(st));
   hflag &= 5;  // bit 0: rchol, bit 2: psi (bit 1 is bh1, bit 3 the spin-block comparison of the ERI setup)
+  if (kmul(d) == 2) hflag = 0;  // PXB_FLAG_COMPLEX_CHOLESKY: both may be complex
   if (hflag != 0) {
     char buf[160];
     snprintf(buf, sizeof buf,
-             "complex-valued trial orbitals are not supported in this version (determinant %d: rchol:%d psi:%d)",
+             "complex-valued Cholesky vectors / trial orbitals: create the handle with PXB_FLAG_COMPLEX_CHOLESKY "
+             "(determinant %d: rchol:%d psi:%d)",
              det, hflag & 1, (hflag >> 2) & 1);
     return fail(h, PXB_ERR_UNSUPPORTED, buf);
   }

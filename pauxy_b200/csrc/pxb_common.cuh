@@ -41,11 +41,15 @@ constexpr int FLAG_FREE_PROJECTION = 1;  // == PXB_FLAG_FREE_PROJECTION
 constexpr int FLAG_NO_FORCE_BIAS = 2;    // == PXB_FLAG_NO_FORCE_BIAS
 constexpr int FLAG_LOCAL_ENERGY_WEIGHT = 4;  // == PXB_FLAG_LOCAL_ENERGY_WEIGHT
 constexpr int FLAG_COMPLEX_ONE_BODY = 8;     // == PXB_FLAG_COMPLEX_ONE_BODY
+constexpr int FLAG_COMPLEX_CHOLESKY = 16;    // == PXB_FLAG_COMPLEX_CHOLESKY
 #ifndef PXB_MAX_DETS
 #define PXB_MAX_DETS 8  // == include/pauxy_b200.h
 #endif
 
 __host__ __device__ inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+// Complex Cholesky vectors / trial orbitals: every GEMM with a constant A operand runs as the REAL
+// fragment-major GEMM over a doubled k range, [Re A | Im A] [B ; i B]; kmul is that factor.
+__host__ __device__ inline int kmul(const Dims& d) { return (d.flags & FLAG_COMPLEX_CHOLESKY) ? 2 : 1; }
 
 // ---- layout index helpers (doubles) -----------------------------------------
 // OF: orbital-fragment layout of phi / Theta: [WG][ne][KC][wl 4][t 4][c 2]
@@ -58,14 +62,16 @@ __host__ __device__ inline size_t xf_index(const Dims& d, int w, int n, int c) {
   return (((size_t)(w >> 2) * d.NKC + (n >> 2)) * 4 + (w & 3)) * 8 + (n & 3) * 2 + c;
 }
 __host__ __device__ inline size_t xf_size(const Dims& d) { return (size_t)d.WG * d.NKC * 32; }
-// RF: half-rotated Cholesky, per spin [XG][n_s][KC][g 8][t 4]; spin 1 follows spin 0
+// RF: half-rotated Cholesky, per spin [XG][n_s][kmul KC][g 8][t 4]; spin 1 follows spin 0
+// (complex: k-steps [0, KC) of an orbital hold the real part, [KC, 2 KC) the imaginary part)
 __host__ __device__ inline size_t rf_spin_base(const Dims& d, int s) {
-  return s == 0 ? 0 : (size_t)d.XG * d.na * d.KC * 32;
+  return s == 0 ? 0 : (size_t)d.XG * d.na * d.KC * 32 * kmul(d);
 }
-__host__ __device__ inline size_t rf_size(const Dims& d) { return (size_t)d.XG * d.ne * d.KC * 32; }
+__host__ __device__ inline size_t rf_size(const Dims& d) { return (size_t)d.XG * d.ne * d.KC * 32 * kmul(d); }
 // LF: Cholesky for the VHS GEMM [RT][NKC][g' 8][t 4]; row tile rt = (mt*4+s)*KC + kc
 // holds rows (p, q) = (8mt + 2s + (g'>>2), 4kc + (g'&3))
-__host__ __device__ inline size_t lf_size(const Dims& d) { return (size_t)d.RT * d.NKC * 32; }
+// (complex: [RT][2 NKC]..., real part in k-steps [0, NKC), imaginary part in [NKC, 2 NKC))
+__host__ __device__ inline size_t lf_size(const Dims& d) { return (size_t)d.RT * d.NKC * 32 * kmul(d); }
 // VF: VHS per walker as Taylor A-operand [W][MT][KC][c 2][g 8][t 4]
 __host__ __device__ inline size_t vf_walker(const Dims& d) { return (size_t)d.MT * d.KC * 64; }
 // BF: one-body propagator [2][MT][KC][g 8][t 4]

@@ -278,8 +278,9 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
 }
 
 // exx[s][w] = sum over the slots of spin s, fixed order (deterministic)
-__global__ void exx_eri_reduce_kernel(const double2* __restrict__ part, double2* __restrict__ exx, Dims d,
-                                      int nslot, int* __restrict__ counter) {
+// part_i (complex K only): the partial sums of theta^T Ki theta; exx = Er + i Ei
+__global__ void exx_eri_reduce_kernel(const double2* __restrict__ part, const double2* __restrict__ part_i,
+                                      double2* __restrict__ exx, Dims d, int nslot, int* __restrict__ counter) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx == 0) *counter = 0;  // re-arm the item scheduler of exx_eri_kernel for its next launch
   if (idx >= 2 * d.Wp) return;
@@ -291,6 +292,16 @@ __global__ void exx_eri_reduce_kernel(const double2* __restrict__ part, double2*
     r += v.x;
     i += v.y;
   }
+  if (part_i != nullptr) {
+    double ri = 0.0, ii = 0.0;
+    for (int k = 0; k < ns; ++k) {
+      const double2 v = part_i[((size_t)s * nslot + k) * d.Wp + w];
+      ri += v.x;
+      ii += v.y;
+    }
+    r -= ii;
+    i += ri;
+  }
   exx[idx] = make_double2(r, i);
 }
 
@@ -298,9 +309,10 @@ __global__ void exx_eri_reduce_kernel(const double2* __restrict__ part, double2*
 // setup: K in A-fragment order from trial._rchol (c128 [(na+nb) M, N], real-valued).
 // One CTA per (orbital pair (i,j), 32 x 32 tile of (q,p)):  K[(i,q),(j,p)] = sum_x R_i[p,x] R_j[q,x]
 // ---------------------------------------------------------------------------------------------
+// part 0: real Cholesky vectors; complex ones (K = Kr + i Ki, both symmetric): part 1 -> Kr, part 2 -> Ki
 __global__ void __launch_bounds__(1024) eri_build_kernel(const double2* __restrict__ rchol, double* __restrict__ KF,
-                                                         Dims d, int s) {
-  __shared__ double sq[32][33], sp[32][33];
+                                                         Dims d, int s, int part) {
+  __shared__ double sq[32][33], sp[32][33], sqi[32][33], spi[32][33];
   const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
   const int tiles = (d.M + 31) / 32;
   const int qt = blockIdx.x % tiles, pt = blockIdx.x / tiles;
@@ -312,11 +324,25 @@ __global__ void __launch_bounds__(1024) eri_build_kernel(const double2* __restri
   for (int x0 = 0; x0 < d.N; x0 += 32) {
     const int x = x0 + tx;
     const int qr = qt * 32 + ty, pr = pt * 32 + ty;
-    sq[ty][tx] = (qr < d.M && x < d.N) ? rchol[((size_t)(ioff + j) * d.M + qr) * d.N + x].x : 0.0;
-    sp[ty][tx] = (pr < d.M && x < d.N) ? rchol[((size_t)(ioff + i) * d.M + pr) * d.N + x].x : 0.0;
+    const double2 zq = (qr < d.M && x < d.N) ? rchol[((size_t)(ioff + j) * d.M + qr) * d.N + x] : make_double2(0.0, 0.0);
+    const double2 zp = (pr < d.M && x < d.N) ? rchol[((size_t)(ioff + i) * d.M + pr) * d.N + x] : make_double2(0.0, 0.0);
+    sq[ty][tx] = zq.x;
+    sp[ty][tx] = zp.x;
+    if (part != 0) {
+      sqi[ty][tx] = zq.y;
+      spi[ty][tx] = zp.y;
+    }
     __syncthreads();
+    if (part == 0) {
 #pragma unroll
-    for (int k = 0; k < 32; ++k) acc += sq[ty][k] * sp[tx][k];
+      for (int k = 0; k < 32; ++k) acc += sq[ty][k] * sp[tx][k];
+    } else if (part == 1) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc += sq[ty][k] * sp[tx][k] - sqi[ty][k] * spi[tx][k];
+    } else {
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc += sq[ty][k] * spi[tx][k] + sqi[ty][k] * sp[tx][k];
+    }
     __syncthreads();
   }
   if (q < d.M && p < d.M) {

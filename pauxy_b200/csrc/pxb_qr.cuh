@@ -141,6 +141,7 @@ __device__ __forceinline__ bool warp_cholesky_inverse(cplx* Gs, cplx* As, int ld
       c[i - 1].y = fma(ri.y, ck.x, fma(-ri.x, ck.y, c[i].y));
     }
     c[NC - 1] = make_double2(0.0, 0.0);
+    __syncwarp();  // the loads above may run past row k (padding slots): order them before the next row's store
   }
   if (bad) return false;
   {  // log det R = -sum_j log(1 / R_jj)

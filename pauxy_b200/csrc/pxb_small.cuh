@@ -11,20 +11,23 @@ namespace pxb {
 // ============================================================================
 // flag[0] |= 1 if a supposedly real input has a non-zero imaginary part
 // rt_map (optional): compact list of the row tiles that are kept (upper triangle of a symmetric L)
+// hs_pot: real [M*M][N] doubles, or (FLAG_COMPLEX_CHOLESKY) complex128: then the k range is doubled
 __global__ void pack_lf_kernel(const double* __restrict__ hs_pot, double* __restrict__ LF, Dims d,
                                const int* __restrict__ rt_map, int nrt) {
-  const size_t total = (size_t)nrt * d.NKC * 32;
+  const int km = kmul(d);
+  const size_t total = (size_t)nrt * d.NKC * 32 * km;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int tt = idx & 3, gp = (idx >> 2) & 7;
     const size_t r = idx >> 5;
-    const int kcn = r % d.NKC;
-    const int rtc = r / d.NKC;
+    const int kc2 = r % (d.NKC * km);
+    const int kcn = kc2 < d.NKC ? kc2 : kc2 - d.NKC, part = kc2 < d.NKC ? 0 : 1;
+    const int rtc = r / (d.NKC * km);
     const int rt = rt_map != nullptr ? rt_map[rtc] : rtc;
     const int kc = rt % d.KC, ms = rt / d.KC, s = ms & 3, mtv = ms >> 2;
     const int p = 8 * mtv + 2 * s + (gp >> 2), q = 4 * kc + (gp & 3), n = 4 * kcn + tt;
     double v = 0.0;
-    if (p < d.M && q < d.M && n < d.N) v = hs_pot[((size_t)p * d.M + q) * d.N + n];
+    if (p < d.M && q < d.M && n < d.N) v = hs_pot[(((size_t)p * d.M + q) * d.N + n) * km + part];
     LF[idx] = v;
   }
 }
@@ -39,10 +42,13 @@ __global__ void hs_symmetry_kernel(const double* __restrict__ hs_pot, Dims d, in
     const size_t pq = idx / d.N;
     const int q = pq % d.M, p = pq / d.M;
     if (p < q) {
-      const double a = hs_pot[idx], b = hs_pot[((size_t)q * d.M + p) * d.N + n];
+      const int km = kmul(d);
+      for (int part = 0; part < km; ++part) {
+      const double a = hs_pot[idx * km + part], b = hs_pot[(((size_t)q * d.M + p) * d.N + n) * km + part];
       if (a != b) {
         // 16: not bit-symmetric; 32: not symmetric even to rounding (back propagation then needs L^T)
         atomicOr(flag, fabs(a - b) > 1e-12 * (fabs(a) + fabs(b)) + 1e-14 ? 48 : 16);
+      }
       }
     }
   }
@@ -63,15 +69,17 @@ __global__ void pack_rf_kernel(const double2* __restrict__ rchol, double* __rest
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     const int tt = rel & 3, g = (rel >> 2) & 7;
     size_t r = rel >> 5;
-    const int pc = r % d.KC;
-    r /= d.KC;
+    const int km = kmul(d);
+    const int pc2 = r % (d.KC * km);
+    const int pc = pc2 < d.KC ? pc2 : pc2 - d.KC;
+    r /= d.KC * km;
     const int il = r % ns, xg = r / ns;
     const int p = 4 * pc + tt, n = 8 * xg + g;
     double v = 0.0;
     if (p < d.M && n < d.N) {
       double2 z = rchol[((size_t)(ioff + il) * d.M + p) * d.N + n];
-      v = z.x;
-      if (z.y != 0.0) atomicOr(flag, 1);
+      v = pc2 < d.KC ? z.x : z.y;
+      if (km == 1 && z.y != 0.0) atomicOr(flag, 1);
     }
     RF[idx] = v;
   }
@@ -121,6 +129,22 @@ __global__ void pack_bf2_kernel(const double2* __restrict__ bh1, double* __restr
     BF2[idx] = v;
   }
 }
+// [B ; i B] stacked along k for rows of kc 32-double blocks (OF rows: kc = KC, nrows = WG ne; XF rows:
+// kc = NKC, nrows = WG): out[row][2 kc][wl][t][c]
+__global__ void stack_rows_kernel(const double* __restrict__ in, double* __restrict__ out, size_t nrows, int kc) {
+  const size_t total = nrows * kc * 16;  // complex elements
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (size_t)gridDim.x * blockDim.x) {
+    const int e = idx & 15;
+    const size_t r = idx >> 4;
+    const int k = r % kc;
+    const size_t row = r / kc;
+    const double2 v = *reinterpret_cast<const double2*>(in + (row * kc + k) * 32 + e * 2);
+    double* o = out + (row * 2 * kc + k) * 32 + e * 2;
+    *reinterpret_cast<double2*>(o) = v;
+    *reinterpret_cast<double2*>(o + (size_t)kc * 32) = make_double2(-v.y, v.x);
+  }
+}
 // [phi ; i phi] stacked along k per (walker group, orbital): out[(wg, i)][kc'][wl][t][c]
 __global__ void phi_stack_kernel(const double* __restrict__ in, double* __restrict__ out, Dims d) {
   const size_t total = (size_t)d.WG * d.ne * d.KC * 16;  // complex elements
@@ -161,22 +185,26 @@ __global__ void pack_small_kernel(const double2* __restrict__ psi, const double2
 }
 
 // psi as DMMA B-fragments for the overlap GEMM: PF[s][jt][pc][lane=(g,t)] = psi[4pc+t][ioff_s + 8jt+g]
+// (complex orbitals: the operand is conj(psi); k-steps [KC, 2 KC) hold its imaginary part, -Im psi)
 __global__ void pack_pf_kernel(const double2* __restrict__ psi, double* __restrict__ PF, Dims d) {
   const int jt0 = (d.na + 7) >> 3, jt1 = (d.nb + 7) >> 3;
-  const size_t total = (size_t)(jt0 + jt1) * d.KC * 32;
+  const int km = kmul(d);
+  const size_t total = (size_t)(jt0 + jt1) * d.KC * 32 * km;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
        idx += (size_t)gridDim.x * blockDim.x) {
     const int lane = idx & 31, g = lane >> 2, t = lane & 3;
     size_t r = idx >> 5;
-    const int pc = r % d.KC;
-    int jt = r / d.KC, s = 0;
+    const int pc2 = r % (d.KC * km);
+    const int pc = pc2 < d.KC ? pc2 : pc2 - d.KC;
+    int jt = r / (d.KC * km), s = 0;
     if (jt >= jt0) {
       s = 1;
       jt -= jt0;
     }
     const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
     const int p = 4 * pc + t, j = 8 * jt + g;
-    PF[idx] = (p < d.M && j < ns) ? psi[(size_t)p * d.ne + ioff + j].x : 0.0;
+    const double2 z = (p < d.M && j < ns) ? psi[(size_t)p * d.ne + ioff + j] : make_double2(0.0, 0.0);
+    PF[idx] = pc2 < d.KC ? z.x : -z.y;
   }
 }
 

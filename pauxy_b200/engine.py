@@ -25,7 +25,8 @@ class Engine(object):
 
     def __init__(self, nbasis, nup, ndown, nchol, nwalkers, dt, exp_order=6, device=None,
                  total_walkers=None, exchange='auto', free_projection=False, force_bias=True,
-                 nbp=0, ndets=1, local_energy_weight=False, complex_one_body=False):
+                 nbp=0, ndets=1, local_energy_weight=False, complex_one_body=False,
+                 complex_cholesky=False):
         if not torch.cuda.is_available():
             raise RuntimeError("pauxy_b200.Engine needs a CUDA device (no CPU fallback)")
         self.lib = L.load()
@@ -43,11 +44,13 @@ class Engine(object):
                           (L.FLAG_FREE_PROJECTION if free_projection else 0) |
                           (0 if force_bias else L.FLAG_NO_FORCE_BIAS) |
                           (L.FLAG_LOCAL_ENERGY_WEIGHT if local_energy_weight else 0) |
-                          (L.FLAG_COMPLEX_ONE_BODY if complex_one_body else 0), int(nbp or 0),
+                          (L.FLAG_COMPLEX_ONE_BODY if complex_one_body else 0) |
+                          (L.FLAG_COMPLEX_CHOLESKY if complex_cholesky else 0), int(nbp or 0),
                           int(ndets))
         if ndets > L.MAX_DETS:
             raise L.PxbError(-4, "at most %d determinants in the trial" % L.MAX_DETS)
         self.ndets = int(ndets)
+        self.complex_cholesky = bool(complex_cholesky)
         self._eshift_im = 0.0
         self.nbp = int(nbp or 0)
         self._h = ctypes.c_void_p()
@@ -137,12 +140,16 @@ class Engine(object):
         M, ne, N = self.M, self.ne, self.N
         assert hs_pot.shape == (M * M, N) and rchol.shape == (ne * M, N)
         assert bh1.shape == (2, M, M) and h1rot.shape == (ne, M) and psi.shape == (M, ne)
-        if numpy.iscomplexobj(hs_pot):
-            if numpy.abs(hs_pot.imag).max() != 0.0:
-                raise L.PxbError(-4, "complex Cholesky vectors are not supported in this version")
-            hs_pot = hs_pot.real
+        if self.complex_cholesky:
+            hs_dtype = numpy.complex128          # PXB_FLAG_COMPLEX_CHOLESKY: interleaved (re, im)
+        else:
+            hs_dtype = numpy.float64
+            if numpy.iscomplexobj(hs_pot):
+                if numpy.abs(hs_pot.imag).max() != 0.0:
+                    raise L.PxbError(-4, "complex Cholesky vectors: create the Engine with complex_cholesky=True")
+                hs_pot = hs_pot.real
         with torch.cuda.device(self.device):
-            t = [self._dev(hs_pot, numpy.float64), self._dev(rchol, numpy.complex128),
+            t = [self._dev(hs_pot, hs_dtype), self._dev(rchol, numpy.complex128),
                  self._dev(bh1, numpy.complex128), self._dev(h1rot, numpy.complex128),
                  self._dev(psi, numpy.complex128), self._dev(mf_shift, numpy.complex128)]
             self._check(self.lib.pxb_set_hamiltonian(self._h, *[x.data_ptr() for x in t],

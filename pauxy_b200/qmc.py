@@ -122,7 +122,8 @@ class AFQMC(object):
                              ndets=self.trial.ndets,
                              local_energy_weight=not self.propagators.hybrid,
                              complex_one_body=bool(numpy.abs(numpy.imag(
-                                 self.propagators.propagator.BH1)).max() > 0.0))
+                                 self.propagators.propagator.BH1)).max() > 0.0),
+                             complex_cholesky=self._complex_operands())
         p = self.propagators.propagator
         t = self.trial
         self.engine.set_hamiltonian(s.hs_pot, t.rchol(0), p.BH1, t.half_rotated_h1(s, 0), t.det(0),
@@ -148,6 +149,15 @@ class AFQMC(object):
             self.engine.step_graphs(False)
         if verbose:
             self.estimators.estimators['mixed'].print_header()
+
+    def _complex_operands(self):
+        """True when system.hs_pot, the half-rotated Cholesky vectors or the trial orbitals have an
+        imaginary part (systems/generic.py:126, generate_hamiltonian(cplx=True))."""
+        def im(a):
+            return numpy.iscomplexobj(a) and float(numpy.abs(numpy.imag(a)).max()) > 0.0
+        t = self.trial
+        return bool(im(self.system.hs_pot) or
+                    any(im(t.rchol(i)) or im(t.det(i)) for i in range(t.ndets)))
 
     def _tick(self):
         if self.sync_timers:

@@ -29,8 +29,12 @@ def host_setup(h1e, hs_pot, ecore, nelec, dt, psi=None):
 def make_engine(system, trial, prop, nwalkers, dt, total_walkers=None, exp_order=6,
                 exchange='auto', nbp=0):
     from pauxy_b200.engine import Engine
+    def im(a):
+        return numpy.iscomplexobj(a) and float(numpy.abs(numpy.imag(a)).max()) > 0.0
     eng = Engine(system.nbasis, system.nup, system.ndown, system.nfields, nwalkers, dt,
-                 exp_order=exp_order, total_walkers=total_walkers, exchange=exchange, nbp=nbp)
+                 exp_order=exp_order, total_walkers=total_walkers, exchange=exchange, nbp=nbp,
+                 complex_one_body=im(prop.BH1),
+                 complex_cholesky=im(system.hs_pot) or im(trial._rchol) or im(trial.psi))
     eng.set_hamiltonian(system.hs_pot, trial._rchol, prop.BH1, trial.half_rotated_h1(system),
                         trial.psi, prop.mf_shift, system.ecore)
     eng.init_walkers(trial.init, total_walkers or nwalkers)

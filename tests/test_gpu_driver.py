@@ -61,7 +61,7 @@ def _close(a, b, rtol=RTOL, atol=0.0):
     numpy.testing.assert_allclose(a, b, rtol=rtol, atol=atol)
 
 
-@pytest.mark.parametrize('name', ['test_generic', 'c1', 'stress_comb'])
+@pytest.mark.parametrize('name', ['test_generic', 'c1', 'stress_comb', 'cplx_driver', 'cplx_stress'])
 def test_trace_matches_reference(golden, name):
     g = golden(name)
     afqmc, h = _run(g, g['h1e'], g['hs_pot'], float(g['ecore']))

@@ -36,6 +36,20 @@ def _case(name):
         rs = numpy.random.RandomState(6)
         hs = hs + 0.02 * rs.normal(size=hs.shape)
         return h1e, hs, enuc, (5, 3), 0.005, None
+    if name == 'cplx':   # complex integrals (systems/tests/test_generic.py:30), the reference's identity trial
+        numpy.random.seed(7)
+        h1e, chol, enuc, _ = generate_hamiltonian(10, (3, 3), cplx=True, sym=4)
+        h1e = 0.5 * (h1e + h1e.conj().T)
+        return h1e, chol.reshape((-1, 100)).T.copy(), enuc, (3, 3), 0.005, None
+    if name == 'cplx_psi':   # complex integrals AND complex trial orbitals, nup != ndown, M % 4 != 0
+        numpy.random.seed(13)
+        h1e, chol, enuc, _ = generate_hamiltonian(9, (4, 2), cplx=True, sym=4)
+        h1e = 0.5 * (h1e + h1e.conj().T)
+        rs = numpy.random.RandomState(15)
+        psi = rs.normal(size=(9, 6)) + 1j * rs.normal(size=(9, 6))
+        psi[:, :4] = numpy.linalg.qr(psi[:, :4])[0]
+        psi[:, 4:] = numpy.linalg.qr(psi[:, 4:])[0]
+        return h1e, chol.reshape((-1, 81)).T.copy(), enuc, (4, 2), 0.005, psi
     if name == 'c2':
         h1e, hs, ecore = synthetic_cholesky_hamiltonian(24, 120, 1002)
         return h1e, hs, ecore, (5, 5), 0.005, None
@@ -51,7 +65,7 @@ def _case(name):
     raise KeyError(name)
 
 
-CASES = [('c1', 13), ('odd', 7), ('asym', 9), ('c2', 18), ('c3', 9), ('c4', 6), ('c5', 3)]
+CASES = [('c1', 13), ('odd', 7), ('asym', 9), ('cplx', 11), ('cplx_psi', 6), ('c2', 18), ('c3', 9), ('c4', 6), ('c5', 3)]
 
 
 @pytest.fixture(scope='module', params=CASES, ids=[c[0] for c in CASES])
@@ -176,14 +190,20 @@ def test_exchange_modes(setup, mode):
     phi, ham = setup['phi'], setup['ham']
     h1e, hs, ecore, nelec, dt, psi = _case(setup['name'])
     system, trial, prop = host_setup(h1e, hs, ecore, nelec, dt, psi)
+    if mode == 'cholesky' and setup['name'].startswith('cplx'):
+        # complex Cholesky vectors run the ERI form only: the configuration is refused, not mis-evaluated
+        from pauxy_b200._lib import PxbError
+        with pytest.raises(PxbError):
+            make_engine(system, trial, prop, setup['W'], dt, exchange=mode)
+        return
     eng = make_engine(system, trial, prop, setup['W'], dt, exchange=mode)
     eng.set_phi(phi)
     eng.stage_exchange()
     exx = eng.get_exx().cpu().numpy()
     tha, thb, _ = orc.greens_function(ham, phi)
     na, M = ham.nup, ham.nbasis
-    ra = ham.rchol[:na * M].real.reshape(na, M, -1)
-    rb = ham.rchol[na * M:].real.reshape(ham.ndown, M, -1)
+    ra = ham.rchol[:na * M].reshape(na, M, -1)
+    rb = ham.rchol[na * M:].reshape(ham.ndown, M, -1)
     Ta = numpy.einsum('ipx,wjp->wxij', ra, tha, optimize=True)
     Tb = numpy.einsum('ipx,wjp->wxij', rb, thb, optimize=True)
     ref = numpy.array([numpy.einsum('wxij,wxji->w', Ta, Ta), numpy.einsum('wxij,wxji->w', Tb, Tb)])
