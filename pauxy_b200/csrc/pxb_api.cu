@@ -473,7 +473,8 @@ int run_one_body(pxb_handle h, const double* in, double* out, const int* active,
   if (cplx) {
     if (transposed) return fail(h, PXB_ERR_UNSUPPORTED, "back propagation with a complex one-body propagator");
     ++h->launches;
-    phi_stack_kernel<<<grid_for((size_t)d.WG * d.ne * d.KC * 16), 256, 0, st>>>(in, h->ptr<double>(A_PHI_STACK), d);
+    stack_rows_kernel<<<grid_for((size_t)d.WG * d.ne * d.KC * 16), 256, 0, st>>>(in, h->ptr<double>(A_PHI_STACK),
+                                                                              (size_t)d.WG * d.ne, d.KC);
     PXB_CUDA(h, cudaGetLastError());
     in = h->ptr<double>(A_PHI_STACK);
   }
@@ -652,14 +653,17 @@ int run_taylor3(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
   const int base = d.MT / 4, rem = d.MT % 4;
   const int wmx = base + (rem ? 1 : 0);
   // three column groups (12 consumer warps) when the columns split evenly and the rectangle fits
-  // 160 registers, else two (8 warps at 232 registers)
+  // 160 registers, else two (8 warps at 232 registers); with at most 16 columns ONE group of 4 warps
+  // and two CTAs per SM (two walkers in flight) instead of 6 DMMAs per k-step and warp
   int NG = (NT8 % 3 == 0 && wmx * (NT8 / 3) <= 8) ? 3 : 2;
+  if (NT8 <= 2 && wmx * NT8 <= 6) NG = 1;
 #ifdef PXB_EXPERIMENTS
   {
     const char* e = getenv("PXB_TAYLOR_GROUPS");
     if (e && atoi(e) == 2) NG = 2;
   }
 #endif
+  const int ctas = NG == 1 ? 2 : 1;
   int msize[4];
   a.m_off[0] = 0;
   for (int g = 0; g < 4; ++g) {
@@ -686,7 +690,7 @@ int run_taylor3(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
     }
   }
   const int wnx = nbase + (nrem ? 1 : 0);
-  if (wmx * wnx > (NG == 3 ? 8 : 12)) return 1;
+  if (wmx * wnx > (NG == 3 ? 8 : NG == 2 ? 12 : 6)) return 1;
   // shared memory: iterate buffer + phi tile (+ a second phi tile, fetched one item ahead, when a
   // >= 4-deep ring still fits beside it)
   a.nstage = 0;
@@ -700,20 +704,21 @@ int run_taylor3(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
 #endif
   for (int nbuf = 3; nbuf >= 2 && a.nbuf == 0; --nbuf)
     for (int nstage = 12; nstage >= (nbuf == 3 ? 4 : 3); --nstage)
-      if (taylor3_smem_bytes(d, NT8, nbuf, nstage) <= (size_t)h->max_smem_optin) {
+      if (taylor3_smem_bytes(d, NT8, nbuf, nstage) <= (size_t)h->max_smem_optin / ctas - (ctas - 1) * 1024) {
         a.nbuf = nbuf;
         a.nstage = nstage;
         break;
       }
   if (a.nbuf == 0) return 1;
   const size_t smem = taylor3_smem_bytes(d, NT8, a.nbuf, a.nstage);
-  const int grid = std::min(d.W * nchunks, h->sm_count);
+  const int grid = std::min(d.W * nchunks, ctas * h->sm_count);
 #define PXB_T3(WM_, WN_, NG_) \
   if (wmx == WM_ && wnx == WN_ && NG == NG_) return launch_taylor3<WM_, WN_, NG_>(h, a, smem, grid, st);
   PXB_T3(1, 1, 3) PXB_T3(1, 2, 3) PXB_T3(2, 1, 3) PXB_T3(2, 2, 3) PXB_T3(3, 1, 3) PXB_T3(3, 2, 3)
   PXB_T3(4, 1, 3) PXB_T3(4, 2, 3)
   PXB_T3(1, 1, 2) PXB_T3(1, 2, 2) PXB_T3(1, 3, 2) PXB_T3(2, 1, 2) PXB_T3(2, 2, 2) PXB_T3(2, 3, 2)
   PXB_T3(3, 1, 2) PXB_T3(3, 2, 2) PXB_T3(3, 3, 2) PXB_T3(4, 1, 2) PXB_T3(4, 2, 2) PXB_T3(4, 3, 2)
+  PXB_T3(1, 2, 1) PXB_T3(2, 2, 1) PXB_T3(3, 2, 1)
 #undef PXB_T3
   return 1;
 }

@@ -145,22 +145,6 @@ __global__ void stack_rows_kernel(const double* __restrict__ in, double* __restr
     *reinterpret_cast<double2*>(o + (size_t)kc * 32) = make_double2(-v.y, v.x);
   }
 }
-// [phi ; i phi] stacked along k per (walker group, orbital): out[(wg, i)][kc'][wl][t][c]
-__global__ void phi_stack_kernel(const double* __restrict__ in, double* __restrict__ out, Dims d) {
-  const size_t total = (size_t)d.WG * d.ne * d.KC * 16;  // complex elements
-  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (size_t)gridDim.x * blockDim.x) {
-    const int e = idx & 15;
-    size_t r = idx >> 4;
-    const int kc = r % d.KC;
-    const size_t col = r / d.KC;  // (wg, orbital)
-    const double2 v = *reinterpret_cast<const double2*>(in + (col * d.KC + kc) * 32 + e * 2);
-    double* o = out + (col * 2 * d.KC + kc) * 32 + e * 2;
-    *reinterpret_cast<double2*>(o) = v;
-    *reinterpret_cast<double2*>(o + (size_t)d.KC * 32) = make_double2(-v.y, v.x);
-  }
-}
-
 // psiT[p][j] (real, [Mp][ne]), h1rot [ne][Mp] complex, vbar [Np] complex
 __global__ void pack_small_kernel(const double2* __restrict__ psi, const double2* __restrict__ h1rot,
                                   const double2* __restrict__ mf, double* __restrict__ psiT,

@@ -46,13 +46,19 @@ struct Taylor3Args {
 //   NG = 3: 12 consumer warps at 160 registers, up to 4 x 2: three warps per sub-partition cover
 //           each other's epilogues better and nothing spills, at the price of an uneven split of
 //           14 m-tiles x 3 groups over 4 sub-partitions (11 : 10)
+//   NG = 1:  4 consumer warps, TWO CTAs per SM (two walkers in flight, each with its own VHS ring): shapes
+//           with at most 16 orbital columns (c3: 14), where splitting the columns would leave a warp
+//           6 DMMAs per k-step; 128 registers, no rebalancing
 template <int NG>
 struct T3Cfg {
   static constexpr int consumers = 4 * NG;
   static constexpr int threads = (consumers + 4) * 32;
+  static constexpr int ctas_per_sm = NG == 1 ? 2 : 1;
+  static constexpr bool rebalance = NG > 1;  // setmaxnreg: producer warpgroup -> consumers
   static constexpr int regs_producer = NG == 2 ? 40 : 24;
   static constexpr int regs_consumer = NG == 2 ? 232 : 160;
-  static_assert(consumers * (regs_consumer - (65536 / threads) / 8 * 8) <= 4 * ((65536 / threads) / 8 * 8 - regs_producer),
+  static_assert(!rebalance ||
+                    consumers * (regs_consumer - (65536 / threads) / 8 * 8) <= 4 * ((65536 / threads) / 8 * 8 - regs_producer),
                 "setmaxnreg.inc would block: more registers requested than the producer warpgroup releases");
 };
 constexpr int T3_MIN_STAGES2 = 3;  // fewest ring stages accepted with two iterate buffers
@@ -278,7 +284,7 @@ __device__ __forceinline__ void taylor3_orders(const Taylor3Args& a, uint32_t ph
 
 // WMX = ceil(MT / 4), WNX = ceil(NT8 / NG): the largest warp rectangle; smaller groups use WMX-1 / WNX-1
 template <int WMX, int WNX, int NG>
-__global__ void __launch_bounds__(T3Cfg<NG>::threads, 1) taylor3_kernel(Taylor3Args a) {
+__global__ void __launch_bounds__(T3Cfg<NG>::threads, T3Cfg<NG>::ctas_per_sm) taylor3_kernel(Taylor3Args a) {
   constexpr int T3_CONSUMERS = T3Cfg<NG>::consumers;
   extern __shared__ __align__(128) double t3_smem[];
   const Dims& d = a.d;
@@ -303,7 +309,7 @@ __global__ void __launch_bounds__(T3Cfg<NG>::threads, 1) taylor3_kernel(Taylor3A
   const int nks = (d.KC + T2_KS - 1) / T2_KS;
 
   if (warp >= T3_CONSUMERS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG>::regs_producer));
+    if constexpr (T3Cfg<NG>::rebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG>::regs_producer));
     if (warp != T3_CONSUMERS || (a.dbg & 2)) return;
     // ---------------- producer: lane mt streams m-tile mt of the walker's VHS ----------------
     unsigned s = 0, ph = 0;
@@ -332,7 +338,7 @@ __global__ void __launch_bounds__(T3Cfg<NG>::threads, 1) taylor3_kernel(Taylor3A
   }
 
   // ---------------- consumers ----------------
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG>::regs_consumer));
+  if constexpr (T3Cfg<NG>::rebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG>::regs_consumer));
   const int ng = warp >> 2, mg = a.mperm[ng][warp & 3];
   const int m0 = a.m_off[mg], wm = a.m_off[mg + 1] - m0;
   const int n0 = a.n_off[ng], wn = a.n_off[ng + 1] - n0;
