@@ -26,7 +26,9 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + SOURCES
+    # PXB_EXTRA_NVCC_FLAGS: development builds only (e.g. -DPXB_EXPERIMENTS for the timing switches)
+    extra = os.environ.get('PXB_EXTRA_NVCC_FLAGS', '').split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB] + SOURCES
     res = subprocess.run(cmd, cwd=CSRC, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
                          text=True)
     if verbose or res.returncode != 0:
