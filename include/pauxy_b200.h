@@ -58,6 +58,19 @@ typedef struct {
 } pxb_config;
 #define PXB_MAX_DETS 8
 
+/* Shape limits of this version (a call outside them returns PXB_ERR_ARG / PXB_ERR_UNSUPPORTED with a
+ * message in pxb_last_error; nothing is evaluated by a slower path silently):
+ *   nbasis <= 256                        Taylor kernels: taylor3 4 <= ceil(M/8) <= 16, taylor2 up to M = 224 with at
+ *                                        most 48 orbitals per item, the direct kernel up to 256
+ *   nup, ndown <= 64                     Green's function and exchange kernels; up to 32 per spin the inverse and
+ *                                        the re-orthogonalisation run register-resident (Gauss-Jordan, CholeskyQR2),
+ *                                        above in shared memory (Gauss-Jordan, modified Gram-Schmidt)
+ *   ndets <= PXB_MAX_DETS                and no back propagation with several determinants
+ *   half-rotated ERI (exchange_mode ERI / AUTO): (nup^2 + ndown^2) M^2 doubles per determinant; AUTO falls
+ *                                        back to the Cholesky form above 16 GiB
+ *   the overlap / Theta / QR tiles of one (walker, spin) must fit 227 KB of shared memory (true within the
+ *   limits above). */
+
 /* propagator options of pauxy/propagation/continuous.py:14-33 */
 #define PXB_FLAG_FREE_PROJECTION 1 /* propagate_walker_free (continuous.py:175-200), the free-projection
                                       branches of Walkers.orthogonalise (handler.py:178-181) and of
