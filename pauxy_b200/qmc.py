@@ -116,7 +116,8 @@ class AFQMC(object):
         self.engine = Engine(s.nbasis, s.nup, s.ndown, s.nfields, self.qmc.nwalkers, self.qmc.dt,
                              exp_order=self.propagators.exp_nmax, device=device,
                              total_walkers=self.qmc.ntot_walkers,
-                             exchange=est_opts.get('mixed', {}).get('exchange', 'auto'),
+                             exchange=('eri' if getattr(s, 'exact_eri', False) else
+                                       est_opts.get('mixed', {}).get('exchange', 'auto')),
                              free_projection=self.propagators.free_projection,
                              force_bias=self.propagators.force_bias, nbp=nbp,
                              ndets=self.trial.ndets,

@@ -23,7 +23,7 @@ class Generic(object):
     """
 
     def __init__(self, nelec=None, h1e=None, chol=None, ecore=None, h1e_mod=None,
-                 verbose=False):
+                 verbose=False, exact_eri=False, stochastic_ri=False, pno=False, control_variate=False):
         self.name = "Generic"
         self.verbose = verbose
         self.nup, self.ndown = nelec
@@ -44,9 +44,17 @@ class Generic(object):
         self.h1e_mod = h1e_mod if h1e_mod is not None else construct_h1e_mod(self.chol_vecs, self.H1)
         self.hs_pot = self.chol_vecs
         self.ktwist = numpy.array([None])
+        # Alternative local-energy evaluators of the reference (systems/generic.py:77-124,
+        # estimators/mixed.py:415-437).  exact_eri: the half-rotated ERI contraction
+        # local_energy_generic_opt (estimators/generic.py:133-150) -- the device's ERI form of the
+        # exchange, same numbers as the Cholesky form to rounding.  The sampled / truncated ones
+        # (stochastic RI, PNO, control variates) are not built.
+        if stochastic_ri or pno or control_variate:
+            raise NotImplementedError("stochastic_ri / pno / control_variate energy evaluators "
+                                      "(SURVEY.md 8f.4) are not built")
         self.control_variate = False
         self.stochastic_ri = False
-        self.exact_eri = False
+        self.exact_eri = bool(exact_eri)
         self.pno = False
 
     def hijkl(self, i, j, k, l):

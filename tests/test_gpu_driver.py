@@ -78,6 +78,23 @@ def test_trace_matches_reference(golden, name):
     _close(afqmc.psi.phi_host(), g['phi_final'], atol=1e-11)
 
 
+def test_exact_eri_option_matches_reference(golden):
+    """system.exact_eri (systems/generic.py:77, estimators/mixed.py:427-428): the reference then
+    contracts the half-rotated ERI built from the same Cholesky vectors (local_energy_generic_opt) --
+    the same numbers as the default evaluator to rounding; here it selects the ERI form of the
+    exchange kernel."""
+    g = golden('c1')
+    nelec = tuple(int(x) for x in g['nelec'])
+    system = Generic(nelec=nelec, h1e=numpy.array([g['h1e'], g['h1e']]), chol=g['hs_pot'],
+                     ecore=float(g['ecore']), exact_eri=True)
+    afqmc = AFQMC(options=_options(g, None, None, None), system=system, verbose=0)
+    assert afqmc.engine.exchange_is_eri()
+    afqmc.run(verbose=0)
+    _close(afqmc.estimators.rows()[:, :10], g['rows'][:, :10], atol=1e-10)
+    with pytest.raises(NotImplementedError):
+        Generic(nelec=nelec, h1e=g['h1e'], chol=g['hs_pot'], ecore=0.0, stochastic_ri=True)
+
+
 @pytest.mark.parametrize('top,replays', [({}, True), ({'cuda_graphs': False}, False),
                                          ({'fused_step': False}, False)])
 def test_fused_step_and_graph_replay(golden, top, replays):
