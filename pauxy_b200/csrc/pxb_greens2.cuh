@@ -56,7 +56,8 @@ inline size_t theta_smem_per_warp(int nmax) {
   // inverse [nmax][nld], colk [nmax] + 3 elements of slack (the A fragments of the last k-step read up
   // to 3 entries past a row), the pivot-row exchange buffer [2][nc] of the register path, piv [nc]
   // and its pivots with their reciprocals [2][nc]
-  return ((size_t)nmax * nld * sizeof(cplx) + (size_t)(nmax + 3) * sizeof(cplx) + (size_t)4 * nc * sizeof(cplx) +
+  const int regpath = nmax <= 32 ? 4 * nc : 0;  // exchange buffer + pivots: only where gj_invert_regs runs
+  return ((size_t)nmax * nld * sizeof(cplx) + (size_t)(nmax + 3) * sizeof(cplx) + (size_t)regpath * sizeof(cplx) +
           (size_t)nc * sizeof(int) + 15) / 16 * 16;
 }
 
@@ -215,62 +216,88 @@ __device__ __forceinline__ void warp_apply_left(const cplx* A, int lda, int ns, 
   bool rowok[NMT];
 #pragma unroll
   for (int m = 0; m < NMT; ++m) rowok[m] = 8 * m + g < ns;
-  double bn[KSM];
+  // CH basis chunks per iteration: one when the A fragments sit in registers, two when they are read
+  // from shared memory (each A fragment then serves both chunks)
+  constexpr int CH = AREG ? 1 : 2;
+  double bn[KSM][CH];
   // KFULL: every k-step slot is in use (KS == KSM, e.g. 21 orbitals in 6 k-steps): no guards
   auto chunks = [&](auto kfull_tag) {
   constexpr bool KFULL = decltype(kfull_tag)::value;
-  auto load_b = [&]() {  // slot KSM - 1 holds k-step KS - 1, whatever KS is
+  auto load_b = [&](int pc0) {  // slot KSM - 1 holds k-step KS - 1, whatever KS is
 #pragma unroll
-    for (int ks = 0; ks < KSM - 1; ++ks)
-      if (KFULL || ks < KS - 1) bn[ks] = NC ? ldg_nc(bp + ks * brow4) : bp[ks * brow4];
-    bn[KSM - 1] = last_pad ? 0.0 : NC ? ldg_nc(bl) : *bl;
-    bp += 32;
-    bl += 32;
+    for (int q = 0; q < CH; ++q) {
+      // a chunk past the end (odd KC with CH = 2) repeats the last one; its results are not stored
+      const int o = (q > 0 && pc0 + q >= d.KC) ? 0 : 32 * q;
+#pragma unroll
+      for (int ks = 0; ks < KSM - 1; ++ks)
+        if (KFULL || ks < KS - 1) bn[ks][q] = NC ? ldg_nc(bp + ks * brow4 + o) : bp[ks * brow4 + o];
+      bn[KSM - 1][q] = last_pad ? 0.0 : NC ? ldg_nc(bl + o) : bl[o];
+    }
+    bp += 32 * CH;
+    bl += 32 * CH;
   };
-  load_b();
+  load_b(0);
   const int pz0 = d.M - t;  // entries with 4 pc >= pz0 are basis padding
-  for (int pc = 0; pc < d.KC; ++pc) {
-    double b[KSM];
+  for (int pc = 0; pc < d.KC; pc += CH) {
+    double b[KSM][CH];
 #pragma unroll
-    for (int ks = 0; ks < KSM; ++ks) b[ks] = bn[ks];
-    if (pc + 1 < d.KC) load_b();
-    double2 hq[NMT];
+    for (int ks = 0; ks < KSM; ++ks)
 #pragma unroll
-    for (int m = 0; m < NMT; ++m) hq[m] = E1B && rowok[m] ? hp[m * hrow8] : make_double2(0.0, 0.0);
-    if (E1B) hp += 4;
-    double acc[NMT][2];
+      for (int q = 0; q < CH; ++q) b[ks][q] = bn[ks][q];
+    if (pc + CH < d.KC) load_b(pc + CH);
+    double2 hq[NMT][CH];
 #pragma unroll
-    for (int m = 0; m < NMT; ++m) acc[m][0] = acc[m][1] = 0.0;
+    for (int q = 0; q < CH; ++q)
+#pragma unroll
+      for (int m = 0; m < NMT; ++m)
+        hq[m][q] = E1B && rowok[m] && pc + q < d.KC ? hp[m * hrow8 + 4 * q] : make_double2(0.0, 0.0);
+    if (E1B) hp += 4 * CH;
+    double acc[NMT][CH][2];
+#pragma unroll
+    for (int m = 0; m < NMT; ++m)
+#pragma unroll
+      for (int q = 0; q < CH; ++q) acc[m][q][0] = acc[m][q][1] = 0.0;
 #pragma unroll
     for (int ks = 0; ks < KSM; ++ks) {
       const bool lastk = ks == KSM - 1;
       if (KFULL || lastk || ks < KS - 1) {
-        const double o = __shfl_xor_sync(0xffffffffu, b[ks], 4);  // the other component of the same element
-        const double bq = __hiloint2double(__double2hiint(o) ^ (int)smask, __double2loint(o));
+        double bq[CH];
+#pragma unroll
+        for (int q = 0; q < CH; ++q) {
+          const double o = __shfl_xor_sync(0xffffffffu, b[ks][q], 4);  // the other component of the same element
+          bq[q] = __hiloint2double(__double2hiint(o) ^ (int)smask, __double2loint(o));
+        }
 #pragma unroll
         for (int m = 0; m < NMT; ++m) {  // m-tiles beyond ceil(ns / 8) (uneven spins) compute on clamped rows
           if (LOWER && KFULL && 4 * ks > 8 * m + 7) continue;  // A[8m..8m+7][4ks..] = 0
           double2 av;
           if constexpr (AREG) av = af[m][ks];
           else av = lastk ? Am[m][klast] : Am[m][4 * ks];
-          dmma(acc[m][0], acc[m][1], av.x, b[ks]);
-          dmma(acc[m][0], acc[m][1], av.y, bq);
-        }
-      }
-    }
-    const bool pz = 4 * pc >= pz0;
 #pragma unroll
-    for (int m = 0; m < NMT; ++m) {
-      if (rowok[m]) {
-        const double vr = pz ? 0.0 : acc[m][0], vi = pz ? 0.0 : acc[m][1];
-        *reinterpret_cast<double2*>(tp + m * trow8) = make_double2(vr, vi);
-        if (E1B) {
-          er += hq[m].x * vr - hq[m].y * vi;
-          ei += hq[m].x * vi + hq[m].y * vr;
+          for (int q = 0; q < CH; ++q) {
+            dmma(acc[m][q][0], acc[m][q][1], av.x, b[ks][q]);
+            dmma(acc[m][q][0], acc[m][q][1], av.y, bq[q]);
+          }
         }
       }
     }
-    tp += 32;
+#pragma unroll
+    for (int q = 0; q < CH; ++q) {
+      if (pc + q >= d.KC) continue;
+      const bool pz = 4 * (pc + q) >= pz0;
+#pragma unroll
+      for (int m = 0; m < NMT; ++m) {
+        if (rowok[m]) {
+          const double vr = pz ? 0.0 : acc[m][q][0], vi = pz ? 0.0 : acc[m][q][1];
+          *reinterpret_cast<double2*>(tp + m * trow8 + 32 * q) = make_double2(vr, vi);
+          if (E1B) {
+            er += hq[m][q].x * vr - hq[m][q].y * vi;
+            ei += hq[m][q].x * vi + hq[m][q].y * vr;
+          }
+        }
+      }
+    }
+    tp += 32 * CH;
   }
   };
   if (KS == KSM) chunks(std::true_type{});
@@ -279,7 +306,7 @@ __device__ __forceinline__ void warp_apply_left(const cplx* A, int lda, int ns, 
 
 // NMT: 8-row tiles over the occupied orbitals of one spin (ceil(ns/8) <= NMT)
 template <int NMT>
-__global__ void __launch_bounds__(TH_WARPS * 32, NMT == 1 ? 6 : NMT == 2 ? 4 : NMT == 3 ? 3 : NMT == 4 ? 2 : 1)
+__global__ void __launch_bounds__(TH_WARPS * 32, NMT == 1 ? 6 : NMT == 2 ? 4 : NMT == 3 ? 3 : NMT <= 5 ? 2 : 1)
     theta_kernel(ThetaArgs a, int smem_per_warp) {
   extern __shared__ __align__(16) unsigned char th_raw[];
   const Dims& d = a.d;
@@ -303,7 +330,7 @@ __global__ void __launch_bounds__(TH_WARPS * 32, NMT == 1 ? 6 : NMT == 2 ? 4 : N
   cplx* A = reinterpret_cast<cplx*>(th_raw + (size_t)warp * smem_per_warp);  // [ns][lda]
   cplx* colk = A + (size_t)nmax * lda;                                        // [ns] + 3 (slack, zero)
   cplx* prow = colk + nmax + 3;                                               // [2][nc], register path
-  int* piv = reinterpret_cast<int*>(prow + 4 * ((nmax + 7) / 8 * 8));         // [nc], behind the pivots [2][nc]
+  int* piv = reinterpret_cast<int*>(prow + (nmax <= 32 ? 4 * ((nmax + 7) / 8 * 8) : 0));  // [nc], behind the pivots [2][nc]
   const int g = lane >> 2, t = lane & 3;
   const int wg = w >> 2, wl = w & 3;
 
