@@ -339,9 +339,14 @@ static int run_qr(pxb_handle h, double* phi, cudaStream_t st) {
   a.mask = rc == PXB_OK ? h->ptr<int>(A_QRMASK) : nullptr;
   const size_t smem = qr_smem_bytes(d);
   if (smem > (size_t)h->max_smem_optin) return fail(h, PXB_ERR_ARG, "qr: problem too large for shared memory");
-  PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->launches;
-  qr_kernel<<<2 * d.Wp, GR_THREADS, smem, st>>>(a);
+  if (smem > (size_t)56 * 1024) {  // at most 3 CTAs per SM: more warps per problem instead
+    PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qr_kernel<512><<<2 * d.Wp, 512, smem, st>>>(a);
+  } else {
+    PXB_CUDA(h, cudaFuncSetAttribute(qr_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qr_kernel<128><<<2 * d.Wp, 128, smem, st>>>(a);
+  }
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }

@@ -260,14 +260,17 @@ struct QrArgs {
   const int* mask = nullptr;  // when set: only the (walker, spin) items it marks, and logdet is ADDED to
 };
 
-__global__ void __launch_bounds__(GR_THREADS) qr_kernel(QrArgs a) {
+// QT threads per (walker, spin): 128 where several CTAs share an SM, 512 where the walker's orbitals fill most of
+// its shared memory (one CTA per SM: the columns after v_k are then orthogonalised 16 at a time)
+template <int QT>
+__global__ void __launch_bounds__(QT) qr_kernel(QrArgs a) {
   extern __shared__ __align__(16) unsigned char qs_raw[];
   const Dims& d = a.d;
   if (a.mask != nullptr && a.mask[blockIdx.x] == 0) return;  // CholeskyQR2 (pxb_qr.cuh) has done this one
   const int w = blockIdx.x >> 1, s = blockIdx.x & 1;
   const int ns = s ? d.nb : d.na, ioff = s ? d.na : 0;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  constexpr int NW = GR_THREADS / 32;
+  constexpr int NW = QT / 32;
   const int LD = greens_ld(d);
   cplx* ph = reinterpret_cast<cplx*>(qs_raw);                     // [ns][LD]
   double* red = reinterpret_cast<double*>(ph + (size_t)max(ns, 1) * LD);  // [NW]
@@ -277,7 +280,7 @@ __global__ void __launch_bounds__(GR_THREADS) qr_kernel(QrArgs a) {
     if (tid == 0) a.logdet[(size_t)w * 2 + s] = 0.0;
     return;
   }
-  for (int idx = tid; idx < ns * d.Mp; idx += GR_THREADS) {
+  for (int idx = tid; idx < ns * d.Mp; idx += QT) {
     const int p = idx % d.Mp, i = idx / d.Mp;
     double2 v = *reinterpret_cast<const double2*>(a.phi + (((size_t)wg * d.ne + ioff + i) * d.KC + (p >> 2)) * 32 +
                                                   wl * 8 + (p & 3) * 2);
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(GR_THREADS) qr_kernel(QrArgs a) {
   for (int k = 0; k < ns; ++k) {
     cplx* vk = ph + (size_t)k * LD;
     double part = 0.0;
-    for (int p = tid; p < d.M; p += GR_THREADS) part += vk[p].re * vk[p].re + vk[p].im * vk[p].im;
+    for (int p = tid; p < d.M; p += QT) part += vk[p].re * vk[p].re + vk[p].im * vk[p].im;
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) part += __shfl_xor_sync(0xffffffffu, part, m);
     if (lane == 0) red[warp] = part;
@@ -301,7 +304,7 @@ __global__ void __launch_bounds__(GR_THREADS) qr_kernel(QrArgs a) {
     __syncthreads();
     const double nrm = s_norm;
     logdet += log(nrm);
-    for (int p = tid; p < d.M; p += GR_THREADS) {
+    for (int p = tid; p < d.M; p += QT) {
       vk[p].re /= nrm;
       vk[p].im /= nrm;
     }
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(GR_THREADS) qr_kernel(QrArgs a) {
     }
     __syncthreads();
   }
-  for (int idx = tid; idx < ns * d.Mp; idx += GR_THREADS) {
+  for (int idx = tid; idx < ns * d.Mp; idx += QT) {
     const int p = idx % d.Mp, i = idx / d.Mp;
     const cplx v = ph[i * LD + p];
     *reinterpret_cast<double2*>(a.phi + (((size_t)wg * d.ne + ioff + i) * d.KC + (p >> 2)) * 32 + wl * 8 +
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(GR_THREADS) qr_kernel(QrArgs a) {
 
 inline size_t qr_smem_bytes(const Dims& d) {
   const int nmax = d.na > d.nb ? d.na : d.nb;
-  return sizeof(cplx) * (size_t)nmax * greens_ld(d) + sizeof(double) * (GR_THREADS / 32) + 32;
+  return sizeof(cplx) * (size_t)nmax * greens_ld(d) + sizeof(double) * (512 / 32) + 32;
 }
 
 // detR = exp(log_det - detR_shift); log_detR += log(detR); ot = ot / detR (single_det.py:245-254).
