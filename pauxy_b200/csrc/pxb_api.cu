@@ -625,12 +625,12 @@ int run_taylor2(pxb_handle h, double* phi, const int* active, int ochunk, int nc
   return 1;
 }
 
-template <int WMX, int WNX, int NG>
+template <int WMX, int WNX, int NG, int MG = 4>
 int launch_taylor3(pxb_handle h, const Taylor3Args& a, size_t smem, int grid, cudaStream_t st) {
-  auto kern = taylor3_kernel<WMX, WNX, NG>;
+  auto kern = taylor3_kernel<WMX, WNX, NG, MG>;
   PXB_CUDA(h, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   ++h->launches;
-  kern<<<grid, T3Cfg<NG>::threads, smem, st>>>(a);
+  kern<<<grid, T3Cfg<NG, MG>::threads, smem, st>>>(a);
   PXB_CUDA(h, cudaGetLastError());
   return PXB_OK;
 }
@@ -668,6 +668,48 @@ int run_taylor3(pxb_handle h, double* phi, const int* active, cudaStream_t st) {
     if (e && atoi(e) == 2) NG = 2;
   }
 #endif
+  // 48 columns and an even number of m-tiles (c4: 14 x 6 tile pairs): six column groups of TWO warps,
+  // 7 x 1 tile pairs per warp -- every sub-partition gets the same 21 tile pairs (22 : 20 with three
+  // groups of four warps) and a group rendez-vous is between two warps
+  bool six = NT8 == 6 && d.MT % 2 == 0 && d.MT / 2 >= 5 && d.MT / 2 <= 7;
+#ifdef PXB_EXPERIMENTS
+  {
+    const char* e = getenv("PXB_TAYLOR_GROUPS");
+    if (e && atoi(e) != 6) six = false;
+  }
+#endif
+  if (six) {
+    const int half = d.MT / 2;
+    a.m_off[0] = 0;
+    a.m_off[1] = half;
+    a.m_off[2] = a.m_off[3] = a.m_off[4] = d.MT;
+    for (int g = 0; g <= 6; ++g) a.n_off[g] = g;
+    for (int g = 0; g < 6; ++g)
+      for (int k = 0; k < 4; ++k) a.mperm[g][k] = k & 1;
+    a.nstage = 0;
+    a.nbuf = 0;
+    a.dbg = 0;
+#ifdef PXB_EXPERIMENTS
+    {
+      const char* e3 = getenv("PXB_T3_DBG");
+      if (e3) a.dbg = atoi(e3);
+    }
+#endif
+    for (int nbuf = 3; nbuf >= 2 && a.nbuf == 0; --nbuf)
+      for (int nstage = 12; nstage >= (nbuf == 3 ? 4 : 3); --nstage)
+        if (taylor3_smem_bytes(d, NT8, nbuf, nstage) <= (size_t)h->max_smem_optin) {
+          a.nbuf = nbuf;
+          a.nstage = nstage;
+          break;
+        }
+    if (a.nbuf != 0) {
+      const size_t smem6 = taylor3_smem_bytes(d, NT8, a.nbuf, a.nstage);
+      const int grid6 = std::min(d.W * nchunks, h->sm_count);
+      if (half == 7) return launch_taylor3<7, 1, 6, 2>(h, a, smem6, grid6, st);
+      if (half == 6) return launch_taylor3<6, 1, 6, 2>(h, a, smem6, grid6, st);
+      return launch_taylor3<5, 1, 6, 2>(h, a, smem6, grid6, st);
+    }
+  }
   const int ctas = NG == 1 ? 2 : 1;
   int msize[4];
   a.m_off[0] = 0;

@@ -35,9 +35,9 @@ struct Taylor3Args {
   int S;                // doubles per kc row of an iterate buffer: NT8 * 64 + 4 (skewed rows)
   int nstage;           // ring depth
   int nbuf;             // tile buffers: iterate + 1 phi tile (2) or iterate + 2 alternating phi tiles (3)
-  int m_off[5];         // m-group boundaries (4 groups)
-  int n_off[4];         // column-group boundaries (NG = 2 or 3 groups)
-  int mperm[3][4];      // m-group of the warp of column group g on sub-partition s
+  int m_off[5];         // m-group boundaries (MG = 4 or 2 groups)
+  int n_off[7];         // column-group boundaries (NG = 1, 2, 3 or 6 groups)
+  int mperm[6][4];      // m-group of the k-th warp of column group g
   int dbg;              // timing experiments (PXB_EXPERIMENTS builds): 1 no epilogue / barriers, 2 no ring hand-shake, 4 no phi reload
 };
 
@@ -49,14 +49,17 @@ struct Taylor3Args {
 //   NG = 1:  4 consumer warps, TWO CTAs per SM (two walkers in flight, each with its own VHS ring): shapes
 //           with at most 16 orbital columns (c3: 14), where splitting the columns would leave a warp
 //           6 DMMAs per k-step; 128 registers, no rebalancing
-template <int NG>
+//   NG = 6, MG = 2: 12 consumer warps in six column groups of TWO warps (7 x 1 tile pairs each at c4:
+//           14 m-tiles x 6 column tiles split evenly, 21 tile pairs on every sub-partition instead of
+//           22 : 20, and a group rendez-vous between two warps instead of four)
+template <int NG, int MG = 4>
 struct T3Cfg {
-  static constexpr int consumers = 4 * NG;
+  static constexpr int consumers = MG * NG;
   static constexpr int threads = (consumers + 4) * 32;
   static constexpr int ctas_per_sm = NG == 1 ? 2 : 1;
   static constexpr bool rebalance = NG > 1;  // setmaxnreg: producer warpgroup -> consumers
-  static constexpr int regs_producer = NG == 2 ? 40 : 24;
-  static constexpr int regs_consumer = NG == 2 ? 232 : 160;
+  static constexpr int regs_producer = consumers == 8 ? 40 : 24;
+  static constexpr int regs_consumer = consumers == 8 ? 232 : 160;
   static_assert(!rebalance ||
                     consumers * (regs_consumer - (65536 / threads) / 8 * 8) <= 4 * ((65536 / threads) / 8 * 8 - regs_producer),
                 "setmaxnreg.inc would block: more registers requested than the producer warpgroup releases");
@@ -65,25 +68,28 @@ constexpr int T3_MIN_STAGES2 = 3;  // fewest ring stages accepted with two itera
 
 inline size_t taylor3_smem_bytes(const Dims& d, int NT8, int nbuf, int nstage) {
   const size_t S = (size_t)NT8 * 64 + 4;
-  return ((size_t)nbuf * d.KC * S + (size_t)nstage * d.MT * T2_KS * 64) * sizeof(double) + 2 * (size_t)nstage * 8 + 6 * 8 + 128;
+  return ((size_t)nbuf * d.KC * S + (size_t)nstage * d.MT * T2_KS * 64) * sizeof(double) + 2 * (size_t)nstage * 8 + 12 * 8 + 128;
 }
 
+__device__ __forceinline__ void bar_sync_threads(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void cp_async_8(void* smem_dst, const void* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 
 // phi columns o0 .. o0 + no of walker (wg, wl) -> planar B fragments of the n8-tiles [nt0, nt0 + ntn)
 // of buffer T (element (k = p & 3, n = ol & 7) of fragment (kc = p >> 2, nt = ol >> 3, plane) sits at
-// 4 n + k), by the 128 threads of a column group; 8-byte cp.async copies de-interleave (re, im) on
+// 4 n + k), by the 128 (or 64) threads of a column group; 8-byte cp.async copies de-interleave (re, im) on
 // the fly and complete in the background, padding orbitals are zero-filled with plain stores
 __device__ __forceinline__ void taylor3_load_tile(const Taylor3Args& a, double* T, int wg, int wl, int o0, int no,
-                                                  int gtid, int nt0, int ntn) {
+                                                  int gtid, int nt0, int ntn, int gthreads = 128) {
   const Dims& d = a.d;
   const int tc = gtid & 7, tt = tc >> 1, c = tc & 1;
   const int ncol = 8 * ntn;
   for (int kc = 0; kc < d.KC; ++kc) {
     double* row = T + (size_t)kc * a.S + c * 32 + tt;
-    for (int oll = gtid >> 3; oll < ncol; oll += 16) {
+    for (int oll = gtid >> 3; oll < ncol; oll += gthreads >> 3) {
       const int ol = 8 * nt0 + oll;
       double* dst = row + (ol >> 3) * 64 + 4 * (ol & 7);
       if (ol < no)
@@ -94,8 +100,8 @@ __device__ __forceinline__ void taylor3_load_tile(const Taylor3Args& a, double* 
   }
 }
 
-struct T3Frag {  // fragments of one k-step for a WM x WN warp block (WM <= 4, WN <= 3)
-  double ar[4], ai[4], br[3], bi[3];
+struct T3Frag {  // fragments of one k-step for a WM x WN warp block (WM <= 7, WN <= 3)
+  double ar[7], ai[7], br[3], bi[3];
 };
 static_assert(T2_KS == 2, "the k loop of taylor3_orders is written for two k-steps per ring stage");
 
@@ -283,9 +289,9 @@ __device__ __forceinline__ void taylor3_orders(const Taylor3Args& a, uint32_t ph
 }
 
 // WMX = ceil(MT / 4), WNX = ceil(NT8 / NG): the largest warp rectangle; smaller groups use WMX-1 / WNX-1
-template <int WMX, int WNX, int NG>
-__global__ void __launch_bounds__(T3Cfg<NG>::threads, T3Cfg<NG>::ctas_per_sm) taylor3_kernel(Taylor3Args a) {
-  constexpr int T3_CONSUMERS = T3Cfg<NG>::consumers;
+template <int WMX, int WNX, int NG, int MG = 4>
+__global__ void __launch_bounds__(T3Cfg<NG, MG>::threads, T3Cfg<NG, MG>::ctas_per_sm) taylor3_kernel(Taylor3Args a) {
+  constexpr int T3_CONSUMERS = T3Cfg<NG, MG>::consumers;
   extern __shared__ __align__(128) double t3_smem[];
   const Dims& d = a.d;
   const size_t tsz = (size_t)d.KC * a.S;
@@ -301,7 +307,7 @@ __global__ void __launch_bounds__(T3Cfg<NG>::threads, T3Cfg<NG>::ctas_per_sm) ta
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], T3_CONSUMERS * kReleaseArrivals);
     }
-    for (int g2 = 0; g2 < 2 * NG; ++g2) mbar_init(&group_bar[g2], 4);
+    for (int g2 = 0; g2 < 2 * NG; ++g2) mbar_init(&group_bar[g2], MG);
     fence_barrier_init();
   }
   __syncthreads();
@@ -309,7 +315,7 @@ __global__ void __launch_bounds__(T3Cfg<NG>::threads, T3Cfg<NG>::ctas_per_sm) ta
   const int nks = (d.KC + T2_KS - 1) / T2_KS;
 
   if (warp >= T3_CONSUMERS) {
-    if constexpr (T3Cfg<NG>::rebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG>::regs_producer));
+    if constexpr (T3Cfg<NG, MG>::rebalance) asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG, MG>::regs_producer));
     if (warp != T3_CONSUMERS || (a.dbg & 2)) return;
     // ---------------- producer: lane mt streams m-tile mt of the walker's VHS ----------------
     unsigned s = 0, ph = 0;
@@ -338,14 +344,14 @@ __global__ void __launch_bounds__(T3Cfg<NG>::threads, T3Cfg<NG>::ctas_per_sm) ta
   }
 
   // ---------------- consumers ----------------
-  if constexpr (T3Cfg<NG>::rebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG>::regs_consumer));
-  const int ng = warp >> 2, mg = a.mperm[ng][warp & 3];
+  if constexpr (T3Cfg<NG, MG>::rebalance) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(T3Cfg<NG, MG>::regs_consumer));
+  const int ng = warp / MG, mg = a.mperm[ng][warp % MG];
   const int m0 = a.m_off[mg], wm = a.m_off[mg + 1] - m0;
   const int n0 = a.n_off[ng], wn = a.n_off[ng + 1] - n0;
   unsigned rs = 0, rph = 0;
   unsigned gph = 0;  // phases of this group's two barriers
   const uint32_t gbar = smem_u32(group_bar + 2 * ng);
-  const int gtid = tid & 127;  // thread index inside the column group
+  const int gtid = tid % (32 * MG);  // thread index inside the column group
   auto next_active = [&](int item) {
     while (item < nitems && a.active != nullptr && a.active[item / a.nchunks] == 0) item += gridDim.x;
     return item;
@@ -362,17 +368,17 @@ __global__ void __launch_bounds__(T3Cfg<NG>::threads, T3Cfg<NG>::ctas_per_sm) ta
     const int wg = w >> 2, wl = w & 3;
     const int nitem = next_active(item + gridDim.x);
     if (!prefetched) {
-      if (a.nbuf == 2) bar_sync_group(ng);  // the group has finished with the previous item's phi tile
-      taylor3_load_tile(a, Tbuf + (size_t)pcur * tsz, wg, wl, o0, no, gtid, n0, wn);
+      if (a.nbuf == 2) bar_sync_threads(1 + ng, 32 * MG);  // the group has finished with the previous item's phi tile
+      taylor3_load_tile(a, Tbuf + (size_t)pcur * tsz, wg, wl, o0, no, gtid, n0, wn, 32 * MG);
     }
     cp_async_wait_all();
-    bar_sync_group(ng);
+    bar_sync_threads(1 + ng, 32 * MG);
     prefetched = false;
     if (a.nbuf == 3 && nitem < nitems) {  // next item's phi tile into the other phi buffer
       const int w2 = nitem / a.nchunks, c2 = nitem % a.nchunks;
       const int no0 = c2 * a.ochunk;
       taylor3_load_tile(a, Tbuf + (size_t)(pcur ^ 3) * tsz, w2 >> 2, w2 & 3, no0, min(a.ochunk, d.ne - no0), gtid, n0,
-                        wn);
+                        wn, 32 * MG);
       prefetched = true;
     }
     double* gphi = a.phi + ((size_t)wg * d.ne + o0) * d.KC * 32 + wl * 8 + ((lane >> 2) & 3) * 2;
