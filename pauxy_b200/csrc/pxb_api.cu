@@ -464,7 +464,13 @@ int run_vhs_gemm(pxb_handle h, cudaStream_t st) {
   EpiVHS epi{h->ptr<double>(A_VF), d.KC, d.MT, d.sqrt_dt, vf_walker(d),
              h->vhs_sym ? h->ptr<int>(A_RTMAP) : nullptr};
   ++h->launches;
-  PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
+  // CTA tile 16 x 16 tiles; 16 x 8 when the finer tiles fill the last wave of the persistent grid so much
+  // better that it outweighs their lower reuse of L (1024 walkers per GPU: 11 half-size rounds
+  // instead of 6 full ones)
+  const int mb = (g.MTiles + 15) / 16, sms = h->sm_count;
+  const int r16 = (mb * ((d.WG + 15) / 16) + sms - 1) / sms, r8 = (mb * ((d.WG + 7) / 8) + sms - 1) / sms;
+  if (0.52 * r8 < 0.985 * r16) PXB_CUDA(h, (launch_gemm_tma<4, 4, 4, 2>(g, epi, 1, h->sm_count, st)));
+  else PXB_CUDA(h, (launch_gemm_tma<4, 8, 4, 2>(g, epi, 1, h->sm_count, st)));
   return PXB_OK;
 }
 
