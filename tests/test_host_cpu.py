@@ -42,6 +42,17 @@ def test_create_validates_arguments_without_gpu():
     assert lib.pxb_propagate(h, None, 0, 0, 0.0, 1, None) == -3
     assert lib.pxb_local_energy(h, None) == -3
     lib.pxb_destroy(h)
+    # complex Cholesky vectors (PXB_FLAG_COMPLEX_CHOLESKY): stacked operands make the arena larger; they
+    # are refused together with the Cholesky-form exchange and with back propagation
+    cc = _lib.PxbConfig(108, 21, 21, 500, 8192, 6, 0, 0, 0.005, _lib.EXCHANGE_MODES['auto'],
+                        _lib.FLAG_COMPLEX_CHOLESKY, 0, 1)
+    assert lib.pxb_create(ctypes.byref(h), ctypes.byref(cc)) == 0
+    n2 = ctypes.c_size_t()
+    assert lib.pxb_arena_bytes(h, ctypes.byref(n2)) == 0 and n2.value > n.value
+    lib.pxb_destroy(h)
+    for mode, nbp in ((_lib.EXCHANGE_MODES['cholesky'], 0), (_lib.EXCHANGE_MODES['auto'], 5)):
+        bad = _lib.PxbConfig(108, 21, 21, 500, 64, 6, 0, 0, 0.005, mode, _lib.FLAG_COMPLEX_CHOLESKY, nbp, 1)
+        assert lib.pxb_create(ctypes.byref(h), ctypes.byref(bad)) == -1
 
 
 def test_comb_host_bit_exact(golden):
@@ -71,7 +82,7 @@ def test_pair_branch_plan_matches_oracle():
         assert numpy.array_equal(a[0], b[0]) and a[1] == b[1]
 
 
-@pytest.mark.parametrize('name', ['test_generic', 'c1', 'stress_comb'])
+@pytest.mark.parametrize('name', ['test_generic', 'c1', 'stress_comb', 'cplx_driver', 'cplx_stress'])
 def test_host_setup_matches_reference(golden, name):
     g = golden(name)
     system, trial, prop = host_setup(g['h1e'], g['hs_pot'], float(g['ecore']),
@@ -117,6 +128,13 @@ def test_unsupported_modes_fail_loudly():
     assert Continuous(system, trial, Q(), options={'hybrid': False}).hybrid is False
     # continuous.py:30-33: free projection switches the force bias off
     assert Continuous(system, trial, Q(), options={'free_projection': True}).force_bias is False
+    # alternative energy evaluators (systems/generic.py:77-124): exact_eri is honoured (ERI form of
+    # the exchange), the sampled / truncated ones are refused
+    from pauxy_b200.systems import Generic
+    assert Generic(nelec=(1, 1), h1e=g_h1e, chol=hs, ecore=0.0, exact_eri=True).exact_eri
+    for kw in ('stochastic_ri', 'pno', 'control_variate'):
+        with pytest.raises(NotImplementedError):
+            Generic(nelec=(1, 1), h1e=g_h1e, chol=hs, ecore=0.0, **{kw: True})
 
 
 def test_plan_moves_partitions_pairs():
