@@ -283,6 +283,39 @@ def case_multi_det_driver(name, hybrid=True):
                                     mf_core=numpy.array(p.mf_core)))
 
 
+def case_multi_det_nomsd_complex(name):
+    """Driver run with a NON-orthogonal multi-determinant trial whose orbitals and coefficients are
+    complex (utils/testing.py:31-45 get_random_nomsd(cplx=True)): complex per-determinant orbitals,
+    half-rotated Cholesky vectors and one-body integrals on a real Hamiltonian."""
+    rh._install_paths()
+    from pauxy.utils.testing import get_random_nomsd
+    numpy.random.seed(7)
+    nmo, nelec = 10, (4, 3)
+    h1e, chol, enuc, _ = generate_hamiltonian(nmo, nelec, cplx=False)
+    hs = 2.0 * chol.reshape((-1, nmo * nmo)).T.copy()
+
+    class _S(object):
+        nbasis, nup, ndown = nmo, nelec[0], nelec[1]
+    coeffs, wfn = get_random_nomsd(_S, ndet=3, cplx=True)
+    # orthonormal columns per determinant and spin keep the overlaps O(1)
+    for i in range(wfn.shape[0]):
+        wfn[i, :, :nelec[0]] = numpy.linalg.qr(wfn[i, :, :nelec[0]])[0]
+        wfn[i, :, nelec[0]:] = numpy.linalg.qr(wfn[i, :, nelec[0]:])[0]
+    init = wfn[0].copy()
+
+    def factory(system):
+        from pauxy.trial_wavefunction.multi_slater import MultiSlater
+        return MultiSlater(system, (coeffs, wfn), init=init)
+    opts = options(12, 0.01, 5, 3, 8, stab=3, popc=1)
+    a, tr = rh.run_reference_traced(h1e, hs, enuc, nelec, opts, trial_factory=factory)
+    meta = dict(h1e=h1e, hs_pot=hs, ecore=enuc, nelec=numpy.array(nelec), dt=0.01,
+                nwalkers=12, steps=5, blocks=3, seed=8, stab=3, popc=1, hybrid=True,
+                coeffs=numpy.array(coeffs), orbitals=numpy.array(wfn), init=init)
+    p = a.propagators.propagator
+    save(name, meta, tr, setup=dict(mf_shift=numpy.array(p.mf_shift), BH1=numpy.array(p.BH1),
+                                    mf_core=numpy.array(p.mf_core)))
+
+
 def case_local_energy():
     """pauxy/estimators/tests/test_generic.py:33-64 inputs and golden."""
     rh._install_paths()
@@ -355,6 +388,8 @@ if __name__ == '__main__':
                     walkers={'population_control': 'pair_branch',
                              'min_weight': 0.9, 'max_weight': 1.1},
                     scale_chol=3.0, dt=0.01)
+    if 'mdc' in which:
+        case_multi_det_nomsd_complex('md_nomsd_cplx')
     if 'cplx' in which:
         case_complex('cplx_driver', 10, (3, 3), 12)
         case_complex('cplx_stress', 10, (4, 2), 16, scale_chol=4.0, dt=0.02, steps=5, blocks=4, stab=3)

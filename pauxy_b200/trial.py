@@ -23,7 +23,7 @@ class MultiSlater(object):
     wfn = (coeffs, psi[ndets, M, ne])  non-orthogonal expansion, or one determinant psi[M, ne];
     wfn = (coeffs, occa, occb)         particle-hole (orthogonal) expansion: occupied orbital lists
                                        per determinant (multi_slater.py:190-205).
-    The device kernels need real-valued orbitals; the CI coefficients may be complex."""
+    Orbitals and CI coefficients may be complex (complex orbitals select PXB_FLAG_COMPLEX_CHOLESKY)."""
 
     def __init__(self, system, wfn, init=None, options=None, verbose=False):
         self.name = "MultiSlater"

@@ -296,6 +296,8 @@ def _md_trial(g):
     from pauxy_b200.trial import MultiSlater
 
     def factory(system):
+        if 'orbitals' in g:      # non-orthogonal expansion given by its (possibly complex) orbitals
+            return MultiSlater(system, (g['coeffs'], g['orbitals']), init=g['init'])
         return MultiSlater(system, (g['coeffs'], g['occa'], g['occb']), init=g['init'])
     return factory
 
@@ -332,7 +334,7 @@ def test_multi_det_walker_reference_tests(golden, name):
     assert eng.weight[0].item() == pytest.approx(float(g['ref_test_golden_weight']), rel=1e-9)
 
 
-@pytest.mark.parametrize('name', ['md_driver', 'md_driver_le'])
+@pytest.mark.parametrize('name', ['md_driver', 'md_driver_le', 'md_nomsd_cplx'])
 def test_multi_det_driver(golden, name):
     """Whole driver loop with a 3-determinant particle-hole trial (MultiDetWalker population, comb,
     re-orthogonalisation, local_energy_multi_det in the mixed estimator) against traces of the
