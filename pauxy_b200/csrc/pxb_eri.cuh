@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
 #pragma unroll
     for (int q = 0; q < EQ_QD; ++q) {
       mbar_init(&qfull[q], 1);
-      mbar_init(&qempty[q], NCW);
+      mbar_init(&qempty[q], NCW * kReleaseArrivals);
     }
     fence_barrier_init();
   }
@@ -183,8 +183,7 @@ __global__ void __launch_bounds__(gemm_tma_threads<EQ_CWM * EQ_CWN>(), 1) exx_er
       const unsigned q = qc % EQ_QD, qph = (qc / EQ_QD) & 1u;
       mbar_wait(&qfull[q], qph);
       item = qitem[q];
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&qempty[q]);
+      ring_release(&qempty[q], lane);
       ++qc;
     }
     if (item < 0) break;

@@ -197,6 +197,7 @@ __device__ __forceinline__ void taylor3_orders(const Taylor3Args& a, uint32_t ph
   // buffer: kc = 2 mt + (g >> 2), position 4 (2t + e) + (g & 3)
   const uint32_t st_off = (uint32_t)((g >> 2) * a.S + 8 * t + (g & 3)) * 8 + (uint32_t)(2 * m0) * Sb + n0 * 512;
 
+  const uint32_t pad_last = 2 * (m0 + WM - 1) + (g >> 2) >= d.KC ? (uint32_t)Sb : 0u;
   double P1[WM][WN][2], P2[WM][WN][2], P3[WM][WN][2];
   for (int n = d.exp_order; n >= 1; --n) {
 #pragma unroll
@@ -236,17 +237,18 @@ __device__ __forceinline__ void taylor3_orders(const Taylor3Args& a, uint32_t ph
     // before it overwrites its part of the iterate in place.
     const bool inplace = n > 1 && n < d.exp_order;
     if (inplace) {
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar) : "memory");
+      ring_release_u32(gbar, lane);  // __syncwarp + lane-0 arrive (every lane in the checker build)
     }
 #pragma unroll
     for (int i = 0; i < WM; ++i) {
 #pragma unroll
       for (int j = 0; j < WN; ++j) {
-        const uint32_t so = st_off + (uint32_t)(2 * i) * Sb + j * 512;
+        // a padding row (kc row KC of the last m-tile when KC is odd; only the warp's last tile can
+        // hold it) reads row KC - 1 of the phi tile instead of whatever lies behind the tile (the VHS
+        // ring); its values are never stored
+        const uint32_t so = st_off + (uint32_t)(2 * i) * Sb + j * 512 - (i == WM - 1 ? pad_last : 0u);
 #pragma unroll
         for (int e = 0; e < 2; ++e) {
-          // (values of padding rows are computed from in-range shared memory and never stored)
           const double re = (P1[i][j][e] - P2[i][j][e]) * rn + lds_f64(phib + so + e * 32);
           const double im = ((P3[i][j][e] - P1[i][j][e]) - P2[i][j][e]) * rn + lds_f64(phib + so + e * 32 + 256);
           P1[i][j][e] = re;
@@ -280,8 +282,7 @@ __device__ __forceinline__ void taylor3_orders(const Taylor3Args& a, uint32_t ph
       }
     }
     if (n > 1) {  // S_{n-1} complete
-      __syncwarp();
-      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(gbar + 8) : "memory");
+      ring_release_u32(gbar + 8, lane);
       mbar_wait_u32(gbar + 8, (gph >> 1) & 1u);
       gph ^= 2u;
     }
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(T3Cfg<NG, MG>::threads, T3Cfg<NG, MG>::ctas_pe
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], T3_CONSUMERS * kReleaseArrivals);
     }
-    for (int g2 = 0; g2 < 2 * NG; ++g2) mbar_init(&group_bar[g2], MG);
+    for (int g2 = 0; g2 < 2 * NG; ++g2) mbar_init(&group_bar[g2], MG * kReleaseArrivals);
     fence_barrier_init();
   }
   __syncthreads();

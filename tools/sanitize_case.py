@@ -2,7 +2,8 @@
     compute-sanitizer --tool memcheck|racecheck python tools/sanitize_case.py
 Runs (1) the c1 smoke walk (32 walkers x 10 steps, comb every step, one re-orthogonalisation, local
 energy, block output), (2) a c2-shaped walk with 64 walkers so that the TMA-fed persistent kernels
-(taylor2, gemm_tma, exx_eri, theta) run under the tool, (3) with >= 2 GPUs: the 64-walker stress
+(taylor2, gemm_tma, exx_eri, theta) run under the tool, c3- and c4-shaped walks with a handful of
+walkers for the taylor3 variants, CholeskyQR2 and the exchange item queue, (3) with >= 2 GPUs: the 64-walker stress
 walk on 2 ranks with the peer-memory comb (cross-device pulls of live arenas)."""
 import os
 import sys
@@ -62,11 +63,15 @@ def two_rank_worker(rank, world, port):
 
 
 if __name__ == '__main__':
-    which = sys.argv[1:] or ['c1', 'c2', 'multi']
+    which = sys.argv[1:] or ['c1', 'c2', 'c3', 'c4', 'multi']
     if 'c1' in which:
         walk('c1', 32, 5, 2, 5)
     if 'c2' in which:
         walk('c2', 64, 3, 1, 2, rng='philox')
+    if 'c3' in which:   # taylor3 with one column group and two CTAs per SM, register-resident Gauss-Jordan / CholeskyQR2
+        walk('c3', 12, 3, 1, 2, rng='philox')
+    if 'c4' in which:   # taylor3 with six column groups of two warps, the dynamic exchange queue, 16 x 8 VHS tiles
+        walk('c4', 8, 2, 1, 2, rng='philox')
     if 'multi' in which and torch.cuda.device_count() >= 2:
         import torch.multiprocessing as mp
         mp.start_processes(two_rank_worker, args=(2, 29733), nprocs=2, start_method='spawn')
