@@ -2,6 +2,7 @@
 import ctypes
 import os
 import re
+import sys
 
 import numpy
 import pytest
@@ -413,3 +414,33 @@ def test_hdf5_formats_round_trip(golden, tmp_path, monkeypatch):
     io.write_walkers_h5(fn, buf[2:], 2, create=False)
     numpy.testing.assert_array_equal(io.read_walkers_h5(fn, 1, 3), buf[1:])
     sys.modules.pop('h5py', None)
+
+
+def test_hot_kernels_are_dmma_and_tma_in_the_built_library():
+    """Static check of the built library (cuobjdump -sass, no GPU needed): the GEMM-like kernels of the
+    path issue FP64 tensor instructions (DMMA = mma.sync.m8n8k4.f64) and are fed by TMA bulk copies
+    (UBLKCP) with mbarriers (SYNCS); the warp-level kernels (Green's function, CholeskyQR2) use DMMA
+    and warp reductions.  What profiles/r02/sass_summary.txt tabulates."""
+    import shutil
+    import subprocess
+    if shutil.which('cuobjdump') is None:
+        pytest.skip('cuobjdump not available')
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, 'tools', 'sass_summary.py')],
+                         capture_output=True, text=True, timeout=600).stdout
+    rows = {}
+    for line in out.splitlines():
+        if line.startswith('#') or line.startswith('kernel'):
+            continue
+        f = line.split()
+        name = ' '.join(f[:-16])
+        rows[name] = [int(x) for x in f[-16:]]      # instr regs stack DMMA UBLKCP SYNCS LDGSTS ...
+    def col(name, idx):
+        hits = [v for k, v in rows.items() if k.startswith(name)]
+        assert hits, name
+        return [h[idx] for h in hits]
+    for k in ('taylor3_kernel', 'taylor2_kernel', 'exx_eri_kernel', 'gemm_tma_kernel'):
+        assert min(col(k, 3)) > 0 and min(col(k, 4)) > 0 and min(col(k, 5)) > 0, k   # DMMA, UBLKCP, SYNCS
+    for k in ('theta_kernel', 'cholqr_kernel'):
+        assert min(col(k, 3)) > 0, k
+    assert max(col('theta_kernel<3>', 13)) > 0      # REDUX: the register-resident pivot search
