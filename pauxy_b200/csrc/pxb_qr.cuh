@@ -34,8 +34,10 @@ constexpr double CQR_TOL2 = 0.25;   // second pass: G is the identity to ~1e-5 u
 
 inline size_t cholqr_smem_per_warp(int nmax) {
   const int lda = nmax | 1;
-  // G / R [nmax][lda], A = R^-T [nmax][lda] + 3 elements of slack, reciprocal diagonal [nmax]
-  return ((size_t)(2 * nmax * lda + 3) * sizeof(cplx) + (size_t)nmax * sizeof(double) + 15) / 16 * 16;
+  const int nc = (nmax + 7) / 8 * 8;
+  // G / R [nmax][lda], A = R^-T [nmax][lda] + 3 elements of slack (apply step), + nc elements of slack: the
+  // rotating-slot Cholesky reads up to nc - 1 elements past the end of a row of R (padding slots)
+  return ((size_t)(2 * nmax * lda + 3 + nc) * sizeof(cplx) + 15) / 16 * 16;
 }
 
 // G = V^H V for the ns orbitals of one (walker, spin) -> Gs (full Hermitian matrix)
